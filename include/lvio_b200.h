@@ -28,6 +28,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define LVB_API __attribute__((visibility("default")))
+#else
+#define LVB_API
+#endif
+
 #define LVB_OK 0
 #define LVB_ERR_INVALID (-1)     /* bad argument / index out of range */
 #define LVB_ERR_CUDA (-2)        /* no usable device, launch or runtime failure */
@@ -89,94 +95,94 @@ typedef struct lvb_solve_summary {
     double total_time_in_seconds;
 } lvb_solve_summary;
 
-int lvb_version(void);
-void lvb_default_options(lvb_solve_options* o);
+LVB_API int lvb_version(void);
+LVB_API void lvb_default_options(lvb_solve_options* o);
 
 /* ---- context ------------------------------------------------------------------------- */
 /* cuda_stream: a cudaStream_t to launch on (e.g. torch.cuda.current_stream().cuda_stream),
  * or NULL to let the context create its own non-blocking stream. */
-int lvb_ctx_create(int device, void* cuda_stream, lvb_ctx** out);
-void lvb_ctx_destroy(lvb_ctx* ctx);
-const char* lvb_last_error(void);            /* thread-local text of the last failure */
-long long lvb_launch_count(lvb_ctx* ctx);    /* kernels launched through this context so far */
-int lvb_ctx_synchronize(lvb_ctx* ctx);
+LVB_API int lvb_ctx_create(int device, void* cuda_stream, lvb_ctx** out);
+LVB_API void lvb_ctx_destroy(lvb_ctx* ctx);
+LVB_API const char* lvb_last_error(void);            /* thread-local text of the last failure */
+LVB_API long long lvb_launch_count(lvb_ctx* ctx);    /* kernels launched through this context so far */
+LVB_API int lvb_ctx_synchronize(lvb_ctx* ctx);
 
 /* Multi-GPU: one process per GPU; the id is produced on rank 0 and shipped to
  * the other ranks by the caller (torch.distributed broadcast in bench.py). After init every
  * lvb_ba_solve / lvb_icp_scan_to_map on this context all-reduces its reduced normal
  * equations (one ncclAllReduce(sum,f64) per LM iteration). */
-int lvb_comm_unique_id(char id[128]);
-int lvb_comm_init(lvb_ctx* ctx, int rank, int world_size, const char id[128]);
+LVB_API int lvb_comm_unique_id(char id[128]);
+LVB_API int lvb_comm_init(lvb_ctx* ctx, int rank, int world_size, const char id[128]);
 
 /* ---- bundle adjustment: stands behind adapt::Problem + ceres::Solve -------------------
  * (adapt/problem.h:34-88, backend.cpp:96-183,192-211)                                   */
-int lvb_ba_create(lvb_ctx* ctx, lvb_ba** out);
-void lvb_ba_destroy(lvb_ba* ba);
+LVB_API int lvb_ba_create(lvb_ctx* ctx, lvb_ba** out);
+LVB_API void lvb_ba_destroy(lvb_ba* ba);
 /* cam[22] = 2 x { fx fy cx cy  extrinsic[7] (T_body_cam) } : Camera::Get(0), Camera::Get(1)
  * (visual/camera.h:79-80, sensor.h:21-24) */
-int lvb_ba_set_cameras(lvb_ba* ba, const double cam[22]);
+LVB_API int lvb_ba_set_cameras(lvb_ba* ba, const double cam[22]);
 /* Problem::AddParameterBlock(double*, size[, parameterization]) + SetParameterBlockConstant
  * (adapt/problem.h:49-63): poses use ProductParameterization(EigenQuaternion, Identity3)
  * (backend.cpp:99-101); vec3 blocks (Vw, linearized_ba, linearized_bg, backend.cpp:147-152)
  * and inverse depths (backend.cpp:121) are Euclidean.  is_const may be NULL. */
-int lvb_ba_set_poses(lvb_ba* ba, int n, const double* poses7, const uint8_t* is_const);
-int lvb_ba_set_vec3(lvb_ba* ba, int n, const double* v3, const uint8_t* is_const);
-int lvb_ba_set_inv_depths(lvb_ba* ba, int n, const double* rho, const uint8_t* is_const);
+LVB_API int lvb_ba_set_poses(lvb_ba* ba, int n, const double* poses7, const uint8_t* is_const);
+LVB_API int lvb_ba_set_vec3(lvb_ba* ba, int n, const double* v3, const uint8_t* is_const);
+LVB_API int lvb_ba_set_inv_depths(lvb_ba* ba, int n, const double* rho, const uint8_t* is_const);
 /* Problem::AddResidualBlock(cost, loss, x0, xs...) in bulk (adapt/problem.h:37-47):
  * consts is n x stride(kind) (AoS, one record per block), idx is n x nidx(kind). Appends. */
-int lvb_ba_add_factors(lvb_ba* ba, int kind, int n, const double* consts, const int32_t* idx);
+LVB_API int lvb_ba_add_factors(lvb_ba* ba, int kind, int n, const double* consts, const int32_t* idx);
 /* ceres::HuberLoss(a) for every block of `kind` (backend.cpp:98 uses 1.0 on the visual kinds);
  * a <= 0 means NULL / TrivialLoss. */
-int lvb_ba_set_loss(lvb_ba* ba, int kind, double huber_a);
+LVB_API int lvb_ba_set_loss(lvb_ba* ba, int kind, double huber_a);
 /* Freeze the structure, sort/transpose to the device layout, upload.  */
-int lvb_ba_finalize(lvb_ba* ba);
-int lvb_ba_dims(lvb_ba* ba, int* dim_camera, int* n_inv_depth_free, int* n_residual_rows);
+LVB_API int lvb_ba_finalize(lvb_ba* ba);
+LVB_API int lvb_ba_dims(lvb_ba* ba, int* dim_camera, int* n_inv_depth_free, int* n_residual_rows);
 /* Re-upload parameter values only (same structure) -- used between solves / by the bench. */
-int lvb_ba_update_params(lvb_ba* ba, const double* poses7, const double* v3, const double* rho);
+LVB_API int lvb_ba_update_params(lvb_ba* ba, const double* poses7, const double* v3, const double* rho);
 
 /* CostFunction::Evaluate for every block of `kind` at the current parameters (parity entry):
  * r is n x n_res, J is n x n_res x cols(kind) with cols = 15, 7, 1, 32, 14, 7.  Raw values:
  * no loss correction, ambient (not tangent) Jacobians, as Ceres' Evaluate returns them.
  * r or J may be NULL.  The *_device variant runs the same kernel without the copy back
  * (bench roofline entry). */
-int lvb_ba_eval(lvb_ba* ba, int kind, double* r, double* J);
-int lvb_ba_eval_device(lvb_ba* ba, int kind);
+LVB_API int lvb_ba_eval(lvb_ba* ba, int kind, double* r, double* J);
+LVB_API int lvb_ba_eval_device(lvb_ba* ba, int kind);
 
 /* The Schur-reduced, LM-damped camera system of the first trust-region step at the current
  * parameters with the given radius (Jacobi scaling taken at this point): S is
  * dim_camera x dim_camera row-major, b the right-hand side (S dx = b), cost = 1/2 sum rho.
  * Parity entry for kernels K4/K5. */
-int lvb_ba_reduced_system(lvb_ba* ba, double radius, double* S, double* b, double* cost);
+LVB_API int lvb_ba_reduced_system(lvb_ba* ba, double radius, double* S, double* b, double* cost);
 
 /* ceres::Solve(options, &problem, &summary) (adapt/problem.h:83-88). Parameters are updated
  * on the device; fetch them with the getters (the shim writes them back in place). */
-int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary* summary);
-int lvb_ba_get_poses(lvb_ba* ba, double* poses7);
-int lvb_ba_get_vec3(lvb_ba* ba, double* v3);
-int lvb_ba_get_inv_depths(lvb_ba* ba, double* rho);
+LVB_API int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary* summary);
+LVB_API int lvb_ba_get_poses(lvb_ba* ba, double* poses7);
+LVB_API int lvb_ba_get_vec3(lvb_ba* ba, double* v3);
+LVB_API int lvb_ba_get_inv_depths(lvb_ba* ba, double* rho);
 /* compute_reprojection_error over all LVB_POSE_ONLY-shaped (ob, pw, pose) triples
  * (backend.cpp:185-190, outlier pass :229-245): err[i] = |pi(pw_i, pose_i) - ob_i|, weight 1. */
-int lvb_ba_reprojection_errors(lvb_ba* ba, int n, const double* ob_pw /* n x 5 */, const int32_t* pose_idx, double* err);
+LVB_API int lvb_ba_reprojection_errors(lvb_ba* ba, int n, const double* ob_pw /* n x 5 */, const int32_t* pose_idx, double* err);
 
 /* ---- lidar scan-to-map: stands behind pcl::KdTreeFLANN + FeatureAssociation::ScanToMapWith*
  * (association.cpp:270-384) and the two Solve calls of Mapping::Optimize (mapping.cpp:139-191) */
-int lvb_icp_create(lvb_ctx* ctx, lvb_icp** out);
-void lvb_icp_destroy(lvb_icp* icp);
+LVB_API int lvb_icp_create(lvb_ctx* ctx, lvb_icp** out);
+LVB_API void lvb_icp_destroy(lvb_icp* icp);
 /* KdTreeFLANN::setInputCloud (association.cpp:278-279,336-337).  points: n records of
  * stride_bytes (>= 12) whose first three floats are x,y,z -- 32 for pcl::PointXYZI, 16 for a
  * packed float4.  cell_size: edge of the voxel grid the cloud is hashed into; queries are
  * exact within that radius. */
-int lvb_icp_set_map(lvb_icp* icp, const void* points, int n, int stride_bytes, float cell_size);
+LVB_API int lvb_icp_set_map(lvb_icp* icp, const void* points, int n, int stride_bytes, float cell_size);
 /* Batched KdTreeFLANN::nearestKSearch(point, 3, idx, d2) for every scan point after the
  * float32 SE3 transform of association.cpp:287-294.  Exact 3-NN among map points with
  * d2 <= max_d2 (max_d2 <= cell_size^2), ascending by (d2, index); missing neighbours are
  * idx = -1, d2 = +inf.  idx, d2 are n x 3. */
-int lvb_icp_knn3(lvb_icp* icp, const void* scan, int n, int stride_bytes, const double frame_pose[7],
+LVB_API int lvb_icp_knn3(lvb_icp* icp, const void* scan, int n, int stride_bytes, const double frame_pose[7],
                  float max_d2, int32_t* idx, float* d2);
 /* Per scan point: the gate of association.cpp:296-300 and, for accepted points, the raw
  * LidarPlaneErrorRPZ (mode 0) / LidarPlaneErrorYXY (mode 1) residual and 1x3 Jacobian
  * (ceres/lidar_error.hpp:42-110) at rpyxyz.  Rejected rows are zero.  Parity entry. */
-int lvb_icp_eval(lvb_icp* icp, int mode, const void* scan, int n, int stride_bytes,
+LVB_API int lvb_icp_eval(lvb_icp* icp, int mode, const void* scan, int n, int stride_bytes,
                  const double frame_pose[7], const double map_pose[7], const double rpyxyz[6],
                  double weight, double dist_thr, uint8_t* accepted, double* r, double* J);
 /* ScanToMapWithGround (mode 0) / ScanToMapWithSegmented (mode 1) followed by adapt::Solve:
@@ -184,7 +190,7 @@ int lvb_icp_eval(lvb_icp* icp, int mode, const void* scan, int n, int stride_byt
  * prior_weight < 0 omits the PoseErrorRPZ/YXY prior (relocate = true); huber_a <= 0 is
  * TrivialLoss (association.cpp:272), 0.1 for the segmented cloud (:330).
  * summary->num_residual_blocks = accepted correspondences (+1 with the prior). */
-int lvb_icp_scan_to_map(lvb_icp* icp, int mode, const void* scan, int n, int stride_bytes,
+LVB_API int lvb_icp_scan_to_map(lvb_icp* icp, int mode, const void* scan, int n, int stride_bytes,
                         const double frame_pose[7], const double map_pose[7], double rpyxyz[6],
                         double weight, double prior_weight, double huber_a, double dist_thr,
                         const lvb_solve_options* options, lvb_solve_summary* summary);

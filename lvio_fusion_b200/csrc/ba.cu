@@ -1,0 +1,1201 @@
+// ba.cu -- sliding-window bundle adjustment on the device: the kernels behind
+// adapt::Problem / ceres::Solve for the factor mix of Backend::BuildProblem
+// (/root/reference/src/lvio_fusion/src/backend.cpp:96-183,192-211).
+//
+// Data layout in HBM (all FP64 unless noted):
+//   parameter blocks   poses[n][7] (AoS, 56 B), vec3[n][3], rho[n]           + candidate copies
+//   factor constants   SoA planes per kind: plane k of kind K at fc[K] + k*n[K]  (coalesced reads)
+//   factor indices     SoA int32 planes fi[K] + k*n[K]
+//   IMU constants      AoS per factor, 287 doubles: 17 scalars, five 3x3 sub-blocks, U (15x15)
+//   accumulators       Hpp (dimc x dimc, lower), gc, Hll, gl, per-TwoFrame-factor W rows (12 planes)
+//   reduction arena    [ S | rhs | gc | diag(Hpp) | 16 scalars ]  -- the one buffer all-reduced per iteration
+//
+// Kernels (K-numbers of SURVEY.md section 2):
+//   K1  ba_eval_*            residual + ambient Jacobian materialised (parity / roofline entry)
+//   K1-K4 ba_linearize       fused evaluate + robustify + J^T J / J^T r assembly (atomics on the lower triangle)
+//   K5  ba_schur             eliminate the 1-dim inverse-depth blocks into S
+//   K6  ba_cholesky + ba_update + lm control   reduced solve, back-substitution, (+) update, LM decisions
+#include <math.h>
+#include <algorithm>
+#include <chrono>
+#include <string.h>
+#include "lvb_internal.cuh"
+#include "lvb_math.cuh"
+
+using namespace lvb;
+
+namespace {
+
+enum { TPB = 128, IMU_STRIDE = 17 + 45 + 225, IMU_RAW = 467, MAX_DIMC = 736, MAX_STAGE_POSES = 512, MAX_TRACK = 16, CHOL_T = 512 };
+
+__constant__ unsigned char c_tri_a[465];
+__constant__ unsigned char c_tri_b[465];
+
+struct BaDev {
+    int n_poses, n_vec3, n_rho, dimc, n_pose_free;
+    double *poses, *vec3, *rho, *c_poses, *c_vec3, *c_rho;
+    const int *pose_off, *vec3_off, *rho_slot;
+    int n[6];
+    const double* fc[6];
+    const int* fi[6];
+    double huber[6];
+    const int *lm_start, *lm_fac;
+    double *Hpp, *gc, *Hll, *gl, *tf_w;
+    double *S, *rhs, *gcr, *diagH, *scal;      // inside the arena
+    double *scale_c, *scale_l, *lam_c, *lam_l;
+    LmState* st;
+    int rank0, rank, world;
+    int stage_poses;
+    Cams cams;
+};
+
+struct BlockRanges { int b[7]; };   // cumulative block starts per kind, b[6] = total
+
+// ------------------------------------------------------------------ small device helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    // TMA 1-D bulk copy global -> shared, completion counted on the mbarrier (SASS: UBLKCP)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok = 0;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    } while (!ok);
+}
+
+// Stage the pose array into shared memory (TMA bulk copy when enabled) and return the pointer
+// the block should read poses from.
+__device__ __forceinline__ const double* stage_poses(const BaDev& d, const double* src, double* s_poses, uint64_t* bar) {
+    if (!d.stage_poses) return src;
+    const uint32_t bytes = ((uint32_t)d.n_poses * 56u + 15u) & ~15u;
+    if (d.stage_poses == 2) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) { mbar_expect_tx(bar, bytes); bulk_load_1d(s_poses, src, bytes, bar); }
+        mbar_wait(bar, 0);
+    } else {
+        for (int i = threadIdx.x; i < d.n_poses * 7; i += blockDim.x) s_poses[i] = src[i];
+        __syncthreads();
+    }
+    return s_poses;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void block_add(double v, double* target, double* s_red /*>= blockDim/32*/) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = (lane < (int)(blockDim.x >> 5)) ? s_red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0 && t != 0.0) atomicAdd(target, t);
+    }
+    __syncthreads();
+}
+
+// H(lower) += JA^T JB for two distinct blocks; offsets are global camera-system offsets (>= 0)
+__device__ __forceinline__ void add_cross(double* H, int dimc, int offA, const double* JA, int wa, int offB, const double* JB, int wb, int rows) {
+    for (int i = 0; i < wa; ++i) for (int j = 0; j < wb; ++j) {
+        double s = 0; for (int k = 0; k < rows; ++k) s += JA[k * wa + i] * JB[k * wb + j];
+        const int ra = offA + i, cb = offB + j;
+        if (ra > cb) atomicAdd(&H[(size_t)ra * dimc + cb], s); else atomicAdd(&H[(size_t)cb * dimc + ra], s);
+    }
+}
+__device__ __forceinline__ void add_diag(double* H, double* g, int dimc, int off, const double* J, int w, int rows, const double* r) {
+    for (int i = 0; i < w; ++i) {
+        double gi = 0; for (int k = 0; k < rows; ++k) gi += J[k * w + i] * r[k];
+        atomicAdd(&g[off + i], gi);
+        for (int j = 0; j <= i; ++j) {
+            double s = 0; for (int k = 0; k < rows; ++k) s += J[k * w + i] * J[k * w + j];
+            atomicAdd(&H[(size_t)(off + i) * dimc + off + j], s);
+        }
+    }
+}
+
+__device__ __forceinline__ ImuConst load_imu_const(const double* c) {
+    ImuConst k;
+    k.dp = v3(c[0], c[1], c[2]); k.dq = q4(c[3], c[4], c[5], c[6]); k.dv = v3(c[7], c[8], c[9]);
+    k.lin_ba = v3(c[10], c[11], c[12]); k.lin_bg = v3(c[13], c[14], c[15]); k.sum_dt = c[16];
+    const double* m = c + 17;
+    for (int i = 0; i < 9; ++i) { k.dp_dba.m[i] = m[i]; k.dp_dbg.m[i] = m[9 + i]; k.dq_dbg.m[i] = m[18 + i]; k.dv_dba.m[i] = m[27 + i]; k.dv_dbg.m[i] = m[36 + i]; }
+    return k;
+}
+
+// ------------------------------------------------------------------ IMU prepare (once per finalize)
+// raw 467 -> packed 287 (scalars, five sub-blocks, U); status[f] != 0 when cov^-1 is not SPD
+__global__ void imu_prepare_kernel(const double* raw, double* packed, int n, int* status) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    const double* c = raw + (size_t)f * IMU_RAW;
+    double* o = packed + (size_t)f * IMU_STRIDE;
+    for (int i = 0; i < 17; ++i) o[i] = c[i];
+    const double* jac = c + 17;
+    const int br[5] = {0, 0, 3, 6, 6}, bc[5] = {9, 12, 12, 9, 12};
+    for (int b = 0; b < 5; ++b) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o[17 + 9 * b + 3 * i + j] = jac[(br[b] + i) * 15 + bc[b] + j];
+    double a[225], inv[225];
+    status[f] = sqrt_information(c + 242, o + 62, a, inv);
+}
+
+// ------------------------------------------------------------------ K1 eval kernels (parity / roofline)
+// TwoFrame: 308 algorithmic bytes per block (40 const + 12 idx + 16 r + 240 J); output staged through
+// shared memory so that the 240 B Jacobian record leaves the SM as full 128 B lines.
+__global__ void __launch_bounds__(TPB) ba_eval_two_frame_kernel(BaDev d, double* __restrict__ r_out, double* __restrict__ J_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_J = reinterpret_cast<double*>(smem_raw);          // TPB x 31
+    double* s_poses = s_J + TPB * 31;                            // TPB*31*8 = 31744 B, a multiple of 16
+    __shared__ __align__(8) uint64_t bar;
+    const double* poses = stage_poses(d, d.poses, s_poses, &bar);
+    const int n = d.n[0];
+    const int f = blockIdx.x * TPB + threadIdx.x;
+    if (f < n) {
+        const double* c = d.fc[0];
+        const int* ix = d.fi[0];
+        const double fo_x = c[f], fo_y = c[n + f], ob_x = c[2 * n + f], ob_y = c[3 * n + f], w = c[4 * n + f];
+        const int il = ix[f], i1 = ix[n + f], i2 = ix[2 * n + f];
+        TwoFrameLin o; UQ u1, u2;
+        two_frame_lin(d.cams, fo_x, fo_y, ob_x, ob_y, w, d.rho[il], poses + 7 * i1, poses + 7 * i2, o, &u1, &u2);
+        if (r_out) reinterpret_cast<double2*>(r_out)[f] = make_double2(o.r[0], o.r[1]);
+        double* row = s_J + threadIdx.x * 31;
+        row[0] = o.Jrho[0]; row[15] = o.Jrho[1];
+        pose_block_to_ambient(u1, o.J1, 2, row + 1, 15);
+        pose_block_to_ambient(u2, o.J2, 2, row + 8, 15);
+    }
+    __syncthreads();
+    if (J_out) {
+        const int first = blockIdx.x * TPB;
+        const int cnt = min(TPB, n - first) * 15;                // double2 elements
+        double2* out = reinterpret_cast<double2*>(J_out + (size_t)first * 30);
+        for (int e = threadIdx.x; e < cnt; e += TPB) {
+            const int t = e / 15, k = (e - t * 15) * 2;
+            out[e] = make_double2(s_J[t * 31 + k], s_J[t * 31 + k + 1]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TPB) ba_eval_pose_only_kernel(BaDev d, double* __restrict__ r_out, double* __restrict__ J_out) {
+    const int n = d.n[1];
+    const int f = blockIdx.x * TPB + threadIdx.x;
+    if (f >= n) return;
+    const double* c = d.fc[1];
+    const int ip = d.fi[1][f];
+    PoseOnlyLin o; UQ u;
+    pose_only_lin(d.cams, c[f], c[n + f], v3(c[2 * n + f], c[3 * n + f], c[4 * n + f]), c[5 * n + f], d.poses + 7 * ip, o, &u);
+    if (r_out) { r_out[2 * f] = o.r[0]; r_out[2 * f + 1] = o.r[1]; }
+    if (J_out) { double Ja[14]; pose_block_to_ambient(u, o.J, 2, Ja, 7); for (int k = 0; k < 14; ++k) J_out[(size_t)f * 14 + k] = Ja[k]; }
+}
+
+__global__ void __launch_bounds__(TPB) ba_eval_two_camera_kernel(BaDev d, double* __restrict__ r_out, double* __restrict__ J_out) {
+    const int n = d.n[2];
+    const int f = blockIdx.x * TPB + threadIdx.x;
+    if (f >= n) return;
+    const double* c = d.fc[2];
+    TwoCameraLin o;
+    two_camera_lin(d.cams, c[f], c[n + f], c[2 * n + f], c[3 * n + f], c[4 * n + f], d.rho[d.fi[2][f]], o);
+    if (r_out) { r_out[2 * f] = o.r[0]; r_out[2 * f + 1] = o.r[1]; }
+    if (J_out) { J_out[2 * f] = o.Jrho[0]; J_out[2 * f + 1] = o.Jrho[1]; }
+}
+
+// IMU: one warp per factor.  Fills s_r (whitened residual, 15) and s_Jw (whitened ambient Jacobian 15x32).
+__device__ void imu_warp_eval(const BaDev& d, int f, const double* P, const double* V, double* s_raw /*480*/, double* s_Jw /*480*/, double* s_r /*32: raw 0..14, whitened 16..30*/) {
+    const int lane = threadIdx.x & 31;
+    const double* c = d.fc[3] + (size_t)f * IMU_STRIDE;
+    const int n = d.n[3];
+    const int* ix = d.fi[3];
+    for (int e = lane; e < 480; e += 32) s_raw[e] = 0.0;
+    __syncwarp();
+    if (lane == 0) {
+        const ImuConst k = load_imu_const(c);
+        const double* Ti = P + 7 * ix[f]; const double* Vi = V + 3 * ix[n + f]; const double* Bai = V + 3 * ix[2 * n + f]; const double* Bgi = V + 3 * ix[3 * n + f];
+        const double* Tj = P + 7 * ix[4 * n + f]; const double* Vj = V + 3 * ix[5 * n + f]; const double* Baj = V + 3 * ix[6 * n + f]; const double* Bgj = V + 3 * ix[7 * n + f];
+        imu_raw_residual(k, Ti, Vi, Bai, Bgi, Tj, Vj, Baj, Bgj, s_r);
+        imu_raw_jacobian(k, Ti, Vi, Bgi, Tj, Vj, s_raw);
+    }
+    __syncwarp();
+    const double* U = c + 62;
+    if (lane < 15) { double s = 0; for (int k = 0; k < 15; ++k) s += U[15 * lane + k] * s_r[k]; s_r[16 + lane] = s; }
+    for (int e = lane; e < 480; e += 32) {
+        const int i = e >> 5, j = e & 31;
+        double s = 0; for (int k = 0; k < 15; ++k) s += U[15 * i + k] * s_raw[32 * k + j];
+        s_Jw[e] = s;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(TPB) ba_eval_imu_kernel(BaDev d, double* __restrict__ r_out, double* __restrict__ J_out) {
+    __shared__ double s_raw[4][480], s_Jw[4][480], s_r[4][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * 4 + warp;
+    if (f >= d.n[3]) return;
+    imu_warp_eval(d, f, d.poses, d.vec3, s_raw[warp], s_Jw[warp], s_r[warp]);
+    if (r_out && lane < 15) r_out[(size_t)f * 15 + lane] = s_r[warp][16 + lane];
+    if (J_out) for (int e = lane; e < 480; e += 32) J_out[(size_t)f * 480 + e] = s_Jw[warp][e];
+}
+
+__global__ void ba_eval_prior_kernel(BaDev d, int kind, double* __restrict__ r_out, double* __restrict__ J_out) {
+    const int n = d.n[kind];
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    const int stride = kind == 4 ? 8 : 9;
+    double c[9];
+    for (int k = 0; k < stride; ++k) c[k] = d.fc[kind][(size_t)k * n + f];
+    double r[6], J[84];
+    if (kind == 4) pose_graph_eval(c, d.poses + 7 * d.fi[4][f], d.poses + 7 * d.fi[4][n + f], r, J);
+    else pose_prior_eval(c, d.poses + 7 * d.fi[5][f], r, J);
+    const int cols = kind == 4 ? 14 : 7;
+    if (r_out) for (int k = 0; k < 6; ++k) r_out[(size_t)f * 6 + k] = r[k];
+    if (J_out) for (int k = 0; k < 6 * cols; ++k) J_out[(size_t)f * 6 * cols + k] = J[k];
+}
+
+// ------------------------------------------------------------------ fused linearize / cost kernel
+// MODE 0: at x      -> Hpp, gc, Hll, gl, tf_w, st->cost_acc      (skipped unless st->need_linearize)
+// MODE 1: at cand   -> st->cand_cost_acc only
+template <int MODE>
+__global__ void __launch_bounds__(TPB) ba_linearize_kernel(BaDev d, BlockRanges R) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double s_red[TPB / 32];
+    const LmState* st = d.st;
+    if (st->done) return;
+    if (MODE == 0 && !st->need_linearize) return;
+    const double* Psrc = MODE == 0 ? d.poses : d.c_poses;
+    const double* V = MODE == 0 ? d.vec3 : d.c_vec3;
+    const double* Rho = MODE == 0 ? d.rho : d.c_rho;
+    double* cost_target = MODE == 0 ? &d.st->cost_acc : &d.st->cand_cost_acc;
+    const int b = blockIdx.x;
+    double cost = 0.0;
+
+    {   // ---- the three visual kinds: one thread per block, poses staged in shared memory
+        const double* P = stage_poses(d, Psrc, reinterpret_cast<double*>(smem_raw), &bar);
+        if (b < R.b[1]) {
+            const int n = d.n[0];
+            const int f = (b - R.b[0]) * TPB + threadIdx.x;
+            if (f < n) {
+                const double* c = d.fc[0]; const int* ix = d.fi[0];
+                const int il = ix[f]; int i1 = ix[n + f], i2 = ix[2 * n + f];
+                TwoFrameLin o;
+                two_frame_lin(d.cams, c[f], c[n + f], c[2 * n + f], c[3 * n + f], c[4 * n + f], Rho[il], P + 7 * i1, P + 7 * i2, o, nullptr, nullptr);
+                double rho_v, sr;
+                huber(d.huber[0], o.r[0] * o.r[0] + o.r[1] * o.r[1], &rho_v, &sr);
+                cost = 0.5 * rho_v;
+                if (MODE == 0) {
+                    o.r[0] *= sr; o.r[1] *= sr; o.Jrho[0] *= sr; o.Jrho[1] *= sr;
+                    for (int k = 0; k < 12; ++k) { o.J1[k] *= sr; o.J2[k] *= sr; }
+                    int off1 = d.pose_off[i1], off2 = d.pose_off[i2];
+                    if (i1 == i2) { for (int k = 0; k < 12; ++k) o.J1[k] += o.J2[k]; off2 = -1; }
+                    const bool lfree = d.rho_slot[il] >= 0;
+                    double* w = d.tf_w;
+                    if (lfree) {
+                        atomicAdd(&d.Hll[il], o.Jrho[0] * o.Jrho[0] + o.Jrho[1] * o.Jrho[1]);
+                        atomicAdd(&d.gl[il], o.Jrho[0] * o.r[0] + o.Jrho[1] * o.r[1]);
+                    }
+                    for (int k = 0; k < 6; ++k) {
+                        w[(size_t)k * n + f] = (lfree && off1 >= 0) ? o.Jrho[0] * o.J1[k] + o.Jrho[1] * o.J1[6 + k] : 0.0;
+                        w[(size_t)(6 + k) * n + f] = (lfree && off2 >= 0) ? o.Jrho[0] * o.J2[k] + o.Jrho[1] * o.J2[6 + k] : 0.0;
+                    }
+                    if (off1 >= 0) add_diag(d.Hpp, d.gc, d.dimc, off1, o.J1, 6, 2, o.r);
+                    if (off2 >= 0) add_diag(d.Hpp, d.gc, d.dimc, off2, o.J2, 6, 2, o.r);
+                    if (off1 >= 0 && off2 >= 0) add_cross(d.Hpp, d.dimc, off1, o.J1, 6, off2, o.J2, 6, 2);
+                }
+            }
+        } else if (b < R.b[2]) {
+            const int n = d.n[1];
+            const int f = (b - R.b[1]) * TPB + threadIdx.x;
+            if (f < n) {
+                const double* c = d.fc[1];
+                const int ip = d.fi[1][f];
+                PoseOnlyLin o;
+                pose_only_lin(d.cams, c[f], c[n + f], v3(c[2 * n + f], c[3 * n + f], c[4 * n + f]), c[5 * n + f], P + 7 * ip, o, nullptr);
+                double rho_v, sr;
+                huber(d.huber[1], o.r[0] * o.r[0] + o.r[1] * o.r[1], &rho_v, &sr);
+                cost = 0.5 * rho_v;
+                if (MODE == 0) {
+                    const int off = d.pose_off[ip];
+                    if (off >= 0) {
+                        o.r[0] *= sr; o.r[1] *= sr; for (int k = 0; k < 12; ++k) o.J[k] *= sr;
+                        add_diag(d.Hpp, d.gc, d.dimc, off, o.J, 6, 2, o.r);
+                    }
+                }
+            }
+        } else {
+            const int n = d.n[2];
+            const int f = (b - R.b[2]) * TPB + threadIdx.x;
+            if (f < n) {
+                const double* c = d.fc[2];
+                const int il = d.fi[2][f];
+                TwoCameraLin o;
+                two_camera_lin(d.cams, c[f], c[n + f], c[2 * n + f], c[3 * n + f], c[4 * n + f], Rho[il], o);
+                double rho_v, sr;
+                huber(d.huber[2], o.r[0] * o.r[0] + o.r[1] * o.r[1], &rho_v, &sr);
+                cost = 0.5 * rho_v;
+                if (MODE == 0 && d.rho_slot[il] >= 0) {
+                    const double j0 = o.Jrho[0] * sr, j1 = o.Jrho[1] * sr;
+                    atomicAdd(&d.Hll[il], j0 * j0 + j1 * j1);
+                    atomicAdd(&d.gl[il], j0 * o.r[0] * sr + j1 * o.r[1] * sr);
+                }
+            }
+        }
+    }
+    block_add(cost, cost_target, s_red);
+}
+
+
+// IMU (one warp per factor) and the two prior kinds: rare, register-hungry blocks kept out of the visual kernel
+template <int MODE>
+__global__ void __launch_bounds__(TPB) ba_linearize_other_kernel(BaDev d, BlockRanges R) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_red[TPB / 32];
+    const LmState* st = d.st;
+    if (st->done) return;
+    if (MODE == 0 && !st->need_linearize) return;
+    const double* Psrc = MODE == 0 ? d.poses : d.c_poses;
+    const double* V = MODE == 0 ? d.vec3 : d.c_vec3;
+    double* cost_target = MODE == 0 ? &d.st->cost_acc : &d.st->cand_cost_acc;
+    const int b = blockIdx.x + R.b[3];
+    double cost = 0.0;
+    if (b < R.b[4]) {   // ---- IMU: one warp per factor
+        double* s_raw = reinterpret_cast<double*>(smem_raw);     // 4 x 480
+        double* s_Jw = s_raw + 4 * 480;                          // 4 x 480
+        double* s_r = s_Jw + 4 * 480;                            // 4 x 32
+        int* s_gidx = reinterpret_cast<int*>(s_r + 4 * 32);      // 4 x 32
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int f = (b - R.b[3]) * 4 + warp;
+        const int n = d.n[3];
+        if (f < n) {
+            double* raw = s_raw + warp * 480; double* Jw = s_Jw + warp * 480; double* rr = s_r + warp * 32; int* gidx = s_gidx + warp * 32;
+            imu_warp_eval(d, f, Psrc, V, raw, Jw, rr);
+            double s = (lane < 15) ? rr[16 + lane] * rr[16 + lane] : 0.0;
+            s = warp_sum(s);
+            double rho_v, sr;
+            huber(d.huber[3], s, &rho_v, &sr);
+            if (lane == 0) cost = 0.5 * rho_v;
+            if (MODE == 0) {
+                const int* ix = d.fi[3];
+                // tangent Jacobian Jt[15][30] into `raw` (cols: pose_i 6 | v ba bg 9 | pose_j 6 | v ba bg 9)
+                if (lane < 15) {
+                    const double* a = Jw + 32 * lane;
+                    double* t = raw + 30 * lane;
+                    double t6[6];
+                    ambient_row_to_tangent(Psrc + 7 * ix[f], a, t6);
+                    for (int k = 0; k < 6; ++k) t[k] = t6[k] * sr;
+                    for (int k = 0; k < 9; ++k) t[6 + k] = a[7 + k] * sr;
+                    ambient_row_to_tangent(Psrc + 7 * ix[4 * n + f], a + 16, t6);
+                    for (int k = 0; k < 6; ++k) t[15 + k] = t6[k] * sr;
+                    for (int k = 0; k < 9; ++k) t[21 + k] = a[23 + k] * sr;
+                    rr[16 + lane] *= sr;
+                }
+                if (lane < 30) {
+                    int blk, loc;
+                    if (lane < 6) { blk = 0; loc = lane; } else if (lane < 15) { blk = 1 + (lane - 6) / 3; loc = (lane - 6) % 3; }
+                    else if (lane < 21) { blk = 4; loc = lane - 15; } else { blk = 5 + (lane - 21) / 3; loc = (lane - 21) % 3; }
+                    const int id = ix[(size_t)blk * n + f];
+                    const int off = (blk == 0 || blk == 4) ? d.pose_off[id] : d.vec3_off[id];
+                    gidx[lane] = off < 0 ? -1 : off + loc;
+                }
+                __syncwarp();
+                if (lane < 30 && gidx[lane] >= 0) {
+                    double g = 0; for (int i = 0; i < 15; ++i) g += raw[30 * i + lane] * rr[16 + i];
+                    atomicAdd(&d.gc[gidx[lane]], g);
+                }
+                for (int e = lane; e < 465; e += 32) {
+                    const int a = c_tri_a[e], bb = c_tri_b[e];
+                    const int ga = gidx[a], gb = gidx[bb];
+                    if (ga < 0 || gb < 0) continue;
+                    double h = 0; for (int i = 0; i < 15; ++i) h += raw[30 * i + a] * raw[30 * i + bb];
+                    if (ga >= gb) atomicAdd(&d.Hpp[(size_t)ga * d.dimc + gb], h); else atomicAdd(&d.Hpp[(size_t)gb * d.dimc + ga], h);
+                }
+            }
+        }
+    } else {   // ---- PoseGraphError / PoseError priors: one thread per block
+        const int kind = b < R.b[5] ? 4 : 5;
+        const int n = d.n[kind];
+        const int f = (b - R.b[kind]) * TPB + threadIdx.x;
+        if (f < n) {
+            const int stride = kind == 4 ? 8 : 9;
+            double c[9];
+            for (int k = 0; k < stride; ++k) c[k] = d.fc[kind][(size_t)k * n + f];
+            double r[6], J[84];
+            const int i1 = d.fi[kind][f];
+            const int i2 = kind == 4 ? d.fi[kind][n + f] : -1;
+            if (kind == 4) pose_graph_eval(c, Psrc + 7 * i1, Psrc + 7 * i2, r, MODE == 0 ? J : nullptr);
+            else pose_prior_eval(c, Psrc + 7 * i1, r, MODE == 0 ? J : nullptr);
+            double s = 0; for (int k = 0; k < 6; ++k) s += r[k] * r[k];
+            double rho_v, sr;
+            huber(d.huber[kind], s, &rho_v, &sr);
+            cost = 0.5 * rho_v;
+            if (MODE == 0) {
+                const int cols = kind == 4 ? 14 : 7;
+                double J1[36], J2[36];
+                for (int k = 0; k < 36; ++k) J2[k] = 0.0;
+                for (int k = 0; k < 6; ++k) {
+                    r[k] *= sr;
+                    ambient_row_to_tangent(Psrc + 7 * i1, J + cols * k, J1 + 6 * k);
+                    if (kind == 4) ambient_row_to_tangent(Psrc + 7 * i2, J + cols * k + 7, J2 + 6 * k);
+                }
+                for (int k = 0; k < 36; ++k) { J1[k] *= sr; J2[k] *= sr; }
+                const int off1 = d.pose_off[i1], off2 = kind == 4 ? d.pose_off[i2] : -1;
+                if (off1 >= 0) add_diag(d.Hpp, d.gc, d.dimc, off1, J1, 6, 6, r);
+                if (off2 >= 0) add_diag(d.Hpp, d.gc, d.dimc, off2, J2, 6, 6, r);
+                if (off1 >= 0 && off2 >= 0 && off1 != off2) add_cross(d.Hpp, d.dimc, off1, J1, 6, off2, J2, 6, 6);
+            }
+        }
+    }
+    block_add(cost, cost_target, s_red);
+}
+
+// ------------------------------------------------------------------ per-iteration system assembly
+__global__ void ba_zero_kernel(BaDev d) {
+    const LmState* st = d.st;
+    if (st->done || !st->need_linearize) return;
+    const size_t nH = (size_t)d.dimc * d.dimc;
+    const size_t total = nH + d.dimc + 2 * (size_t)d.n_rho;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < nH) d.Hpp[i] = 0.0;
+        else if (i < nH + d.dimc) d.gc[i - nH] = 0.0;
+        else if (i < nH + d.dimc + d.n_rho) d.Hll[i - nH - d.dimc] = 0.0;
+        else d.gl[i - nH - d.dimc - d.n_rho] = 0.0;
+    }
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(unsigned long long* p, double v) {
+    if (v == v) atomicMax(p, (unsigned long long)__double_as_longlong(fabs(v)));
+    else atomicMax(p, 0x7ff0000000000000ull);   // NaN -> +inf so the tolerance test fails
+}
+
+// landmarks: Jacobi scale (first pass), LM damping, gradient max-norm contribution
+__global__ void ba_prepare_landmark_kernel(BaDev d) {
+    LmState* st = d.st;
+    if (st->done) return;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= d.n_rho) return;
+    if (d.rho_slot[l] < 0) { d.lam_l[l] = 0.0; return; }
+    const double h = d.Hll[l];
+    if (!st->scale_valid) d.scale_l[l] = st->jacobi ? 1.0 / (1.0 + sqrt(h)) : 1.0;
+    const double s = d.scale_l[l], s2 = s * s;
+    d.lam_l[l] = fmin(fmax(s2 * h, st->min_diag), st->max_diag) / (st->radius * s2);
+    if (st->need_linearize && d.lm_start[l + 1] > d.lm_start[l]) atomic_max_nonneg(&st->grad_max_bits, d.gl[l]);
+}
+
+// S <- lower(Hpp), rhs <- -gc, gcr <- gc, diagH <- diag(Hpp), scalars <- 0
+__global__ void ba_build_S_kernel(BaDev d) {
+    if (d.st->done) return;
+    const size_t nH = (size_t)d.dimc * d.dimc;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < 16) d.scal[gid] = 0.0;
+    for (size_t i = gid; i < nH; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / d.dimc), c = (int)(i - (size_t)r * d.dimc);
+        const double v = d.Hpp[i];
+        d.S[i] = (c <= r) ? v : 0.0;
+        if (c == r) { d.diagH[r] = v; d.rhs[r] = -d.gc[r]; d.gcr[r] = d.gc[r]; }
+    }
+}
+
+// K5: eliminate the inverse depths.  One thread per landmark; its TwoFrame couplings are merged by
+// pose, then S -= w_a^T w_b / h, rhs += w_a g / h on the lower triangle.
+__global__ void __launch_bounds__(TPB) ba_schur_kernel(BaDev d) {
+    if (d.st->done) return;
+    const int l = blockIdx.x * TPB + threadIdx.x;
+    if (l >= d.n_rho || d.rho_slot[l] < 0) return;
+    const int e0 = d.lm_start[l], e1 = d.lm_start[l + 1];
+    if (e1 == e0) return;
+    const double hl = d.Hll[l] + d.lam_l[l];
+    if (!(hl > 0.0)) return;
+    const double hinv = 1.0 / hl, g = d.gl[l];
+    const int n = d.n[0];
+    const int* ix = d.fi[0];
+    int offs[MAX_TRACK]; double w[MAX_TRACK][6]; int ns = 0;      // finalize() guarantees <= MAX_TRACK distinct poses
+    for (int e = e0; e < e1; ++e) {
+        const int f = d.lm_fac[e];
+        if (f < 0) continue;                        // TwoCamera entries are encoded as -(f+1)
+        for (int side = 0; side < 2; ++side) {
+            const int off = d.pose_off[ix[(size_t)(1 + side) * n + f]];
+            if (off < 0) continue;
+            double v[6]; bool nz = false;
+            for (int k = 0; k < 6; ++k) { v[k] = d.tf_w[(size_t)(6 * side + k) * n + f]; nz |= (v[k] != 0.0); }
+            if (!nz) continue;
+            int j = 0; for (; j < ns; ++j) if (offs[j] == off) break;
+            if (j == ns) { if (ns == MAX_TRACK) continue; offs[ns] = off; for (int k = 0; k < 6; ++k) w[ns][k] = 0.0; ++ns; }
+            for (int k = 0; k < 6; ++k) w[j][k] += v[k];
+        }
+    }
+    for (int a = 0; a < ns; ++a) {
+        for (int p = 0; p < 6; ++p) atomicAdd(&d.rhs[offs[a] + p], w[a][p] * g * hinv);
+        for (int c = 0; c < ns; ++c) {
+            if (offs[c] > offs[a]) continue;
+            for (int p = 0; p < 6; ++p) for (int q = 0; q < 6; ++q) {
+                if (offs[c] == offs[a] && q > p) continue;
+                atomicAdd(&d.S[(size_t)(offs[a] + p) * d.dimc + offs[c] + q], -w[a][p] * w[c][q] * hinv);
+            }
+        }
+    }
+}
+
+__global__ void ba_pack_scalars_kernel(BaDev d) {
+    LmState* st = d.st;
+    if (st->done) return;
+    d.scal[0] = st->need_linearize ? st->cost_acc : 0.0;
+    d.scal[1 + d.rank] = __longlong_as_double((long long)st->grad_max_bits);
+}
+__global__ void ba_unpack_scalars_kernel(BaDev d) {
+    LmState* st = d.st;
+    if (st->done) return;
+    if (st->need_linearize) st->cost_acc = d.scal[0];
+    double m = 0.0;
+    for (int r = 0; r < d.world; ++r) m = fmax(m, d.scal[1 + r]);
+    st->grad_max_bits = (unsigned long long)__double_as_longlong(m);
+}
+
+// camera blocks: Jacobi scale, damping added to diag(S), gradient max-norm ||x - Plus(x,-g)||_inf
+__global__ void ba_prepare_camera_kernel(BaDev d) {
+    LmState* st = d.st;
+    if (st->done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n_poses + d.n_vec3) return;
+    const bool is_pose = i < d.n_poses;
+    const int off = is_pose ? d.pose_off[i] : d.vec3_off[i - d.n_poses];
+    if (off < 0) return;
+    const int w = is_pose ? 6 : 3;
+    for (int k = 0; k < w; ++k) {
+        const double h = d.diagH[off + k];
+        if (!st->scale_valid) d.scale_c[off + k] = st->jacobi ? 1.0 / (1.0 + sqrt(h)) : 1.0;
+        const double s = d.scale_c[off + k], s2 = s * s;
+        const double lam = fmin(fmax(s2 * h, st->min_diag), st->max_diag) / (st->radius * s2);
+        d.lam_c[off + k] = lam;
+        d.S[(size_t)(off + k) * d.dimc + off + k] += lam;
+    }
+    if (st->need_linearize) {
+        double gm = 0.0;
+        if (is_pose) {
+            double ng[6], out[7];
+            for (int k = 0; k < 6; ++k) ng[k] = -d.gcr[off + k];
+            const double* x = d.poses + 7 * i;
+            pose_plus(x, ng, out);
+            for (int k = 0; k < 7; ++k) { const double df = fabs(x[k] - out[k]); gm = (df == df) ? fmax(gm, df) : INFINITY; }
+        } else for (int k = 0; k < 3; ++k) { const double df = fabs(d.gcr[off + k]); gm = (df == df) ? fmax(gm, df) : INFINITY; }
+        atomic_max_nonneg(&st->grad_max_bits, gm);
+    }
+}
+
+__global__ void lm_control_pre_kernel(LmState* st) { lm_control_pre(*st); }
+__global__ void lm_control_post_kernel(LmState* st) { lm_control_post(*st); if (st->accept) st->x_cost = st->cand_cost_acc; }
+
+// ------------------------------------------------------------------ K6 dense Cholesky, one CTA
+// Right-looking blocked (32) factorisation of the lower triangle of S (n x n, row-major, in L2/HBM) with
+// the right-hand side carried along as an extra row (so the forward substitution is free), then a
+// blocked backward substitution.  Result: rhs <- S^-1 rhs.
+__global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict__ S, double* __restrict__ rhs, int n, LmState* st) {
+    if (st->done) return;
+    extern __shared__ __align__(16) double sm[];
+    double* D = sm;               // 32 x 33   diagonal block
+    double* P = sm + 32 * 34;     // rows x 34 panel (16 B aligned rows for broadcast double2 loads)
+    __shared__ int fail;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    if (tid == 0) fail = 0;
+    __syncthreads();
+    for (int kb = 0; kb < n; kb += 32) {
+        const int bs = min(32, n - kb);
+        for (int e = tid; e < 32 * 32; e += nt) {
+            const int i = e >> 5, j = e & 31;
+            D[i * 33 + j] = (i < bs && j <= i) ? S[(size_t)(kb + i) * n + kb + j] : ((i == j) ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int j = 0; j < bs; ++j) {
+                double djj = D[j * 33 + j];
+                if (!(djj > 0.0)) { if (lane == 0) fail = 1; djj = 1.0; }
+                const double dj = sqrt(djj);
+                __syncwarp();
+                double lij = 0.0;
+                if (lane == j) D[j * 33 + j] = dj;
+                if (lane > j && lane < bs) { lij = D[lane * 33 + j] / dj; D[lane * 33 + j] = lij; }
+                __syncwarp();
+                if (lane > j && lane < bs) for (int k = j + 1; k <= lane; ++k) D[lane * 33 + k] -= lij * D[k * 33 + j];
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < bs * bs; e += nt) { const int i = e / bs, j = e - i * bs; if (j <= i) S[(size_t)(kb + i) * n + kb + j] = D[i * 33 + j]; }
+        // panel: rows below the block + the rhs row (last):  x D^T = a
+        const int m = n - kb - bs + 1;
+        for (int rr = tid; rr < m; rr += nt) {
+            const bool is_rhs = (rr == m - 1);
+            double* src = is_rhs ? (rhs + kb) : (S + (size_t)(kb + bs + rr) * n + kb);
+            double a[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = (j < bs) ? src[j] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                double s = a[j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) s -= a[k] * D[j * 33 + k];
+                a[j] = s / D[j * 33 + j];
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { P[rr * 34 + j] = a[j]; if (j < bs) src[j] = a[j]; }
+        }
+        __syncthreads();
+        // trailing update A22 -= P P^T on the lower triangle, 32x32 register tiles: lane = column, the
+        // column's panel row lives in registers, the row's panel entries are broadcast from shared memory.
+        const int ntile = (m + 31) >> 5;
+        const int total = ntile * (ntile + 1) / 2;
+        for (int t = warp; t < total; t += nw) {
+            int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+            while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+            while (ti * (ti + 1) / 2 > t) --ti;
+            const int tj = t - ti * (ti + 1) / 2;
+            const int jp = tj * 32 + lane;
+            const bool col_ok = jp < m - 1;              // the rhs row is not a column
+            double pj[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) pj[k] = col_ok ? P[jp * 34 + k] : 0.0;
+            const int r_end = min(32, m - ti * 32);
+            for (int r = 0; r < r_end; ++r) {
+                const int ip = ti * 32 + r;
+                const double2* prow = reinterpret_cast<const double2*>(P + ip * 34);
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 16; k += 2) {
+                    const double2 a = prow[k], b = prow[k + 1];
+                    s0 += a.x * pj[2 * k]; s1 += a.y * pj[2 * k + 1]; s2 += b.x * pj[2 * k + 2]; s3 += b.y * pj[2 * k + 3];
+                }
+                if (col_ok && jp <= ip) {
+                    double* dst = (ip == m - 1) ? (rhs + kb + bs) : (S + (size_t)(kb + bs + ip) * n + kb + bs);
+                    dst[jp] -= (s0 + s1) + (s2 + s3);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // backward substitution  L^T x = y  (y is in rhs)
+    const int last = ((n - 1) / 32) * 32;
+    for (int kb = last; kb >= 0; kb -= 32) {
+        const int bs = min(32, n - kb);
+        for (int e = tid; e < 32 * 32; e += nt) {
+            const int i = e >> 5, j = e & 31;
+            D[i * 33 + j] = (i < bs && j <= i) ? S[(size_t)(kb + i) * n + kb + j] : ((i == j) ? 1.0 : 0.0);
+        }
+        double acc = 0.0;
+        if (lane < bs) for (int i = kb + bs + warp; i < n; i += nw) acc += S[(size_t)i * n + kb + lane] * rhs[i];
+        P[warp * 34 + lane] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            double t = (lane < bs) ? rhs[kb + lane] : 0.0;
+            for (int w = 0; w < nw; ++w) t -= P[w * 34 + lane];
+            for (int j = bs - 1; j >= 0; --j) {
+                const double xj = __shfl_sync(0xffffffffu, t, j) / D[j * 33 + j];
+                if (lane == j) t = xj;
+                else if (lane < j) t -= D[j * 33 + lane] * xj;
+            }
+            if (lane < bs) rhs[kb + lane] = t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && fail) st->solve_fail = 1;
+}
+
+// ------------------------------------------------------------------ back-substitution + candidate point
+__global__ void __launch_bounds__(TPB) ba_update_kernel(BaDev d) {
+    __shared__ double s_red[TPB / 32];
+    LmState* st = d.st;
+    if (st->done) return;
+    const double* dc = d.rhs;
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    double a = 0, b = 0, sn = 0, xn = 0;
+    if (i < d.n_poses) {
+        const double* x = d.poses + 7 * i; double* c = d.c_poses + 7 * i;
+        const int off = d.pose_off[i];
+        if (off < 0) { for (int k = 0; k < 7; ++k) c[k] = x[k]; }
+        else {
+            double dl[6], out[7];
+            for (int k = 0; k < 6; ++k) dl[k] = dc[off + k];
+            pose_plus(x, dl, out);
+            for (int k = 0; k < 7; ++k) { c[k] = out[k]; if (d.rank0) { sn += (x[k] - out[k]) * (x[k] - out[k]); xn += x[k] * x[k]; } }
+            if (d.rank0) for (int k = 0; k < 6; ++k) { a += dl[k] * d.lam_c[off + k] * dl[k]; b += d.gcr[off + k] * dl[k]; }
+        }
+    } else if (i < d.n_poses + d.n_vec3) {
+        const int j = i - d.n_poses;
+        const double* x = d.vec3 + 3 * j; double* c = d.c_vec3 + 3 * j;
+        const int off = d.vec3_off[j];
+        for (int k = 0; k < 3; ++k) {
+            const double dl = off < 0 ? 0.0 : dc[off + k];
+            c[k] = x[k] + dl;
+            if (off >= 0 && d.rank0) { sn += dl * dl; xn += x[k] * x[k]; a += dl * d.lam_c[off + k] * dl; b += d.gcr[off + k] * dl; }
+        }
+    } else if (i < d.n_poses + d.n_vec3 + d.n_rho) {
+        const int l = i - d.n_poses - d.n_vec3;
+        double dl = 0.0;
+        const int e0 = d.lm_start[l], e1 = d.lm_start[l + 1];
+        if (d.rho_slot[l] >= 0 && e1 > e0) {
+            const int n = d.n[0];
+            const int* ix = d.fi[0];
+            double s = d.gl[l];
+            for (int e = e0; e < e1; ++e) {
+                const int f = d.lm_fac[e];
+                if (f < 0) continue;
+                for (int side = 0; side < 2; ++side) {
+                    const int off = d.pose_off[ix[(size_t)(1 + side) * n + f]];
+                    if (off < 0) continue;
+                    for (int k = 0; k < 6; ++k) s += d.tf_w[(size_t)(6 * side + k) * n + f] * dc[off + k];
+                }
+            }
+            const double lam = d.lam_l[l];
+            dl = -s / (d.Hll[l] + lam);
+            sn = dl * dl; xn = d.rho[l] * d.rho[l]; a = dl * lam * dl; b = d.gl[l] * dl;
+        }
+        d.c_rho[l] = d.rho[l] + dl;
+    }
+    block_add(a, &st->mcc_a, s_red);
+    block_add(b, &st->mcc_b, s_red);
+    block_add(sn, &st->step_norm2, s_red);
+    block_add(xn, &st->x_norm2, s_red);
+}
+
+__global__ void ba_accept_kernel(BaDev d) {
+    const LmState* st = d.st;
+    if (!st->accept) return;
+    const size_t np = (size_t)d.n_poses * 7, nv = (size_t)d.n_vec3 * 3, nr = d.n_rho;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < np + nv + nr; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < np) d.poses[i] = d.c_poses[i];
+        else if (i < np + nv) d.vec3[i - np] = d.c_vec3[i - np];
+        else d.rho[i - np - nv] = d.c_rho[i - np - nv];
+    }
+}
+
+__global__ void ba_reproj_error_kernel(BaDev d, int n, const double* __restrict__ ob_pw, const int* __restrict__ pose_idx, double* __restrict__ err) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    PoseOnlyLin o;
+    const double* e = ob_pw + 5 * (size_t)f;
+    pose_only_lin(d.cams, e[0], e[1], v3(e[2], e[3], e[4]), 1.0, d.poses + 7 * pose_idx[f], o, nullptr);
+    err[f] = sqrt(o.r[0] * o.r[0] + o.r[1] * o.r[1]);
+}
+
+}  // namespace
+
+// ====================================================================================== host side
+struct lvb_ba {
+    lvb_ctx* ctx = nullptr;
+    bool finalized = false, solvable = false;
+    double cam[22];
+    bool have_cam = false;
+    std::vector<double> h_poses, h_vec3, h_rho;
+    std::vector<uint8_t> h_pose_const, h_vec3_const, h_rho_const;
+    std::vector<double> h_fc[6];
+    std::vector<int32_t> h_fi[6];
+    int n[6] = {0, 0, 0, 0, 0, 0};
+    double huber[6] = {0, 0, 0, 0, 0, 0};
+    int dimc = 0, n_pose_free = 0, n_vec3_free = 0, n_rho_free = 0;
+    // device
+    DevBuf<double> poses, vec3, rho, c_poses, c_vec3, c_rho;
+    DevBuf<int> pose_off, vec3_off, rho_slot, lm_start, lm_fac;
+    DevBuf<double> fc[6];
+    DevBuf<int> fi[6];
+    DevBuf<double> imu_raw;
+    DevBuf<int> imu_status;
+    DevBuf<double> Hpp, gc, Hll, gl, tf_w, arena, scale_c, scale_l, lam_c, lam_l;
+    DevBuf<double> eval_r, eval_J;
+    DevBuf<LmState> st;
+    BaDev dev;
+    BlockRanges ranges;
+    size_t pose_smem = 0, imu_smem = 0;
+};
+
+static const int kConstStride[6] = {5, 6, 5, IMU_RAW, 8, 9};
+static const int kIdxStride[6] = {3, 1, 1, 8, 2, 1};
+static const int kResDim[6] = {2, 2, 2, 15, 6, 6};
+static const int kJacCols[6] = {15, 7, 1, 32, 14, 7};
+
+static bool g_tables_ready = false;
+static int init_tables() {
+    if (g_tables_ready) return LVB_OK;
+    unsigned char a[465], b[465]; int e = 0;
+    for (int i = 0; i < 30; ++i) for (int j = 0; j <= i; ++j) { a[e] = (unsigned char)i; b[e] = (unsigned char)j; ++e; }
+    LVB_CUDA(cudaMemcpyToSymbol(c_tri_a, a, sizeof(a)));
+    LVB_CUDA(cudaMemcpyToSymbol(c_tri_b, b, sizeof(b)));
+    LVB_CUDA(cudaFuncSetAttribute(ba_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * 34 + (MAX_DIMC + 2) * 34) * 8));
+    LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (TPB * 31 + MAX_STAGE_POSES * 7 + 2) * 8));
+    LVB_CUDA(cudaFuncSetAttribute(ba_linearize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    LVB_CUDA(cudaFuncSetAttribute(ba_linearize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    g_tables_ready = true;
+    return LVB_OK;
+}
+
+static inline int nblk(size_t n, int per) { return (int)((n + per - 1) / per); }
+#define LAUNCH(ba, kernel, grid, block, smem, ...)                                        \
+    do { if ((grid) > 0) { kernel<<<(grid), (block), (smem), (ba)->ctx->stream>>>(__VA_ARGS__); (ba)->ctx->launches++; } } while (0)
+
+static int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("kernel launch failed in %s: %s", what, cudaGetErrorString(e)); return LVB_ERR_CUDA; }
+    return LVB_OK;
+}
+
+extern "C" {
+
+int lvb_ba_create(lvb_ctx* ctx, lvb_ba** out) {
+    if (!ctx || !out) { set_error("null argument"); return LVB_ERR_INVALID; }
+    LVB_CUDA(cudaSetDevice(ctx->device));
+    LVB_TRY(init_tables());
+    lvb_ba* b = new lvb_ba();
+    b->ctx = ctx;
+    *out = b;
+    return LVB_OK;
+}
+void lvb_ba_destroy(lvb_ba* ba) { if (ba) { cudaSetDevice(ba->ctx->device); delete ba; } }
+
+int lvb_ba_set_cameras(lvb_ba* ba, const double cam[22]) { memcpy(ba->cam, cam, sizeof(ba->cam)); ba->have_cam = true; ba->finalized = false; return LVB_OK; }
+
+static void assign_const(std::vector<uint8_t>& dst, const uint8_t* c, int n) { if (c) dst.assign(c, c + n); else dst.assign(n, 0); }
+int lvb_ba_set_poses(lvb_ba* ba, int n, const double* v, const uint8_t* c) {
+    if (n < 0 || (n && !v)) { set_error("bad poses"); return LVB_ERR_INVALID; }
+    ba->h_poses.assign(v, v + (size_t)7 * n); assign_const(ba->h_pose_const, c, n); ba->finalized = false; return LVB_OK;
+}
+int lvb_ba_set_vec3(lvb_ba* ba, int n, const double* v, const uint8_t* c) {
+    if (n < 0 || (n && !v)) { set_error("bad vec3"); return LVB_ERR_INVALID; }
+    ba->h_vec3.assign(v, v + (size_t)3 * n); assign_const(ba->h_vec3_const, c, n); ba->finalized = false; return LVB_OK;
+}
+int lvb_ba_set_inv_depths(lvb_ba* ba, int n, const double* v, const uint8_t* c) {
+    if (n < 0 || (n && !v)) { set_error("bad inverse depths"); return LVB_ERR_INVALID; }
+    ba->h_rho.assign(v, v + n); assign_const(ba->h_rho_const, c, n); ba->finalized = false; return LVB_OK;
+}
+int lvb_ba_add_factors(lvb_ba* ba, int kind, int n, const double* consts, const int32_t* idx) {
+    if (kind < 0 || kind >= 6 || n < 0 || (n && (!consts || !idx))) { set_error("bad factor arguments"); return LVB_ERR_INVALID; }
+    ba->h_fc[kind].insert(ba->h_fc[kind].end(), consts, consts + (size_t)n * kConstStride[kind]);
+    ba->h_fi[kind].insert(ba->h_fi[kind].end(), idx, idx + (size_t)n * kIdxStride[kind]);
+    ba->n[kind] += n; ba->finalized = false;
+    return LVB_OK;
+}
+int lvb_ba_set_loss(lvb_ba* ba, int kind, double a) {
+    if (kind < 0 || kind >= 6) { set_error("bad kind"); return LVB_ERR_INVALID; }
+    ba->huber[kind] = a; if (ba->finalized) ba->dev.huber[kind] = a; return LVB_OK;
+}
+
+int lvb_ba_finalize(lvb_ba* ba) {
+    lvb_ctx* ctx = ba->ctx;
+    LVB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (!ba->have_cam) { set_error("cameras not set"); return LVB_ERR_STATE; }
+    const int np = (int)ba->h_poses.size() / 7, nv = (int)ba->h_vec3.size() / 3, nr = (int)ba->h_rho.size();
+    // validate indices
+    for (int k = 0; k < 6; ++k) for (int f = 0; f < ba->n[k]; ++f) for (int j = 0; j < kIdxStride[k]; ++j) {
+        const int v = ba->h_fi[k][(size_t)f * kIdxStride[k] + j];
+        int lim = np;
+        if ((k == 0 && j == 0) || k == 2) lim = nr;
+        if (k == 3 && j != 0 && j != 4) lim = nv;
+        if (v < 0 || v >= lim) { set_error("factor kind %d block %d: index %d out of range [0,%d)", k, f, v, lim); return LVB_ERR_INVALID; }
+    }
+    // slots / offsets
+    std::vector<int> pose_off(np), vec3_off(nv), rho_slot(nr);
+    int npf = 0, nvf = 0, nrf = 0;
+    for (int i = 0; i < np; ++i) pose_off[i] = ba->h_pose_const[i] ? -1 : 6 * npf++;
+    for (int i = 0; i < nv; ++i) vec3_off[i] = ba->h_vec3_const[i] ? -1 : 3 * nvf++;
+    for (int i = 0; i < nv; ++i) if (vec3_off[i] >= 0) vec3_off[i] += 6 * npf;
+    for (int i = 0; i < nr; ++i) rho_slot[i] = ba->h_rho_const[i] ? -1 : nrf++;
+    ba->n_pose_free = npf; ba->n_vec3_free = nvf; ba->n_rho_free = nrf; ba->dimc = 6 * npf + 3 * nvf;
+    // larger camera systems can still be evaluated (lvb_ba_eval*); the dense reduced solve is capped
+    ba->solvable = ba->dimc <= MAX_DIMC && ba->dimc > 0;
+    // landmark CSR: TwoFrame f -> f, TwoCamera f -> -(f+1)
+    std::vector<int> lm_start(nr + 1, 0);
+    for (int f = 0; f < ba->n[0]; ++f) lm_start[ba->h_fi[0][3 * (size_t)f] + 1]++;
+    for (int f = 0; f < ba->n[2]; ++f) lm_start[ba->h_fi[2][f] + 1]++;
+    for (int i = 0; i < nr; ++i) lm_start[i + 1] += lm_start[i];
+    std::vector<int> lm_fac(std::max(1, lm_start[nr])), fill(lm_start.begin(), lm_start.end() - 1);
+    for (int f = 0; f < ba->n[0]; ++f) lm_fac[fill[ba->h_fi[0][3 * (size_t)f]]++] = f;
+    for (int f = 0; f < ba->n[2]; ++f) lm_fac[fill[ba->h_fi[2][f]]++] = -(f + 1);
+
+    for (int l = 0; l < nr; ++l) {      // the Schur kernel merges a landmark's couplings by pose in registers
+        int seen[MAX_TRACK + 1], ns = 0;
+        for (int e = lm_start[l]; e < lm_start[l + 1]; ++e) {
+            const int f = lm_fac[e]; if (f < 0) continue;
+            for (int side = 1; side <= 2; ++side) {
+                const int p = ba->h_fi[0][3 * (size_t)f + side];
+                int j = 0; for (; j < ns; ++j) if (seen[j] == p) break;
+                if (j == ns) { if (ns == MAX_TRACK) { set_error("landmark %d is observed from more than %d keyframes", l, (int)MAX_TRACK); return LVB_ERR_UNSUPPORTED; } seen[ns++] = p; }
+            }
+        }
+    }
+    LVB_TRY(ba->poses.upload(ba->h_poses.data(), ba->h_poses.size(), s));
+    LVB_TRY(ba->vec3.upload(ba->h_vec3.data(), ba->h_vec3.size(), s));
+    LVB_TRY(ba->rho.upload(ba->h_rho.data(), ba->h_rho.size(), s));
+    LVB_TRY(ba->c_poses.upload(ba->h_poses.data(), ba->h_poses.size(), s));
+    LVB_TRY(ba->c_vec3.upload(ba->h_vec3.data(), ba->h_vec3.size(), s));
+    LVB_TRY(ba->c_rho.upload(ba->h_rho.data(), ba->h_rho.size(), s));
+    LVB_TRY(ba->pose_off.upload(pose_off.data(), np, s));
+    LVB_TRY(ba->vec3_off.upload(vec3_off.data(), nv, s));
+    LVB_TRY(ba->rho_slot.upload(rho_slot.data(), nr, s));
+    LVB_TRY(ba->lm_start.upload(lm_start.data(), nr + 1, s));
+    LVB_TRY(ba->lm_fac.upload(lm_fac.data(), lm_fac.size(), s));
+
+    // factor planes (AoS -> SoA transpose on the host; IMU stays AoS and is packed on the device)
+    std::vector<double> planes; std::vector<int> iplanes;
+    for (int k = 0; k < 6; ++k) {
+        const int n = ba->n[k];
+        iplanes.assign((size_t)std::max(1, n) * kIdxStride[k], 0);
+        for (int f = 0; f < n; ++f) for (int j = 0; j < kIdxStride[k]; ++j) iplanes[(size_t)j * n + f] = ba->h_fi[k][(size_t)f * kIdxStride[k] + j];
+        LVB_TRY(ba->fi[k].upload(iplanes.data(), iplanes.size(), s));
+        if (k == 3) {
+            LVB_TRY(ba->imu_raw.upload(ba->h_fc[3].data(), ba->h_fc[3].size(), s));
+            LVB_TRY(ba->fc[3].ensure((size_t)std::max(1, n) * IMU_STRIDE));
+            LVB_TRY(ba->imu_status.ensure(std::max(1, n)));
+            if (n) {
+                imu_prepare_kernel<<<nblk(n, 64), 64, 0, s>>>(ba->imu_raw.p, ba->fc[3].p, n, ba->imu_status.p);
+                ctx->launches++;
+                LVB_TRY(check_launch("imu_prepare"));
+                std::vector<int> status(n);
+                LVB_TRY(ba->imu_status.download(status.data(), n, s));
+                LVB_CUDA(cudaStreamSynchronize(s));
+                for (int f = 0; f < n; ++f) if (status[f]) { set_error("ImuError %d: covariance inverse is not SPD (code %d)", f, status[f]); return LVB_ERR_NUMERIC; }
+            }
+            continue;
+        }
+        planes.assign((size_t)std::max(1, n) * kConstStride[k], 0.0);
+        for (int f = 0; f < n; ++f) for (int j = 0; j < kConstStride[k]; ++j) planes[(size_t)j * n + f] = ba->h_fc[k][(size_t)f * kConstStride[k] + j];
+        LVB_TRY(ba->fc[k].upload(planes.data(), planes.size(), s));
+        LVB_CUDA(cudaStreamSynchronize(s));   // planes is reused
+    }
+    LVB_CUDA(cudaStreamSynchronize(s));
+
+    const size_t nH = ba->solvable ? (size_t)ba->dimc * ba->dimc : 1;
+    LVB_TRY(ba->Hpp.ensure(nH)); LVB_TRY(ba->gc.ensure(ba->dimc));
+    LVB_TRY(ba->Hll.ensure(std::max(1, nr))); LVB_TRY(ba->gl.ensure(std::max(1, nr)));
+    LVB_TRY(ba->tf_w.ensure((size_t)std::max(1, ba->n[0]) * 12));
+    LVB_TRY(ba->arena.ensure(nH + 3 * (size_t)ba->dimc + 16));
+    LVB_TRY(ba->scale_c.ensure(ba->dimc)); LVB_TRY(ba->lam_c.ensure(ba->dimc));
+    LVB_TRY(ba->scale_l.ensure(std::max(1, nr))); LVB_TRY(ba->lam_l.ensure(std::max(1, nr)));
+    LVB_TRY(ba->st.ensure(1));
+
+    BaDev& d = ba->dev;
+    d.n_poses = np; d.n_vec3 = nv; d.n_rho = nr; d.dimc = ba->dimc; d.n_pose_free = npf;
+    d.poses = ba->poses.p; d.vec3 = ba->vec3.p; d.rho = ba->rho.p; d.c_poses = ba->c_poses.p; d.c_vec3 = ba->c_vec3.p; d.c_rho = ba->c_rho.p;
+    d.pose_off = ba->pose_off.p; d.vec3_off = ba->vec3_off.p; d.rho_slot = ba->rho_slot.p;
+    for (int k = 0; k < 6; ++k) { d.n[k] = ba->n[k]; d.fc[k] = ba->fc[k].p; d.fi[k] = ba->fi[k].p; d.huber[k] = ba->huber[k]; }
+    d.lm_start = ba->lm_start.p; d.lm_fac = ba->lm_fac.p;
+    d.Hpp = ba->Hpp.p; d.gc = ba->gc.p; d.Hll = ba->Hll.p; d.gl = ba->gl.p; d.tf_w = ba->tf_w.p;
+    d.S = ba->arena.p; d.rhs = d.S + nH; d.gcr = d.rhs + ba->dimc; d.diagH = d.gcr + ba->dimc; d.scal = d.diagH + ba->dimc;
+    d.scale_c = ba->scale_c.p; d.scale_l = ba->scale_l.p; d.lam_c = ba->lam_c.p; d.lam_l = ba->lam_l.p;
+    d.st = ba->st.p;
+    d.rank = ctx->rank; d.world = ctx->world; d.rank0 = (ctx->rank == 0) ? 1 : 0;
+    d.stage_poses = (np <= MAX_STAGE_POSES) ? (ctx->use_tma ? 2 : 1) : 0;
+    d.cams.c0 = make_cam(ba->cam); d.cams.c1 = make_cam(ba->cam + 11);
+
+    BlockRanges& R = ba->ranges;
+    R.b[0] = 0;
+    R.b[1] = R.b[0] + nblk(ba->n[0], TPB);
+    R.b[2] = R.b[1] + nblk(ba->n[1], TPB);
+    R.b[3] = R.b[2] + nblk(ba->n[2], TPB);
+    R.b[4] = R.b[3] + nblk(ba->n[3], 4);
+    R.b[5] = R.b[4] + nblk(ba->n[4], TPB);
+    R.b[6] = R.b[5] + nblk(ba->n[5], TPB);
+    const size_t smem_imu = (size_t)(4 * 480 * 2 + 4 * 32) * 8 + 4 * 32 * 4;
+    const size_t smem_pose = d.stage_poses ? ((size_t)np * 56 + 16) : 0;
+    ba->pose_smem = smem_pose; ba->imu_smem = smem_imu;
+    ba->finalized = true;
+    return LVB_OK;
+}
+
+int lvb_ba_dims(lvb_ba* ba, int* dimc, int* nrf, int* rows) {
+    if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
+    if (dimc) *dimc = ba->dimc;
+    if (nrf) *nrf = ba->n_rho_free;
+    if (rows) { int r = 0; for (int k = 0; k < 6; ++k) r += ba->n[k] * kResDim[k]; *rows = r; }
+    return LVB_OK;
+}
+
+int lvb_ba_update_params(lvb_ba* ba, const double* P, const double* V, const double* R) {
+    if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
+    cudaStream_t s = ba->ctx->stream;
+    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    if (P) { ba->h_poses.assign(P, P + ba->h_poses.size()); LVB_TRY(ba->poses.upload(P, ba->h_poses.size(), s)); }
+    if (V) { ba->h_vec3.assign(V, V + ba->h_vec3.size()); LVB_TRY(ba->vec3.upload(V, ba->h_vec3.size(), s)); }
+    if (R) { ba->h_rho.assign(R, R + ba->h_rho.size()); LVB_TRY(ba->rho.upload(R, ba->h_rho.size(), s)); }
+    LVB_CUDA(cudaStreamSynchronize(s));
+    return LVB_OK;
+}
+
+static int launch_eval(lvb_ba* ba, int kind, double* r_dev, double* J_dev) {
+    const int n = ba->n[kind];
+    if (n == 0) return LVB_OK;
+    BaDev& d = ba->dev;
+    switch (kind) {
+    case 0: {
+        const size_t smem = (size_t)(TPB * 31) * 8 + (d.stage_poses ? (size_t)d.n_poses * 56 + 16 : 0);
+        LAUNCH(ba, ba_eval_two_frame_kernel, nblk(n, TPB), TPB, smem, d, r_dev, J_dev); break; }
+    case 1: LAUNCH(ba, ba_eval_pose_only_kernel, nblk(n, TPB), TPB, 0, d, r_dev, J_dev); break;
+    case 2: LAUNCH(ba, ba_eval_two_camera_kernel, nblk(n, TPB), TPB, 0, d, r_dev, J_dev); break;
+    case 3: LAUNCH(ba, ba_eval_imu_kernel, nblk(n, 4), TPB, 0, d, r_dev, J_dev); break;
+    default: LAUNCH(ba, ba_eval_prior_kernel, nblk(n, 64), 64, 0, d, kind, r_dev, J_dev); break;
+    }
+    return check_launch("ba_eval");
+}
+
+static int ensure_eval_buffers(lvb_ba* ba, int kind) {
+    const size_t n = ba->n[kind];
+    LVB_TRY(ba->eval_r.ensure(std::max<size_t>(1, n * kResDim[kind])));
+    LVB_TRY(ba->eval_J.ensure(std::max<size_t>(1, n * kResDim[kind] * kJacCols[kind])));
+    return LVB_OK;
+}
+
+int lvb_ba_eval(lvb_ba* ba, int kind, double* r, double* J) {
+    if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
+    if (kind < 0 || kind >= 6) { set_error("bad kind"); return LVB_ERR_INVALID; }
+    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    LVB_TRY(ensure_eval_buffers(ba, kind));
+    LVB_TRY(launch_eval(ba, kind, ba->eval_r.p, ba->eval_J.p));
+    const size_t n = ba->n[kind];
+    if (r) LVB_TRY(ba->eval_r.download(r, n * kResDim[kind], ba->ctx->stream));
+    if (J) LVB_TRY(ba->eval_J.download(J, n * kResDim[kind] * kJacCols[kind], ba->ctx->stream));
+    LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream));
+    return LVB_OK;
+}
+
+int lvb_ba_eval_device(lvb_ba* ba, int kind) {
+    if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
+    if (kind < 0 || kind >= 6) { set_error("bad kind"); return LVB_ERR_INVALID; }
+    LVB_TRY(ensure_eval_buffers(ba, kind));
+    return launch_eval(ba, kind, ba->eval_r.p, ba->eval_J.p);
+}
+
+// one pass = one LM iteration attempt (all decisions on the device)
+static int launch_linearize_and_reduce(lvb_ba* ba) {
+    BaDev& d = ba->dev;
+    lvb_ctx* ctx = ba->ctx;
+    const size_t nH = (size_t)d.dimc * d.dimc;
+    LAUNCH(ba, ba_zero_kernel, std::min(1024, nblk(nH + d.dimc + 2 * (size_t)d.n_rho, 256)), 256, 0, d);
+    LAUNCH(ba, ba_linearize_kernel<0>, ba->ranges.b[3], TPB, ba->pose_smem, d, ba->ranges);
+    LAUNCH(ba, ba_linearize_other_kernel<0>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
+    LAUNCH(ba, ba_prepare_landmark_kernel, nblk(d.n_rho, 256), 256, 0, d);
+    LAUNCH(ba, ba_build_S_kernel, std::min(1024, nblk(nH, 256)), 256, 0, d);
+    LAUNCH(ba, ba_schur_kernel, nblk(d.n_rho, TPB), TPB, 0, d);
+    if (ctx->world > 1) {
+        LAUNCH(ba, ba_pack_scalars_kernel, 1, 1, 0, d);
+        LVB_TRY(comm_allreduce_sum_f64(ctx, d.S, nH + 3 * (size_t)d.dimc + 16));
+        LAUNCH(ba, ba_unpack_scalars_kernel, 1, 1, 0, d);
+    }
+    LAUNCH(ba, ba_prepare_camera_kernel, nblk(d.n_poses + d.n_vec3, 128), 128, 0, d);
+    LAUNCH(ba, lm_control_pre_kernel, 1, 1, 0, d.st);
+    return check_launch("linearize");
+}
+
+static int launch_step(lvb_ba* ba) {
+    BaDev& d = ba->dev;
+    lvb_ctx* ctx = ba->ctx;
+    const size_t chol_smem = (size_t)(32 * 34 + (d.dimc + 2) * 34) * 8;
+    LAUNCH(ba, ba_cholesky_kernel, 1, CHOL_T, chol_smem, d.S, d.rhs, d.dimc, d.st);
+    LAUNCH(ba, ba_update_kernel, nblk((size_t)d.n_poses + d.n_vec3 + d.n_rho, TPB), TPB, 0, d);
+    LAUNCH(ba, ba_linearize_kernel<1>, ba->ranges.b[3], TPB, ba->pose_smem, d, ba->ranges);
+    LAUNCH(ba, ba_linearize_other_kernel<1>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
+    if (ctx->world > 1) LVB_TRY(comm_allreduce_sum_f64(ctx, &d.st->cand_cost_acc, 5));
+    LAUNCH(ba, lm_control_post_kernel, 1, 1, 0, d.st);
+    LAUNCH(ba, ba_accept_kernel, std::min(1024, nblk((size_t)d.n_poses * 7 + d.n_vec3 * 3 + d.n_rho, 256)), 256, 0, d);
+    return check_launch("step");
+}
+
+static int upload_state(lvb_ba* ba, const lvb_solve_options* o, double radius_override) {
+    lvb_solve_options opt;
+    if (o) opt = *o; else lvb_default_options(&opt);
+    if (radius_override > 0) opt.initial_trust_region_radius = radius_override;
+    LmState h;
+    lm_init(h, opt);
+    LVB_CUDA(cudaMemcpyAsync(ba->st.p, &h, sizeof(h), cudaMemcpyHostToDevice, ba->ctx->stream));
+    LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream));
+    return LVB_OK;
+}
+
+static int require_solvable(lvb_ba* ba) {
+    if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
+    if (!ba->solvable) { set_error("camera system dimension %d is outside the dense solver range (1..%d) of this build", ba->dimc, (int)MAX_DIMC); return LVB_ERR_UNSUPPORTED; }
+    return LVB_OK;
+}
+
+int lvb_ba_reduced_system(lvb_ba* ba, double radius, double* S, double* b, double* cost) {
+    LVB_TRY(require_solvable(ba));
+    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    LVB_TRY(upload_state(ba, nullptr, radius));
+    LVB_TRY(launch_linearize_and_reduce(ba));
+    const int n = ba->dimc;
+    std::vector<double> hS((size_t)n * n);
+    LmState h;
+    cudaStream_t s = ba->ctx->stream;
+    LVB_CUDA(cudaMemcpyAsync(hS.data(), ba->dev.S, hS.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (b) LVB_CUDA(cudaMemcpyAsync(b, ba->dev.rhs, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    LVB_CUDA(cudaMemcpyAsync(&h, ba->st.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    LVB_CUDA(cudaStreamSynchronize(s));
+    if (S) for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) S[(size_t)i * n + j] = (j <= i) ? hS[(size_t)i * n + j] : hS[(size_t)j * n + i];
+    if (cost) *cost = h.x_cost;
+    return LVB_OK;
+}
+
+int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary* summary) {
+    LVB_TRY(require_solvable(ba));
+    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    lvb_solve_options opt;
+    if (options) opt = *options; else lvb_default_options(&opt);
+    LVB_TRY(upload_state(ba, &opt, -1.0));
+    cudaStream_t s = ba->ctx->stream;
+    LmState h;
+    memset(&h, 0, sizeof(h));
+    for (int pass = 0; pass <= opt.max_num_iterations; ++pass) {
+        LVB_TRY(launch_linearize_and_reduce(ba));
+        LVB_TRY(launch_step(ba));
+        LVB_CUDA(cudaMemcpyAsync(&h, ba->st.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+        LVB_CUDA(cudaStreamSynchronize(s));
+        if (h.done) break;
+        const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (el >= opt.max_solver_time_in_seconds) break;   // backend.cpp:208 wall-clock cap
+    }
+    if (summary) {
+        int nb = 0; for (int k = 0; k < 6; ++k) nb += ba->n[k];
+        summary->initial_cost = h.initial_cost; summary->final_cost = h.x_cost;
+        summary->num_iterations = h.iter; summary->num_successful_steps = h.num_successful;
+        summary->termination_type = h.termination; summary->num_residual_blocks = nb; summary->num_residual_blocks_reduced = nb;
+        summary->final_radius = h.radius;
+        summary->total_time_in_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (h.termination == 2) { set_error("LM failed: %d consecutive invalid steps", h.invalid); }
+    return LVB_OK;
+}
+
+int lvb_ba_get_poses(lvb_ba* ba, double* out) {
+    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    LVB_TRY(ba->poses.download(out, ba->h_poses.size(), ba->ctx->stream)); LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream)); return LVB_OK;
+}
+int lvb_ba_get_vec3(lvb_ba* ba, double* out) {
+    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    LVB_TRY(ba->vec3.download(out, ba->h_vec3.size(), ba->ctx->stream)); LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream)); return LVB_OK;
+}
+int lvb_ba_get_inv_depths(lvb_ba* ba, double* out) {
+    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    LVB_TRY(ba->rho.download(out, ba->h_rho.size(), ba->ctx->stream)); LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream)); return LVB_OK;
+}
+
+int lvb_ba_reprojection_errors(lvb_ba* ba, int n, const double* ob_pw, const int32_t* pose_idx, double* err) {
+    if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
+    if (n <= 0) return LVB_OK;
+    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    const int np = (int)ba->h_poses.size() / 7;
+    for (int i = 0; i < n; ++i) if (pose_idx[i] < 0 || pose_idx[i] >= np) { set_error("pose index out of range"); return LVB_ERR_INVALID; }
+    DevBuf<double> d_in, d_err; DevBuf<int> d_idx;
+    cudaStream_t s = ba->ctx->stream;
+    LVB_TRY(d_in.upload(ob_pw, (size_t)5 * n, s)); LVB_TRY(d_idx.upload(pose_idx, n, s)); LVB_TRY(d_err.ensure(n));
+    LAUNCH(ba, ba_reproj_error_kernel, nblk(n, 128), 128, 0, ba->dev, n, d_in.p, d_idx.p, d_err.p);
+    LVB_TRY(check_launch("reproj"));
+    LVB_TRY(d_err.download(err, n, s));
+    LVB_CUDA(cudaStreamSynchronize(s));
+    return LVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+// lvb_internal.cuh -- context, error plumbing, device buffers, LM state shared by ba.cu / icp.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/lvio_b200.h"
+
+namespace lvb {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define LVB_CUDA(expr)                                                              \
+    do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return lvb::cuda_fail(e_, #expr, __FILE__, __LINE__); } while (0)
+#define LVB_TRY(expr)                                                               \
+    do { int rc_ = (expr); if (rc_ != LVB_OK) return rc_; } while (0)
+
+}  // namespace lvb
+
+struct lvb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    long long launches = 0;
+    int sm_count = 148;
+    bool use_tma = true;          // cp.async.bulk staging of the pose array (env LVB_NO_TMA=1 disables)
+    // NCCL (resolved at run time through dlopen, see comm.cu)
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+namespace lvb {
+
+int comm_allreduce_sum_f64(lvb_ctx* ctx, double* buf, size_t count);   // no-op when world == 1
+
+// Minimal owning device buffer.
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    int ensure(size_t count) {
+        if (count <= n && p) return LVB_OK;
+        release();
+        if (count == 0) count = 1;
+        // round up to 16 B so cp.async.bulk sources stay 16-byte sized
+        size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
+        LVB_CUDA(cudaMalloc((void**)&p, bytes));
+        n = count;
+        return LVB_OK;
+    }
+    int upload(const T* h, size_t count, cudaStream_t s) {
+        LVB_TRY(ensure(count));
+        if (count) LVB_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+        return LVB_OK;
+    }
+    int download(T* h, size_t count, cudaStream_t s) const {
+        if (count) LVB_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+        return LVB_OK;
+    }
+    int zero(cudaStream_t s) { if (p) LVB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); return LVB_OK; }
+};
+
+// Trust-region state kept on the device so that an LM iteration needs no host round trip for
+// its decisions.  Semantics: Ceres TrustRegionMinimizer + LevenbergMarquardtStrategy defaults
+// [upstream, not vendored in the reference]; see oracle/lm.h for the CPU restatement.
+struct LmState {
+    // accumulators (zeroed by the kernels named in the comments)
+    double cost_acc;        // 1/2 sum rho at x           (linearize)
+    double cand_cost_acc;   // 1/2 sum rho at candidate   (cost kernel)
+    double mcc_a, mcc_b;    // sum d.L.d , sum g.d        (update kernel)
+    double step_norm2, x_norm2;
+    unsigned long long grad_max_bits;
+    // trust region
+    double x_cost, initial_cost;
+    double radius, decrease_factor;
+    int iter, num_successful, invalid, done, termination, need_linearize, scale_valid, accept, solve_fail, last_successful;
+    int n_accepted;         // ICP: accepted correspondences
+    // options
+    double f_tol, g_tol, p_tol, min_radius, max_radius, min_diag, max_diag, min_rel_dec;
+    int jacobi, max_invalid, max_iter;
+};
+
+__host__ __device__ inline void lm_init(LmState& s, const lvb_solve_options& o) {
+    s.cost_acc = s.cand_cost_acc = s.mcc_a = s.mcc_b = s.step_norm2 = s.x_norm2 = 0.0;
+    s.grad_max_bits = 0ull;
+    s.x_cost = s.initial_cost = 0.0;
+    s.radius = o.initial_trust_region_radius; s.decrease_factor = 2.0;
+    s.iter = 0; s.num_successful = 0; s.invalid = 0; s.done = 0; s.termination = 1; s.need_linearize = 1;
+    s.scale_valid = 0; s.accept = 0; s.solve_fail = 0; s.last_successful = 0; s.n_accepted = 0;
+    s.f_tol = o.function_tolerance; s.g_tol = o.gradient_tolerance; s.p_tol = o.parameter_tolerance;
+    s.min_radius = 1e-32; s.max_radius = 1e16; s.min_diag = 1e-6; s.max_diag = 1e32; s.min_rel_dec = 1e-3;
+    s.jacobi = o.jacobi_scaling; s.max_invalid = 5; s.max_iter = o.max_num_iterations;
+}
+
+#if defined(__CUDACC__)
+// Runs once per iteration after the linearisation (and its all-reduce) is complete and before
+// the step is computed: FinalizeIterationAndCheckIfMinimizerCanContinue.
+__device__ inline void lm_control_pre(LmState& s) {
+    if (s.done) return;
+    if (s.need_linearize) { s.x_cost = s.cost_acc; if (s.iter == 0 && s.num_successful == 0 && s.scale_valid == 0) s.initial_cost = s.x_cost; }
+    s.scale_valid = 1;
+    const double gmax = __longlong_as_double((long long)s.grad_max_bits);
+    if ((s.iter == 0 || s.last_successful) && gmax <= s.g_tol) { s.done = 1; s.termination = 0; return; }
+    if (s.iter >= s.max_iter) { s.done = 1; return; }
+    if (s.radius <= s.min_radius) { s.done = 1; s.termination = 0; return; }
+    s.iter += 1;
+    s.last_successful = 0;
+    s.mcc_a = s.mcc_b = s.step_norm2 = s.x_norm2 = 0.0;
+    s.cand_cost_acc = 0.0;
+    s.solve_fail = 0;
+    s.accept = 0;
+}
+// Runs after the candidate cost is known: step validity, tolerances, accept / reject, radius.
+__device__ inline void lm_control_post(LmState& s) {
+    if (s.done) return;
+    s.need_linearize = 0;
+    const double model_cost_change = 0.5 * (s.mcc_a - s.mcc_b);
+    if (s.solve_fail || !(model_cost_change > 0.0) || !isfinite(model_cost_change)) {
+        if (++s.invalid >= s.max_invalid) { s.done = 1; s.termination = 2; return; }
+        s.radius = s.radius / s.decrease_factor; s.decrease_factor *= 2.0;
+        return;
+    }
+    s.invalid = 0;
+    const double cand = s.cand_cost_acc;
+    if (sqrt(s.step_norm2) <= s.p_tol * (sqrt(s.x_norm2) + s.p_tol)) { s.done = 1; s.termination = 0; return; }
+    if (fabs(s.x_cost - cand) <= s.f_tol * s.x_cost) { s.done = 1; s.termination = 0; return; }
+    const double rel = (s.x_cost - cand) / model_cost_change;
+    if (rel > s.min_rel_dec) {
+        s.accept = 1; s.need_linearize = 1; s.last_successful = 1; s.num_successful += 1;
+        s.cost_acc = 0.0; s.grad_max_bits = 0ull;
+        const double t = 2.0 * rel - 1.0;
+        s.radius = fmin(s.max_radius, s.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+        s.decrease_factor = 2.0;
+    } else {
+        s.radius = s.radius / s.decrease_factor; s.decrease_factor *= 2.0;
+    }
+}
+#endif
+
+}  // namespace lvb

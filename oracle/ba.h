@@ -11,6 +11,10 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include "factors.h"
@@ -56,6 +60,42 @@ inline void pose_to_tangent(const double* Ja, int rows, int ld, const double* po
         for (int c = 0; c < 3; ++c) Jt[r * 6 + 3 + c] = Ja[r * ld + 4 + c];
     }
 }
+
+// Persistent worker pool (Ceres keeps one too): parallel_for(T, fn) runs fn(0..T-1), task 0 on the caller.
+class WorkerPool {
+public:
+    static WorkerPool& get() { static WorkerPool p; return p; }
+    void run(int T, const std::function<void(int)>& fn) {
+        if (T <= 1) { fn(0); return; }
+        std::unique_lock<std::mutex> lk(m_);
+        while ((int)workers_.size() < T - 1) { const int id = (int)workers_.size(); workers_.emplace_back([this, id] { loop(id); }); }
+        fn_ = &fn; tasks_ = T; pending_ = T - 1; ++epoch_;
+        cv_.notify_all();
+        lk.unlock();
+        fn(0);
+        lk.lock();
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+private:
+    WorkerPool() {}
+    ~WorkerPool() { { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++epoch_; } cv_.notify_all(); for (auto& w : workers_) w.join(); }
+    void loop(int id) {
+        unsigned long seen = 0;
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
+            if (stop_) return;
+            seen = epoch_;
+            if (id + 1 < tasks_) { const auto* f = fn_; lk.unlock(); (*f)(id + 1); lk.lock(); if (--pending_ == 0) done_.notify_all(); }
+        }
+    }
+    std::mutex m_; std::condition_variable cv_, done_;
+    std::vector<std::thread> workers_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int tasks_ = 0, pending_ = 0; unsigned long epoch_ = 0; bool stop_ = false;
+};
+inline void parallel_for(int T, const std::function<void(int)>& fn) { WorkerPool::get().run(T, fn); }
 
 struct FactorGroup {
     int n = 0;
@@ -164,12 +204,7 @@ struct BaProblem {
         double c = 0; for (double p : part) c += p; return c;
     }
 
-    template <class F> static void run_threads(int T, F&& work) {
-        if (T == 1) { work(0); return; }
-        std::vector<std::thread> th;
-        for (int t = 0; t < T; ++t) th.emplace_back(work, t);
-        for (auto& x : th) x.join();
-    }
+    template <class F> static void run_threads(int T, F&& work) { parallel_for(T, std::function<void(int)>(work)); }
 
     // ------------------------------------------------------------------ linearisation
     // Builds Hcc (dense dimc x dimc, full symmetric), gc, per-factor landmark couplings, Hll, gl.

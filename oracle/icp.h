@@ -13,6 +13,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <functional>
 #include <limits>
 #include <thread>
 #include <vector>
@@ -20,6 +21,8 @@
 #include "lm.h"
 
 namespace oracle {
+
+void icp_parallel(int T, const std::function<void(int)>& fn);   // defined in oracle_capi.cpp (shares the BA worker pool)
 
 struct Pt { float x, y, z; };
 
@@ -145,7 +148,7 @@ struct IcpProblem {
                     for (int p = 0; p < 3; ++p) { a[9 + p] += J[p] * r; for (int q = 0; q < 3; ++q) a[3 * p + q] += J[p] * J[q]; } }
             }
         };
-        if (T == 1) work(0); else { std::vector<std::thread> th; for (int t = 0; t < T; ++t) th.emplace_back(work, t); for (auto& z : th) z.join(); }
+        icp_parallel(T, work);
         double acc[13] = {0};
         for (int t = 0; t < T; ++t) for (int k = 0; k < 13; ++k) acc[k] += part[(size_t)t * 13 + k];
         if (prior_weight >= 0.0) {

@@ -15,6 +15,8 @@
 
 using namespace oracle;
 
+namespace oracle { void icp_parallel(int T, const std::function<void(int)>& fn) { parallel_for(T, fn); } }
+
 struct orc_ctx { int dummy; };
 struct orc_ba { BaProblem p; bool finalized = false; };
 struct orc_icp {

@@ -1,0 +1,147 @@
+"""The closed-form factor arithmetic of lvio_fusion_b200/csrc/lvb_math.cuh, compiled for the
+host (tests/hostcheck), against the CPU oracle's autodiff.  Runs without a GPU; the GPU tests
+repeat the comparison through the kernels and the C ABI."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from lvio_fusion_b200 import backend, synth
+from lvio_fusion_b200.backend import IMU, POSE_GRAPH, POSE_ONLY, POSE_PRIOR, TWO_CAMERA, TWO_FRAME
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DP = C.POINTER(C.c_double)
+
+
+def _dp(a):
+    return a.ctypes.data_as(DP)
+
+
+@pytest.fixture(scope="module")
+def hc():
+    src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
+    lib = os.path.join(HERE, "hostcheck", "libhostcheck.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", lib, src])
+    return C.CDLL(lib)
+
+
+@pytest.fixture(scope="module")
+def prob(orc_ctx):
+    d = synth.make_ba_problem(6, 300, with_imu=True, seed=5)
+    # make the stored quaternions slightly non-unit: the normalisation must be differentiated through
+    d["poses"][:, :4] *= (1.0 + 0.01 * np.arange(len(d["poses"])))[:, None]
+    p = backend.Problem.from_dict(orc_ctx, d)
+    return d, p
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b)) / max(1.0, np.max(np.abs(b)))
+
+
+def test_two_frame(hc, prob):
+    d, p = prob
+    r_o, J_o = p.evaluate(TWO_FRAME)
+    c, ix = d["factors"][TWO_FRAME]
+    cam = d["cameras"]
+    for f in range(0, len(c), 7):
+        r = np.zeros(2); J = np.zeros((2, 15)); Jt = np.zeros((2, 13))
+        hc.hc_two_frame(_dp(cam), _dp(c[f].copy()), C.c_double(d["rho"][ix[f, 0]]), _dp(d["poses"][ix[f, 1]].copy()), _dp(d["poses"][ix[f, 2]].copy()), _dp(r), _dp(J), _dp(Jt))
+        assert _rel(r, r_o[f]) < 1e-11
+        assert _rel(J, J_o[f]) < 1e-10
+        # tangent block = ambient block times Ceres' plus-Jacobian
+        for blk, col in ((1, 1), (2, 8)):
+            q = d["poses"][ix[f, blk]].copy()
+            for row in range(2):
+                t6 = np.zeros(6)
+                hc.hc_ambient_row_to_tangent(_dp(q), _dp(J_o[f, row, col:col + 7].copy()), _dp(t6))
+                got = Jt[row, 1 + 6 * (blk - 1):7 + 6 * (blk - 1)]
+                assert np.max(np.abs(t6 - got)) / max(1.0, np.abs(t6).max()) < 1e-10
+
+
+def test_pose_only_and_two_camera(hc, prob):
+    d, p = prob
+    cam = d["cameras"]
+    r_o, J_o = p.evaluate(POSE_ONLY)
+    c, ix = d["factors"][POSE_ONLY]
+    for f in range(0, len(c), 3):
+        r = np.zeros(2); J = np.zeros((2, 7)); Jt = np.zeros((2, 6))
+        hc.hc_pose_only(_dp(cam), _dp(c[f].copy()), _dp(d["poses"][ix[f, 0]].copy()), _dp(r), _dp(J), _dp(Jt))
+        assert _rel(r, r_o[f]) < 1e-11 and _rel(J, J_o[f]) < 1e-10
+    r_o, J_o = p.evaluate(TWO_CAMERA)
+    c, ix = d["factors"][TWO_CAMERA]
+    for f in range(0, len(c), 5):
+        r = np.zeros(2); J = np.zeros(2)
+        hc.hc_two_camera(_dp(cam), _dp(c[f].copy()), C.c_double(d["rho"][ix[f, 0]]), _dp(r), _dp(J))
+        assert _rel(r, r_o[f]) < 1e-11 and _rel(J, J_o[f, :, 0]) < 1e-10
+
+
+def test_imu(hc, prob):
+    d, p = prob
+    r_o, J_o = p.evaluate(IMU)
+    c, ix = d["factors"][IMU]
+    P, V = d["poses"], d["vec3"]
+    for f in range(len(c)):
+        r = np.zeros(15); J = np.zeros((15, 32))
+        a = [P[ix[f, 0]], V[ix[f, 1]], V[ix[f, 2]], V[ix[f, 3]], P[ix[f, 4]], V[ix[f, 5]], V[ix[f, 6]], V[ix[f, 7]]]
+        a = [x.copy() for x in a]
+        assert hc.hc_imu(_dp(c[f].copy()), *[_dp(x) for x in a], _dp(r), _dp(J)) == 0
+        assert _rel(r, r_o[f]) < 1e-9
+        assert _rel(J, J_o[f]) < 1e-9
+
+
+def test_priors(hc, orc, orc_ctx, prob):
+    d, _ = prob
+    P = d["poses"]
+    rng = np.random.default_rng(0)
+    cg = np.concatenate([rng.normal(0, 0.1, 6), [100.0, 0.3]])
+    cp = np.concatenate([P[1] + rng.normal(0, 0.01, 7), [50.0, 0.7]])
+    dd = dict(d); dd["factors"] = {POSE_GRAPH: (cg[None], np.array([[0, 2]], dtype=np.int32)), POSE_PRIOR: (cp[None], np.array([[3]], dtype=np.int32))}
+    p = backend.Problem.from_dict(orc_ctx, dd)
+    r_o, J_o = p.evaluate(POSE_GRAPH)
+    r = np.zeros(6); J = np.zeros((6, 14))
+    hc.hc_pose_graph(_dp(cg), _dp(P[0].copy()), _dp(P[2].copy()), _dp(r), _dp(J))
+    assert _rel(r, r_o[0]) < 1e-12 and _rel(J, J_o[0]) < 1e-11
+    r_o, J_o = p.evaluate(POSE_PRIOR)
+    r = np.zeros(6); J = np.zeros((6, 7))
+    hc.hc_pose_prior(_dp(cp), _dp(P[3].copy()), _dp(r), _dp(J))
+    assert _rel(r, r_o[0]) < 1e-12 and _rel(J, J_o[0]) < 1e-11
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_icp_point(hc, orc, mode):
+    rng = np.random.default_rng(mode)
+    from lvio_fusion_b200 import _capi
+    Twc1 = np.array([0.02, -0.01, 0.3, 0.95, 10.0, -4.0, 1.5]); Twc1[:4] *= 1.003
+    e = np.array([0.05, -0.01, 0.02, 1.0, 0.2, -0.05])
+    # oracle single-point evaluation through its ICP entry is association-bound; use the BA-free helper path:
+    # compare against central differences of hc itself plus the oracle composite transform
+    for _ in range(20):
+        c10 = np.concatenate([rng.normal(0, 10, 3), rng.normal(0, 10, 3), rng.normal(0, 1, 3), [0.7]])
+        c10[6:9] /= np.linalg.norm(c10[6:9])
+        r = np.zeros(1); J = np.zeros(3)
+        hc.hc_icp_point(mode, _dp(Twc1), _dp(e), _dp(c10), _dp(r), _dp(J))
+        # oracle value: Twc2 = Twc1 * se3(e); r = w n.(Twc2 p - pa)
+        rel = np.zeros(7); T2 = np.zeros(7)
+        orc.rpyxyz_to_se3(_dp(e.copy()), _dp(rel)); orc.se3_compose(_dp(Twc1.copy()), _dp(rel), _dp(T2))
+        lp = synth.se3_apply(np.concatenate([T2[:4] / np.linalg.norm(T2[:4]), T2[4:]]), c10[:3])
+        assert abs(r[0] - 0.7 * np.dot(lp - c10[3:6], c10[6:9])) < 1e-10
+        free = [1, 2, 5] if mode == 0 else [0, 3, 4]
+        for k, fi in enumerate(free):
+            h = 1e-6; num = 0
+            for s in (1, -1):
+                ee = e.copy(); ee[fi] += s * h
+                rr = np.zeros(1)
+                hc.hc_icp_point(mode, _dp(Twc1), _dp(ee), _dp(c10), _dp(rr), None)
+                num += s * rr[0]
+            assert abs(num / (2 * h) - J[k]) < 1e-6 * max(1, abs(J[k]))
+
+
+def test_pose_plus(hc, orc):
+    rng = np.random.default_rng(1)
+    for _ in range(10):
+        x = rng.normal(0, 1, 7); d = rng.normal(0, 0.1, 6)
+        a = np.zeros(7); b = np.zeros(7)
+        hc.hc_pose_plus(_dp(x), _dp(d), _dp(a)); orc.pose_plus(_dp(x), _dp(d), _dp(b))
+        assert np.max(np.abs(a - b)) < 1e-15
