@@ -18,6 +18,7 @@
 #include <math.h>
 #include <algorithm>
 #include <chrono>
+#include <map>
 #include <string.h>
 #include "lvb_internal.cuh"
 #include "lvb_math.cuh"
@@ -26,7 +27,7 @@ using namespace lvb;
 
 namespace {
 
-enum { TPB = 128, IMU_STRIDE = 17 + 45 + 225, IMU_RAW = 467, MAX_DIMC = 736, MAX_STAGE_POSES = 512, MAX_TRACK = 16, CHOL_T = 512 };
+enum { TPB = 128, IMU_STRIDE = 17 + 45 + 225, IMU_RAW = 467, MAX_DIMC = 736, MAX_STAGE_POSES = 512, MAX_TRACK = 16, CHOL_T = 256, SYRK_ROWS = 64, SYRK_LD = 14 };
 
 __constant__ unsigned char c_tri_a[465];
 __constant__ unsigned char c_tri_b[465];
@@ -40,6 +41,9 @@ struct BaDev {
     const int* fi[6];
     double huber[6];
     const int *lm_start, *lm_fac;
+    const int *tf_slot;                 // 2 planes: slot of pose_1 / pose_2 inside the landmark's Schur group (-1: constant pose)
+    const int *sw_group, *sw_lm, *grp_ns, *grp_off;   // Schur warps: group id, 32 landmark ids (-1 pad); per group: #slots, offsets
+    int n_schur_warps, warp_syrk;
     double *Hpp, *gc, *Hll, *gl, *tf_w;
     double *S, *rhs, *gcr, *diagH, *scal;      // inside the arena
     double *scale_c, *scale_l, *lam_c, *lam_l;
@@ -263,6 +267,28 @@ __global__ void ba_eval_prior_kernel(BaDev d, int kind, double* __restrict__ r_o
 // ------------------------------------------------------------------ fused linearize / cost kernel
 // MODE 0: at x      -> Hpp, gc, Hll, gl, tf_w, st->cost_acc      (skipped unless st->need_linearize)
 // MODE 1: at cand   -> st->cand_cost_acc only
+// Warp-level SYRK: the 32 blocks of a warp share their pose key (finalize() sorts and pads), so the warp
+// writes its Jacobian rows [2 x ncol per lane] to shared memory, each lane then owns a few entries of the
+// lower triangle of A^T A (A = [J_1 | J_2 | r] or [J | r]) and issues ONE red.global per entry instead of 32.
+__device__ __forceinline__ void warp_syrk_flush(const BaDev& d, const double* A /*64 x SYRK_LD*/, int ncol, int off1, int off2) {
+    const int lane = threadIdx.x & 31;
+    const int nent = ncol * (ncol + 1) / 2;
+    for (int e = lane; e < nent; e += 32) {
+        const int a = c_tri_a[e], b = c_tri_b[e];                 // a >= b, both < ncol <= 13
+        if (a == ncol - 1 && b == ncol - 1) continue;             // r.r : the cost goes through block_add
+        double v = 0.0;
+#pragma unroll 8
+        for (int r = 0; r < SYRK_ROWS; ++r) v += A[r * SYRK_LD + a] * A[r * SYRK_LD + b];
+        if (v == 0.0) continue;
+        const int gb = (ncol == 13) ? (b < 6 ? (off1 < 0 ? -1 : off1 + b) : (off2 < 0 ? -1 : off2 + b - 6)) : (off1 < 0 ? -1 : off1 + b);
+        if (gb < 0) continue;
+        if (a == ncol - 1) { atomicAdd(&d.gc[gb], v); continue; }
+        const int ga = (ncol == 13) ? (a < 6 ? (off1 < 0 ? -1 : off1 + a) : (off2 < 0 ? -1 : off2 + a - 6)) : (off1 < 0 ? -1 : off1 + a);
+        if (ga < 0) continue;
+        if (ga >= gb) atomicAdd(&d.Hpp[(size_t)ga * d.dimc + gb], v); else atomicAdd(&d.Hpp[(size_t)gb * d.dimc + ga], v);
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(TPB) ba_linearize_kernel(BaDev d, BlockRanges R) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -272,86 +298,109 @@ __global__ void __launch_bounds__(TPB) ba_linearize_kernel(BaDev d, BlockRanges 
     if (st->done) return;
     if (MODE == 0 && !st->need_linearize) return;
     const double* Psrc = MODE == 0 ? d.poses : d.c_poses;
-    const double* V = MODE == 0 ? d.vec3 : d.c_vec3;
     const double* Rho = MODE == 0 ? d.rho : d.c_rho;
     double* cost_target = MODE == 0 ? &d.st->cost_acc : &d.st->cand_cost_acc;
     const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double cost = 0.0;
-
-    {   // ---- the three visual kinds: one thread per block, poses staged in shared memory
-        const double* P = stage_poses(d, Psrc, reinterpret_cast<double*>(smem_raw), &bar);
-        if (b < R.b[1]) {
-            const int n = d.n[0];
-            const int f = (b - R.b[0]) * TPB + threadIdx.x;
-            if (f < n) {
-                const double* c = d.fc[0]; const int* ix = d.fi[0];
-                const int il = ix[f]; int i1 = ix[n + f], i2 = ix[2 * n + f];
-                TwoFrameLin o;
-                two_frame_lin(d.cams, c[f], c[n + f], c[2 * n + f], c[3 * n + f], c[4 * n + f], Rho[il], P + 7 * i1, P + 7 * i2, o, nullptr, nullptr);
-                double rho_v, sr;
-                huber(d.huber[0], o.r[0] * o.r[0] + o.r[1] * o.r[1], &rho_v, &sr);
-                cost = 0.5 * rho_v;
-                if (MODE == 0) {
-                    o.r[0] *= sr; o.r[1] *= sr; o.Jrho[0] *= sr; o.Jrho[1] *= sr;
-                    for (int k = 0; k < 12; ++k) { o.J1[k] *= sr; o.J2[k] *= sr; }
-                    int off1 = d.pose_off[i1], off2 = d.pose_off[i2];
-                    if (i1 == i2) { for (int k = 0; k < 12; ++k) o.J1[k] += o.J2[k]; off2 = -1; }
-                    const bool lfree = d.rho_slot[il] >= 0;
-                    double* w = d.tf_w;
-                    if (lfree) {
-                        atomicAdd(&d.Hll[il], o.Jrho[0] * o.Jrho[0] + o.Jrho[1] * o.Jrho[1]);
-                        atomicAdd(&d.gl[il], o.Jrho[0] * o.r[0] + o.Jrho[1] * o.r[1]);
-                    }
-                    for (int k = 0; k < 6; ++k) {
-                        w[(size_t)k * n + f] = (lfree && off1 >= 0) ? o.Jrho[0] * o.J1[k] + o.Jrho[1] * o.J1[6 + k] : 0.0;
-                        w[(size_t)(6 + k) * n + f] = (lfree && off2 >= 0) ? o.Jrho[0] * o.J2[k] + o.Jrho[1] * o.J2[6 + k] : 0.0;
-                    }
-                    if (off1 >= 0) add_diag(d.Hpp, d.gc, d.dimc, off1, o.J1, 6, 2, o.r);
-                    if (off2 >= 0) add_diag(d.Hpp, d.gc, d.dimc, off2, o.J2, 6, 2, o.r);
-                    if (off1 >= 0 && off2 >= 0) add_cross(d.Hpp, d.dimc, off1, o.J1, 6, off2, o.J2, 6, 2);
+    const size_t pose_bytes = d.stage_poses ? (((size_t)d.n_poses * 56 + 16 + 15) & ~(size_t)15) : 0;
+    double* A = reinterpret_cast<double*>(smem_raw + pose_bytes) + (size_t)warp * SYRK_ROWS * SYRK_LD;
+    const double* P = stage_poses(d, Psrc, reinterpret_cast<double*>(smem_raw), &bar);
+    if (b < R.b[1]) {            // ---- a1 TwoFrameReprojectionError
+        const int n = d.n[0];
+        const int f = (b - R.b[0]) * TPB + threadIdx.x;
+        const bool valid = f < n;
+        const double* c = d.fc[0]; const int* ix = d.fi[0];
+        int il = 0, i1 = -1, i2 = -1, off1 = -1, off2 = -1;
+        TwoFrameLin o;
+        bool lfree = false;
+        if (valid) {
+            il = ix[f]; i1 = ix[n + f]; i2 = ix[2 * n + f];
+            two_frame_lin(d.cams, c[f], c[n + f], c[2 * n + f], c[3 * n + f], c[4 * n + f], Rho[il], P + 7 * i1, P + 7 * i2, o, nullptr, nullptr);
+            double rho_v, sr;
+            huber(d.huber[0], o.r[0] * o.r[0] + o.r[1] * o.r[1], &rho_v, &sr);
+            cost = 0.5 * rho_v;
+            if (MODE == 0) {
+                o.r[0] *= sr; o.r[1] *= sr; o.Jrho[0] *= sr; o.Jrho[1] *= sr;
+                for (int k = 0; k < 12; ++k) { o.J1[k] *= sr; o.J2[k] *= sr; }
+                off1 = d.pose_off[i1]; off2 = d.pose_off[i2];
+                if (i1 == i2) { for (int k = 0; k < 12; ++k) o.J1[k] += o.J2[k]; off2 = -1; }
+                lfree = d.rho_slot[il] >= 0;
+                double* w = d.tf_w;
+                if (lfree) {
+                    const double h = o.Jrho[0] * o.Jrho[0] + o.Jrho[1] * o.Jrho[1], g = o.Jrho[0] * o.r[0] + o.Jrho[1] * o.r[1];
+                    if (h != 0.0) atomicAdd(&d.Hll[il], h);
+                    if (g != 0.0) atomicAdd(&d.gl[il], g);
+                }
+                for (int k = 0; k < 6; ++k) {
+                    w[(size_t)k * n + f] = (lfree && off1 >= 0) ? o.Jrho[0] * o.J1[k] + o.Jrho[1] * o.J1[6 + k] : 0.0;
+                    w[(size_t)(6 + k) * n + f] = (lfree && off2 >= 0) ? o.Jrho[0] * o.J2[k] + o.Jrho[1] * o.J2[6 + k] : 0.0;
                 }
             }
-        } else if (b < R.b[2]) {
-            const int n = d.n[1];
-            const int f = (b - R.b[1]) * TPB + threadIdx.x;
-            if (f < n) {
-                const double* c = d.fc[1];
-                const int ip = d.fi[1][f];
-                PoseOnlyLin o;
-                pose_only_lin(d.cams, c[f], c[n + f], v3(c[2 * n + f], c[3 * n + f], c[4 * n + f]), c[5 * n + f], P + 7 * ip, o, nullptr);
-                double rho_v, sr;
-                huber(d.huber[1], o.r[0] * o.r[0] + o.r[1] * o.r[1], &rho_v, &sr);
-                cost = 0.5 * rho_v;
-                if (MODE == 0) {
-                    const int off = d.pose_off[ip];
-                    if (off >= 0) {
-                        o.r[0] *= sr; o.r[1] *= sr; for (int k = 0; k < 12; ++k) o.J[k] *= sr;
-                        add_diag(d.Hpp, d.gc, d.dimc, off, o.J, 6, 2, o.r);
-                    }
-                }
+        }
+        if (MODE == 0) {
+            const int k1 = __shfl_sync(0xffffffffu, i1, 0), k2 = __shfl_sync(0xffffffffu, i2, 0);
+            const bool uniform = d.warp_syrk && __all_sync(0xffffffffu, valid && i1 == k1 && i2 == k2 && i1 != i2);
+            if (uniform) {
+                double* row0 = A + (2 * lane) * SYRK_LD; double* row1 = row0 + SYRK_LD;
+                for (int k = 0; k < 6; ++k) { row0[k] = o.J1[k]; row1[k] = o.J1[6 + k]; row0[6 + k] = o.J2[k]; row1[6 + k] = o.J2[6 + k]; }
+                row0[12] = o.r[0]; row1[12] = o.r[1];
+                __syncwarp();
+                warp_syrk_flush(d, A, 13, off1, off2);
+                __syncwarp();
+            } else if (valid) {
+                if (off1 >= 0) add_diag(d.Hpp, d.gc, d.dimc, off1, o.J1, 6, 2, o.r);
+                if (off2 >= 0) add_diag(d.Hpp, d.gc, d.dimc, off2, o.J2, 6, 2, o.r);
+                if (off1 >= 0 && off2 >= 0) add_cross(d.Hpp, d.dimc, off1, o.J1, 6, off2, o.J2, 6, 2);
             }
-        } else {
-            const int n = d.n[2];
-            const int f = (b - R.b[2]) * TPB + threadIdx.x;
-            if (f < n) {
-                const double* c = d.fc[2];
-                const int il = d.fi[2][f];
-                TwoCameraLin o;
-                two_camera_lin(d.cams, c[f], c[n + f], c[2 * n + f], c[3 * n + f], c[4 * n + f], Rho[il], o);
-                double rho_v, sr;
-                huber(d.huber[2], o.r[0] * o.r[0] + o.r[1] * o.r[1], &rho_v, &sr);
-                cost = 0.5 * rho_v;
-                if (MODE == 0 && d.rho_slot[il] >= 0) {
-                    const double j0 = o.Jrho[0] * sr, j1 = o.Jrho[1] * sr;
-                    atomicAdd(&d.Hll[il], j0 * j0 + j1 * j1);
-                    atomicAdd(&d.gl[il], j0 * o.r[0] * sr + j1 * o.r[1] * sr);
-                }
+        }
+    } else if (b < R.b[2]) {     // ---- a2 PoseOnlyReprojectionError
+        const int n = d.n[1];
+        const int f = (b - R.b[1]) * TPB + threadIdx.x;
+        const bool valid = f < n;
+        const double* c = d.fc[1];
+        int ip = -1, off = -1;
+        PoseOnlyLin o;
+        if (valid) {
+            ip = d.fi[1][f];
+            pose_only_lin(d.cams, c[f], c[n + f], v3(c[2 * n + f], c[3 * n + f], c[4 * n + f]), c[5 * n + f], P + 7 * ip, o, nullptr);
+            double rho_v, sr;
+            huber(d.huber[1], o.r[0] * o.r[0] + o.r[1] * o.r[1], &rho_v, &sr);
+            cost = 0.5 * rho_v;
+            if (MODE == 0) { off = d.pose_off[ip]; o.r[0] *= sr; o.r[1] *= sr; for (int k = 0; k < 12; ++k) o.J[k] *= sr; }
+        }
+        if (MODE == 0) {
+            const int k1 = __shfl_sync(0xffffffffu, ip, 0);
+            const bool uniform = d.warp_syrk && __all_sync(0xffffffffu, valid && ip == k1);
+            if (uniform) {
+                double* row0 = A + (2 * lane) * SYRK_LD; double* row1 = row0 + SYRK_LD;
+                for (int k = 0; k < 6; ++k) { row0[k] = o.J[k]; row1[k] = o.J[6 + k]; }
+                row0[6] = o.r[0]; row1[6] = o.r[1];
+                __syncwarp();
+                warp_syrk_flush(d, A, 7, off, -1);
+                __syncwarp();
+            } else if (valid && off >= 0) add_diag(d.Hpp, d.gc, d.dimc, off, o.J, 6, 2, o.r);
+        }
+    } else {                     // ---- a3 TwoCameraReprojectionError
+        const int n = d.n[2];
+        const int f = (b - R.b[2]) * TPB + threadIdx.x;
+        if (f < n) {
+            const double* c = d.fc[2];
+            const int il = d.fi[2][f];
+            TwoCameraLin o;
+            two_camera_lin(d.cams, c[f], c[n + f], c[2 * n + f], c[3 * n + f], c[4 * n + f], Rho[il], o);
+            double rho_v, sr;
+            huber(d.huber[2], o.r[0] * o.r[0] + o.r[1] * o.r[1], &rho_v, &sr);
+            cost = 0.5 * rho_v;
+            if (MODE == 0 && d.rho_slot[il] >= 0) {
+                const double j0 = o.Jrho[0] * sr, j1 = o.Jrho[1] * sr;
+                atomicAdd(&d.Hll[il], j0 * j0 + j1 * j1);
+                atomicAdd(&d.gl[il], j0 * o.r[0] * sr + j1 * o.r[1] * sr);
             }
         }
     }
     block_add(cost, cost_target, s_red);
 }
-
 
 // IMU (one warp per factor) and the two prior kinds: rare, register-hungry blocks kept out of the visual kernel
 template <int MODE>
@@ -503,43 +552,57 @@ __global__ void ba_build_S_kernel(BaDev d) {
     }
 }
 
-// K5: eliminate the inverse depths.  One thread per landmark; its TwoFrame couplings are merged by
-// pose, then S -= w_a^T w_b / h, rhs += w_a g / h on the lower triangle.
-__global__ void __launch_bounds__(TPB) ba_schur_kernel(BaDev d) {
+// K5: eliminate the inverse depths.  One warp per 32 landmarks that share their set of pose offsets
+// (finalize() groups and pads them).  Lane l writes u_l = sqrt(1/h_l) [w_l | g_l] (its couplings merged by
+// pose slot) as a row of a shared-memory tile; the warp then forms the lower triangle of U^T U and subtracts
+// it from S / adds the last column to rhs with one red.global per entry:  S -= sum_l w_l^T w_l / h_l.
+__global__ void __launch_bounds__(TPB) ba_schur_kernel(BaDev d, int cols_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     if (d.st->done) return;
-    const int l = blockIdx.x * TPB + threadIdx.x;
-    if (l >= d.n_rho || d.rho_slot[l] < 0) return;
-    const int e0 = d.lm_start[l], e1 = d.lm_start[l + 1];
-    if (e1 == e0) return;
-    const double hl = d.Hll[l] + d.lam_l[l];
-    if (!(hl > 0.0)) return;
-    const double hinv = 1.0 / hl, g = d.gl[l];
-    const int n = d.n[0];
-    const int* ix = d.fi[0];
-    int offs[MAX_TRACK]; double w[MAX_TRACK][6]; int ns = 0;      // finalize() guarantees <= MAX_TRACK distinct poses
-    for (int e = e0; e < e1; ++e) {
-        const int f = d.lm_fac[e];
-        if (f < 0) continue;                        // TwoCamera entries are encoded as -(f+1)
-        for (int side = 0; side < 2; ++side) {
-            const int off = d.pose_off[ix[(size_t)(1 + side) * n + f]];
-            if (off < 0) continue;
-            double v[6]; bool nz = false;
-            for (int k = 0; k < 6; ++k) { v[k] = d.tf_w[(size_t)(6 * side + k) * n + f]; nz |= (v[k] != 0.0); }
-            if (!nz) continue;
-            int j = 0; for (; j < ns; ++j) if (offs[j] == off) break;
-            if (j == ns) { if (ns == MAX_TRACK) continue; offs[ns] = off; for (int k = 0; k < 6; ++k) w[ns][k] = 0.0; ++ns; }
-            for (int k = 0; k < 6; ++k) w[j][k] += v[k];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * (TPB / 32) + warp;
+    if (w >= d.n_schur_warps) return;
+    const int g = d.sw_group[w];
+    const int ns = d.grp_ns[g];
+    const int ncol = 6 * ns + 1;
+    double* U = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 32 * cols_max;
+    double* row = U + (size_t)lane * ncol;
+    for (int k = 0; k < ncol; ++k) row[k] = 0.0;
+    const int l = d.sw_lm[(size_t)w * 32 + lane];
+    if (l >= 0) {
+        const double hl = d.Hll[l] + d.lam_l[l];
+        if (hl > 0.0) {
+            const int n = d.n[0];
+            for (int e = d.lm_start[l]; e < d.lm_start[l + 1]; ++e) {
+                const int f = d.lm_fac[e];
+                if (f < 0) continue;
+                for (int side = 0; side < 2; ++side) {
+                    const int sl = d.tf_slot[(size_t)side * n + f];
+                    if (sl < 0) continue;
+                    for (int k = 0; k < 6; ++k) row[6 * sl + k] += d.tf_w[(size_t)(6 * side + k) * n + f];
+                }
+            }
+            const double sh = sqrt(1.0 / hl);
+            for (int k = 0; k < ncol - 1; ++k) row[k] *= sh;
+            row[ncol - 1] = d.gl[l] * sh;
         }
     }
-    for (int a = 0; a < ns; ++a) {
-        for (int p = 0; p < 6; ++p) atomicAdd(&d.rhs[offs[a] + p], w[a][p] * g * hinv);
-        for (int c = 0; c < ns; ++c) {
-            if (offs[c] > offs[a]) continue;
-            for (int p = 0; p < 6; ++p) for (int q = 0; q < 6; ++q) {
-                if (offs[c] == offs[a] && q > p) continue;
-                atomicAdd(&d.S[(size_t)(offs[a] + p) * d.dimc + offs[c] + q], -w[a][p] * w[c][q] * hinv);
-            }
-        }
+    __syncwarp();
+    const int* offs = d.grp_off + (size_t)g * MAX_TRACK;
+    const int nent = ncol * (ncol + 1) / 2 - 1;                   // the (v,v) corner is not needed
+    for (int e = lane; e < nent; e += 32) {
+        int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while ((a + 1) * (a + 2) / 2 <= e) ++a;
+        while (a * (a + 1) / 2 > e) --a;
+        const int b = e - a * (a + 1) / 2;
+        double v = 0.0;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) v += U[r * ncol + a] * U[r * ncol + b];
+        if (v == 0.0) continue;
+        const int gb = offs[b / 6] + b % 6;
+        if (a == ncol - 1) { atomicAdd(&d.rhs[gb], v); continue; }
+        const int ga = offs[a / 6] + a % 6;
+        if (ga >= gb) atomicAdd(&d.S[(size_t)ga * d.dimc + gb], -v); else atomicAdd(&d.S[(size_t)gb * d.dimc + ga], -v);
     }
 }
 
@@ -599,36 +662,45 @@ __global__ void lm_control_post_kernel(LmState* st) { lm_control_post(*st); if (
 __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict__ S, double* __restrict__ rhs, int n, LmState* st) {
     if (st->done) return;
     extern __shared__ __align__(16) double sm[];
-    double* D = sm;               // 32 x 33   diagonal block
-    double* P = sm + 32 * 34;     // rows x 34 panel (16 B aligned rows for broadcast double2 loads)
+    double* D = sm;                    // 32 x 33   diagonal block of L
+    double* invd = sm + 32 * 33;       // n (+32)   reciprocals of diag(L)
+    double* P = invd + ((n + 32 + 1) & ~1);   // rows x 34 panel (16 B aligned rows for broadcast double2 loads)
     __shared__ int fail;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     if (tid == 0) fail = 0;
     __syncthreads();
     for (int kb = 0; kb < n; kb += 32) {
         const int bs = min(32, n - kb);
-        for (int e = tid; e < 32 * 32; e += nt) {
-            const int i = e >> 5, j = e & 31;
-            D[i * 33 + j] = (i < bs && j <= i) ? S[(size_t)(kb + i) * n + kb + j] : ((i == j) ? 1.0 : 0.0);
-        }
-        __syncthreads();
+        // ---- diagonal block: warp 0 holds one row per lane in registers and factors it with shuffles
         if (warp == 0) {
-            for (int j = 0; j < bs; ++j) {
-                double djj = D[j * 33 + j];
-                if (!(djj > 0.0)) { if (lane == 0) fail = 1; djj = 1.0; }
-                const double dj = sqrt(djj);
-                __syncwarp();
-                double lij = 0.0;
-                if (lane == j) D[j * 33 + j] = dj;
-                if (lane > j && lane < bs) { lij = D[lane * 33 + j] / dj; D[lane * 33 + j] = lij; }
-                __syncwarp();
-                if (lane > j && lane < bs) for (int k = j + 1; k <= lane; ++k) D[lane * 33 + k] -= lij * D[k * 33 + j];
-                __syncwarp();
+            double a[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = (lane < bs && j <= lane) ? S[(size_t)(kb + lane) * n + kb + j] : ((j == lane) ? 1.0 : 0.0);
+            int bad = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                double djj = __shfl_sync(0xffffffffu, a[j], j);
+                if (!(djj > 0.0)) { bad = 1; djj = 1.0; }
+                const double inv = rsqrt(djj);
+                if (lane >= j) a[j] *= inv;                       // l_ij (lane j: sqrt(d_jj))
+                if (lane == j) invd[kb + j] = inv;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {                    // constant trip count keeps a[] in registers
+                    if (k > j) {
+                        const double lkj = __shfl_sync(0xffffffffu, a[j], k);
+                        if (lane >= k) a[k] -= a[j] * lkj;
+                    }
+                }
             }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                D[lane * 33 + j] = (j <= lane) ? a[j] : 0.0;
+                if (lane < bs && j <= lane && j < bs) S[(size_t)(kb + lane) * n + kb + j] = a[j];
+            }
+            if (bad && lane == 0) fail = 1;
         }
         __syncthreads();
-        for (int e = tid; e < bs * bs; e += nt) { const int i = e / bs, j = e - i * bs; if (j <= i) S[(size_t)(kb + i) * n + kb + j] = D[i * 33 + j]; }
-        // panel: rows below the block + the rhs row (last):  x D^T = a
+        // ---- panel: rows below the block + the rhs row (last):  x L^T = a, right-looking, no divisions
         const int m = n - kb - bs + 1;
         for (int rr = tid; rr < m; rr += nt) {
             const bool is_rhs = (rr == m - 1);
@@ -638,16 +710,15 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
             for (int j = 0; j < 32; ++j) a[j] = (j < bs) ? src[j] : 0.0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                double s = a[j];
+                a[j] *= invd[kb + j];
 #pragma unroll
-                for (int k = 0; k < j; ++k) s -= a[k] * D[j * 33 + k];
-                a[j] = s / D[j * 33 + j];
+                for (int k = 0; k < 32; ++k) if (k > j) a[k] -= a[j] * D[k * 33 + j];
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) { P[rr * 34 + j] = a[j]; if (j < bs) src[j] = a[j]; }
         }
         __syncthreads();
-        // trailing update A22 -= P P^T on the lower triangle, 32x32 register tiles: lane = column, the
+        // ---- trailing update A22 -= P P^T on the lower triangle, 32x32 register tiles: lane = column, the
         // column's panel row lives in registers, the row's panel entries are broadcast from shared memory.
         const int ntile = (m + 31) >> 5;
         const int total = ntile * (ntile + 1) / 2;
@@ -679,13 +750,13 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
         }
         __syncthreads();
     }
-    // backward substitution  L^T x = y  (y is in rhs)
+    // ---- backward substitution  L^T x = y  (y is in rhs)
     const int last = ((n - 1) / 32) * 32;
     for (int kb = last; kb >= 0; kb -= 32) {
         const int bs = min(32, n - kb);
         for (int e = tid; e < 32 * 32; e += nt) {
             const int i = e >> 5, j = e & 31;
-            D[i * 33 + j] = (i < bs && j <= i) ? S[(size_t)(kb + i) * n + kb + j] : ((i == j) ? 1.0 : 0.0);
+            D[i * 33 + j] = (i < bs && j <= i) ? S[(size_t)(kb + i) * n + kb + j] : 0.0;
         }
         double acc = 0.0;
         if (lane < bs) for (int i = kb + bs + warp; i < n; i += nw) acc += S[(size_t)i * n + kb + lane] * rhs[i];
@@ -695,7 +766,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
             double t = (lane < bs) ? rhs[kb + lane] : 0.0;
             for (int w = 0; w < nw; ++w) t -= P[w * 34 + lane];
             for (int j = bs - 1; j >= 0; --j) {
-                const double xj = __shfl_sync(0xffffffffu, t, j) / D[j * 33 + j];
+                const double xj = __shfl_sync(0xffffffffu, t, j) * invd[kb + j];
                 if (lane == j) t = xj;
                 else if (lane < j) t -= D[j * 33 + lane] * xj;
             }
@@ -795,12 +866,17 @@ struct lvb_ba {
     std::vector<uint8_t> h_pose_const, h_vec3_const, h_rho_const;
     std::vector<double> h_fc[6];
     std::vector<int32_t> h_fi[6];
-    int n[6] = {0, 0, 0, 0, 0, 0};
+    int n[6] = {0, 0, 0, 0, 0, 0};      // blocks as added by the caller
+    int nd[6] = {0, 0, 0, 0, 0, 0};     // blocks in the device layout (kinds 0/1: sorted by pose key, each key padded to 32)
+    std::vector<int> order[6];          // device position -> caller index, -1 for padding
     double huber[6] = {0, 0, 0, 0, 0, 0};
     int dimc = 0, n_pose_free = 0, n_vec3_free = 0, n_rho_free = 0;
     // device
     DevBuf<double> poses, vec3, rho, c_poses, c_vec3, c_rho;
     DevBuf<int> pose_off, vec3_off, rho_slot, lm_start, lm_fac;
+    DevBuf<int> tf_slot, sw_group, sw_lm, grp_ns, grp_off;
+    int n_schur_warps = 0, schur_cols_max = 0;
+    size_t schur_smem = 0, lin_smem = 0;
     DevBuf<double> fc[6];
     DevBuf<int> fi[6];
     DevBuf<double> imu_raw;
@@ -825,10 +901,11 @@ static int init_tables() {
     for (int i = 0; i < 30; ++i) for (int j = 0; j <= i; ++j) { a[e] = (unsigned char)i; b[e] = (unsigned char)j; ++e; }
     LVB_CUDA(cudaMemcpyToSymbol(c_tri_a, a, sizeof(a)));
     LVB_CUDA(cudaMemcpyToSymbol(c_tri_b, b, sizeof(b)));
-    LVB_CUDA(cudaFuncSetAttribute(ba_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * 34 + (MAX_DIMC + 2) * 34) * 8));
+    LVB_CUDA(cudaFuncSetAttribute(ba_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * 33 + (MAX_DIMC + 34) + (MAX_DIMC + 2) * 34) * 8));
     LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (TPB * 31 + MAX_STAGE_POSES * 7 + 2) * 8));
     LVB_CUDA(cudaFuncSetAttribute(ba_linearize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     LVB_CUDA(cudaFuncSetAttribute(ba_linearize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    LVB_CUDA(cudaFuncSetAttribute(ba_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (TPB / 32) * 32 * (6 * MAX_TRACK + 1) * 8));
     g_tables_ready = true;
     return LVB_OK;
 }
@@ -907,26 +984,84 @@ int lvb_ba_finalize(lvb_ba* ba) {
     ba->n_pose_free = npf; ba->n_vec3_free = nvf; ba->n_rho_free = nrf; ba->dimc = 6 * npf + 3 * nvf;
     // larger camera systems can still be evaluated (lvb_ba_eval*); the dense reduced solve is capped
     ba->solvable = ba->dimc <= MAX_DIMC && ba->dimc > 0;
-    // landmark CSR: TwoFrame f -> f, TwoCamera f -> -(f+1)
+    // ---- device order of the blocks.  Solvable problems: TwoFrame blocks sorted by (pose_1, pose_2), PoseOnly
+    // blocks by pose, every key run padded to a multiple of 32 with weight-0 copies, so that each warp of the
+    // linearize kernel owns one key and can reduce its J^T J in shared memory before touching HBM.
+    for (int k = 0; k < 6; ++k) {
+        std::vector<int>& ord = ba->order[k];
+        ord.clear();
+        const int n = ba->n[k];
+        if (ba->solvable && (k == 0 || k == 1) && n > 0) {
+            std::vector<int> ids(n);
+            for (int f = 0; f < n; ++f) ids[f] = f;
+            auto key = [&](int f) -> long long {
+                if (k == 0) return (long long)ba->h_fi[0][3 * (size_t)f + 1] * np + ba->h_fi[0][3 * (size_t)f + 2];
+                return ba->h_fi[1][f];
+            };
+            std::stable_sort(ids.begin(), ids.end(), [&](int x, int y) { return key(x) < key(y); });
+            for (int i = 0; i < n;) {
+                int j = i; while (j < n && key(ids[j]) == key(ids[i])) ++j;
+                for (int t = i; t < j; ++t) ord.push_back(ids[t]);
+                while (ord.size() % 32) ord.push_back(-1 - ids[i]);     // padding: encoded source block
+                i = j;
+            }
+        } else { ord.resize(n); for (int f = 0; f < n; ++f) ord[f] = f; }
+        ba->nd[k] = (int)ord.size();
+    }
+    const int n_tf = ba->nd[0];
+    auto tf_src = [&](int i) { const int o = ba->order[0][i]; return o >= 0 ? o : -1 - o; };
+    // landmark CSR over device positions: TwoFrame i -> i, TwoCamera f -> -(f+1); padding is skipped
     std::vector<int> lm_start(nr + 1, 0);
-    for (int f = 0; f < ba->n[0]; ++f) lm_start[ba->h_fi[0][3 * (size_t)f] + 1]++;
+    for (int i = 0; i < n_tf; ++i) if (ba->order[0][i] >= 0) lm_start[ba->h_fi[0][3 * (size_t)ba->order[0][i]] + 1]++;
     for (int f = 0; f < ba->n[2]; ++f) lm_start[ba->h_fi[2][f] + 1]++;
     for (int i = 0; i < nr; ++i) lm_start[i + 1] += lm_start[i];
     std::vector<int> lm_fac(std::max(1, lm_start[nr])), fill(lm_start.begin(), lm_start.end() - 1);
-    for (int f = 0; f < ba->n[0]; ++f) lm_fac[fill[ba->h_fi[0][3 * (size_t)f]]++] = f;
+    for (int i = 0; i < n_tf; ++i) if (ba->order[0][i] >= 0) lm_fac[fill[ba->h_fi[0][3 * (size_t)ba->order[0][i]]]++] = i;
     for (int f = 0; f < ba->n[2]; ++f) lm_fac[fill[ba->h_fi[2][f]]++] = -(f + 1);
 
-    for (int l = 0; l < nr; ++l) {      // the Schur kernel merges a landmark's couplings by pose in registers
-        int seen[MAX_TRACK + 1], ns = 0;
-        for (int e = lm_start[l]; e < lm_start[l + 1]; ++e) {
-            const int f = lm_fac[e]; if (f < 0) continue;
-            for (int side = 1; side <= 2; ++side) {
-                const int p = ba->h_fi[0][3 * (size_t)f + side];
-                int j = 0; for (; j < ns; ++j) if (seen[j] == p) break;
-                if (j == ns) { if (ns == MAX_TRACK) { set_error("landmark %d is observed from more than %d keyframes", l, (int)MAX_TRACK); return LVB_ERR_UNSUPPORTED; } seen[ns++] = p; }
+    // ---- Schur groups: landmarks with the same sorted set of free pose offsets share a warp-sized work item
+    std::vector<int> tf_slot((size_t)std::max(1, n_tf) * 2, -1), sw_group, sw_lm, grp_ns, grp_off;
+    int cols_max = 0;
+    {
+        std::map<std::vector<int>, int> gid;
+        std::vector<std::vector<int>> members;
+        for (int l = 0; l < nr; ++l) {
+            if (rho_slot[l] < 0) continue;
+            std::vector<int> sig;
+            for (int e = lm_start[l]; e < lm_start[l + 1]; ++e) {
+                const int i = lm_fac[e]; if (i < 0) continue;
+                const int f = tf_src(i);
+                for (int side = 1; side <= 2; ++side) { const int off = pose_off[ba->h_fi[0][3 * (size_t)f + side]]; if (off >= 0) sig.push_back(off); }
+            }
+            if (sig.empty()) continue;
+            std::sort(sig.begin(), sig.end()); sig.erase(std::unique(sig.begin(), sig.end()), sig.end());
+            if ((int)sig.size() > MAX_TRACK) { set_error("landmark %d is observed from more than %d keyframes", l, (int)MAX_TRACK); return LVB_ERR_UNSUPPORTED; }
+            auto it = gid.find(sig);
+            int g;
+            if (it == gid.end()) { g = (int)members.size(); gid.emplace(sig, g); members.emplace_back(); grp_ns.push_back((int)sig.size()); for (int k2 = 0; k2 < MAX_TRACK; ++k2) grp_off.push_back(k2 < (int)sig.size() ? sig[k2] : -1); }
+            else g = it->second;
+            members[g].push_back(l);
+            for (int e = lm_start[l]; e < lm_start[l + 1]; ++e) {
+                const int i = lm_fac[e]; if (i < 0) continue;
+                const int f = tf_src(i);
+                for (int side = 1; side <= 2; ++side) {
+                    const int off = pose_off[ba->h_fi[0][3 * (size_t)f + side]];
+                    if (off >= 0) tf_slot[(size_t)(side - 1) * n_tf + i] = (int)(std::lower_bound(sig.begin(), sig.end(), off) - sig.begin());
+                }
+            }
+        }
+        for (size_t g = 0; g < members.size(); ++g) {
+            cols_max = std::max(cols_max, 6 * grp_ns[g] + 1);
+            for (size_t i = 0; i < members[g].size(); i += 32) {
+                sw_group.push_back((int)g);
+                for (size_t t = i; t < i + 32; ++t) sw_lm.push_back(t < members[g].size() ? members[g][t] : -1);
             }
         }
     }
+    ba->n_schur_warps = (int)sw_group.size(); ba->schur_cols_max = cols_max;
+    if (sw_group.empty()) { sw_group.push_back(0); sw_lm.assign(32, -1); }
+    if (grp_ns.empty()) { grp_ns.push_back(0); grp_off.assign(MAX_TRACK, -1); }
+
     LVB_TRY(ba->poses.upload(ba->h_poses.data(), ba->h_poses.size(), s));
     LVB_TRY(ba->vec3.upload(ba->h_vec3.data(), ba->h_vec3.size(), s));
     LVB_TRY(ba->rho.upload(ba->h_rho.data(), ba->h_rho.size(), s));
@@ -938,13 +1073,19 @@ int lvb_ba_finalize(lvb_ba* ba) {
     LVB_TRY(ba->rho_slot.upload(rho_slot.data(), nr, s));
     LVB_TRY(ba->lm_start.upload(lm_start.data(), nr + 1, s));
     LVB_TRY(ba->lm_fac.upload(lm_fac.data(), lm_fac.size(), s));
+    LVB_TRY(ba->tf_slot.upload(tf_slot.data(), tf_slot.size(), s));
+    LVB_TRY(ba->sw_group.upload(sw_group.data(), sw_group.size(), s));
+    LVB_TRY(ba->sw_lm.upload(sw_lm.data(), sw_lm.size(), s));
+    LVB_TRY(ba->grp_ns.upload(grp_ns.data(), grp_ns.size(), s));
+    LVB_TRY(ba->grp_off.upload(grp_off.data(), grp_off.size(), s));
 
-    // factor planes (AoS -> SoA transpose on the host; IMU stays AoS and is packed on the device)
+    // factor planes in device order (AoS -> SoA transpose on the host; IMU stays AoS and is packed on the device)
     std::vector<double> planes; std::vector<int> iplanes;
     for (int k = 0; k < 6; ++k) {
-        const int n = ba->n[k];
+        const int n = ba->nd[k];
+        const std::vector<int>& ord = ba->order[k];
         iplanes.assign((size_t)std::max(1, n) * kIdxStride[k], 0);
-        for (int f = 0; f < n; ++f) for (int j = 0; j < kIdxStride[k]; ++j) iplanes[(size_t)j * n + f] = ba->h_fi[k][(size_t)f * kIdxStride[k] + j];
+        for (int i = 0; i < n; ++i) { const int f = ord[i] >= 0 ? ord[i] : -1 - ord[i]; for (int j = 0; j < kIdxStride[k]; ++j) iplanes[(size_t)j * n + i] = ba->h_fi[k][(size_t)f * kIdxStride[k] + j]; }
         LVB_TRY(ba->fi[k].upload(iplanes.data(), iplanes.size(), s));
         if (k == 3) {
             LVB_TRY(ba->imu_raw.upload(ba->h_fc[3].data(), ba->h_fc[3].size(), s));
@@ -962,7 +1103,11 @@ int lvb_ba_finalize(lvb_ba* ba) {
             continue;
         }
         planes.assign((size_t)std::max(1, n) * kConstStride[k], 0.0);
-        for (int f = 0; f < n; ++f) for (int j = 0; j < kConstStride[k]; ++j) planes[(size_t)j * n + f] = ba->h_fc[k][(size_t)f * kConstStride[k] + j];
+        const int wcol = (k == 0) ? 4 : (k == 1 ? 5 : -1);     // weight column, zeroed on padding
+        for (int i = 0; i < n; ++i) {
+            const bool pad = ord[i] < 0; const int f = pad ? -1 - ord[i] : ord[i];
+            for (int j = 0; j < kConstStride[k]; ++j) planes[(size_t)j * n + i] = (pad && j == wcol) ? 0.0 : ba->h_fc[k][(size_t)f * kConstStride[k] + j];
+        }
         LVB_TRY(ba->fc[k].upload(planes.data(), planes.size(), s));
         LVB_CUDA(cudaStreamSynchronize(s));   // planes is reused
     }
@@ -971,7 +1116,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
     const size_t nH = ba->solvable ? (size_t)ba->dimc * ba->dimc : 1;
     LVB_TRY(ba->Hpp.ensure(nH)); LVB_TRY(ba->gc.ensure(ba->dimc));
     LVB_TRY(ba->Hll.ensure(std::max(1, nr))); LVB_TRY(ba->gl.ensure(std::max(1, nr)));
-    LVB_TRY(ba->tf_w.ensure((size_t)std::max(1, ba->n[0]) * 12));
+    LVB_TRY(ba->tf_w.ensure((size_t)std::max(1, ba->nd[0]) * 12));
     LVB_TRY(ba->arena.ensure(nH + 3 * (size_t)ba->dimc + 16));
     LVB_TRY(ba->scale_c.ensure(ba->dimc)); LVB_TRY(ba->lam_c.ensure(ba->dimc));
     LVB_TRY(ba->scale_l.ensure(std::max(1, nr))); LVB_TRY(ba->lam_l.ensure(std::max(1, nr)));
@@ -981,8 +1126,10 @@ int lvb_ba_finalize(lvb_ba* ba) {
     d.n_poses = np; d.n_vec3 = nv; d.n_rho = nr; d.dimc = ba->dimc; d.n_pose_free = npf;
     d.poses = ba->poses.p; d.vec3 = ba->vec3.p; d.rho = ba->rho.p; d.c_poses = ba->c_poses.p; d.c_vec3 = ba->c_vec3.p; d.c_rho = ba->c_rho.p;
     d.pose_off = ba->pose_off.p; d.vec3_off = ba->vec3_off.p; d.rho_slot = ba->rho_slot.p;
-    for (int k = 0; k < 6; ++k) { d.n[k] = ba->n[k]; d.fc[k] = ba->fc[k].p; d.fi[k] = ba->fi[k].p; d.huber[k] = ba->huber[k]; }
+    for (int k = 0; k < 6; ++k) { d.n[k] = ba->nd[k]; d.fc[k] = ba->fc[k].p; d.fi[k] = ba->fi[k].p; d.huber[k] = ba->huber[k]; }
     d.lm_start = ba->lm_start.p; d.lm_fac = ba->lm_fac.p;
+    d.tf_slot = ba->tf_slot.p; d.sw_group = ba->sw_group.p; d.sw_lm = ba->sw_lm.p; d.grp_ns = ba->grp_ns.p; d.grp_off = ba->grp_off.p;
+    d.n_schur_warps = ba->n_schur_warps; d.warp_syrk = ba->solvable ? 1 : 0;
     d.Hpp = ba->Hpp.p; d.gc = ba->gc.p; d.Hll = ba->Hll.p; d.gl = ba->gl.p; d.tf_w = ba->tf_w.p;
     d.S = ba->arena.p; d.rhs = d.S + nH; d.gcr = d.rhs + ba->dimc; d.diagH = d.gcr + ba->dimc; d.scal = d.diagH + ba->dimc;
     d.scale_c = ba->scale_c.p; d.scale_l = ba->scale_l.p; d.lam_c = ba->lam_c.p; d.lam_l = ba->lam_l.p;
@@ -993,15 +1140,17 @@ int lvb_ba_finalize(lvb_ba* ba) {
 
     BlockRanges& R = ba->ranges;
     R.b[0] = 0;
-    R.b[1] = R.b[0] + nblk(ba->n[0], TPB);
-    R.b[2] = R.b[1] + nblk(ba->n[1], TPB);
-    R.b[3] = R.b[2] + nblk(ba->n[2], TPB);
-    R.b[4] = R.b[3] + nblk(ba->n[3], 4);
-    R.b[5] = R.b[4] + nblk(ba->n[4], TPB);
-    R.b[6] = R.b[5] + nblk(ba->n[5], TPB);
+    R.b[1] = R.b[0] + nblk(ba->nd[0], TPB);
+    R.b[2] = R.b[1] + nblk(ba->nd[1], TPB);
+    R.b[3] = R.b[2] + nblk(ba->nd[2], TPB);
+    R.b[4] = R.b[3] + nblk(ba->nd[3], 4);
+    R.b[5] = R.b[4] + nblk(ba->nd[4], TPB);
+    R.b[6] = R.b[5] + nblk(ba->nd[5], TPB);
     const size_t smem_imu = (size_t)(4 * 480 * 2 + 4 * 32) * 8 + 4 * 32 * 4;
     const size_t smem_pose = d.stage_poses ? ((size_t)np * 56 + 16) : 0;
     ba->pose_smem = smem_pose; ba->imu_smem = smem_imu;
+    ba->lin_smem = ((smem_pose + 15) & ~(size_t)15) + (size_t)(TPB / 32) * SYRK_ROWS * SYRK_LD * 8;
+    ba->schur_smem = (size_t)(TPB / 32) * 32 * (size_t)std::max(1, cols_max) * 8;
     ba->finalized = true;
     return LVB_OK;
 }
@@ -1026,7 +1175,7 @@ int lvb_ba_update_params(lvb_ba* ba, const double* P, const double* V, const dou
 }
 
 static int launch_eval(lvb_ba* ba, int kind, double* r_dev, double* J_dev) {
-    const int n = ba->n[kind];
+    const int n = ba->nd[kind];
     if (n == 0) return LVB_OK;
     BaDev& d = ba->dev;
     switch (kind) {
@@ -1042,7 +1191,7 @@ static int launch_eval(lvb_ba* ba, int kind, double* r_dev, double* J_dev) {
 }
 
 static int ensure_eval_buffers(lvb_ba* ba, int kind) {
-    const size_t n = ba->n[kind];
+    const size_t n = ba->nd[kind];
     LVB_TRY(ba->eval_r.ensure(std::max<size_t>(1, n * kResDim[kind])));
     LVB_TRY(ba->eval_J.ensure(std::max<size_t>(1, n * kResDim[kind] * kJacCols[kind])));
     return LVB_OK;
@@ -1054,10 +1203,27 @@ int lvb_ba_eval(lvb_ba* ba, int kind, double* r, double* J) {
     LVB_CUDA(cudaSetDevice(ba->ctx->device));
     LVB_TRY(ensure_eval_buffers(ba, kind));
     LVB_TRY(launch_eval(ba, kind, ba->eval_r.p, ba->eval_J.p));
-    const size_t n = ba->n[kind];
-    if (r) LVB_TRY(ba->eval_r.download(r, n * kResDim[kind], ba->ctx->stream));
-    if (J) LVB_TRY(ba->eval_J.download(J, n * kResDim[kind] * kJacCols[kind], ba->ctx->stream));
-    LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream));
+    const size_t nd = ba->nd[kind], rd = kResDim[kind], jd = (size_t)kResDim[kind] * kJacCols[kind];
+    const std::vector<int>& ord = ba->order[kind];
+    bool identity = (nd == (size_t)ba->n[kind]);
+    for (size_t i = 0; identity && i < nd; ++i) identity = (ord[i] == (int)i);
+    cudaStream_t s = ba->ctx->stream;
+    if (identity) {
+        if (r) LVB_TRY(ba->eval_r.download(r, nd * rd, s));
+        if (J) LVB_TRY(ba->eval_J.download(J, nd * jd, s));
+        LVB_CUDA(cudaStreamSynchronize(s));
+        return LVB_OK;
+    }
+    // the device layout is sorted / padded: hand the rows back in the caller's block order
+    std::vector<double> hr(r ? nd * rd : 0), hJ(J ? nd * jd : 0);
+    if (r) LVB_TRY(ba->eval_r.download(hr.data(), nd * rd, s));
+    if (J) LVB_TRY(ba->eval_J.download(hJ.data(), nd * jd, s));
+    LVB_CUDA(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < nd; ++i) {
+        if (ord[i] < 0) continue;
+        if (r) memcpy(r + (size_t)ord[i] * rd, hr.data() + i * rd, rd * sizeof(double));
+        if (J) memcpy(J + (size_t)ord[i] * jd, hJ.data() + i * jd, jd * sizeof(double));
+    }
     return LVB_OK;
 }
 
@@ -1074,11 +1240,11 @@ static int launch_linearize_and_reduce(lvb_ba* ba) {
     lvb_ctx* ctx = ba->ctx;
     const size_t nH = (size_t)d.dimc * d.dimc;
     LAUNCH(ba, ba_zero_kernel, std::min(1024, nblk(nH + d.dimc + 2 * (size_t)d.n_rho, 256)), 256, 0, d);
-    LAUNCH(ba, ba_linearize_kernel<0>, ba->ranges.b[3], TPB, ba->pose_smem, d, ba->ranges);
+    LAUNCH(ba, ba_linearize_kernel<0>, ba->ranges.b[3], TPB, ba->lin_smem, d, ba->ranges);
     LAUNCH(ba, ba_linearize_other_kernel<0>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
     LAUNCH(ba, ba_prepare_landmark_kernel, nblk(d.n_rho, 256), 256, 0, d);
     LAUNCH(ba, ba_build_S_kernel, std::min(1024, nblk(nH, 256)), 256, 0, d);
-    LAUNCH(ba, ba_schur_kernel, nblk(d.n_rho, TPB), TPB, 0, d);
+    LAUNCH(ba, ba_schur_kernel, nblk(d.n_schur_warps, TPB / 32), TPB, ba->schur_smem, d, std::max(1, ba->schur_cols_max));
     if (ctx->world > 1) {
         LAUNCH(ba, ba_pack_scalars_kernel, 1, 1, 0, d);
         LVB_TRY(comm_allreduce_sum_f64(ctx, d.S, nH + 3 * (size_t)d.dimc + 16));
@@ -1092,10 +1258,10 @@ static int launch_linearize_and_reduce(lvb_ba* ba) {
 static int launch_step(lvb_ba* ba) {
     BaDev& d = ba->dev;
     lvb_ctx* ctx = ba->ctx;
-    const size_t chol_smem = (size_t)(32 * 34 + (d.dimc + 2) * 34) * 8;
+    const size_t chol_smem = (size_t)(32 * 33 + (d.dimc + 34) + (d.dimc + 2) * 34) * 8;
     LAUNCH(ba, ba_cholesky_kernel, 1, CHOL_T, chol_smem, d.S, d.rhs, d.dimc, d.st);
     LAUNCH(ba, ba_update_kernel, nblk((size_t)d.n_poses + d.n_vec3 + d.n_rho, TPB), TPB, 0, d);
-    LAUNCH(ba, ba_linearize_kernel<1>, ba->ranges.b[3], TPB, ba->pose_smem, d, ba->ranges);
+    LAUNCH(ba, ba_linearize_kernel<1>, ba->ranges.b[3], TPB, ba->lin_smem, d, ba->ranges);
     LAUNCH(ba, ba_linearize_other_kernel<1>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
     if (ctx->world > 1) LVB_TRY(comm_allreduce_sum_f64(ctx, &d.st->cand_cost_acc, 5));
     LAUNCH(ba, lm_control_post_kernel, 1, 1, 0, d.st);

@@ -26,8 +26,9 @@ namespace {
 enum { ITPB = 128, MAX_CELLS = 1 << 26 };
 
 struct Grid {
-    float minx, miny, minz, inv_cell, cell;
+    float minx, miny, minz, inv_cell, cell;   // cell = voxel edge = (search radius * 1.0001) / ring
     int gx, gy, gz;
+    int ring;                                 // voxels per search radius: neighbours within the radius lie within `ring` voxels
 };
 
 struct IcpState {
@@ -180,31 +181,46 @@ __device__ __forceinline__ void best_insert(Best3& b, float d, int i, int p) {
     } else { b.d[2] = d; b.i[2] = i; b.p[2] = p; }
 }
 
-// exact 3-NN of q among map points with d2 <= max_d2 (max_d2 <= cell^2 so the 27 neighbour voxels suffice)
+// exact 3-NN of q among map points with d2 <= max_d2 (max_d2 <= radius^2).  Voxels are visited in Chebyshev
+// rings around the query's voxel; a ring r >= 1 cannot hold a point closer than (r-1)*cell, so the search stops
+// as soon as the third-best distance is strictly below that bound (strict: ties are broken by index).
+__device__ __forceinline__ void scan_voxel(const IcpDev& d, const Grid& g, float3 q, int ix, int iy, int iz, Best3& b) {
+    if (ix < 0 || iy < 0 || iz < 0 || ix >= g.gx || iy >= g.gy || iz >= g.gz) return;
+    const int c = ix + g.gx * (iy + g.gy * iz);
+    const int s = d.cell_start[c], e = d.cell_start[c + 1];
+    if (s == e) return;
+    const float bx0 = g.minx + ix * g.cell, by0 = g.miny + iy * g.cell, bz0 = g.minz + iz * g.cell;
+    const float ex = fmaxf(fmaxf(bx0 - q.x, q.x - (bx0 + g.cell)), 0.0f);
+    const float ey = fmaxf(fmaxf(by0 - q.y, q.y - (by0 + g.cell)), 0.0f);
+    const float ez = fmaxf(fmaxf(bz0 - q.z, q.z - (bz0 + g.cell)), 0.0f);
+    const float bd = (ex * ex + ey * ey + ez * ez) * 0.99f - 1e-6f;     // conservative box distance
+    if (bd > b.d[2] || bd > d.max_d2) return;
+    for (int j = s; j < e; ++j) {
+        const float4 m = __ldg(&d.map[j]);
+        const float dx = __fsub_rn(m.x, q.x), dy = __fsub_rn(m.y, q.y), dz = __fsub_rn(m.z, q.z);
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        best_insert(b, d2, __float_as_int(m.w), j);
+    }
+}
+
 __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
     Best3 b;
     b.d[0] = b.d[1] = b.d[2] = INFINITY; b.i[0] = b.i[1] = b.i[2] = 0x7fffffff; b.p[0] = b.p[1] = b.p[2] = -1;
     const Grid& g = d.g;
     const int cx = cell_coord(q.x, g.minx, g.inv_cell), cy = cell_coord(q.y, g.miny, g.inv_cell), cz = cell_coord(q.z, g.minz, g.inv_cell);
-    for (int k = 0; k < 27; ++k) {
-        // centre voxel first, then the rest: tightens the pruning bound early
-        const int kk = (k == 0) ? 13 : (k <= 13 ? k - 1 : k);
-        const int ix = cx + (kk % 3) - 1, iy = cy + ((kk / 3) % 3) - 1, iz = cz + (kk / 9) - 1;
-        if (ix < 0 || iy < 0 || iz < 0 || ix >= g.gx || iy >= g.gy || iz >= g.gz) continue;
-        // conservative distance from q to the voxel box
-        const float bx0 = g.minx + ix * g.cell, by0 = g.miny + iy * g.cell, bz0 = g.minz + iz * g.cell;
-        const float ex = fmaxf(fmaxf(bx0 - q.x, q.x - (bx0 + g.cell)), 0.0f);
-        const float ey = fmaxf(fmaxf(by0 - q.y, q.y - (by0 + g.cell)), 0.0f);
-        const float ez = fmaxf(fmaxf(bz0 - q.z, q.z - (bz0 + g.cell)), 0.0f);
-        const float bd = (ex * ex + ey * ey + ez * ez) * 0.99f - 1e-6f;
-        if (bd > b.d[2] || bd > d.max_d2) continue;
-        const int c = ix + g.gx * (iy + g.gy * iz);
-        const int s = d.cell_start[c], e = d.cell_start[c + 1];
-        for (int j = s; j < e; ++j) {
-            const float4 m = __ldg(&d.map[j]);
-            const float dx = __fsub_rn(m.x, q.x), dy = __fsub_rn(m.y, q.y), dz = __fsub_rn(m.z, q.z);
-            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            best_insert(b, d2, __float_as_int(m.w), j);
+    scan_voxel(d, g, q, cx, cy, cz, b);
+    for (int r = 1; r <= g.ring; ++r) {
+        const float lb = (r - 1) * g.cell;
+        const float lb2 = lb * lb * 0.99f;
+        if (b.d[2] < lb2 || lb2 > d.max_d2) break;
+        // the six faces of the ring-r shell, each voxel exactly once
+        for (int dz = -r; dz <= r; ++dz) {
+            const bool zface = (dz == -r || dz == r);
+            for (int dy = -r; dy <= r; ++dy) {
+                const bool yface = (dy == -r || dy == r);
+                if (zface || yface) { for (int dx = -r; dx <= r; ++dx) scan_voxel(d, g, q, cx + dx, cy + dy, cz + dz, b); }
+                else { scan_voxel(d, g, q, cx - r, cy + dy, cz + dz, b); scan_voxel(d, g, q, cx + r, cy + dy, cz + dz, b); }
+            }
         }
     }
     for (int j = 0; j < 3; ++j) if (!(b.d[j] <= d.max_d2)) { b.d[j] = INFINITY; b.i[j] = -1; b.p[j] = -1; }
@@ -438,15 +454,22 @@ int lvb_icp_set_map(lvb_icp* h, const void* points, int n, int stride, float cel
     LVB_TRY(h->bbox.download(hb, 6, s));
     LVB_CUDA(cudaStreamSynchronize(s));
     Grid g;
-    // the grid edge is a hair larger than the guaranteed search radius so that float rounding of the
-    // voxel coordinate can never separate two points closer than cell_size by more than one voxel
-    g.cell = cell_size * 1.0001f; g.inv_cell = 1.0f / g.cell;
+    // The voxel edge is (radius * 1.0001) / ring: the hair of slack guarantees that float rounding of the voxel
+    // coordinate never separates two points closer than the radius by more than `ring` voxels.  ring = 4 unless the
+    // bounding box would need more than MAX_CELLS voxels.
     g.minx = ord2f(hb[0]); g.miny = ord2f(hb[1]); g.minz = ord2f(hb[2]);
     const float mx = ord2f(hb[3]), my = ord2f(hb[4]), mz = ord2f(hb[5]);
     if (!(mx >= g.minx) || !(my >= g.miny) || !(mz >= g.minz) || !std::isfinite(mx - g.minx) || !std::isfinite(my - g.miny) || !std::isfinite(mz - g.minz)) {
         set_error("map cloud has no finite bounding box"); return LVB_ERR_INVALID; }
-    const double dx = std::floor((double)(mx - g.minx) * g.inv_cell) + 1, dy = std::floor((double)(my - g.miny) * g.inv_cell) + 1, dz = std::floor((double)(mz - g.minz) * g.inv_cell) + 1;
+    double dx = 0, dy = 0, dz = 0;
+    int ring = 4;
+    for (;; ring >>= 1) {
+        g.cell = cell_size * 1.0001f / (float)ring; g.inv_cell = 1.0f / g.cell;
+        dx = std::floor((double)(mx - g.minx) * g.inv_cell) + 1; dy = std::floor((double)(my - g.miny) * g.inv_cell) + 1; dz = std::floor((double)(mz - g.minz) * g.inv_cell) + 1;
+        if (dx * dy * dz <= (double)MAX_CELLS || ring == 1) break;
+    }
     if (dx * dy * dz > (double)MAX_CELLS) { set_error("voxel grid of %.0f cells exceeds %d; increase cell_size or crop the map", dx * dy * dz, (int)MAX_CELLS); return LVB_ERR_UNSUPPORTED; }
+    g.ring = ring;
     g.gx = (int)dx; g.gy = (int)dy; g.gz = (int)dz;
     const int ncell = g.gx * g.gy * g.gz;
     LVB_TRY(h->cell_of.ensure(n)); LVB_TRY(h->counts.ensure(ncell)); LVB_TRY(h->fill.ensure(ncell));
