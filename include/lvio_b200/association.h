@@ -1,0 +1,68 @@
+// include/lvio_b200/association.h -- scan-to-map registration with the call shape of
+// lvio_fusion::FeatureAssociation::ScanToMapWithGround / ScanToMapWithSegmented
+// (/root/reference/src/lvio_fusion/include/lvio_fusion/lidar/association.h:30-32, src/association.cpp:270-384).
+//
+// In the reference each call builds a pcl::KdTreeFLANN on the map cloud, searches 3 neighbours per scan point on
+// the host and adds one LidarPlaneErrorRPZ/YXY residual block per accepted point; the caller then runs
+// adapt::Solve (mapping.cpp:159-177).  Here the call uploads the map cloud once per call into the voxel hash,
+// and adds ONE lvb::ScanToMapCost describing the whole association; ceres::Solve (ceres_shim.h) runs
+// association + LM on the device and updates para[] in place.  Frame types are duck-typed:
+//   frame->pose.data()                       Sophus::SE3d layout [qx qy qz qw tx ty tz]
+//   frame->feature_lidar->points_ground / points_surf : contiguous clouds of 32-byte pcl::PointXYZI
+//       (anything with .size() and .data() whose records start with float x, y, z)
+//   frame->weights.lidar_ground / lidar_surf / visual,  frame->features_left.size()
+#pragma once
+#include <cmath>
+#include "ceres_shim.h"
+
+namespace lvio_fusion {
+
+class FeatureAssociation {
+public:
+    explicit FeatureAssociation(double lidar_resolution = 0.2) : resolution_(lidar_resolution) {}
+    ~FeatureAssociation() { if (icp_ground_) lvb_icp_destroy(icp_ground_); if (icp_surf_) lvb_icp_destroy(icp_surf_); }
+
+    // association.cpp:270-326 : pitch/roll/z = para+1,+2,+5 ; gate d2 < 100 res^2 ; TrivialLoss ; PoseErrorRPZ prior
+    template <class FramePtr, class Problem>
+    bool ScanToMapWithGround(FramePtr frame, FramePtr map_frame, double* para, Problem& problem, bool relocate = false) {
+        return add(0, frame, map_frame, frame->feature_lidar->points_ground, map_frame->feature_lidar->points_ground, para, problem, relocate,
+                   resolution_ * resolution_ * 100, frame->weights.lidar_ground, new ceres::TrivialLoss(), icp_ground_);
+    }
+    // association.cpp:328-384 : yaw/x/y = para+0,+3,+4 ; gate d2 < 25 res^2 ; HuberLoss(0.1) ; PoseErrorYXY prior
+    template <class FramePtr, class Problem>
+    bool ScanToMapWithSegmented(FramePtr frame, FramePtr map_frame, double* para, Problem& problem, bool relocate = false) {
+        return add(1, frame, map_frame, frame->feature_lidar->points_surf, map_frame->feature_lidar->points_surf, para, problem, relocate,
+                   resolution_ * resolution_ * 25, frame->weights.lidar_surf, new ceres::HuberLoss(0.1), icp_surf_);
+    }
+
+private:
+    template <class FramePtr, class Cloud, class Problem>
+    bool add(int mode, FramePtr frame, FramePtr map_frame, const Cloud& scan, const Cloud& map, double* para, Problem& problem, bool relocate,
+             double thr, double weight, ceres::LossFunction* loss, lvb_icp*& icp) {
+        lvb::Runtime& rt = lvb::Runtime::get();
+        if (!rt.ensure()) { delete loss; return false; }
+        if (!icp && lvb_icp_create(rt.ctx, &icp) != LVB_OK) { delete loss; return false; }
+        const int stride = (int)sizeof(scan.data()[0]);
+        const float cell = std::nextafter((float)std::sqrt(thr), 1e30f) * 1.0001f;
+        if (lvb_icp_set_map(icp, map.data(), (int)map.size(), stride, cell) != LVB_OK) { delete loss; return false; }
+        if (mode == 0) { problem.AddParameterBlock(para + 1, 1); problem.AddParameterBlock(para + 2, 1); problem.AddParameterBlock(para + 5, 1); }
+        else { problem.AddParameterBlock(para + 0, 1); problem.AddParameterBlock(para + 3, 1); problem.AddParameterBlock(para + 4, 1); }
+        double* x0 = mode == 0 ? para + 1 : para + 0; double* x1 = mode == 0 ? para + 2 : para + 3; double* x2 = mode == 0 ? para + 5 : para + 4;
+        lvb::ScanToMapCost* c = new lvb::ScanToMapCost();
+        c->mode = mode; c->icp = icp; c->scan = scan.data(); c->n = (int)scan.size(); c->stride = stride;
+        std::memcpy(c->frame_pose, frame->pose.data(), sizeof(c->frame_pose)); std::memcpy(c->map_pose, map_frame->pose.data(), sizeof(c->map_pose));
+        c->rpyxyz = para; c->weight = weight; c->dist_thr = thr;
+        problem.AddResidualBlock(c, loss, x0, x1, x2);
+        if (!relocate) {
+            lvb::IcpPriorCost* p = new lvb::IcpPriorCost();
+            p->mode = mode; p->weight = (double)frame->features_left.size() * frame->weights.visual;   // association.cpp:323,381
+            problem.AddResidualBlock(p, nullptr, x0, x1, x2);
+        }
+        return true;
+    }
+    double resolution_;
+    lvb_icp* icp_ground_ = nullptr;
+    lvb_icp* icp_surf_ = nullptr;
+};
+
+}  // namespace lvio_fusion

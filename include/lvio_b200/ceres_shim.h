@@ -1,0 +1,311 @@
+// include/lvio_b200/ceres_shim.h -- header-only C++ host side of the drop-in boundary.
+//
+// Keeps the subset of the Ceres API that lvio_fusion's hot path is written against (closed
+// set taken from `grep ceres::` over /root/reference/src/lvio_fusion) and forwards it to the C ABI in
+// include/lvio_b200.h.  What the reference does with these calls:
+//
+//   adapt::Problem : ceres::Problem          include/lvio_fusion/adapt/problem.h:34-81
+//   AddParameterBlock(double*, size[, param]) problem.h:49-63, backend.cpp:111,121,150-152
+//   AddResidualBlock(cost, loss, x0, xs...)   problem.h:37-47 (<= 8 blocks: ImuError)
+//   ceres::Solve(options, &problem, &summary) problem.h:83-88, backend.cpp:204-211, mapping.cpp:159-164
+//   HuberLoss / TrivialLoss / ProductParameterization(EigenQuaternion, Identity3)  backend.cpp:98-101
+//
+// Design: a GPU backend cannot run arbitrary C++ functors, so the cost functions on the hot path are the
+// closed set in factors.h (same class names and Create() signatures as include/lvio_fusion/ceres/*.hpp),
+// each a lvb::DeviceCost carrying its factor kind and constant record.  Problem records pointers exactly
+// like Ceres (pointer identity = block identity, memory owned by the caller's Frame / Landmark objects),
+// Solve() packs them into the flat arrays of lvb_ba_*, runs the LM on the device and writes the
+// parameters back IN PLACE.  Blocks of any other cost type make Solve() report FAILURE with a message --
+// the off-path tiny problems of the reference (navsat, pose graph, relocation) keep using a
+// host solver and are out of scope here.  There is no CPU fallback behind this header.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../lvio_b200.h"
+
+namespace lvb {
+
+// Process-wide device context + the stereo rig constants (Camera::Get(0/1) of the reference).
+struct Runtime {
+    lvb_ctx* ctx = nullptr;
+    double cameras[22] = {0};
+    bool have_cameras = false;
+    std::string error;
+    static Runtime& get() { static Runtime r; return r; }
+    bool ensure(int device = 0) {
+        if (ctx) return true;
+        if (lvb_ctx_create(device, nullptr, &ctx) != LVB_OK) { error = lvb_last_error(); ctx = nullptr; return false; }
+        return true;
+    }
+    // cam = { fx fy cx cy  extrinsic[7] } per camera, Camera::Get(0) then Camera::Get(1)
+    void set_cameras(const double* cam0_11, const double* cam1_11) {
+        std::memcpy(cameras, cam0_11, 11 * sizeof(double)); std::memcpy(cameras + 11, cam1_11, 11 * sizeof(double)); have_cameras = true;
+    }
+};
+
+}  // namespace lvb
+
+namespace ceres {
+
+enum LinearSolverType { DENSE_QR = 2, SPARSE_NORMAL_CHOLESKY = 1, SPARSE_SCHUR = 0, DENSE_SCHUR = 3 };
+enum TerminationType { CONVERGENCE = 0, NO_CONVERGENCE = 1, FAILURE = 2 };
+enum Ownership { DO_NOT_TAKE_OWNERSHIP, TAKE_OWNERSHIP };
+
+class CostFunction {
+public:
+    virtual ~CostFunction() {}
+    // Ceres contract: jacobians == nullptr or jacobians[i] == nullptr means "skip".
+    virtual bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const = 0;
+    const std::vector<int32_t>& parameter_block_sizes() const { return sizes_; }
+    int num_residuals() const { return num_residuals_; }
+protected:
+    std::vector<int32_t>* mutable_parameter_block_sizes() { return &sizes_; }
+    void set_num_residuals(int n) { num_residuals_ = n; }
+private:
+    std::vector<int32_t> sizes_;
+    int num_residuals_ = 0;
+};
+
+template <int kNumResiduals, int... Ns>
+class SizedCostFunction : public CostFunction {
+public:
+    SizedCostFunction() { set_num_residuals(kNumResiduals); *mutable_parameter_block_sizes() = std::vector<int32_t>{Ns...}; }
+};
+
+class LossFunction { public: virtual ~LossFunction() {} virtual double huber_a() const { return 0.0; } };
+class TrivialLoss : public LossFunction {};
+class HuberLoss : public LossFunction { public: explicit HuberLoss(double a) : a_(a) {} double huber_a() const override { return a_; } private: double a_; };
+
+class LocalParameterization { public: virtual ~LocalParameterization() {} virtual int GlobalSize() const = 0; virtual int LocalSize() const = 0; };
+class EigenQuaternionParameterization : public LocalParameterization { public: int GlobalSize() const override { return 4; } int LocalSize() const override { return 3; } };
+class IdentityParameterization : public LocalParameterization { public: explicit IdentityParameterization(int n) : n_(n) {} int GlobalSize() const override { return n_; } int LocalSize() const override { return n_; } private: int n_; };
+class ProductParameterization : public LocalParameterization {
+public:
+    ProductParameterization(LocalParameterization* a, LocalParameterization* b) : a_(a), b_(b) {}
+    int GlobalSize() const override { return a_->GlobalSize() + b_->GlobalSize(); }
+    int LocalSize() const override { return a_->LocalSize() + b_->LocalSize(); }
+private:
+    std::unique_ptr<LocalParameterization> a_, b_;
+};
+
+struct ResidualBlock { CostFunction* cost; LossFunction* loss; std::vector<double*> blocks; };
+typedef ResidualBlock* ResidualBlockId;
+
+}  // namespace ceres
+
+namespace lvb {
+
+// A cost function the device knows: factor kind + constant record (lvb_factor_kind, include/lvio_b200.h).
+class DeviceCost : public ceres::CostFunction {
+public:
+    DeviceCost(int kind, int num_residuals, std::vector<int32_t> sizes, std::vector<double> consts) : kind_(kind), consts_(std::move(consts)) {
+        set_num_residuals(num_residuals); *mutable_parameter_block_sizes() = std::move(sizes);
+    }
+    int kind() const { return kind_; }
+    const std::vector<double>& consts() const { return consts_; }
+    // Host-side single-block evaluation is not part of the device path; callers that need residuals of many
+    // blocks use lvb_ba_eval / lvb_ba_reprojection_errors (compute_reprojection_error, backend.cpp:185-190).
+    bool Evaluate(double const* const*, double*, double**) const override { return false; }
+private:
+    int kind_;
+    std::vector<double> consts_;
+};
+
+// One whole ScanToMapWith{Ground,Segmented} association expressed as a single residual "block group":
+// the per-point LidarPlaneErrorRPZ/YXY factors are created on the device (association.cpp:291-317).
+struct ScanToMapCost : public ceres::CostFunction {
+    int mode = 0;                       // 0 ground (RPZ), 1 segmented (YXY)
+    lvb_icp* icp = nullptr;             // map already set
+    const void* scan = nullptr; int n = 0, stride = 0;
+    double frame_pose[7], map_pose[7];
+    double* rpyxyz = nullptr;           // the live array (lidar_error.hpp:74,109)
+    double weight = 1, dist_thr = 0;
+    bool Evaluate(double const* const*, double*, double**) const override { return false; }
+};
+// PoseErrorRPZ / PoseErrorYXY prior (pose_error.hpp:135-190): folded into the scan-to-map solve.
+struct IcpPriorCost : public ceres::CostFunction {
+    int mode = 0; double weight = 0;
+    bool Evaluate(double const* const*, double*, double**) const override { return false; }
+};
+
+}  // namespace lvb
+
+namespace ceres {
+
+class Solver {
+public:
+    struct Options {
+        LinearSolverType linear_solver_type = SPARSE_NORMAL_CHOLESKY;
+        int max_num_iterations = 50;
+        double max_solver_time_in_seconds = 1e9;
+        int num_threads = 1;
+        double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
+        double initial_trust_region_radius = 1e4;
+        bool jacobi_scaling = true;
+        bool minimizer_progress_to_stdout = false;
+    };
+    struct Summary {
+        double initial_cost = 0, final_cost = 0, total_time_in_seconds = 0;
+        int num_successful_steps = 0, num_unsuccessful_steps = 0;
+        int num_residual_blocks = 0, num_residual_blocks_reduced = 0;
+        TerminationType termination_type = NO_CONVERGENCE;
+        std::string message;
+        std::string BriefReport() const { return "lvio_b200: cost " + std::to_string(initial_cost) + " -> " + std::to_string(final_cost) + " (" + message + ")"; }
+        bool IsSolutionUsable() const { return termination_type != FAILURE; }
+    };
+};
+
+class Problem {
+public:
+    Problem() {}
+    ~Problem() {
+        // default ceres::Problem::Options: the problem owns cost / loss / parameterization objects; a pointer
+        // shared by many blocks (backend.cpp:98-101) is freed once.
+        std::set<CostFunction*> costs; std::set<LossFunction*> losses;
+        for (auto& rb : residuals_) { costs.insert(rb->cost); if (rb->loss) losses.insert(rb->loss); }
+        for (auto* c : costs) delete c;
+        for (auto* l : losses) delete l;
+        for (auto* p : params_owned_) delete p;
+    }
+    Problem(const Problem&) = delete;
+    Problem& operator=(const Problem&) = delete;
+
+    void AddParameterBlock(double* values, int size) { add_block(values, size); }
+    void AddParameterBlock(double* values, int size, LocalParameterization* p) { add_block(values, size); if (p) params_owned_.insert(p); }
+
+    template <typename... Ts>
+    ResidualBlockId AddResidualBlock(CostFunction* cost, LossFunction* loss, double* x0, Ts*... xs) {
+        std::unique_ptr<ResidualBlock> rb(new ResidualBlock{cost, loss, {x0, xs...}});
+        const std::vector<int32_t>& sz = cost->parameter_block_sizes();
+        for (size_t i = 0; i < rb->blocks.size(); ++i) add_block(rb->blocks[i], i < sz.size() ? sz[i] : 0);
+        for (double* b : rb->blocks) by_block_[b].push_back(rb.get());
+        residuals_.push_back(std::move(rb));
+        return residuals_.back().get();
+    }
+    void SetParameterBlockConstant(double* v) { constant_.insert(v); }
+    void SetParameterBlockVariable(double* v) { constant_.erase(v); }
+    bool IsParameterBlockConstant(double* v) const { return constant_.count(v) != 0; }
+    void GetResidualBlocksForParameterBlock(const double* v, std::vector<ResidualBlockId>* out) const {
+        out->clear(); auto it = by_block_.find(const_cast<double*>(v)); if (it != by_block_.end()) *out = it->second;
+    }
+    int NumResidualBlocks() const { return (int)residuals_.size(); }
+    int NumParameterBlocks() const { return (int)blocks_.size(); }
+
+    // ---- used by Solve()
+    const std::vector<std::unique_ptr<ResidualBlock>>& residual_blocks() const { return residuals_; }
+    const std::vector<std::pair<double*, int>>& parameter_blocks() const { return blocks_; }
+
+private:
+    void add_block(double* v, int size) { if (index_.emplace(v, (int)blocks_.size()).second) blocks_.push_back({v, size}); }   // idempotent re-add (tools.cpp:107,151)
+    std::vector<std::pair<double*, int>> blocks_;
+    std::unordered_map<double*, int> index_;
+    std::vector<std::unique_ptr<ResidualBlock>> residuals_;
+    std::unordered_map<double*, std::vector<ResidualBlockId>> by_block_;
+    std::set<double*> constant_;
+    std::set<LocalParameterization*> params_owned_;
+};
+
+inline void fill_options(const Solver::Options& o, lvb_solve_options* out) {
+    lvb_default_options(out);
+    out->max_num_iterations = o.max_num_iterations; out->max_solver_time_in_seconds = o.max_solver_time_in_seconds;
+    out->function_tolerance = o.function_tolerance; out->gradient_tolerance = o.gradient_tolerance; out->parameter_tolerance = o.parameter_tolerance;
+    out->initial_trust_region_radius = o.initial_trust_region_radius; out->jacobi_scaling = o.jacobi_scaling ? 1 : 0;
+    out->linear_solver_type = (int)o.linear_solver_type; out->num_threads = o.num_threads;
+}
+inline void fill_summary(const lvb_solve_summary& s, Solver::Summary* out) {
+    out->initial_cost = s.initial_cost; out->final_cost = s.final_cost; out->total_time_in_seconds = s.total_time_in_seconds;
+    out->num_successful_steps = s.num_successful_steps; out->num_unsuccessful_steps = s.num_iterations - s.num_successful_steps;
+    out->num_residual_blocks = s.num_residual_blocks; out->num_residual_blocks_reduced = s.num_residual_blocks_reduced;
+    out->termination_type = (TerminationType)s.termination_type;
+}
+
+// ceres::Solve: never throws; failure is reported through the Summary (which the reference ignores except in
+// Mapping::Relocate, mapping.cpp:279-280,293-294).
+inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* summary) {
+    Solver::Summary local; if (!summary) summary = &local;
+    *summary = Solver::Summary();
+    lvb::Runtime& rt = lvb::Runtime::get();
+    auto fail = [&](const std::string& m) { summary->termination_type = FAILURE; summary->message = m; };
+    if (!rt.ensure()) return fail("no device: " + rt.error);
+    lvb_solve_options opt; fill_options(options, &opt);
+    lvb_solve_summary sum; std::memset(&sum, 0, sizeof(sum));
+
+    // ---- scan-to-map problems (Mapping::Optimize): one ScanToMapCost (+ optional IcpPriorCost)
+    const lvb::ScanToMapCost* scan = nullptr; const lvb::IcpPriorCost* prior = nullptr; const LossFunction* scan_loss = nullptr;
+    bool has_device = false, has_other = false;
+    for (auto& rb : problem->residual_blocks()) {
+        if (auto* s = dynamic_cast<const lvb::ScanToMapCost*>(rb->cost)) { scan = s; scan_loss = rb->loss; }
+        else if (auto* p = dynamic_cast<const lvb::IcpPriorCost*>(rb->cost)) prior = p;
+        else if (dynamic_cast<const lvb::DeviceCost*>(rb->cost)) has_device = true;
+        else has_other = true;
+    }
+    if (has_other) return fail("a cost function outside the device factor set was added (generic functors are not on the B200 path)");
+    if (scan) {
+        if (has_device) return fail("scan-to-map blocks cannot be mixed with BA blocks");
+        const double huber = scan_loss ? scan_loss->huber_a() : 0.0;
+        const int rc = lvb_icp_scan_to_map(scan->icp, scan->mode, scan->scan, scan->n, scan->stride, scan->frame_pose, scan->map_pose, scan->rpyxyz,
+                                           scan->weight, prior ? prior->weight : -1.0, huber, scan->dist_thr, &opt, &sum);
+        if (rc != LVB_OK) return fail(lvb_last_error());
+        fill_summary(sum, summary); summary->message = "scan-to-map on device";
+        return;
+    }
+    if (!rt.have_cameras) return fail("lvb::Runtime::set_cameras was not called");
+
+    // ---- bundle adjustment: pack pointers into the flat arrays of the C ABI
+    std::vector<double*> pose_ptr, vec3_ptr, rho_ptr;
+    std::unordered_map<double*, int> index;
+    for (auto& pb : problem->parameter_blocks()) {
+        std::vector<double*>* dst = pb.second == 7 ? &pose_ptr : (pb.second == 3 ? &vec3_ptr : (pb.second == 1 ? &rho_ptr : nullptr));
+        if (!dst) return fail("parameter block of size " + std::to_string(pb.second) + " is not pose(7)/vec3(3)/inverse depth(1)");
+        index[pb.first] = (int)dst->size(); dst->push_back(pb.first);
+    }
+    auto gather = [&](const std::vector<double*>& ptrs, int w, std::vector<double>& vals, std::vector<uint8_t>& cst) {
+        vals.resize(ptrs.size() * w); cst.resize(ptrs.size());
+        for (size_t i = 0; i < ptrs.size(); ++i) { std::memcpy(&vals[i * w], ptrs[i], w * sizeof(double)); cst[i] = problem->IsParameterBlockConstant(ptrs[i]) ? 1 : 0; }
+    };
+    std::vector<double> poses, vec3, rho; std::vector<uint8_t> pc, vc, rc_;
+    gather(pose_ptr, 7, poses, pc); gather(vec3_ptr, 3, vec3, vc); gather(rho_ptr, 1, rho, rc_);
+    std::vector<double> consts[LVB_NUM_KINDS]; std::vector<int32_t> idx[LVB_NUM_KINDS]; double huber[LVB_NUM_KINDS]; bool loss_set[LVB_NUM_KINDS] = {false};
+    for (int k = 0; k < LVB_NUM_KINDS; ++k) huber[k] = 0.0;
+    for (auto& rb : problem->residual_blocks()) {
+        const lvb::DeviceCost* dc = static_cast<const lvb::DeviceCost*>(rb->cost);
+        const int k = dc->kind();
+        consts[k].insert(consts[k].end(), dc->consts().begin(), dc->consts().end());
+        for (double* b : rb->blocks) idx[k].push_back(index[b]);
+        const double a = rb->loss ? rb->loss->huber_a() : 0.0;
+        if (loss_set[k] && a != huber[k]) return fail("blocks of one factor kind must share their loss function on the device path");
+        huber[k] = a; loss_set[k] = true;
+    }
+    lvb_ba* ba = nullptr;
+    if (lvb_ba_create(rt.ctx, &ba) != LVB_OK) return fail(lvb_last_error());
+    struct Guard { lvb_ba* p; ~Guard() { lvb_ba_destroy(p); } } guard{ba};
+    int rc = lvb_ba_set_cameras(ba, rt.cameras);
+    if (rc == LVB_OK) rc = lvb_ba_set_poses(ba, (int)pose_ptr.size(), poses.data(), pc.data());
+    if (rc == LVB_OK) rc = lvb_ba_set_vec3(ba, (int)vec3_ptr.size(), vec3.data(), vc.data());
+    if (rc == LVB_OK) rc = lvb_ba_set_inv_depths(ba, (int)rho_ptr.size(), rho.data(), rc_.data());
+    static const int nidx[LVB_NUM_KINDS] = {3, 1, 1, 8, 2, 1};
+    for (int k = 0; k < LVB_NUM_KINDS && rc == LVB_OK; ++k) {
+        const int n = (int)idx[k].size() / nidx[k];
+        if (n) rc = lvb_ba_add_factors(ba, k, n, consts[k].data(), idx[k].data());
+        if (rc == LVB_OK) rc = lvb_ba_set_loss(ba, k, huber[k]);
+    }
+    if (rc == LVB_OK) rc = lvb_ba_finalize(ba);
+    if (rc == LVB_OK) rc = lvb_ba_solve(ba, &opt, &sum);
+    if (rc == LVB_OK && !poses.empty()) rc = lvb_ba_get_poses(ba, poses.data());
+    if (rc == LVB_OK && !vec3.empty()) rc = lvb_ba_get_vec3(ba, vec3.data());
+    if (rc == LVB_OK && !rho.empty()) rc = lvb_ba_get_inv_depths(ba, rho.data());
+    if (rc != LVB_OK) return fail(lvb_last_error());
+    // the solver updates the caller's memory in place (frame->pose.data(), &landmark->inv_depth, ...)
+    for (size_t i = 0; i < pose_ptr.size(); ++i) if (!pc[i]) std::memcpy(pose_ptr[i], &poses[7 * i], 7 * sizeof(double));
+    for (size_t i = 0; i < vec3_ptr.size(); ++i) if (!vc[i]) std::memcpy(vec3_ptr[i], &vec3[3 * i], 3 * sizeof(double));
+    for (size_t i = 0; i < rho_ptr.size(); ++i) if (!rc_[i]) *rho_ptr[i] = rho[i];
+    fill_summary(sum, summary); summary->message = "bundle adjustment on device";
+}
+
+}  // namespace ceres

@@ -1,0 +1,115 @@
+// include/lvio_b200/factors.h -- the reference's cost-function classes on the hot path, re-expressed as
+// device factor records.  Same class names and Create() argument order as
+// /root/reference/src/lvio_fusion/include/lvio_fusion/ceres/{visual_error,imu_error,pose_error}.hpp so that
+// Backend::BuildProblem (src/backend.cpp:96-183) and imu::FullBA (src/tools.cpp:92-171) read unchanged.
+//
+// The value types are duck-typed: anything with .data() returning double* works (Eigen::Vector2d / Vector3d,
+// Sophus::SE3d, Eigen::Quaterniond::coeffs(), or the PODs in types.h when Eigen is not available).  A camera is
+// any pointer-like object with fx, fy, cx, cy and extrinsic.data() (include/lvio_fusion/visual/camera.h:79-80);
+// the rig actually used on the device is the one registered with lvb::Runtime::set_cameras (Camera::Get(0/1)).
+#pragma once
+#include "ceres_shim.h"
+
+namespace lvio_fusion {
+
+namespace detail {
+template <class V> inline const double* ptr(const V& v) { return v.data(); }
+}  // namespace detail
+
+// visual_error.hpp:48-76   AutoDiffCostFunction<PoseOnlyReprojectionError, 2, 7>
+class PoseOnlyReprojectionError {
+public:
+    template <class V2, class V3, class CameraPtr>
+    static ceres::CostFunction* Create(const V2& ob, const V3& pw, CameraPtr /*camera == Camera::Get(0)*/, double weight) {
+        const double* o = detail::ptr(ob); const double* p = detail::ptr(pw);
+        return new lvb::DeviceCost(LVB_POSE_ONLY, 2, {7}, {o[0], o[1], p[0], p[1], p[2], weight});
+    }
+};
+
+// visual_error.hpp:78-107  AutoDiffCostFunction<TwoFrameReprojectionError, 2, 1, 7, 7>
+class TwoFrameReprojectionError {
+public:
+    template <class V2, class CameraPtr>
+    static ceres::CostFunction* Create(const V2& first_ob, const V2& ob, CameraPtr /*left*/, CameraPtr /*right*/, double weight) {
+        const double* f = detail::ptr(first_ob); const double* o = detail::ptr(ob);
+        return new lvb::DeviceCost(LVB_TWO_FRAME, 2, {1, 7, 7}, {f[0], f[1], o[0], o[1], weight});
+    }
+};
+
+// visual_error.hpp:109-137 AutoDiffCostFunction<TwoCameraReprojectionError, 2, 1>
+class TwoCameraReprojectionError {
+public:
+    template <class V2, class CameraPtr>
+    static ceres::CostFunction* Create(const V2& left_ob, const V2& right_ob, CameraPtr /*left*/, CameraPtr /*right*/, double weight) {
+        const double* l = detail::ptr(left_ob); const double* r = detail::ptr(right_ob);
+        return new lvb::DeviceCost(LVB_TWO_CAMERA, 2, {1}, {l[0], l[1], r[0], r[1], weight});
+    }
+};
+
+// imu_error.hpp:12-122     SizedCostFunction<15, 7,3,3,3, 7,3,3,3>
+// `preintegration` is pointer-like with the members of imu::Preintegration (imu/preintegration.h:66-80):
+// delta_p, delta_v, linearized_ba, linearized_bg (.data() -> 3 doubles), delta_q (.coeffs().data() -> xyzw),
+// sum_dt, jacobian / covariance (.data() -> 225 doubles; Eigen is column-major, hence the transpose flag).
+class ImuError {
+public:
+    template <class PreintegrationPtr>
+    static ceres::CostFunction* Create(PreintegrationPtr pre, bool matrices_are_column_major = true) {
+        std::vector<double> c(467);
+        const double* dp = pre->delta_p.data(); const double* dq = pre->delta_q.coeffs().data(); const double* dv = pre->delta_v.data();
+        const double* ba = pre->linearized_ba.data(); const double* bg = pre->linearized_bg.data();
+        for (int i = 0; i < 3; ++i) { c[i] = dp[i]; c[7 + i] = dv[i]; c[10 + i] = ba[i]; c[13 + i] = bg[i]; }
+        for (int i = 0; i < 4; ++i) c[3 + i] = dq[i];
+        c[16] = pre->sum_dt;
+        const double* J = pre->jacobian.data(); const double* C = pre->covariance.data();
+        for (int i = 0; i < 15; ++i) for (int j = 0; j < 15; ++j) {
+            const int src = matrices_are_column_major ? j * 15 + i : i * 15 + j;
+            c[17 + i * 15 + j] = J[src]; c[242 + i * 15 + j] = C[src];
+        }
+        return new lvb::DeviceCost(LVB_IMU, 15, {7, 3, 3, 3, 7, 3, 3, 3}, std::move(c));
+    }
+};
+
+// pose_error.hpp:10-53     AutoDiffCostFunction<PoseGraphError, 6, 7, 7>; rpyxyz_ = SE3ToRpyxyz(last^-1 * pose)
+class PoseGraphError {
+public:
+    template <class SE3>
+    static ceres::CostFunction* Create(const SE3& last_pose, const SE3& pose, double weight = 1, double v = 1) {
+        double e[6]; relative_rpyxyz(detail::ptr(last_pose), detail::ptr(pose), e);
+        return new lvb::DeviceCost(LVB_POSE_GRAPH, 6, {7, 7}, {e[0], e[1], e[2], e[3], e[4], e[5], weight, v});
+    }
+    // base.hpp:40-55,70-77,94-141 on doubles (unit quaternions assumed for the stored poses)
+    static void relative_rpyxyz(const double* a, const double* b, double* e);
+};
+
+// pose_error.hpp:55-86     AutoDiffCostFunction<PoseError, 6, 7>
+class PoseError {
+public:
+    template <class SE3>
+    static ceres::CostFunction* Create(const SE3& pose, double weight = 1, double v = 1) {
+        const double* p = detail::ptr(pose);
+        return new lvb::DeviceCost(LVB_POSE_PRIOR, 6, {7}, {p[0], p[1], p[2], p[3], p[4], p[5], p[6], weight, v});
+    }
+};
+
+inline void PoseGraphError::relative_rpyxyz(const double* a, const double* b, double* e) {
+    auto rot = [](const double* q, const double* p, double* out) {   // normalising rotate, base.hpp:26-31
+        const double s = 1.0 / std::sqrt(q[3] * q[3] + q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+        const double x = q[0] * s, y = q[1] * s, z = q[2] * s, w = q[3] * s;
+        double u0 = y * p[2] - z * p[1], u1 = z * p[0] - x * p[2], u2 = x * p[1] - y * p[0];
+        u0 += u0; u1 += u1; u2 += u2;
+        out[0] = p[0] + w * u0 + (y * u2 - z * u1); out[1] = p[1] + w * u1 + (z * u0 - x * u2); out[2] = p[2] + w * u2 + (x * u1 - y * u0);
+    };
+    const double qi[4] = {-a[0], -a[1], -a[2], a[3]}, nt[3] = {-a[4], -a[5], -a[6]};
+    double ti[3]; rot(qi, nt, ti);
+    // q = qi (x) qb (Hamilton, stored xyzw), t = R(qi) tb + ti
+    const double zw = qi[3], zx = qi[0], zy = qi[1], zz = qi[2], ww = b[3], wx = b[0], wy = b[1], wz = b[2];
+    const double q0 = zw * ww - zx * wx - zy * wy - zz * wz, q1 = zw * wx + zx * ww + zy * wz - zz * wy;
+    const double q2 = zw * wy - zx * wz + zy * ww + zz * wx, q3 = zw * wz + zx * wy - zy * wx + zz * ww;
+    double t[3]; rot(qi, b + 4, t);
+    e[0] = std::atan2(2 * (q1 * q2 + q0 * q3), 1 - 2 * (q2 * q2 + q3 * q3));
+    e[1] = std::asin(2 * (q0 * q2 - q1 * q3));
+    e[2] = std::atan2(2 * (q2 * q3 + q0 * q1), 1 - 2 * (q1 * q1 + q2 * q2));
+    e[3] = t[0] + ti[0]; e[4] = t[1] + ti[1]; e[5] = t[2] + ti[2];
+}
+
+}  // namespace lvio_fusion

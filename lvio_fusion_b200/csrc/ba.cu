@@ -733,18 +733,35 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
 #pragma unroll
             for (int k = 0; k < 32; ++k) pj[k] = col_ok ? P[jp * 34 + k] : 0.0;
             const int r_end = min(32, m - ti * 32);
-            for (int r = 0; r < r_end; ++r) {
-                const int ip = ti * 32 + r;
-                const double2* prow = reinterpret_cast<const double2*>(P + ip * 34);
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            // prefetch the tile's current values in one round trip (the read-modify-write must not serialise per row)
+            double cur[32];
 #pragma unroll
-                for (int k = 0; k < 16; k += 2) {
-                    const double2 a = prow[k], b = prow[k + 1];
-                    s0 += a.x * pj[2 * k]; s1 += a.y * pj[2 * k + 1]; s2 += b.x * pj[2 * k + 2]; s3 += b.y * pj[2 * k + 3];
+            for (int r = 0; r < 32; ++r) {
+                const int ip = ti * 32 + r;
+                const bool w_ok = r < r_end && col_ok && jp <= ip;
+                const double* srcp = (ip == m - 1) ? (rhs + kb + bs) : (S + (size_t)(kb + bs + ip) * n + kb + bs);
+                cur[r] = w_ok ? srcp[jp] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int ip = ti * 32 + r;
+                if (r < r_end) {
+                    const double2* prow = reinterpret_cast<const double2*>(P + ip * 34);
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 16; k += 2) {
+                        const double2 a = prow[k], b = prow[k + 1];
+                        s0 += a.x * pj[2 * k]; s1 += a.y * pj[2 * k + 1]; s2 += b.x * pj[2 * k + 2]; s3 += b.y * pj[2 * k + 3];
+                    }
+                    cur[r] -= (s0 + s1) + (s2 + s3);
                 }
-                if (col_ok && jp <= ip) {
+            }
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int ip = ti * 32 + r;
+                if (r < r_end && col_ok && jp <= ip) {
                     double* dst = (ip == m - 1) ? (rhs + kb + bs) : (S + (size_t)(kb + bs + ip) * n + kb + bs);
-                    dst[jp] -= (s0 + s1) + (s2 + s3);
+                    dst[jp] = cur[r];
                 }
             }
         }
