@@ -29,8 +29,9 @@ namespace {
 
 enum { TPB = 128, IMU_STRIDE = 17 + 45 + 225, IMU_RAW = 467, MAX_DIMC = 736, MAX_STAGE_POSES = 512, MAX_TRACK = 16, CHOL_T = 256, SYRK_ROWS = 64, SYRK_LD = 14 };
 
-__constant__ unsigned char c_tri_a[465];
-__constant__ unsigned char c_tri_b[465];
+__device__ long long g_chol_dbg[8];     // accumulated SM clocks per Cholesky phase (diag, panel, trailing, backward, total)
+__device__ unsigned char c_tri_a[465];   // lower-triangle enumeration e -> (a, b), a >= b; global (not __constant__):
+__device__ unsigned char c_tri_b[465];   // the index differs per lane and would serialise on the constant cache
 
 struct BaDev {
     int n_poses, n_vec3, n_rho, dimc, n_pose_free;
@@ -214,26 +215,26 @@ __global__ void __launch_bounds__(TPB) ba_eval_two_camera_kernel(BaDev d, double
 }
 
 // IMU: one warp per factor.  Fills s_r (whitened residual, 15) and s_Jw (whitened ambient Jacobian 15x32).
-__device__ void imu_warp_eval(const BaDev& d, int f, const double* P, const double* V, double* s_raw /*480*/, double* s_Jw /*480*/, double* s_r /*32: raw 0..14, whitened 16..30*/) {
+__device__ void imu_warp_eval(const BaDev& d, int f, const double* P, const double* V, double* s_raw /*480*/, double* s_Jw /*480*/, double* s_r /*32: raw 0..14, whitened 16..30*/, bool with_jac = true) {
     const int lane = threadIdx.x & 31;
     const double* c = d.fc[3] + (size_t)f * IMU_STRIDE;
     const int n = d.n[3];
     const int* ix = d.fi[3];
     for (int e = lane; e < 480; e += 32) s_raw[e] = 0.0;
     __syncwarp();
-    if (lane == 0) {
+    if (lane < 9) {   // lanes 0..7: one Jacobian block each (disjoint columns), lane 8: the residual
         const ImuConst k = load_imu_const(c);
         const double* Ti = P + 7 * ix[f]; const double* Vi = V + 3 * ix[n + f]; const double* Bai = V + 3 * ix[2 * n + f]; const double* Bgi = V + 3 * ix[3 * n + f];
         const double* Tj = P + 7 * ix[4 * n + f]; const double* Vj = V + 3 * ix[5 * n + f]; const double* Baj = V + 3 * ix[6 * n + f]; const double* Bgj = V + 3 * ix[7 * n + f];
-        imu_raw_residual(k, Ti, Vi, Bai, Bgi, Tj, Vj, Baj, Bgj, s_r);
-        imu_raw_jacobian(k, Ti, Vi, Bgi, Tj, Vj, s_raw);
+        if (lane == 8) imu_raw_residual(k, Ti, Vi, Bai, Bgi, Tj, Vj, Baj, Bgj, s_r);
+        else if (with_jac) imu_raw_jacobian_block(k, lane, Ti, Vi, Bgi, Tj, Vj, s_raw);
     }
     __syncwarp();
     const double* U = c + 62;
     if (lane < 15) { double s = 0; for (int k = 0; k < 15; ++k) s += U[15 * lane + k] * s_r[k]; s_r[16 + lane] = s; }
-    for (int e = lane; e < 480; e += 32) {
+    if (with_jac) for (int e = lane; e < 480; e += 32) {
         const int i = e >> 5, j = e & 31;
-        double s = 0; for (int k = 0; k < 15; ++k) s += U[15 * i + k] * s_raw[32 * k + j];
+        double s = 0; for (int k = i; k < 15; ++k) s += U[15 * i + k] * s_raw[32 * k + j];     // U is upper triangular
         s_Jw[e] = s;
     }
     __syncwarp();
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(TPB) ba_linearize_other_kernel(BaDev d, BlockR
         const int n = d.n[3];
         if (f < n) {
             double* raw = s_raw + warp * 480; double* Jw = s_Jw + warp * 480; double* rr = s_r + warp * 32; int* gidx = s_gidx + warp * 32;
-            imu_warp_eval(d, f, Psrc, V, raw, Jw, rr);
+            imu_warp_eval(d, f, Psrc, V, raw, Jw, rr, MODE == 0);
             double s = (lane < 15) ? rr[16 + lane] * rr[16 + lane] : 0.0;
             s = warp_sum(s);
             double rho_v, sr;
@@ -570,8 +571,16 @@ __global__ void __launch_bounds__(TPB) ba_schur_kernel(BaDev d, int cols_max) {
     for (int k = 0; k < ncol; ++k) row[k] = 0.0;
     const int l = d.sw_lm[(size_t)w * 32 + lane];
     if (l >= 0) {
-        const double hl = d.Hll[l] + d.lam_l[l];
-        if (hl > 0.0) {
+        // Jacobi scale (first pass), LM damping and gradient max-norm of this inverse depth
+        LmState* st = d.st;
+        const double h = d.Hll[l];
+        if (!st->scale_valid) d.scale_l[l] = st->jacobi ? 1.0 / (1.0 + sqrt(h)) : 1.0;
+        const double sc = d.scale_l[l], sc2 = sc * sc;
+        const double lam = fmin(fmax(sc2 * h, st->min_diag), st->max_diag) / (st->radius * sc2);
+        d.lam_l[l] = lam;
+        if (st->need_linearize && d.lm_start[l + 1] > d.lm_start[l]) atomic_max_nonneg(&st->grad_max_bits, d.gl[l]);
+        const double hl = h + lam;
+        if (hl > 0.0 && ns > 0) {
             const int n = d.n[0];
             for (int e = d.lm_start[l]; e < d.lm_start[l + 1]; ++e) {
                 const int f = d.lm_fac[e];
@@ -659,7 +668,8 @@ __global__ void lm_control_post_kernel(LmState* st) { lm_control_post(*st); if (
 // Right-looking blocked (32) factorisation of the lower triangle of S (n x n, row-major, in L2/HBM) with
 // the right-hand side carried along as an extra row (so the forward substitution is free), then a
 // blocked backward substitution.  Result: rhs <- S^-1 rhs.
-__global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict__ S, double* __restrict__ rhs, int n, LmState* st) {
+__global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict__ S, double* __restrict__ rhs, int n, LmState* st, int run_control_pre) {
+    if (run_control_pre) { if (threadIdx.x == 0) lm_control_pre(*st); __syncthreads(); }
     if (st->done) return;
     extern __shared__ __align__(16) double sm[];
     double* D = sm;                    // 32 x 33   diagonal block of L
@@ -668,6 +678,8 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
     __shared__ int fail;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     if (tid == 0) fail = 0;
+    long long t_diag = 0, t_panel = 0, t_trail = 0, t0 = clock64(), tA;
+    const long long t_begin = t0;
     __syncthreads();
     for (int kb = 0; kb < n; kb += 32) {
         const int bs = min(32, n - kb);
@@ -677,20 +689,30 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
 #pragma unroll
             for (int j = 0; j < 32; ++j) a[j] = (lane < bs && j <= lane) ? S[(size_t)(kb + lane) * n + kb + j] : ((j == lane) ? 1.0 : 0.0);
             int bad = 0;
+            double d0 = __shfl_sync(0xffffffffu, a[0], 0);
+            if (!(d0 > 0.0)) { bad = 1; d0 = 1.0; }
+            double inv = rsqrt(d0);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                double djj = __shfl_sync(0xffffffffu, a[j], j);
-                if (!(djj > 0.0)) { bad = 1; djj = 1.0; }
-                const double inv = rsqrt(djj);
                 if (lane >= j) a[j] *= inv;                       // l_ij (lane j: sqrt(d_jj))
                 if (lane == j) invd[kb + j] = inv;
+                // update column j+1 first and start the next pivot's rsqrt: its latency overlaps the rest of the update
+                double inv_next = 1.0;
+                if (j + 1 < 32) {
+                    const double l1 = __shfl_sync(0xffffffffu, a[j], j + 1);
+                    if (lane >= j + 1) a[j + 1] -= a[j] * l1;
+                    double dn = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
+                    if (!(dn > 0.0)) { bad = 1; dn = 1.0; }
+                    inv_next = rsqrt(dn);
+                }
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {                    // constant trip count keeps a[] in registers
-                    if (k > j) {
+                    if (k > j + 1) {
                         const double lkj = __shfl_sync(0xffffffffu, a[j], k);
                         if (lane >= k) a[k] -= a[j] * lkj;
                     }
                 }
+                inv = inv_next;
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -700,6 +722,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
             if (bad && lane == 0) fail = 1;
         }
         __syncthreads();
+        tA = clock64(); t_diag += tA - t0; t0 = tA;
         // ---- panel: rows below the block + the rhs row (last):  x L^T = a, right-looking, no divisions
         const int m = n - kb - bs + 1;
         for (int rr = tid; rr < m; rr += nt) {
@@ -718,8 +741,10 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
             for (int j = 0; j < 32; ++j) { P[rr * 34 + j] = a[j]; if (j < bs) src[j] = a[j]; }
         }
         __syncthreads();
-        // ---- trailing update A22 -= P P^T on the lower triangle, 32x32 register tiles: lane = column, the
-        // column's panel row lives in registers, the row's panel entries are broadcast from shared memory.
+        tA = clock64(); t_panel += tA - t0; t0 = tA;
+        // ---- trailing update A22 -= P P^T on the lower triangle.  One warp per 32x32 tile, each lane a 4x8
+        // register micro-tile (rows ry+8i, columns cx+4j: consecutive lanes touch consecutive panel rows, so the
+        // LDS.128 operand loads are bank-conflict free and every loaded value feeds 4 or 8 DFMAs).
         const int ntile = (m + 31) >> 5;
         const int total = ntile * (ntile + 1) / 2;
         for (int t = warp; t < total; t += nw) {
@@ -727,71 +752,83 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
             while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
             while (ti * (ti + 1) / 2 > t) --ti;
             const int tj = t - ti * (ti + 1) / 2;
-            const int jp = tj * 32 + lane;
-            const bool col_ok = jp < m - 1;              // the rhs row is not a column
-            double pj[32];
+            const int ry = lane >> 2, cx = lane & 3;
+            const int r0 = ti * 32 + ry, c0 = tj * 32 + cx;
+            double acc[4][8];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) pj[k] = col_ok ? P[jp * 34 + k] : 0.0;
-            const int r_end = min(32, m - ti * 32);
-            // prefetch the tile's current values in one round trip (the read-modify-write must not serialise per row)
-            double cur[32];
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                const int ip = ti * 32 + r;
-                const bool w_ok = r < r_end && col_ok && jp <= ip;
-                const double* srcp = (ip == m - 1) ? (rhs + kb + bs) : (S + (size_t)(kb + bs + ip) * n + kb + bs);
-                cur[r] = w_ok ? srcp[jp] : 0.0;
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+            // rows / columns beyond the panel read row 0 (valid memory) and are masked at the store
+            const double2* rp[4]; const double2* cp[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rp[i] = reinterpret_cast<const double2*>(P + (size_t)min(r0 + 8 * i, m - 1) * 34);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cp[j] = reinterpret_cast<const double2*>(P + (size_t)min(c0 + 4 * j, m - 1) * 34);
+#pragma unroll 2
+            for (int k = 0; k < 16; ++k) {
+                double2 rv[4], cv[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rv[i] = rp[i][k];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cv[j] = cp[j][k];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { acc[i][j] += rv[i].x * cv[j].x; acc[i][j] += rv[i].y * cv[j].y; }
+            }
+            // read-modify-write of the tile: all loads first (one round trip), then the stores
+            double cur[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ip = min(r0 + 8 * i, m - 1);
+                const double* src = (ip == m - 1) ? (rhs + kb + bs) : (S + (size_t)(kb + bs + ip) * n + kb + bs);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const int jp = c0 + 4 * j; cur[i][j] = (r0 + 8 * i < m && jp < m - 1 && jp <= ip) ? src[jp] : 0.0; }
             }
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                const int ip = ti * 32 + r;
-                if (r < r_end) {
-                    const double2* prow = reinterpret_cast<const double2*>(P + ip * 34);
-                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int i = 0; i < 4; ++i) {
+                const int ip = r0 + 8 * i;
+                if (ip >= m) continue;
+                double* dst = (ip == m - 1) ? (rhs + kb + bs) : (S + (size_t)(kb + bs + ip) * n + kb + bs);
 #pragma unroll
-                    for (int k = 0; k < 16; k += 2) {
-                        const double2 a = prow[k], b = prow[k + 1];
-                        s0 += a.x * pj[2 * k]; s1 += a.y * pj[2 * k + 1]; s2 += b.x * pj[2 * k + 2]; s3 += b.y * pj[2 * k + 3];
-                    }
-                    cur[r] -= (s0 + s1) + (s2 + s3);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                const int ip = ti * 32 + r;
-                if (r < r_end && col_ok && jp <= ip) {
-                    double* dst = (ip == m - 1) ? (rhs + kb + bs) : (S + (size_t)(kb + bs + ip) * n + kb + bs);
-                    dst[jp] = cur[r];
-                }
+                for (int j = 0; j < 8; ++j) { const int jp = c0 + 4 * j; if (jp < m - 1 && jp <= ip) dst[jp] = cur[i][j] - acc[i][j]; }
             }
         }
         __syncthreads();
+        tA = clock64(); t_trail += tA - t0; t0 = tA;
     }
-    // ---- backward substitution  L^T x = y  (y is in rhs)
+    // ---- backward substitution  L^T x = y  (y is in rhs), right-looking: solve the 32 unknowns of a block with
+    // shuffles in warp 0, then every thread j < kb applies  y_j -= sum_i L[i][j] x_i  with coalesced row reads.
     const int last = ((n - 1) / 32) * 32;
+    double* xs = P;                                   // 32 solved unknowns of the current block
     for (int kb = last; kb >= 0; kb -= 32) {
         const int bs = min(32, n - kb);
-        for (int e = tid; e < 32 * 32; e += nt) {
-            const int i = e >> 5, j = e & 31;
-            D[i * 33 + j] = (i < bs && j <= i) ? S[(size_t)(kb + i) * n + kb + j] : 0.0;
-        }
-        double acc = 0.0;
-        if (lane < bs) for (int i = kb + bs + warp; i < n; i += nw) acc += S[(size_t)i * n + kb + lane] * rhs[i];
-        P[warp * 34 + lane] = acc;
-        __syncthreads();
         if (warp == 0) {
+            double col[32];                           // column `lane` of the block:  col[i] = L[kb+i][kb+lane], i >= lane
+#pragma unroll
+            for (int i = 0; i < 32; ++i) col[i] = (i < bs && lane < bs && i >= lane) ? S[(size_t)(kb + i) * n + kb + lane] : 0.0;
             double t = (lane < bs) ? rhs[kb + lane] : 0.0;
-            for (int w = 0; w < nw; ++w) t -= P[w * 34 + lane];
-            for (int j = bs - 1; j >= 0; --j) {
-                const double xj = __shfl_sync(0xffffffffu, t, j) * invd[kb + j];
+            const double my_inv = (lane < bs) ? invd[kb + lane] : 1.0;
+#pragma unroll
+            for (int j = 31; j >= 0; --j) {
+                const double xj = __shfl_sync(0xffffffffu, t * my_inv, j);     // lane j's t is final here
                 if (lane == j) t = xj;
-                else if (lane < j) t -= D[j * 33 + lane] * xj;
+                else if (lane < j) t -= col[j] * xj;
             }
-            if (lane < bs) rhs[kb + lane] = t;
+            if (lane < bs) { rhs[kb + lane] = t; xs[lane] = t; } else xs[lane] = 0.0;
+        }
+        __syncthreads();
+        for (int j = tid; j < kb; j += nt) {
+            double acc = 0.0;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) if (i < bs) acc += S[(size_t)(kb + i) * n + j] * xs[i];
+            rhs[j] -= acc;
         }
         __syncthreads();
     }
     if (tid == 0 && fail) st->solve_fail = 1;
+    if (tid == 0) { tA = clock64(); g_chol_dbg[0] += t_diag; g_chol_dbg[1] += t_panel; g_chol_dbg[2] += t_trail; g_chol_dbg[3] += tA - t0; g_chol_dbg[4] += tA - t_begin; g_chol_dbg[5] += 1; }
 }
 
 // ------------------------------------------------------------------ back-substitution + candidate point
@@ -851,14 +888,33 @@ __global__ void __launch_bounds__(TPB) ba_update_kernel(BaDev d) {
     block_add(xn, &st->x_norm2, s_red);
 }
 
-__global__ void ba_accept_kernel(BaDev d) {
-    const LmState* st = d.st;
-    if (!st->accept) return;
-    const size_t np = (size_t)d.n_poses * 7, nv = (size_t)d.n_vec3 * 3, nr = d.n_rho;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < np + nv + nr; i += (size_t)gridDim.x * blockDim.x) {
-        if (i < np) d.poses[i] = d.c_poses[i];
-        else if (i < np + nv) d.vec3[i - np] = d.c_vec3[i - np];
-        else d.rho[i - np - nv] = d.c_rho[i - np - nv];
+// One CTA closes the iteration: LM decision (thread 0), then -- if the step was accepted -- candidate -> x and the
+// accumulators of the next linearisation are cleared (problems on the dense-solver path are small: < 1 MB).
+__global__ void __launch_bounds__(1024) ba_post_kernel(BaDev d) {
+    LmState* st = d.st;
+    __shared__ int s_accept, s_zero;
+    if (threadIdx.x == 0) {
+        const int was_done = st->done;
+        if (!was_done) { lm_control_post(*st); if (st->accept) st->x_cost = st->cand_cost_acc; }
+        s_accept = (!was_done && st->accept) ? 1 : 0;
+        s_zero = (!st->done && st->need_linearize) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_accept) {
+        const size_t np = (size_t)d.n_poses * 7, nv = (size_t)d.n_vec3 * 3, nr = d.n_rho;
+        for (size_t i = threadIdx.x; i < np + nv + nr; i += blockDim.x) {
+            if (i < np) d.poses[i] = d.c_poses[i];
+            else if (i < np + nv) d.vec3[i - np] = d.c_vec3[i - np];
+            else d.rho[i - np - nv] = d.c_rho[i - np - nv];
+        }
+    }
+    if (s_zero) {
+        const size_t nH = (size_t)d.dimc * d.dimc;
+        double2* H2 = reinterpret_cast<double2*>(d.Hpp);
+        for (size_t i = threadIdx.x; i < nH / 2; i += blockDim.x) H2[i] = make_double2(0.0, 0.0);
+        if ((nH & 1) && threadIdx.x == 0) d.Hpp[nH - 1] = 0.0;
+        for (size_t i = threadIdx.x; i < (size_t)d.dimc; i += blockDim.x) d.gc[i] = 0.0;
+        for (size_t i = threadIdx.x; i < (size_t)d.n_rho; i += blockDim.x) { d.Hll[i] = 0.0; d.gl[i] = 0.0; }
     }
 }
 
@@ -894,6 +950,8 @@ struct lvb_ba {
     DevBuf<int> tf_slot, sw_group, sw_lm, grp_ns, grp_off;
     int n_schur_warps = 0, schur_cols_max = 0;
     size_t schur_smem = 0, lin_smem = 0;
+    cudaGraphExec_t pass_graph = nullptr;
+    int solves_done = 0;
     DevBuf<double> fc[6];
     DevBuf<int> fi[6];
     DevBuf<double> imu_raw;
@@ -928,8 +986,16 @@ static int init_tables() {
 }
 
 static inline int nblk(size_t n, int per) { return (int)((n + per - 1) / per); }
+static void mark(struct lvb_ba* ba, const char* name);
 #define LAUNCH(ba, kernel, grid, block, smem, ...)                                        \
-    do { if ((grid) > 0) { kernel<<<(grid), (block), (smem), (ba)->ctx->stream>>>(__VA_ARGS__); (ba)->ctx->launches++; } } while (0)
+    do { if ((grid) > 0) { kernel<<<(grid), (block), (smem), (ba)->ctx->stream>>>(__VA_ARGS__); (ba)->ctx->launches++; mark(ba, #kernel); } } while (0)
+
+static std::vector<std::pair<const char*, cudaEvent_t>> g_marks;
+static bool g_timing = false;
+static void mark(lvb_ba* ba, const char* name) {
+    if (!g_timing) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ba->ctx->stream); g_marks.push_back({name, e});
+}
 
 static int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
@@ -941,14 +1007,14 @@ extern "C" {
 
 int lvb_ba_create(lvb_ctx* ctx, lvb_ba** out) {
     if (!ctx || !out) { set_error("null argument"); return LVB_ERR_INVALID; }
-    LVB_CUDA(cudaSetDevice(ctx->device));
+    LVB_CUDA(cudaSetDevice(ctx->device)); lvb::g_alloc_stream = ctx->stream;
     LVB_TRY(init_tables());
     lvb_ba* b = new lvb_ba();
     b->ctx = ctx;
     *out = b;
     return LVB_OK;
 }
-void lvb_ba_destroy(lvb_ba* ba) { if (ba) { cudaSetDevice(ba->ctx->device); delete ba; } }
+void lvb_ba_destroy(lvb_ba* ba) { if (ba) { cudaSetDevice(ba->ctx->device); if (ba->pass_graph) cudaGraphExecDestroy(ba->pass_graph); delete ba; } }
 
 int lvb_ba_set_cameras(lvb_ba* ba, const double cam[22]) { memcpy(ba->cam, cam, sizeof(ba->cam)); ba->have_cam = true; ba->finalized = false; return LVB_OK; }
 
@@ -974,12 +1040,14 @@ int lvb_ba_add_factors(lvb_ba* ba, int kind, int n, const double* consts, const 
 }
 int lvb_ba_set_loss(lvb_ba* ba, int kind, double a) {
     if (kind < 0 || kind >= 6) { set_error("bad kind"); return LVB_ERR_INVALID; }
-    ba->huber[kind] = a; if (ba->finalized) ba->dev.huber[kind] = a; return LVB_OK;
+    ba->huber[kind] = a;
+    if (ba->finalized) { ba->dev.huber[kind] = a; if (ba->pass_graph) { cudaGraphExecDestroy(ba->pass_graph); ba->pass_graph = nullptr; } }
+    return LVB_OK;
 }
 
 int lvb_ba_finalize(lvb_ba* ba) {
     lvb_ctx* ctx = ba->ctx;
-    LVB_CUDA(cudaSetDevice(ctx->device));
+    LVB_CUDA(cudaSetDevice(ctx->device)); lvb::g_alloc_stream = ctx->stream;
     cudaStream_t s = ctx->stream;
     if (!ba->have_cam) { set_error("cameras not set"); return LVB_ERR_STATE; }
     const int np = (int)ba->h_poses.size() / 7, nv = (int)ba->h_vec3.size() / 3, nr = (int)ba->h_rho.size();
@@ -1050,7 +1118,6 @@ int lvb_ba_finalize(lvb_ba* ba) {
                 const int f = tf_src(i);
                 for (int side = 1; side <= 2; ++side) { const int off = pose_off[ba->h_fi[0][3 * (size_t)f + side]]; if (off >= 0) sig.push_back(off); }
             }
-            if (sig.empty()) continue;
             std::sort(sig.begin(), sig.end()); sig.erase(std::unique(sig.begin(), sig.end()), sig.end());
             if ((int)sig.size() > MAX_TRACK) { set_error("landmark %d is observed from more than %d keyframes", l, (int)MAX_TRACK); return LVB_ERR_UNSUPPORTED; }
             auto it = gid.find(sig);
@@ -1165,6 +1232,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
     R.b[6] = R.b[5] + nblk(ba->nd[5], TPB);
     const size_t smem_imu = (size_t)(4 * 480 * 2 + 4 * 32) * 8 + 4 * 32 * 4;
     const size_t smem_pose = d.stage_poses ? ((size_t)np * 56 + 16) : 0;
+    if (ba->pass_graph) { cudaGraphExecDestroy(ba->pass_graph); ba->pass_graph = nullptr; }
     ba->pose_smem = smem_pose; ba->imu_smem = smem_imu;
     ba->lin_smem = ((smem_pose + 15) & ~(size_t)15) + (size_t)(TPB / 32) * SYRK_ROWS * SYRK_LD * 8;
     ba->schur_smem = (size_t)(TPB / 32) * 32 * (size_t)std::max(1, cols_max) * 8;
@@ -1183,7 +1251,7 @@ int lvb_ba_dims(lvb_ba* ba, int* dimc, int* nrf, int* rows) {
 int lvb_ba_update_params(lvb_ba* ba, const double* P, const double* V, const double* R) {
     if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
     cudaStream_t s = ba->ctx->stream;
-    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
     if (P) { ba->h_poses.assign(P, P + ba->h_poses.size()); LVB_TRY(ba->poses.upload(P, ba->h_poses.size(), s)); }
     if (V) { ba->h_vec3.assign(V, V + ba->h_vec3.size()); LVB_TRY(ba->vec3.upload(V, ba->h_vec3.size(), s)); }
     if (R) { ba->h_rho.assign(R, R + ba->h_rho.size()); LVB_TRY(ba->rho.upload(R, ba->h_rho.size(), s)); }
@@ -1217,7 +1285,7 @@ static int ensure_eval_buffers(lvb_ba* ba, int kind) {
 int lvb_ba_eval(lvb_ba* ba, int kind, double* r, double* J) {
     if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
     if (kind < 0 || kind >= 6) { set_error("bad kind"); return LVB_ERR_INVALID; }
-    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
     LVB_TRY(ensure_eval_buffers(ba, kind));
     LVB_TRY(launch_eval(ba, kind, ba->eval_r.p, ba->eval_J.p));
     const size_t nd = ba->nd[kind], rd = kResDim[kind], jd = (size_t)kResDim[kind] * kJacCols[kind];
@@ -1247,19 +1315,20 @@ int lvb_ba_eval(lvb_ba* ba, int kind, double* r, double* J) {
 int lvb_ba_eval_device(lvb_ba* ba, int kind) {
     if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
     if (kind < 0 || kind >= 6) { set_error("bad kind"); return LVB_ERR_INVALID; }
+    lvb::g_alloc_stream = ba->ctx->stream;
     LVB_TRY(ensure_eval_buffers(ba, kind));
     return launch_eval(ba, kind, ba->eval_r.p, ba->eval_J.p);
 }
 
-// one pass = one LM iteration attempt (all decisions on the device)
-static int launch_linearize_and_reduce(lvb_ba* ba) {
+// one pass = one LM iteration attempt (all decisions on the device), 10 launches:
+//   linearize (visual) | linearize (IMU + priors) | build S | Schur | camera damping | Cholesky (+ LM pre-check)
+//   | back-substitution + candidate | cost (visual) | cost (IMU + priors) | LM decision + accept + clear
+static int launch_linearize_and_reduce(lvb_ba* ba, bool standalone) {
     BaDev& d = ba->dev;
     lvb_ctx* ctx = ba->ctx;
     const size_t nH = (size_t)d.dimc * d.dimc;
-    LAUNCH(ba, ba_zero_kernel, std::min(1024, nblk(nH + d.dimc + 2 * (size_t)d.n_rho, 256)), 256, 0, d);
     LAUNCH(ba, ba_linearize_kernel<0>, ba->ranges.b[3], TPB, ba->lin_smem, d, ba->ranges);
     LAUNCH(ba, ba_linearize_other_kernel<0>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
-    LAUNCH(ba, ba_prepare_landmark_kernel, nblk(d.n_rho, 256), 256, 0, d);
     LAUNCH(ba, ba_build_S_kernel, std::min(1024, nblk(nH, 256)), 256, 0, d);
     LAUNCH(ba, ba_schur_kernel, nblk(d.n_schur_warps, TPB / 32), TPB, ba->schur_smem, d, std::max(1, ba->schur_cols_max));
     if (ctx->world > 1) {
@@ -1268,7 +1337,7 @@ static int launch_linearize_and_reduce(lvb_ba* ba) {
         LAUNCH(ba, ba_unpack_scalars_kernel, 1, 1, 0, d);
     }
     LAUNCH(ba, ba_prepare_camera_kernel, nblk(d.n_poses + d.n_vec3, 128), 128, 0, d);
-    LAUNCH(ba, lm_control_pre_kernel, 1, 1, 0, d.st);
+    if (standalone) LAUNCH(ba, lm_control_pre_kernel, 1, 1, 0, d.st);
     return check_launch("linearize");
 }
 
@@ -1276,14 +1345,20 @@ static int launch_step(lvb_ba* ba) {
     BaDev& d = ba->dev;
     lvb_ctx* ctx = ba->ctx;
     const size_t chol_smem = (size_t)(32 * 33 + (d.dimc + 34) + (d.dimc + 2) * 34) * 8;
-    LAUNCH(ba, ba_cholesky_kernel, 1, CHOL_T, chol_smem, d.S, d.rhs, d.dimc, d.st);
+    LAUNCH(ba, ba_cholesky_kernel, 1, CHOL_T, chol_smem, d.S, d.rhs, d.dimc, d.st, 1);
     LAUNCH(ba, ba_update_kernel, nblk((size_t)d.n_poses + d.n_vec3 + d.n_rho, TPB), TPB, 0, d);
     LAUNCH(ba, ba_linearize_kernel<1>, ba->ranges.b[3], TPB, ba->lin_smem, d, ba->ranges);
     LAUNCH(ba, ba_linearize_other_kernel<1>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
     if (ctx->world > 1) LVB_TRY(comm_allreduce_sum_f64(ctx, &d.st->cand_cost_acc, 5));
-    LAUNCH(ba, lm_control_post_kernel, 1, 1, 0, d.st);
-    LAUNCH(ba, ba_accept_kernel, std::min(1024, nblk((size_t)d.n_poses * 7 + d.n_vec3 * 3 + d.n_rho, 256)), 256, 0, d);
+    LAUNCH(ba, ba_post_kernel, 1, 1024, 0, d);
     return check_launch("step");
+}
+
+static int launch_clear(lvb_ba* ba) {
+    BaDev& d = ba->dev;
+    const size_t nH = (size_t)d.dimc * d.dimc;
+    LAUNCH(ba, ba_zero_kernel, std::min(1024, nblk(nH + d.dimc + 2 * (size_t)d.n_rho, 256)), 256, 0, d);
+    return check_launch("clear");
 }
 
 static int upload_state(lvb_ba* ba, const lvb_solve_options* o, double radius_override) {
@@ -1305,9 +1380,10 @@ static int require_solvable(lvb_ba* ba) {
 
 int lvb_ba_reduced_system(lvb_ba* ba, double radius, double* S, double* b, double* cost) {
     LVB_TRY(require_solvable(ba));
-    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
     LVB_TRY(upload_state(ba, nullptr, radius));
-    LVB_TRY(launch_linearize_and_reduce(ba));
+    LVB_TRY(launch_clear(ba));
+    LVB_TRY(launch_linearize_and_reduce(ba, true));
     const int n = ba->dimc;
     std::vector<double> hS((size_t)n * n);
     LmState h;
@@ -1323,7 +1399,7 @@ int lvb_ba_reduced_system(lvb_ba* ba, double radius, double* S, double* b, doubl
 
 int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary* summary) {
     LVB_TRY(require_solvable(ba));
-    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
     const auto t0 = std::chrono::steady_clock::now();
     lvb_solve_options opt;
     if (options) opt = *options; else lvb_default_options(&opt);
@@ -1331,15 +1407,47 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
     cudaStream_t s = ba->ctx->stream;
     LmState h;
     memset(&h, 0, sizeof(h));
-    for (int pass = 0; pass <= opt.max_num_iterations; ++pass) {
-        LVB_TRY(launch_linearize_and_reduce(ba));
-        LVB_TRY(launch_step(ba));
+    LVB_TRY(launch_clear(ba));
+    // The pass is a fixed sequence of launches whose kernels all read their control flags from the device state,
+    // so it is captured once into a CUDA graph and replayed; the host looks at the state only every
+    // `check_every` passes (kernels of a finished solve return immediately).
+    const bool graph_ok = ba->ctx->world == 1 && ba->ctx->use_graph && !g_timing;
+    const int check_every = std::max(1, ba->ctx->check_every);
+    const bool capped = opt.max_solver_time_in_seconds < 1e8;
+    int pass = 0;
+    while (pass <= opt.max_num_iterations) {
+        int chunk = std::min(check_every, opt.max_num_iterations + 1 - pass);
+        if (capped) {      // never overrun the wall-clock budget by more than about one pass
+            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            chunk = pass == 0 ? 1 : std::max(1, std::min(chunk, (int)((opt.max_solver_time_in_seconds - el) / (el / pass))));
+        }
+        // instantiating a graph costs a few hundred microseconds: only worth it for a long solve or a reused problem
+        const bool use_graph = graph_ok && (ba->pass_graph || (pass >= 8 && opt.max_num_iterations - pass >= 16) || ba->solves_done >= 1);
+        if (use_graph && !ba->pass_graph) {
+            cudaGraph_t g = nullptr;
+            LVB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            int rc = launch_linearize_and_reduce(ba, false);
+            if (rc == LVB_OK) rc = launch_step(ba);
+            cudaError_t ce = cudaStreamEndCapture(s, &g);
+            if (rc != LVB_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            LVB_CUDA(ce);
+            ce = cudaGraphInstantiate(&ba->pass_graph, g, 0);
+            cudaGraphDestroy(g);
+            LVB_CUDA(ce);
+            ba->ctx->launches -= 10;      // capture is not execution
+        }
+        for (int c = 0; c < chunk; ++c) {
+            if (use_graph) { LVB_CUDA(cudaGraphLaunch(ba->pass_graph, s)); ba->ctx->launches += 10; }
+            else { LVB_TRY(launch_linearize_and_reduce(ba, false)); LVB_TRY(launch_step(ba)); }
+        }
+        pass += chunk;
         LVB_CUDA(cudaMemcpyAsync(&h, ba->st.p, sizeof(h), cudaMemcpyDeviceToHost, s));
         LVB_CUDA(cudaStreamSynchronize(s));
         if (h.done) break;
         const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (el >= opt.max_solver_time_in_seconds) break;   // backend.cpp:208 wall-clock cap
     }
+    ba->solves_done++;
     if (summary) {
         int nb = 0; for (int k = 0; k < 6; ++k) nb += ba->n[k];
         summary->initial_cost = h.initial_cost; summary->final_cost = h.x_cost;
@@ -1352,23 +1460,40 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
     return LVB_OK;
 }
 
+LVB_API int lvb_debug_timing(int enable) {
+    if (!enable && g_timing) {
+        cudaDeviceSynchronize();
+        for (size_t i = 1; i < g_marks.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, g_marks[i - 1].second, g_marks[i].second); printf("%-40s %8.2f us\n", g_marks[i].first, ms * 1e3); }
+        for (auto& m : g_marks) cudaEventDestroy(m.second);
+        g_marks.clear();
+    }
+    g_timing = enable != 0;
+    return LVB_OK;
+}
+
+LVB_API int lvb_debug_cholesky_clocks(long long out[8], int reset) {
+    LVB_CUDA(cudaMemcpyFromSymbol(out, g_chol_dbg, 8 * sizeof(long long)));
+    if (reset) { long long z[8] = {0}; LVB_CUDA(cudaMemcpyToSymbol(g_chol_dbg, z, sizeof(z))); }
+    return LVB_OK;
+}
+
 int lvb_ba_get_poses(lvb_ba* ba, double* out) {
-    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
     LVB_TRY(ba->poses.download(out, ba->h_poses.size(), ba->ctx->stream)); LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream)); return LVB_OK;
 }
 int lvb_ba_get_vec3(lvb_ba* ba, double* out) {
-    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
     LVB_TRY(ba->vec3.download(out, ba->h_vec3.size(), ba->ctx->stream)); LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream)); return LVB_OK;
 }
 int lvb_ba_get_inv_depths(lvb_ba* ba, double* out) {
-    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
     LVB_TRY(ba->rho.download(out, ba->h_rho.size(), ba->ctx->stream)); LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream)); return LVB_OK;
 }
 
 int lvb_ba_reprojection_errors(lvb_ba* ba, int n, const double* ob_pw, const int32_t* pose_idx, double* err) {
     if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
     if (n <= 0) return LVB_OK;
-    LVB_CUDA(cudaSetDevice(ba->ctx->device));
+    LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
     const int np = (int)ba->h_poses.size() / 7;
     for (int i = 0; i < n; ++i) if (pose_idx[i] < 0 || pose_idx[i] >= np) { set_error("pose index out of range"); return LVB_ERR_INVALID; }
     DevBuf<double> d_in, d_err; DevBuf<int> d_idx;

@@ -12,6 +12,7 @@
 namespace lvb {
 
 static thread_local std::string g_last_error;
+thread_local cudaStream_t g_alloc_stream = nullptr;
 
 void set_error(const char* fmt, ...) {
     char buf[1024];
@@ -101,8 +102,16 @@ int lvb_ctx_create(int device, void* cuda_stream, lvb_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
     else { LVB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    {   // keep freed device memory in the stream-ordered pool (see DevBuf)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { unsigned long long thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
+    }
     const char* no_tma = getenv("LVB_NO_TMA");
     c->use_tma = !(no_tma && no_tma[0] == '1');
+    const char* no_graph = getenv("LVB_NO_GRAPH");
+    c->use_graph = !(no_graph && no_graph[0] == '1');
+    const char* ce = getenv("LVB_CHECK_EVERY");
+    if (ce && atoi(ce) > 0) c->check_every = atoi(ce);
     *out = c;
     return LVB_OK;
 }

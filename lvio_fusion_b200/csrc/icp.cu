@@ -440,7 +440,7 @@ void lvb_icp_destroy(lvb_icp* icp) { if (icp) { cudaSetDevice(icp->ctx->device);
 int lvb_icp_set_map(lvb_icp* h, const void* points, int n, int stride, float cell_size) {
     if (n <= 0 || !points || stride < 12 || (stride & 3) || !(cell_size > 0.0f)) { set_error("bad map arguments"); return LVB_ERR_INVALID; }
     lvb_ctx* ctx = h->ctx;
-    LVB_CUDA(cudaSetDevice(ctx->device));
+    LVB_CUDA(cudaSetDevice(ctx->device)); lvb::g_alloc_stream = ctx->stream;
     cudaStream_t s = ctx->stream;
     LVB_TRY(h->map_raw.upload((const unsigned char*)points, (size_t)n * stride, s));
     LVB_TRY(h->bbox.ensure(6));
@@ -490,7 +490,7 @@ int lvb_icp_set_map(lvb_icp* h, const void* points, int n, int stride, float cel
 }
 
 int lvb_icp_knn3(lvb_icp* h, const void* scan, int n, int stride, const double frame_pose[7], float max_d2, int32_t* idx, float* d2) {
-    LVB_CUDA(cudaSetDevice(h->ctx->device));
+    LVB_CUDA(cudaSetDevice(h->ctx->device)); lvb::g_alloc_stream = h->ctx->stream;
     if (h->have_map && max_d2 > h->cell_size * h->cell_size) { set_error("max_d2 %.6g exceeds cell_size^2 %.6g", max_d2, h->cell_size * h->cell_size); return LVB_ERR_INVALID; }
     IcpDev d;
     LVB_TRY(upload_scan(h, scan, n, stride, frame_pose, max_d2, 0.0, d));
@@ -524,7 +524,7 @@ static int init_state(lvb_icp* h, int mode, const double* map_pose, const double
 int lvb_icp_eval(lvb_icp* h, int mode, const void* scan, int n, int stride, const double frame_pose[7], const double map_pose[7],
                  const double rpyxyz[6], double weight, double dist_thr, uint8_t* accepted, double* r, double* J) {
     if (mode < 0 || mode > 1) { set_error("bad mode"); return LVB_ERR_INVALID; }
-    LVB_CUDA(cudaSetDevice(h->ctx->device));
+    LVB_CUDA(cudaSetDevice(h->ctx->device)); lvb::g_alloc_stream = h->ctx->stream;
     IcpDev d;
     LVB_TRY(upload_scan(h, scan, n, stride, frame_pose, h->cell_size * h->cell_size, dist_thr, d));
     if (n == 0) return LVB_OK;
@@ -545,7 +545,7 @@ int lvb_icp_scan_to_map(lvb_icp* h, int mode, const void* scan, int n, int strid
                         double rpyxyz[6], double weight, double prior_weight, double huber_a, double dist_thr,
                         const lvb_solve_options* options, lvb_solve_summary* summary) {
     if (mode < 0 || mode > 1) { set_error("bad mode"); return LVB_ERR_INVALID; }
-    LVB_CUDA(cudaSetDevice(h->ctx->device));
+    LVB_CUDA(cudaSetDevice(h->ctx->device)); lvb::g_alloc_stream = h->ctx->stream;
     const auto t0 = std::chrono::steady_clock::now();
     lvb_solve_options opt;
     if (options) opt = *options; else lvb_default_options(&opt);

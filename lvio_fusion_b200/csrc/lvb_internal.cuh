@@ -26,6 +26,8 @@ struct lvb_ctx {
     long long launches = 0;
     int sm_count = 148;
     bool use_tma = true;          // cp.async.bulk staging of the pose array (env LVB_NO_TMA=1 disables)
+    bool use_graph = true;        // replay the LM pass as a CUDA graph (env LVB_NO_GRAPH=1 disables)
+    int check_every = 4;          // LM passes between host looks at the device state (env LVB_CHECK_EVERY)
     // NCCL (resolved at run time through dlopen, see comm.cu)
     void* comm = nullptr;
     int rank = 0, world = 1;
@@ -35,32 +37,38 @@ namespace lvb {
 
 int comm_allreduce_sum_f64(lvb_ctx* ctx, double* buf, size_t count);   // no-op when world == 1
 
-// Minimal owning device buffer.
+// Minimal owning device buffer on the stream-ordered allocator: a problem object allocates ~40 arrays, and
+// cudaMalloc (a device-wide synchronising call, ~0.1 ms each) would dominate the end-to-end time of a solve that
+// itself takes a couple of milliseconds.  lvb_ctx_create raises the pool's release threshold so freed blocks are
+// reused by the next problem instead of being returned to the driver.
+extern thread_local cudaStream_t g_alloc_stream;    // stream of the handle currently being operated on
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    cudaStream_t s = nullptr;
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) cudaFreeAsync(p, s); p = nullptr; n = 0; }
     int ensure(size_t count) {
         if (count <= n && p) return LVB_OK;
         release();
         if (count == 0) count = 1;
-        // round up to 16 B so cp.async.bulk sources stay 16-byte sized
+        // round up so cp.async.bulk sources stay 16-byte sized and padded reads stay inside the allocation
         size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
-        LVB_CUDA(cudaMalloc((void**)&p, bytes));
+        s = g_alloc_stream;
+        LVB_CUDA(cudaMallocAsync((void**)&p, bytes, s));
         n = count;
         return LVB_OK;
     }
-    int upload(const T* h, size_t count, cudaStream_t s) {
+    int upload(const T* h, size_t count, cudaStream_t st) {
         LVB_TRY(ensure(count));
-        if (count) LVB_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+        if (count) LVB_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st));
         return LVB_OK;
     }
-    int download(T* h, size_t count, cudaStream_t s) const {
-        if (count) LVB_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    int download(T* h, size_t count, cudaStream_t st) const {
+        if (count) LVB_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, st));
         return LVB_OK;
     }
-    int zero(cudaStream_t s) { if (p) LVB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); return LVB_OK; }
+    int zero(cudaStream_t st) { if (p) LVB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st)); return LVB_OK; }
 };
 
 // Trust-region state kept on the device so that an LM iteration needs no host round trip for

@@ -392,36 +392,49 @@ LVB_HD void imu_raw_residual(const ImuConst& c, const double* Ti, const double* 
 // raw ambient Jacobian, row-major 15 x 32, columns: pose_i(7) v_i(3) ba_i(3) bg_i(3) pose_j(7) v_j(3) ba_j(3) bg_j(3)
 // (imu_error.hpp:43-110; rotation columns at 0..2, column 3 == 0, translation at 4..6)
 LVB_HD void put3(double* J, int r0, int c0, const M3& b, double s) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) J[(r0 + i) * 32 + c0 + j] = s * b.m[3 * i + j]; }
-LVB_HD void imu_raw_jacobian(const ImuConst& c, const double* Ti, const double* Vi, const double* Bgi,
-                             const double* Tj, const double* Vj, double* J /*15x32, pre-zeroed*/) {
+// One parameter block of the raw Jacobian (blk = 0..7 in AddResidualBlock order); the eight blocks touch disjoint
+// columns, so eight lanes of a warp fill the 15x32 matrix concurrently.
+LVB_HD void imu_raw_jacobian_block(const ImuConst& c, int blk, const double* Ti, const double* Vi, const double* Bgi,
+                                   const double* Tj, const double* Vj, double* J /*15x32, pre-zeroed*/) {
     const V3 g = v3(0.0, 0.0, 9.81007);
     const Q4 Qi = q4(Ti[0], Ti[1], Ti[2], Ti[3]), Qj = q4(Tj[0], Tj[1], Tj[2], Tj[3]);
-    const V3 Pi = v3(Ti[4], Ti[5], Ti[6]), Pj = v3(Tj[4], Tj[5], Tj[6]);
-    const V3 vi = v3(Vi[0], Vi[1], Vi[2]), vj = v3(Vj[0], Vj[1], Vj[2]);
     const double dt = c.sum_dt;
-    const Q4 Qi_inv = qinv(Qi), Qj_inv = qinv(Qj);
-    const M3 Ri_inv = qmat(Qi_inv);
-    const V3 th = mul(c.dq_dbg, v3(Bgi[0], Bgi[1], Bgi[2]) - c.lin_bg);
-    const Q4 cq = qmul(c.dq, q4(th.x / 2, th.y / 2, th.z / 2, 1.0));
+    const Q4 Qi_inv = qinv(Qi);
     M3 I; for (int i = 0; i < 9; ++i) I.m[i] = 0; I.m[0] = I.m[4] = I.m[8] = 1.0;
-    // pose_i  (:43-53)
-    put3(J, 0, 4, Ri_inv, -1.0);
-    put3(J, 0, 0, skew(qrot(Qi_inv, ((g * 0.5) * dt) * dt + Pj - Pi - vi * dt)), 1.0);
-    put3(J, 3, 0, left_right_br(qmul(Qj_inv, Qi), cq), -1.0);
-    put3(J, 6, 0, skew(qrot(Qi_inv, g * dt + vj - vi)), 1.0);
-    // v_i (:54-61)
-    put3(J, 0, 7, Ri_inv, -dt); put3(J, 6, 7, Ri_inv, -1.0);
-    // ba_i (:62-70)
-    put3(J, 0, 10, c.dp_dba, -1.0); put3(J, 6, 10, c.dv_dba, -1.0); put3(J, 9, 10, I, -1.0);
-    // bg_i (:71-80)
-    put3(J, 0, 13, c.dp_dbg, -1.0);
-    put3(J, 3, 13, mul(left_br(qmul(qmul(Qj_inv, Qi), c.dq)), c.dq_dbg), -1.0);
-    put3(J, 6, 13, c.dv_dbg, -1.0); put3(J, 12, 13, I, -1.0);
-    // pose_j (:81-89)
-    put3(J, 0, 20, Ri_inv, 1.0);
-    put3(J, 3, 16, left_br(qmul(qmul(qinv(cq), Qi_inv), Qj)), 1.0);
-    // v_j, ba_j, bg_j (:90-110)
-    put3(J, 6, 23, Ri_inv, 1.0); put3(J, 9, 26, I, 1.0); put3(J, 12, 29, I, 1.0);
+    if (blk == 0) {            // pose_i  (:43-53)
+        const V3 Pi = v3(Ti[4], Ti[5], Ti[6]), Pj = v3(Tj[4], Tj[5], Tj[6]);
+        const V3 vi = v3(Vi[0], Vi[1], Vi[2]), vj = v3(Vj[0], Vj[1], Vj[2]);
+        const V3 th = mul(c.dq_dbg, v3(Bgi[0], Bgi[1], Bgi[2]) - c.lin_bg);
+        const Q4 cq = qmul(c.dq, q4(th.x / 2, th.y / 2, th.z / 2, 1.0));
+        put3(J, 0, 4, qmat(Qi_inv), -1.0);
+        put3(J, 0, 0, skew(qrot(Qi_inv, ((g * 0.5) * dt) * dt + Pj - Pi - vi * dt)), 1.0);
+        put3(J, 3, 0, left_right_br(qmul(qinv(Qj), Qi), cq), -1.0);
+        put3(J, 6, 0, skew(qrot(Qi_inv, g * dt + vj - vi)), 1.0);
+    } else if (blk == 1) {     // v_i (:54-61)
+        const M3 Ri_inv = qmat(Qi_inv);
+        put3(J, 0, 7, Ri_inv, -dt); put3(J, 6, 7, Ri_inv, -1.0);
+    } else if (blk == 2) {     // ba_i (:62-70)
+        put3(J, 0, 10, c.dp_dba, -1.0); put3(J, 6, 10, c.dv_dba, -1.0); put3(J, 9, 10, I, -1.0);
+    } else if (blk == 3) {     // bg_i (:71-80)
+        put3(J, 0, 13, c.dp_dbg, -1.0);
+        put3(J, 3, 13, mul(left_br(qmul(qmul(qinv(Qj), Qi), c.dq)), c.dq_dbg), -1.0);
+        put3(J, 6, 13, c.dv_dbg, -1.0); put3(J, 12, 13, I, -1.0);
+    } else if (blk == 4) {     // pose_j (:81-89)
+        const V3 th = mul(c.dq_dbg, v3(Bgi[0], Bgi[1], Bgi[2]) - c.lin_bg);
+        const Q4 cq = qmul(c.dq, q4(th.x / 2, th.y / 2, th.z / 2, 1.0));
+        put3(J, 0, 20, qmat(Qi_inv), 1.0);
+        put3(J, 3, 16, left_br(qmul(qmul(qinv(cq), Qi_inv), Qj)), 1.0);
+    } else if (blk == 5) {     // v_j (:90-96)
+        put3(J, 6, 23, qmat(Qi_inv), 1.0);
+    } else if (blk == 6) {     // ba_j (:97-103)
+        put3(J, 9, 26, I, 1.0);
+    } else {                   // bg_j (:104-110)
+        put3(J, 12, 29, I, 1.0);
+    }
+}
+LVB_HD void imu_raw_jacobian(const ImuConst& c, const double* Ti, const double* Vi, const double* Bgi,
+                             const double* Tj, const double* Vj, double* J /*15x32, pre-zeroed*/) {
+    for (int blk = 0; blk < 8; ++blk) imu_raw_jacobian_block(c, blk, Ti, Vi, Bgi, Tj, Vj, J);
 }
 
 // sqrt_info = LLT(cov^-1).matrixL()^T (imu_error.hpp:32): partial-pivot LU inverse, then Cholesky.
