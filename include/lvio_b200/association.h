@@ -15,12 +15,18 @@
 #include <cmath>
 #include "ceres_shim.h"
 
+// Inside the reference tree the class of the same name already exists (it also owns the feature extraction):
+// compile with -DLVB_ASSOCIATION_CLASS=ScanToMapDevice and forward the two members to it.
+#ifndef LVB_ASSOCIATION_CLASS
+#define LVB_ASSOCIATION_CLASS FeatureAssociation
+#endif
+
 namespace lvio_fusion {
 
-class FeatureAssociation {
+class LVB_ASSOCIATION_CLASS {
 public:
-    explicit FeatureAssociation(double lidar_resolution = 0.2) : resolution_(lidar_resolution) {}
-    ~FeatureAssociation() { if (icp_ground_) lvb_icp_destroy(icp_ground_); if (icp_surf_) lvb_icp_destroy(icp_surf_); }
+    explicit LVB_ASSOCIATION_CLASS(double lidar_resolution = 0.2) : resolution_(lidar_resolution) {}
+    ~LVB_ASSOCIATION_CLASS() { if (icp_ground_) lvb_icp_destroy(icp_ground_); if (icp_surf_) lvb_icp_destroy(icp_surf_); }
 
     // association.cpp:270-326 : pitch/roll/z = para+1,+2,+5 ; gate d2 < 100 res^2 ; TrivialLoss ; PoseErrorRPZ prior
     template <class FramePtr, class Problem>
