@@ -668,7 +668,8 @@ __global__ void lm_control_post_kernel(LmState* st) { lm_control_post(*st); if (
 // Right-looking blocked (32) factorisation of the lower triangle of S (n x n, row-major, in L2/HBM) with
 // the right-hand side carried along as an extra row (so the forward substitution is free), then a
 // blocked backward substitution.  Result: rhs <- S^-1 rhs.
-__global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict__ S, double* __restrict__ rhs, int n, LmState* st, int run_control_pre) {
+__global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict__ S, double* __restrict__ rhs, int n, LmState* st, int run_control_pre,
+                                                                  const int* __restrict__ env_rmax, const int* __restrict__ env_cmin) {
     if (run_control_pre) { if (threadIdx.x == 0) lm_control_pre(*st); __syncthreads(); }
     if (st->done) return;
     extern __shared__ __align__(16) double sm[];
@@ -724,7 +725,8 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
         __syncthreads();
         tA = clock64(); t_diag += tA - t0; t0 = tA;
         // ---- panel: rows below the block + the rhs row (last):  x L^T = a, right-looking, no divisions
-        const int m = n - kb - bs + 1;
+        // only rows inside the envelope of this block column take part (S is block-banded by construction)
+        const int m = env_rmax[kb >> 5] - (kb + bs) + 1 + 1;
         for (int rr = tid; rr < m; rr += nt) {
             const bool is_rhs = (rr == m - 1);
             double* src = is_rhs ? (rhs + kb) : (S + (size_t)(kb + bs + rr) * n + kb);
@@ -819,7 +821,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
             if (lane < bs) { rhs[kb + lane] = t; xs[lane] = t; } else xs[lane] = 0.0;
         }
         __syncthreads();
-        for (int j = tid; j < kb; j += nt) {
+        for (int j = env_cmin[kb >> 5] + tid; j < kb; j += nt) {
             double acc = 0.0;
 #pragma unroll 8
             for (int i = 0; i < 32; ++i) if (i < bs) acc += S[(size_t)(kb + i) * n + j] * xs[i];
@@ -944,6 +946,8 @@ struct lvb_ba {
     std::vector<int> order[6];          // device position -> caller index, -1 for padding
     double huber[6] = {0, 0, 0, 0, 0, 0};
     int dimc = 0, n_pose_free = 0, n_vec3_free = 0, n_rho_free = 0;
+    std::vector<int> canon;             // internal camera-system offset -> canonical (poses first, then vec3) offset
+    DevBuf<int> chol_rmax, chol_cmin;   // envelope of S per 32-column block step
     // device
     DevBuf<double> poses, vec3, rho, c_poses, c_vec3, c_rho;
     DevBuf<int> pose_off, vec3_off, rho_slot, lm_start, lm_fac;
@@ -1059,14 +1063,44 @@ int lvb_ba_finalize(lvb_ba* ba) {
         if (k == 3 && j != 0 && j != 4) lim = nv;
         if (v < 0 || v >= lim) { set_error("factor kind %d block %d: index %d out of range [0,%d)", k, f, v, lim); return LVB_ERR_INVALID; }
     }
-    // slots / offsets
-    std::vector<int> pose_off(np), vec3_off(nv), rho_slot(nr);
+    // slots / offsets.  Unknowns of the reduced camera system are ordered keyframe by keyframe
+    // (pose_i, then the velocity / bias blocks an ImuError ties to pose_i): co-visibility and the IMU chain only
+    // couple neighbouring keyframes, so S is block-banded and the Cholesky works inside its envelope.
+    // `canon` is the caller-visible order (all poses, then all vec3 blocks) used by lvb_ba_reduced_system.
+    std::vector<int> pose_off(np, -1), vec3_off(nv, -1), rho_slot(nr);
     int npf = 0, nvf = 0, nrf = 0;
-    for (int i = 0; i < np; ++i) pose_off[i] = ba->h_pose_const[i] ? -1 : 6 * npf++;
-    for (int i = 0; i < nv; ++i) vec3_off[i] = ba->h_vec3_const[i] ? -1 : 3 * nvf++;
-    for (int i = 0; i < nv; ++i) if (vec3_off[i] >= 0) vec3_off[i] += 6 * npf;
+    for (int i = 0; i < np; ++i) if (!ba->h_pose_const[i]) ++npf;
+    for (int i = 0; i < nv; ++i) if (!ba->h_vec3_const[i]) ++nvf;
     for (int i = 0; i < nr; ++i) rho_slot[i] = ba->h_rho_const[i] ? -1 : nrf++;
     ba->n_pose_free = npf; ba->n_vec3_free = nvf; ba->n_rho_free = nrf; ba->dimc = 6 * npf + 3 * nvf;
+    struct Blk { long long key; int type, idx, width; };
+    std::vector<Blk> blks;
+    {
+        std::vector<long long> vkey(nv, -1);
+        for (int f = 0; f < ba->n[3]; ++f) {
+            const int32_t* ix = &ba->h_fi[3][8 * (size_t)f];
+            for (int b = 1; b < 8; ++b) { if (b == 4) continue; const int v = ix[b]; const int p = ix[b < 4 ? 0 : 4]; if (vkey[v] < 0) vkey[v] = (long long)p * 8 + (b & 3); }
+        }
+        for (int i = 0; i < np; ++i) if (!ba->h_pose_const[i]) blks.push_back({(long long)i * 8, 0, i, 6});
+        for (int i = 0; i < nv; ++i) if (!ba->h_vec3_const[i]) blks.push_back({vkey[i] >= 0 ? vkey[i] : (long long)np * 8 + i, 1, i, 3});
+        std::stable_sort(blks.begin(), blks.end(), [](const Blk& a, const Blk& b) { return a.key < b.key; });
+    }
+    std::vector<int> blk_of_off(ba->dimc, 0), blk_start(blks.size() + 1, 0);
+    ba->canon.assign(ba->dimc, 0);
+    {
+        int off = 0, ps = 0, vs = 0;
+        std::vector<int> pslot(np, -1), vslot(nv, -1);
+        for (int i = 0; i < np; ++i) if (!ba->h_pose_const[i]) pslot[i] = ps++;
+        for (int i = 0; i < nv; ++i) if (!ba->h_vec3_const[i]) vslot[i] = vs++;
+        for (size_t b = 0; b < blks.size(); ++b) {
+            blk_start[b] = off;
+            const int c0 = blks[b].type == 0 ? 6 * pslot[blks[b].idx] : 6 * npf + 3 * vslot[blks[b].idx];
+            if (blks[b].type == 0) pose_off[blks[b].idx] = off; else vec3_off[blks[b].idx] = off;
+            for (int k = 0; k < blks[b].width; ++k) { blk_of_off[off + k] = (int)b; ba->canon[off + k] = c0 + k; }
+            off += blks[b].width;
+        }
+        blk_start[blks.size()] = off;
+    }
     // larger camera systems can still be evaluated (lvb_ba_eval*); the dense reduced solve is capped
     ba->solvable = ba->dimc <= MAX_DIMC && ba->dimc > 0;
     // ---- device order of the blocks.  Solvable problems: TwoFrame blocks sorted by (pose_1, pose_2), PoseOnly
@@ -1143,6 +1177,38 @@ int lvb_ba_finalize(lvb_ba* ba) {
         }
     }
     ba->n_schur_warps = (int)sw_group.size(); ba->schur_cols_max = cols_max;
+    // ---- envelope of S: first structurally non-zero column per row, from every coupling the assembly can create
+    std::vector<int> chol_rmax(ba->dimc / 32 + 2, 0), chol_cmin(ba->dimc / 32 + 2, 0);
+    if (ba->solvable) {
+        std::vector<int> first(ba->dimc);
+        std::vector<int> fb(blks.size());
+        for (size_t b = 0; b < blks.size(); ++b) fb[b] = blk_start[b];
+        auto couple = [&](int offA, int offB) {
+            if (offA < 0 || offB < 0) return;
+            const int a = blk_of_off[offA], b = blk_of_off[offB];
+            const int lo = std::min(a, b), hi = std::max(a, b);
+            fb[hi] = std::min(fb[hi], blk_start[lo]);
+        };
+        for (size_t g = 0; g < grp_ns.size(); ++g) for (int a = 0; a < grp_ns[g]; ++a) for (int b = 0; b < a; ++b) couple(grp_off[g * MAX_TRACK + a], grp_off[g * MAX_TRACK + b]);
+        for (int f = 0; f < ba->n[0]; ++f) couple(pose_off[ba->h_fi[0][3 * (size_t)f + 1]], pose_off[ba->h_fi[0][3 * (size_t)f + 2]]);
+        for (int f = 0; f < ba->n[3]; ++f) {
+            const int32_t* ix = &ba->h_fi[3][8 * (size_t)f];
+            int offs[8];
+            for (int b = 0; b < 8; ++b) offs[b] = (b == 0 || b == 4) ? pose_off[ix[b]] : vec3_off[ix[b]];
+            for (int a = 0; a < 8; ++a) for (int b = 0; b < a; ++b) couple(offs[a], offs[b]);
+        }
+        for (int f = 0; f < ba->n[4]; ++f) couple(pose_off[ba->h_fi[4][2 * (size_t)f]], pose_off[ba->h_fi[4][2 * (size_t)f + 1]]);
+        for (int r = 0; r < ba->dimc; ++r) first[r] = fb[blk_of_off[r]];
+        for (int kb = 0, step = 0; kb < ba->dimc; kb += 32, ++step) {
+            const int bs = std::min(32, ba->dimc - kb);
+            int rmax = kb + bs - 1, cmin = kb;
+            for (int r = kb + bs; r < ba->dimc; ++r) if (first[r] < kb + bs) rmax = r;
+            for (int r = kb; r < kb + bs; ++r) cmin = std::min(cmin, first[r]);
+            // sharded problems: the other ranks' couplings arrive with the all-reduce, so no local envelope is valid
+            if (ctx->world > 1) { rmax = ba->dimc - 1; cmin = 0; }
+            chol_rmax[step] = rmax; chol_cmin[step] = cmin;
+        }
+    }
     if (sw_group.empty()) { sw_group.push_back(0); sw_lm.assign(32, -1); }
     if (grp_ns.empty()) { grp_ns.push_back(0); grp_off.assign(MAX_TRACK, -1); }
 
@@ -1162,6 +1228,8 @@ int lvb_ba_finalize(lvb_ba* ba) {
     LVB_TRY(ba->sw_lm.upload(sw_lm.data(), sw_lm.size(), s));
     LVB_TRY(ba->grp_ns.upload(grp_ns.data(), grp_ns.size(), s));
     LVB_TRY(ba->grp_off.upload(grp_off.data(), grp_off.size(), s));
+    LVB_TRY(ba->chol_rmax.upload(chol_rmax.data(), chol_rmax.size(), s));
+    LVB_TRY(ba->chol_cmin.upload(chol_cmin.data(), chol_cmin.size(), s));
 
     // factor planes in device order (AoS -> SoA transpose on the host; IMU stays AoS and is packed on the device)
     std::vector<double> planes; std::vector<int> iplanes;
@@ -1345,7 +1413,7 @@ static int launch_step(lvb_ba* ba) {
     BaDev& d = ba->dev;
     lvb_ctx* ctx = ba->ctx;
     const size_t chol_smem = (size_t)(32 * 33 + (d.dimc + 34) + (d.dimc + 2) * 34) * 8;
-    LAUNCH(ba, ba_cholesky_kernel, 1, CHOL_T, chol_smem, d.S, d.rhs, d.dimc, d.st, 1);
+    LAUNCH(ba, ba_cholesky_kernel, 1, CHOL_T, chol_smem, d.S, d.rhs, d.dimc, d.st, 1, ba->chol_rmax.p, ba->chol_cmin.p);
     LAUNCH(ba, ba_update_kernel, nblk((size_t)d.n_poses + d.n_vec3 + d.n_rho, TPB), TPB, 0, d);
     LAUNCH(ba, ba_linearize_kernel<1>, ba->ranges.b[3], TPB, ba->lin_smem, d, ba->ranges);
     LAUNCH(ba, ba_linearize_other_kernel<1>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
@@ -1392,7 +1460,10 @@ int lvb_ba_reduced_system(lvb_ba* ba, double radius, double* S, double* b, doubl
     if (b) LVB_CUDA(cudaMemcpyAsync(b, ba->dev.rhs, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     LVB_CUDA(cudaMemcpyAsync(&h, ba->st.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     LVB_CUDA(cudaStreamSynchronize(s));
-    if (S) for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) S[(size_t)i * n + j] = (j <= i) ? hS[(size_t)i * n + j] : hS[(size_t)j * n + i];
+    // hand the system back in the caller-visible order (all poses, then all vec3 blocks)
+    const std::vector<int>& cn = ba->canon;
+    if (S) for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) S[(size_t)cn[i] * n + cn[j]] = (j <= i) ? hS[(size_t)i * n + j] : hS[(size_t)j * n + i];
+    if (b) { std::vector<double> hb(b, b + n); for (int i = 0; i < n; ++i) b[cn[i]] = hb[i]; }
     if (cost) *cost = h.x_cost;
     return LVB_OK;
 }

@@ -57,6 +57,7 @@ struct IcpDev {
     double* nrm;                 // 3 planes
     IcpState* st;
     int rank, world;
+    const int* order;            // query visiting order (spatially sorted) or nullptr
 };
 
 // ---- float ordering helpers for atomic min / max
@@ -227,9 +228,31 @@ __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
     return b;
 }
 
-__global__ void __launch_bounds__(ITPB) icp_knn_kernel(IcpDev d, int* __restrict__ idx_out, float* __restrict__ d2_out) {
-    const int i = blockIdx.x * ITPB + threadIdx.x;
+// Coarse spatial key of a query (blocks of 4x4x4 voxels) so that the lanes of a warp walk the same voxel lists and
+// their 16-byte map loads hit the same L1 lines instead of 32 different L2 sectors.
+__global__ void icp_query_key_kernel(IcpDev d, int cgx, int cgy, int cgz, int* __restrict__ key, int* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.K) return;
+    const float3 q = transform_f32(d.tf, load_xyz(d.scan, i, d.stride));
+    const Grid& g = d.g;
+    const int ix = clampi(cell_coord(q.x, g.minx, g.inv_cell), 0, g.gx - 1) >> 2;
+    const int iy = clampi(cell_coord(q.y, g.miny, g.inv_cell), 0, g.gy - 1) >> 2;
+    const int iz = clampi(cell_coord(q.z, g.minz, g.inv_cell), 0, g.gz - 1) >> 2;
+    const int c = ix + cgx * (iy + cgy * iz);
+    key[i] = c;
+    atomicAdd(&counts[c], 1);
+}
+__global__ void icp_query_scatter_kernel(int n, const int* __restrict__ key, const int* __restrict__ start, int* __restrict__ fill, int* __restrict__ order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = key[i];
+    order[start[c] + atomicAdd(&fill[c], 1)] = i;
+}
+
+__global__ void __launch_bounds__(ITPB) icp_knn_kernel(IcpDev d, int* __restrict__ idx_out, float* __restrict__ d2_out) {
+    const int t = blockIdx.x * ITPB + threadIdx.x;
+    if (t >= d.K) return;
+    const int i = d.order ? d.order[t] : t;
     const float3 q = transform_f32(d.tf, load_xyz(d.scan, i, d.stride));
     const Best3 b = knn3_query(d, q);
     for (int j = 0; j < 3; ++j) { idx_out[3 * i + j] = b.i[j]; d2_out[3 * i + j] = b.d[j]; }
@@ -237,8 +260,9 @@ __global__ void __launch_bounds__(ITPB) icp_knn_kernel(IcpDev d, int* __restrict
 
 // K8: transform + 3-NN + gate (association.cpp:296-300) + plane constants (lidar_error.hpp:13-18)
 __global__ void __launch_bounds__(ITPB) icp_associate_kernel(IcpDev d) {
-    const int i = blockIdx.x * ITPB + threadIdx.x;
-    if (i >= d.K) return;
+    const int t = blockIdx.x * ITPB + threadIdx.x;
+    if (t >= d.K) return;
+    const int i = d.order ? d.order[t] : t;
     const float3 q = transform_f32(d.tf, load_xyz(d.scan, i, d.stride));
     const Best3 b = knn3_query(d, q);
     int ok = 1;
@@ -396,6 +420,7 @@ struct lvb_icp {
     DevBuf<int> knn_idx;
     DevBuf<float> knn_d2;
     DevBuf<IcpState> st;
+    DevBuf<int> q_key, q_counts, q_start, q_fill, q_sums, q_total, q_order;
 };
 
 #define ILAUNCH(h, kernel, grid, block, ...)                                              \
@@ -423,6 +448,22 @@ static int upload_scan(lvb_icp* h, const void* scan, int n, int stride, const do
     d.max_d2 = max_d2; d.thr = thr;
     d.accepted = h->accepted.p; d.pa = h->pa.p; d.nrm = h->nrm.p; d.st = h->st.p;
     d.rank = h->ctx->rank; d.world = h->ctx->world;
+    d.order = nullptr;
+    if (n >= 4096) {       // spatial visiting order: counting sort of the queries by coarse voxel block
+        const Grid& g = h->grid;
+        const int cgx = (g.gx + 3) >> 2, cgy = (g.gy + 3) >> 2, cgz = (g.gz + 3) >> 2;
+        const int nc = cgx * cgy * cgz, nb = (nc + 1023) / 1024;
+        LVB_TRY(h->q_key.ensure(n)); LVB_TRY(h->q_order.ensure(n)); LVB_TRY(h->q_counts.ensure(nc)); LVB_TRY(h->q_fill.ensure(nc));
+        LVB_TRY(h->q_start.ensure((size_t)nc + 1)); LVB_TRY(h->q_sums.ensure(nb)); LVB_TRY(h->q_total.ensure(1));
+        LVB_CUDA(cudaMemsetAsync(h->q_counts.p, 0, (size_t)nc * sizeof(int), s));
+        LVB_CUDA(cudaMemsetAsync(h->q_fill.p, 0, (size_t)nc * sizeof(int), s));
+        ILAUNCH(h, icp_query_key_kernel, (n + 255) / 256, 256, d, cgx, cgy, cgz, h->q_key.p, h->q_counts.p);
+        ILAUNCH(h, scan_block_kernel, nb, 1024, h->q_counts.p, h->q_start.p, nc, h->q_sums.p);
+        ILAUNCH(h, scan_sums_kernel, 1, 1024, h->q_sums.p, nb, h->q_total.p);
+        ILAUNCH(h, scan_add_kernel, nb, 1024, h->q_start.p, nc, h->q_sums.p, h->q_start.p + nc, h->q_total.p);
+        ILAUNCH(h, icp_query_scatter_kernel, (n + 255) / 256, 256, n, h->q_key.p, h->q_start.p, h->q_fill.p, h->q_order.p);
+        d.order = h->q_order.p;
+    }
     return LVB_OK;
 }
 
