@@ -682,119 +682,127 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
     long long t_diag = 0, t_panel = 0, t_trail = 0, t0 = clock64(), tA;
     const long long t_begin = t0;
     __syncthreads();
-    for (int kb = 0; kb < n; kb += 32) {
+    // Software-pipelined over the 32-column block steps with look-ahead: while warps 1.. finish the trailing update
+    // of step kb, warp 0 updates the next diagonal block first (tile 0) and factors it, so the serial shuffle
+    // chain of the diagonal factorisation overlaps the FP64-throughput part.  Iteration kb = -32 only factors block 0.
+    for (int kb = -32; kb < n; kb += 32) {
         const int bs = min(32, n - kb);
-        // ---- diagonal block: warp 0 holds one row per lane in registers and factors it with shuffles
-        if (warp == 0) {
-            double a[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) a[j] = (lane < bs && j <= lane) ? S[(size_t)(kb + lane) * n + kb + j] : ((j == lane) ? 1.0 : 0.0);
-            int bad = 0;
-            double d0 = __shfl_sync(0xffffffffu, a[0], 0);
-            if (!(d0 > 0.0)) { bad = 1; d0 = 1.0; }
-            double inv = rsqrt(d0);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (lane >= j) a[j] *= inv;                       // l_ij (lane j: sqrt(d_jj))
-                if (lane == j) invd[kb + j] = inv;
-                // update column j+1 first and start the next pivot's rsqrt: its latency overlaps the rest of the update
-                double inv_next = 1.0;
-                if (j + 1 < 32) {
-                    const double l1 = __shfl_sync(0xffffffffu, a[j], j + 1);
-                    if (lane >= j + 1) a[j + 1] -= a[j] * l1;
-                    double dn = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
-                    if (!(dn > 0.0)) { bad = 1; dn = 1.0; }
-                    inv_next = rsqrt(dn);
+        int m = 0;
+        if (kb >= 0) {
+            // ---- panel: rows below the block + the rhs row (last):  x L^T = a, right-looking, no divisions
+            // only rows inside the envelope of this block column take part (S is block-banded by construction)
+            m = env_rmax[kb >> 5] - (kb + bs) + 1 + 1;
+            for (int rr = tid; rr < m; rr += nt) {
+                const bool is_rhs = (rr == m - 1);
+                double* src = is_rhs ? (rhs + kb) : (S + (size_t)(kb + bs + rr) * n + kb);
+                double a[32];
+    #pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] = (j < bs) ? src[j] : 0.0;
+    #pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    a[j] *= invd[kb + j];
+    #pragma unroll
+                    for (int k = 0; k < 32; ++k) if (k > j) a[k] -= a[j] * D[k * 33 + j];
                 }
-#pragma unroll
-                for (int k = 0; k < 32; ++k) {                    // constant trip count keeps a[] in registers
-                    if (k > j + 1) {
-                        const double lkj = __shfl_sync(0xffffffffu, a[j], k);
-                        if (lane >= k) a[k] -= a[j] * lkj;
-                    }
-                }
-                inv = inv_next;
+    #pragma unroll
+                for (int j = 0; j < 32; ++j) { P[rr * 34 + j] = a[j]; if (j < bs) src[j] = a[j]; }
             }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                D[lane * 33 + j] = (j <= lane) ? a[j] : 0.0;
-                if (lane < bs && j <= lane && j < bs) S[(size_t)(kb + lane) * n + kb + j] = a[j];
-            }
-            if (bad && lane == 0) fail = 1;
-        }
-        __syncthreads();
-        tA = clock64(); t_diag += tA - t0; t0 = tA;
-        // ---- panel: rows below the block + the rhs row (last):  x L^T = a, right-looking, no divisions
-        // only rows inside the envelope of this block column take part (S is block-banded by construction)
-        const int m = env_rmax[kb >> 5] - (kb + bs) + 1 + 1;
-        for (int rr = tid; rr < m; rr += nt) {
-            const bool is_rhs = (rr == m - 1);
-            double* src = is_rhs ? (rhs + kb) : (S + (size_t)(kb + bs + rr) * n + kb);
-            double a[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) a[j] = (j < bs) ? src[j] : 0.0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                a[j] *= invd[kb + j];
-#pragma unroll
-                for (int k = 0; k < 32; ++k) if (k > j) a[k] -= a[j] * D[k * 33 + j];
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { P[rr * 34 + j] = a[j]; if (j < bs) src[j] = a[j]; }
-        }
-        __syncthreads();
-        tA = clock64(); t_panel += tA - t0; t0 = tA;
-        // ---- trailing update A22 -= P P^T on the lower triangle.  One warp per 32x32 tile, each lane a 4x8
-        // register micro-tile (rows ry+8i, columns cx+4j: consecutive lanes touch consecutive panel rows, so the
-        // LDS.128 operand loads are bank-conflict free and every loaded value feeds 4 or 8 DFMAs).
-        const int ntile = (m + 31) >> 5;
-        const int total = ntile * (ntile + 1) / 2;
-        for (int t = warp; t < total; t += nw) {
-            int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-            while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-            while (ti * (ti + 1) / 2 > t) --ti;
-            const int tj = t - ti * (ti + 1) / 2;
-            const int ry = lane >> 2, cx = lane & 3;
-            const int r0 = ti * 32 + ry, c0 = tj * 32 + cx;
-            double acc[4][8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
-            // rows / columns beyond the panel read row 0 (valid memory) and are masked at the store
-            const double2* rp[4]; const double2* cp[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rp[i] = reinterpret_cast<const double2*>(P + (size_t)min(r0 + 8 * i, m - 1) * 34);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cp[j] = reinterpret_cast<const double2*>(P + (size_t)min(c0 + 4 * j, m - 1) * 34);
-#pragma unroll 2
-            for (int k = 0; k < 16; ++k) {
-                double2 rv[4], cv[8];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) rv[i] = rp[i][k];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) cv[j] = cp[j][k];
-#pragma unroll
+            __syncthreads();
+            tA = clock64(); t_panel += tA - t0; t0 = tA;
+            // ---- trailing update A22 -= P P^T on the lower triangle.  One warp per 32x32 tile, each lane a 4x8
+            // register micro-tile (rows ry+8i, columns cx+4j: consecutive lanes touch consecutive panel rows, so the
+            // LDS.128 operand loads are bank-conflict free and every loaded value feeds 4 or 8 DFMAs).
+            const int ntile = (m + 31) >> 5;
+            const int total = ntile * (ntile + 1) / 2;
+            for (int t = (warp == 0) ? 0 : warp; t < total; t += (warp == 0) ? total : (nw - 1)) {
+                int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+                while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+                while (ti * (ti + 1) / 2 > t) --ti;
+                const int tj = t - ti * (ti + 1) / 2;
+                const int ry = lane >> 2, cx = lane & 3;
+                const int r0 = ti * 32 + ry, c0 = tj * 32 + cx;
+                double acc[4][8];
+    #pragma unroll
                 for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { acc[i][j] += rv[i].x * cv[j].x; acc[i][j] += rv[i].y * cv[j].y; }
+    #pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+                // rows / columns beyond the panel read row 0 (valid memory) and are masked at the store
+                const double2* rp[4]; const double2* cp[8];
+    #pragma unroll
+                for (int i = 0; i < 4; ++i) rp[i] = reinterpret_cast<const double2*>(P + (size_t)min(r0 + 8 * i, m - 1) * 34);
+    #pragma unroll
+                for (int j = 0; j < 8; ++j) cp[j] = reinterpret_cast<const double2*>(P + (size_t)min(c0 + 4 * j, m - 1) * 34);
+    #pragma unroll 2
+                for (int k = 0; k < 16; ++k) {
+                    double2 rv[4], cv[8];
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i) rv[i] = rp[i][k];
+    #pragma unroll
+                    for (int j = 0; j < 8; ++j) cv[j] = cp[j][k];
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i)
+    #pragma unroll
+                        for (int j = 0; j < 8; ++j) { acc[i][j] += rv[i].x * cv[j].x; acc[i][j] += rv[i].y * cv[j].y; }
+                }
+                // read-modify-write of the tile: all loads first (one round trip), then the stores
+                double cur[4][8];
+    #pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ip = min(r0 + 8 * i, m - 1);
+                    const double* src = (ip == m - 1) ? (rhs + kb + bs) : (S + (size_t)(kb + bs + ip) * n + kb + bs);
+    #pragma unroll
+                    for (int j = 0; j < 8; ++j) { const int jp = c0 + 4 * j; cur[i][j] = (r0 + 8 * i < m && jp < m - 1 && jp <= ip) ? src[jp] : 0.0; }
+                }
+    #pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ip = r0 + 8 * i;
+                    if (ip >= m) continue;
+                    double* dst = (ip == m - 1) ? (rhs + kb + bs) : (S + (size_t)(kb + bs + ip) * n + kb + bs);
+    #pragma unroll
+                    for (int j = 0; j < 8; ++j) { const int jp = c0 + 4 * j; if (jp < m - 1 && jp <= ip) dst[jp] = cur[i][j] - acc[i][j]; }
+                }
             }
-            // read-modify-write of the tile: all loads first (one round trip), then the stores
-            double cur[4][8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int ip = min(r0 + 8 * i, m - 1);
-                const double* src = (ip == m - 1) ? (rhs + kb + bs) : (S + (size_t)(kb + bs + ip) * n + kb + bs);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { const int jp = c0 + 4 * j; cur[i][j] = (r0 + 8 * i < m && jp < m - 1 && jp <= ip) ? src[jp] : 0.0; }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int ip = r0 + 8 * i;
-                if (ip >= m) continue;
-                double* dst = (ip == m - 1) ? (rhs + kb + bs) : (S + (size_t)(kb + bs + ip) * n + kb + bs);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { const int jp = c0 + 4 * j; if (jp < m - 1 && jp <= ip) dst[jp] = cur[i][j] - acc[i][j]; }
+        }
+        const int kn = kb + 32, bn = min(32, n - kn);
+        // ---- diagonal block kn: warp 0 holds one row per lane in registers and factors it with shuffles
+        if (kn < n) {
+            __syncwarp();
+            if (warp == 0) {
+                double a[32];
+    #pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] = (lane < bn && j <= lane) ? S[(size_t)(kn + lane) * n + kn + j] : ((j == lane) ? 1.0 : 0.0);
+                int bad = 0;
+                double d0 = __shfl_sync(0xffffffffu, a[0], 0);
+                if (!(d0 > 0.0)) { bad = 1; d0 = 1.0; }
+                double inv = rsqrt(d0);
+    #pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (lane >= j) a[j] *= inv;                       // l_ij (lane j: sqrt(d_jj))
+                    if (lane == j) invd[kn + j] = inv;
+                    // update column j+1 first and start the next pivot's rsqrt: its latency overlaps the rest of the update
+                    double inv_next = 1.0;
+                    if (j + 1 < 32) {
+                        const double l1 = __shfl_sync(0xffffffffu, a[j], j + 1);
+                        if (lane >= j + 1) a[j + 1] -= a[j] * l1;
+                        double dn = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
+                        if (!(dn > 0.0)) { bad = 1; dn = 1.0; }
+                        inv_next = rsqrt(dn);
+                    }
+    #pragma unroll
+                    for (int k = 0; k < 32; ++k) {                    // constant trip count keeps a[] in registers
+                        if (k > j + 1) {
+                            const double lkj = __shfl_sync(0xffffffffu, a[j], k);
+                            if (lane >= k) a[k] -= a[j] * lkj;
+                        }
+                    }
+                    inv = inv_next;
+                }
+    #pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    D[lane * 33 + j] = (j <= lane) ? a[j] : 0.0;
+                    if (lane < bn && j <= lane && j < bn) S[(size_t)(kn + lane) * n + kn + j] = a[j];
+                }
+                if (bad && lane == 0) fail = 1;
             }
         }
         __syncthreads();
@@ -955,6 +963,7 @@ struct lvb_ba {
     int n_schur_warps = 0, schur_cols_max = 0;
     size_t schur_smem = 0, lin_smem = 0;
     cudaGraphExec_t pass_graph = nullptr;
+    bool imu_checked = true;
     int solves_done = 0;
     DevBuf<double> fc[6];
     DevBuf<int> fi[6];
@@ -1232,8 +1241,9 @@ int lvb_ba_finalize(lvb_ba* ba) {
     LVB_TRY(ba->chol_cmin.upload(chol_cmin.data(), chol_cmin.size(), s));
 
     // factor planes in device order (AoS -> SoA transpose on the host; IMU stays AoS and is packed on the device)
-    std::vector<double> planes; std::vector<int> iplanes;
+    std::vector<double> planes_k[6]; std::vector<int> iplanes_k[6];      // kept alive until the single sync below
     for (int k = 0; k < 6; ++k) {
+        std::vector<double>& planes = planes_k[k]; std::vector<int>& iplanes = iplanes_k[k];
         const int n = ba->nd[k];
         const std::vector<int>& ord = ba->order[k];
         iplanes.assign((size_t)std::max(1, n) * kIdxStride[k], 0);
@@ -1247,10 +1257,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
                 imu_prepare_kernel<<<nblk(n, 64), 64, 0, s>>>(ba->imu_raw.p, ba->fc[3].p, n, ba->imu_status.p);
                 ctx->launches++;
                 LVB_TRY(check_launch("imu_prepare"));
-                std::vector<int> status(n);
-                LVB_TRY(ba->imu_status.download(status.data(), n, s));
-                LVB_CUDA(cudaStreamSynchronize(s));
-                for (int f = 0; f < n; ++f) if (status[f]) { set_error("ImuError %d: covariance inverse is not SPD (code %d)", f, status[f]); return LVB_ERR_NUMERIC; }
+                ba->imu_checked = false;      // status is read back with the first solve / eval (no extra round trip here)
             }
             continue;
         }
@@ -1261,7 +1268,6 @@ int lvb_ba_finalize(lvb_ba* ba) {
             for (int j = 0; j < kConstStride[k]; ++j) planes[(size_t)j * n + i] = (pad && j == wcol) ? 0.0 : ba->h_fc[k][(size_t)f * kConstStride[k] + j];
         }
         LVB_TRY(ba->fc[k].upload(planes.data(), planes.size(), s));
-        LVB_CUDA(cudaStreamSynchronize(s));   // planes is reused
     }
     LVB_CUDA(cudaStreamSynchronize(s));
 
@@ -1327,6 +1333,16 @@ int lvb_ba_update_params(lvb_ba* ba, const double* P, const double* V, const dou
     return LVB_OK;
 }
 
+static int check_imu_status(lvb_ba* ba) {
+    if (ba->imu_checked || ba->nd[3] == 0) { ba->imu_checked = true; return LVB_OK; }
+    std::vector<int> status(ba->nd[3]);
+    LVB_TRY(ba->imu_status.download(status.data(), status.size(), ba->ctx->stream));
+    LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream));
+    for (size_t f = 0; f < status.size(); ++f) if (status[f]) { set_error("ImuError %d: covariance inverse is not SPD (code %d)", (int)f, status[f]); return LVB_ERR_NUMERIC; }
+    ba->imu_checked = true;
+    return LVB_OK;
+}
+
 static int launch_eval(lvb_ba* ba, int kind, double* r_dev, double* J_dev) {
     const int n = ba->nd[kind];
     if (n == 0) return LVB_OK;
@@ -1354,6 +1370,7 @@ int lvb_ba_eval(lvb_ba* ba, int kind, double* r, double* J) {
     if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
     if (kind < 0 || kind >= 6) { set_error("bad kind"); return LVB_ERR_INVALID; }
     LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
+    LVB_TRY(check_imu_status(ba));
     LVB_TRY(ensure_eval_buffers(ba, kind));
     LVB_TRY(launch_eval(ba, kind, ba->eval_r.p, ba->eval_J.p));
     const size_t nd = ba->nd[kind], rd = kResDim[kind], jd = (size_t)kResDim[kind] * kJacCols[kind];
@@ -1443,7 +1460,7 @@ static int upload_state(lvb_ba* ba, const lvb_solve_options* o, double radius_ov
 static int require_solvable(lvb_ba* ba) {
     if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
     if (!ba->solvable) { set_error("camera system dimension %d is outside the dense solver range (1..%d) of this build", ba->dimc, (int)MAX_DIMC); return LVB_ERR_UNSUPPORTED; }
-    return LVB_OK;
+    return check_imu_status(ba);
 }
 
 int lvb_ba_reduced_system(lvb_ba* ba, double radius, double* S, double* b, double* cost) {
