@@ -156,6 +156,10 @@ LVB_API int lvb_ba_reduced_system(lvb_ba* ba, double radius, double* S, double* 
 
 /* ceres::Solve(options, &problem, &summary) (adapt/problem.h:83-88). Parameters are updated
  * on the device; fetch them with the getters (the shim writes them back in place). */
+/* Default Schur mode of the handle (used by lvb_ba_reduced_system and by lvb_ba_solve(options == NULL)): 0 = FP64
+ * CUDA-core elimination (parity reference), 1 = tcgen05 split-bf16 contraction with FP32 accumulation in TMEM, taken
+ * only when 6 x (free poses) <= 128 on a single GPU, else the handle silently stays on mode 0. */
+LVB_API int lvb_ba_set_schur_mode(lvb_ba* ba, int mode);
 LVB_API int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary* summary);
 LVB_API int lvb_ba_get_poses(lvb_ba* ba, double* poses7);
 LVB_API int lvb_ba_get_vec3(lvb_ba* ba, double* v3);

@@ -142,6 +142,10 @@ class Problem:
     def set_loss(self, kind, huber_a):
         self.api.check(self.api.ba_set_loss(self.h, kind, float(huber_a)), "ba_set_loss")
 
+    def set_schur_mode(self, mode):
+        """0 = FP64 Schur (parity reference), 1 = tcgen05 split-bf16 tensor-core Schur (CUDA library only)."""
+        self.api.check(self.api.ba_set_schur_mode(self.h, int(mode)), "ba_set_schur_mode")
+
     def finalize(self):
         self.api.check(self.api.ba_finalize(self.h), "ba_finalize")
 

@@ -20,6 +20,7 @@
 #include <chrono>
 #include <map>
 #include <string.h>
+#include <cuda_bf16.h>
 #include "lvb_internal.cuh"
 #include "lvb_math.cuh"
 
@@ -45,6 +46,11 @@ struct BaDev {
     const int *tf_slot;                 // 2 planes: slot of pose_1 / pose_2 inside the landmark's Schur group (-1: constant pose)
     const int *sw_group, *sw_lm, *grp_ns, *grp_off;   // Schur warps: group id, 32 landmark ids (-1 pad); per group: #slots, offsets
     int n_schur_warps, warp_syrk;
+    int tc_mode;                        // 1: Schur contraction on the tensor cores (tcgen05, split bf16), FP64 rhs only here
+    unsigned short* tc_u;               // packed U^T: [chunk of 16 landmarks][3 splits][128 x 16 bf16 UMMA K-major tile]
+    const int* tc_cdim;                 // camera offset -> compact pose dimension (0..127) or -1
+    const int* tc_off;                  // compact pose dimension -> camera offset
+    int tc_ndim;                        // 6 * free poses (<= 128)
     double *Hpp, *gc, *Hll, *gl, *tf_w;
     double *S, *rhs, *gcr, *diagH, *scal;      // inside the arena
     double *scale_c, *scale_l, *lam_c, *lam_l;
@@ -598,6 +604,33 @@ __global__ void __launch_bounds__(TPB) ba_schur_kernel(BaDev d, int cols_max) {
     }
     __syncwarp();
     const int* offs = d.grp_off + (size_t)g * MAX_TRACK;
+    if (d.tc_mode) {
+        // tensor-core mode: this warp only (a) adds its rhs column  sum_l u_l g_l / h_l  in FP64 and (b) writes its 32
+        // rows of U as three bf16 planes (x ~ hi + mid + lo, 24 mantissa bits) into the UMMA K-major tiles of its two
+        // 16-landmark chunks.  Positions outside the group's pose set were zeroed once at finalize and never change.
+        for (int b = lane; b < ncol - 1; b += 32) {
+            double v = 0.0;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) v += U[r * ncol + ncol - 1] * U[r * ncol + b];
+            if (v != 0.0) atomicAdd(&d.rhs[offs[b / 6] + b % 6], v);
+        }
+        const size_t chunk = (size_t)w * 2 + (lane >> 4);
+        const int k = lane & 15;
+        unsigned short* tile = d.tc_u + chunk * (3 * 2048);       // 2048 bf16 = 4096 B per split tile
+        for (int b = 0; b < ncol - 1; ++b) {
+            const int r = d.tc_cdim[offs[b / 6]] + b % 6;         // compact pose dimension of this column
+            const double x = row[b];
+            const __nv_bfloat16 hi = __float2bfloat16_rn((float)x);
+            const double r1 = x - (double)__bfloat162float(hi);
+            const __nv_bfloat16 mid = __float2bfloat16_rn((float)r1);
+            const double r2 = r1 - (double)__bfloat162float(mid);
+            const __nv_bfloat16 lo = __float2bfloat16_rn((float)r2);
+            // canonical no-swizzle K-major tile: 8x16B core matrices, SBO = 256 B between 8-row groups, LBO = 128 B
+            const int e = (r >> 3) * 128 + (k >> 3) * 64 + (r & 7) * 8 + (k & 7);
+            tile[e] = __bfloat16_as_ushort(hi); tile[2048 + e] = __bfloat16_as_ushort(mid); tile[4096 + e] = __bfloat16_as_ushort(lo);
+        }
+        return;
+    }
     const int nent = ncol * (ncol + 1) / 2 - 1;                   // the (v,v) corner is not needed
     for (int e = lane; e < nent; e += 32) {
         int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
@@ -613,6 +646,92 @@ __global__ void __launch_bounds__(TPB) ba_schur_kernel(BaDev d, int cols_max) {
         const int ga = offs[a / 6] + a % 6;
         if (ga >= gb) atomicAdd(&d.S[(size_t)ga * d.dimc + gb], -v); else atomicAdd(&d.S[(size_t)gb * d.dimc + ga], -v);
     }
+}
+
+// K5 on the tensor cores.  S_pose -= U^T U with U^T staged as bf16 split planes (hi, mid, lo); per 16-landmark chunk six
+// 128x128x16 UMMAs (hi.hi, hi.mid, mid.hi, mid.mid, hi.lo, lo.hi) accumulate in FP32 in TMEM, which keeps ~2^-23 of each
+// product; one CTA owns TC_CHUNKS chunks (a 256-landmark slice of K), so the FP32 accumulation stays short and the
+// cross-CTA sum happens in FP64 (red.global.add.f64 on the lower triangle).  The FP64 kernel above remains the parity
+// reference; this path is selected with lvb_solve_options.schur_mode = 1 when 6 * (free poses) <= 128.
+enum { TC_CHUNKS = 16, TC_TILE_BYTES = 4096, TC_CHUNK_BYTES = 3 * TC_TILE_BYTES };
+
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start >> 4 [0,14) | LBO >> 4 [16,30) | SBO >> 4 [32,46) | version 1 [46,48)
+    // | layout_type SWIZZLE_NONE (0) [61,64).  K-major canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units.
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __launch_bounds__(128) ba_schur_tc_kernel(BaDev d, int n_chunks) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar_load, bar_mma;
+    __shared__ uint32_t tmem_base_slot;
+    if (d.st->done) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c0 = blockIdx.x * TC_CHUNKS;
+    const int nc = min(TC_CHUNKS, n_chunks - c0);
+    if (tid == 0) { mbar_init(&bar_load, 1); mbar_init(&bar_mma, 1); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;
+    if (tid == 0) {
+        // TMA 1-D bulk copies of this CTA's chunks (contiguous in HBM), one mbarrier transaction
+        mbar_expect_tx(&bar_load, (uint32_t)nc * TC_CHUNK_BYTES);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(d.tc_u) + (size_t)c0 * TC_CHUNK_BYTES;
+        for (int c = 0; c < nc; ++c) bulk_load_1d(smem_raw + (size_t)c * TC_CHUNK_BYTES, src + (size_t)c * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &bar_load);
+        mbar_wait(&bar_load, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // InstrDescriptor: D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), both K-major, N = 128 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t base = smem_u32(smem_raw);
+        uint32_t acc = 0;
+        for (int c = 0; c < nc; ++c) {
+            const uint64_t hi = umma_smem_desc(base + c * TC_CHUNK_BYTES), mid = umma_smem_desc(base + c * TC_CHUNK_BYTES + TC_TILE_BYTES),
+                           lo = umma_smem_desc(base + c * TC_CHUNK_BYTES + 2 * TC_TILE_BYTES);
+            umma_bf16_ss(tmem_d, hi, hi, idesc, acc); acc = 1;
+            umma_bf16_ss(tmem_d, hi, mid, idesc, 1); umma_bf16_ss(tmem_d, mid, hi, idesc, 1);
+            umma_bf16_ss(tmem_d, mid, mid, idesc, 1);
+            umma_bf16_ss(tmem_d, hi, lo, idesc, 1); umma_bf16_ss(tmem_d, lo, hi, idesc, 1);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_mma)) : "memory");
+    }
+    // epilogue: thread t owns accumulator row t (TMEM lane t): FP32 -> FP64, subtract from the lower triangle of S
+    mbar_wait(&bar_mma, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int a = tid;
+    const int ga = a < d.tc_ndim ? d.tc_off[a] : -1;
+    for (int cb = 0; cb < 128; cb += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+                       "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                     : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (ga >= 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int b = cb + j;
+                if (b > a || b >= d.tc_ndim) continue;              // lower triangle in compact order
+                const float f = __uint_as_float(v[j]);
+                if (f == 0.0f) continue;
+                const int gb = d.tc_off[b];
+                if (ga >= gb) atomicAdd(&d.S[(size_t)ga * d.dimc + gb], -(double)f); else atomicAdd(&d.S[(size_t)gb * d.dimc + ga], -(double)f);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(128) : "memory");
 }
 
 __global__ void ba_pack_scalars_kernel(BaDev d) {
@@ -964,6 +1083,9 @@ struct lvb_ba {
     size_t schur_smem = 0, lin_smem = 0;
     cudaGraphExec_t pass_graph = nullptr;
     bool imu_checked = true;
+    // tensor-core Schur (schur_mode 1)
+    bool tc_ok = false; int schur_mode = 0, graph_mode = -1, n_tc_chunks = 0;
+    DevBuf<unsigned short> tc_u; DevBuf<int> tc_cdim, tc_off;
     int solves_done = 0;
     DevBuf<double> fc[6];
     DevBuf<int> fi[6];
@@ -993,6 +1115,7 @@ static int init_tables() {
     LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (TPB * 31 + MAX_STAGE_POSES * 7 + 2) * 8));
     LVB_CUDA(cudaFuncSetAttribute(ba_linearize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     LVB_CUDA(cudaFuncSetAttribute(ba_linearize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    LVB_CUDA(cudaFuncSetAttribute(ba_schur_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_CHUNKS * TC_CHUNK_BYTES));
     LVB_CUDA(cudaFuncSetAttribute(ba_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (TPB / 32) * 32 * (6 * MAX_TRACK + 1) * 8));
     g_tables_ready = true;
     return LVB_OK;
@@ -1239,6 +1362,18 @@ int lvb_ba_finalize(lvb_ba* ba) {
     LVB_TRY(ba->grp_off.upload(grp_off.data(), grp_off.size(), s));
     LVB_TRY(ba->chol_rmax.upload(chol_rmax.data(), chol_rmax.size(), s));
     LVB_TRY(ba->chol_cmin.upload(chol_cmin.data(), chol_cmin.size(), s));
+    // tensor-core Schur operands: compact pose dimensions (<= 128) and the zero-initialised split-bf16 U^T tiles
+    ba->tc_ok = ba->solvable && 6 * npf <= 128 && npf > 0 && ctx->world == 1;
+    {
+        std::vector<int> cdim(std::max(1, ba->dimc), -1), coff(128, -1);
+        int c = 0;
+        for (size_t b = 0; b < blks.size(); ++b) if (blks[b].type == 0 && c + 6 <= 128) { for (int k = 0; k < 6; ++k) { cdim[blk_start[b] + k] = c + k; coff[c + k] = blk_start[b] + k; } c += 6; }
+        LVB_TRY(ba->tc_cdim.upload(cdim.data(), cdim.size(), s));
+        LVB_TRY(ba->tc_off.upload(coff.data(), coff.size(), s));
+        ba->n_tc_chunks = ba->tc_ok ? ((2 * ba->n_schur_warps + TC_CHUNKS - 1) / TC_CHUNKS) * TC_CHUNKS : 0;
+        LVB_TRY(ba->tc_u.ensure((size_t)std::max(1, ba->n_tc_chunks) * 3 * 2048));
+        LVB_CUDA(cudaMemsetAsync(ba->tc_u.p, 0, (size_t)std::max(1, ba->n_tc_chunks) * 3 * 2048 * sizeof(unsigned short), s));
+    }
 
     // factor planes in device order (AoS -> SoA transpose on the host; IMU stays AoS and is packed on the device)
     std::vector<double> planes_k[6]; std::vector<int> iplanes_k[6];      // kept alive until the single sync below
@@ -1288,6 +1423,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
     d.lm_start = ba->lm_start.p; d.lm_fac = ba->lm_fac.p;
     d.tf_slot = ba->tf_slot.p; d.sw_group = ba->sw_group.p; d.sw_lm = ba->sw_lm.p; d.grp_ns = ba->grp_ns.p; d.grp_off = ba->grp_off.p;
     d.n_schur_warps = ba->n_schur_warps; d.warp_syrk = ba->solvable ? 1 : 0;
+    d.tc_mode = 0; d.tc_u = ba->tc_u.p; d.tc_cdim = ba->tc_cdim.p; d.tc_off = ba->tc_off.p; d.tc_ndim = 6 * npf;
     d.Hpp = ba->Hpp.p; d.gc = ba->gc.p; d.Hll = ba->Hll.p; d.gl = ba->gl.p; d.tf_w = ba->tf_w.p;
     d.S = ba->arena.p; d.rhs = d.S + nH; d.gcr = d.rhs + ba->dimc; d.diagH = d.gcr + ba->dimc; d.scal = d.diagH + ba->dimc;
     d.scale_c = ba->scale_c.p; d.scale_l = ba->scale_l.p; d.lam_c = ba->lam_c.p; d.lam_l = ba->lam_l.p;
@@ -1416,6 +1552,7 @@ static int launch_linearize_and_reduce(lvb_ba* ba, bool standalone) {
     LAUNCH(ba, ba_linearize_other_kernel<0>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
     LAUNCH(ba, ba_build_S_kernel, std::min(1024, nblk(nH, 256)), 256, 0, d);
     LAUNCH(ba, ba_schur_kernel, nblk(d.n_schur_warps, TPB / 32), TPB, ba->schur_smem, d, std::max(1, ba->schur_cols_max));
+    if (d.tc_mode) LAUNCH(ba, ba_schur_tc_kernel, ba->n_tc_chunks / TC_CHUNKS, 128, (size_t)TC_CHUNKS * TC_CHUNK_BYTES, d, ba->n_tc_chunks);
     if (ctx->world > 1) {
         LAUNCH(ba, ba_pack_scalars_kernel, 1, 1, 0, d);
         LVB_TRY(comm_allreduce_sum_f64(ctx, d.S, nH + 3 * (size_t)d.dimc + 16));
@@ -1457,6 +1594,13 @@ static int upload_state(lvb_ba* ba, const lvb_solve_options* o, double radius_ov
     return LVB_OK;
 }
 
+static void apply_schur_mode(lvb_ba* ba, int mode) {
+    const int m = (mode == 1 && ba->tc_ok) ? 1 : 0;
+    ba->dev.tc_mode = m;
+    if (ba->pass_graph && ba->graph_mode != m) { cudaGraphExecDestroy(ba->pass_graph); ba->pass_graph = nullptr; }
+    ba->graph_mode = m;
+}
+
 static int require_solvable(lvb_ba* ba) {
     if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
     if (!ba->solvable) { set_error("camera system dimension %d is outside the dense solver range (1..%d) of this build", ba->dimc, (int)MAX_DIMC); return LVB_ERR_UNSUPPORTED; }
@@ -1466,6 +1610,7 @@ static int require_solvable(lvb_ba* ba) {
 int lvb_ba_reduced_system(lvb_ba* ba, double radius, double* S, double* b, double* cost) {
     LVB_TRY(require_solvable(ba));
     LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
+    apply_schur_mode(ba, ba->schur_mode);
     LVB_TRY(upload_state(ba, nullptr, radius));
     LVB_TRY(launch_clear(ba));
     LVB_TRY(launch_linearize_and_reduce(ba, true));
@@ -1491,6 +1636,7 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
     const auto t0 = std::chrono::steady_clock::now();
     lvb_solve_options opt;
     if (options) opt = *options; else lvb_default_options(&opt);
+    apply_schur_mode(ba, options ? opt.schur_mode : ba->schur_mode);
     LVB_TRY(upload_state(ba, &opt, -1.0));
     cudaStream_t s = ba->ctx->stream;
     LmState h;
@@ -1522,10 +1668,10 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
             ce = cudaGraphInstantiate(&ba->pass_graph, g, 0);
             cudaGraphDestroy(g);
             LVB_CUDA(ce);
-            ba->ctx->launches -= 10;      // capture is not execution
+            ba->ctx->launches -= 10 + ba->dev.tc_mode;      // capture is not execution
         }
         for (int c = 0; c < chunk; ++c) {
-            if (use_graph) { LVB_CUDA(cudaGraphLaunch(ba->pass_graph, s)); ba->ctx->launches += 10; }
+            if (use_graph) { LVB_CUDA(cudaGraphLaunch(ba->pass_graph, s)); ba->ctx->launches += 10 + ba->dev.tc_mode; }
             else { LVB_TRY(launch_linearize_and_reduce(ba, false)); LVB_TRY(launch_step(ba)); }
         }
         pass += chunk;
@@ -1545,6 +1691,12 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
         summary->total_time_in_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
     if (h.termination == 2) { set_error("LM failed: %d consecutive invalid steps", h.invalid); }
+    return LVB_OK;
+}
+
+int lvb_ba_set_schur_mode(lvb_ba* ba, int mode) {
+    if (mode != 0 && mode != 1) { set_error("schur_mode must be 0 (FP64) or 1 (tcgen05)"); return LVB_ERR_INVALID; }
+    ba->schur_mode = mode;
     return LVB_OK;
 }
 
