@@ -55,9 +55,12 @@ enum lvb_factor_kind {
     LVB_TWO_CAMERA = 2, /* TwoCameraReprojectionError ceres/visual_error.hpp:109-137 <2,1>
                            consts[5] = left_ob.xy right_ob.xy weight ; idx[1] = inv_depth */
     LVB_IMU = 3,        /* ImuError                   ceres/imu_error.hpp:12-122     <15,7,3,3,3,7,3,3,3>
-                           consts[467] = delta_p[3] delta_q[4 xyzw] delta_v[3] linearized_ba[3]
+                           consts[469] = delta_p[3] delta_q[4 xyzw] delta_v[3] linearized_ba[3]
                            linearized_bg[3] sum_dt jacobian[15x15 rm] covariance[15x15 rm]
-                           (imu/preintegration.h:66-80) ;
+                           (imu/preintegration.h:66-80) prior_a prior_g ;
+                           prior_a = prior_g = -1 : ImuError.  Both >= 0 : ImuInitError (ceres/imu_error.hpp:124-229,
+                           <15,7,3,3,3,7,3>, imu::FullBA tools.cpp:138-162): idx[6] = idx[7] = -1, Baj = Bgj = 0, the
+                           bias blocks of cov^-1 are replaced by prior * I before the LLT ;
                            idx[8] = pose_i v_i ba_i bg_i pose_j v_j ba_j bg_j (v/ba/bg index the vec3 blocks) */
     LVB_POSE_GRAPH = 4, /* PoseGraphError             ceres/pose_error.hpp:10-53     <6,7,7>
                            consts[8] = rpyxyz_[6] weight v ; idx[2] = pose_1 pose_2 */
@@ -183,6 +186,10 @@ LVB_API int lvb_icp_set_map(lvb_icp* icp, const void* points, int n, int stride_
  * idx = -1, d2 = +inf.  idx, d2 are n x 3. */
 LVB_API int lvb_icp_knn3(lvb_icp* icp, const void* scan, int n, int stride_bytes, const double frame_pose[7],
                  float max_d2, int32_t* idx, float* d2);
+/* Mapping::MergeScan / ToWorld (mapping.cpp:193-220): out[i].xyz = float32 SE3 transform of points[i].xyz with
+ * pose.cast<float>() (same arithmetic as the query transform of association.cpp:294); the remaining bytes of each
+ * record (intensity, padding) are copied.  points and out are n records of stride_bytes. */
+LVB_API int lvb_icp_transform_cloud(lvb_icp* icp, const void* points, int n, int stride_bytes, const double pose[7], void* out);
 /* Per scan point: the gate of association.cpp:296-300 and, for accepted points, the raw
  * LidarPlaneErrorRPZ (mode 0) / LidarPlaneErrorYXY (mode 1) residual and 1x3 Jacobian
  * (ceres/lidar_error.hpp:42-110) at rpyxyz.  Rejected rows are zero.  Parity entry. */

@@ -277,7 +277,10 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
         const lvb::DeviceCost* dc = static_cast<const lvb::DeviceCost*>(rb->cost);
         const int k = dc->kind();
         consts[k].insert(consts[k].end(), dc->consts().begin(), dc->consts().end());
-        for (double* b : rb->blocks) idx[k].push_back(index[b]);
+        static const int nidx_k[LVB_NUM_KINDS] = {3, 1, 1, 8, 2, 1};
+        int added = 0;
+        for (double* b : rb->blocks) { idx[k].push_back(index[b]); ++added; }
+        for (; added < nidx_k[k]; ++added) idx[k].push_back(-1);     // ImuInitError has no ba_j / bg_j blocks
         const double a = rb->loss ? rb->loss->huber_a() : 0.0;
         if (loss_set[k] && a != huber[k]) return fail("blocks of one factor kind must share their loss function on the device path");
         huber[k] = a; loss_set[k] = true;

@@ -54,7 +54,8 @@ class ImuError {
 public:
     template <class PreintegrationPtr>
     static ceres::CostFunction* Create(PreintegrationPtr pre, bool matrices_are_column_major = true) {
-        std::vector<double> c(467);
+        std::vector<double> c(469);
+        c[467] = c[468] = -1.0;
         const double* dp = pre->delta_p.data(); const double* dq = pre->delta_q.coeffs().data(); const double* dv = pre->delta_v.data();
         const double* ba = pre->linearized_ba.data(); const double* bg = pre->linearized_bg.data();
         for (int i = 0; i < 3; ++i) { c[i] = dp[i]; c[7 + i] = dv[i]; c[10 + i] = ba[i]; c[13 + i] = bg[i]; }
@@ -66,6 +67,19 @@ public:
             c[17 + i * 15 + j] = J[src]; c[242 + i * 15 + j] = C[src];
         }
         return new lvb::DeviceCost(LVB_IMU, 15, {7, 3, 3, 3, 7, 3, 3, 3}, std::move(c));
+    }
+};
+
+// imu_error.hpp:124-229    SizedCostFunction<15, 7,3,3,3, 7,3>  (imu::FullBA, tools.cpp:138-162: ba / bg are one shared block)
+class ImuInitError {
+public:
+    template <class PreintegrationPtr>
+    static ceres::CostFunction* Create(PreintegrationPtr pre, double prior_a, double prior_g, bool matrices_are_column_major = true) {
+        lvb::DeviceCost* base = static_cast<lvb::DeviceCost*>(ImuError::Create(pre, matrices_are_column_major));
+        std::vector<double> c = base->consts();
+        delete base;
+        c[467] = prior_a; c[468] = prior_g;
+        return new lvb::DeviceCost(LVB_IMU, 15, {7, 3, 3, 3, 7, 3}, std::move(c));
     }
 };
 

@@ -84,6 +84,7 @@ _SIGS = {
     "icp_create": (C.c_int, [VP, C.POINTER(VP)]),
     "icp_destroy": (None, [VP]),
     "icp_set_map": (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_float]),
+    "icp_transform_cloud": (C.c_int, [VP, VP, C.c_int, C.c_int, c_double_p, VP]),
     "icp_knn3": (C.c_int, [VP, VP, C.c_int, C.c_int, c_double_p, C.c_float, c_int32_p, c_float_p]),
     "icp_eval": (C.c_int, [VP, C.c_int, VP, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
                            C.c_double, C.c_double, c_uint8_p, c_double_p, c_double_p]),

@@ -23,7 +23,7 @@ from ._capi import SolveOptions, SolveSummary
 TWO_FRAME, POSE_ONLY, TWO_CAMERA, IMU, POSE_GRAPH, POSE_PRIOR = range(6)
 KIND_NAMES = ["TwoFrameReprojectionError", "PoseOnlyReprojectionError", "TwoCameraReprojectionError",
               "ImuError", "PoseGraphError", "PoseError"]
-CONST_STRIDE = [5, 6, 5, 467, 8, 9]
+CONST_STRIDE = [5, 6, 5, 469, 8, 9]
 IDX_STRIDE = [3, 1, 1, 8, 2, 1]
 RES_DIM = [2, 2, 2, 15, 6, 6]
 JAC_COLS = [15, 7, 1, 32, 14, 7]
@@ -260,6 +260,14 @@ class FeatureAssociation:
         pts, n, stride = self._cloud(points)
         self._map_keepalive = pts
         self.api.check(self.api.icp_set_map(self.h, pts.ctypes.data_as(C.c_void_p), n, stride, float(cell_size)), "icp_set_map")
+
+    def transform_cloud(self, points, pose):
+        """Mapping::MergeScan (mapping.cpp:193-203): float32 SE3 transform of a cloud, other fields carried over."""
+        pts, n, stride = self._cloud(points)
+        out = np.empty_like(pts)
+        p = _f64(pose).reshape(7)
+        self.api.check(self.api.icp_transform_cloud(self.h, pts.ctypes.data_as(C.c_void_p), n, stride, _dp(p), out.ctypes.data_as(C.c_void_p)), "icp_transform_cloud")
+        return out
 
     def knn3(self, scan, frame_pose, max_d2):
         pts, n, stride = self._cloud(scan)

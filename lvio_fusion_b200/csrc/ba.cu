@@ -28,7 +28,7 @@ using namespace lvb;
 
 namespace {
 
-enum { TPB = 128, IMU_STRIDE = 17 + 45 + 225, IMU_RAW = 467, MAX_DIMC = 736, MAX_STAGE_POSES = 512, MAX_TRACK = 16, CHOL_T = 256, SYRK_ROWS = 64, SYRK_LD = 14 };
+enum { TPB = 128, IMU_STRIDE = 17 + 45 + 225 + 1, IMU_RAW = 469, MAX_DIMC = 736, MAX_STAGE_POSES = 512, MAX_TRACK = 16, CHOL_T = 256, SYRK_ROWS = 64, SYRK_LD = 14 };
 
 __device__ long long g_chol_dbg[8];     // accumulated SM clocks per Cholesky phase (diag, panel, trailing, backward, total)
 __device__ unsigned char c_tri_a[465];   // lower-triangle enumeration e -> (a, b), a >= b; global (not __constant__):
@@ -158,16 +158,18 @@ __global__ void imu_prepare_kernel(const double* raw, double* packed, int n, int
     const int br[5] = {0, 0, 3, 6, 6}, bc[5] = {9, 12, 12, 9, 12};
     for (int b = 0; b < 5; ++b) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o[17 + 9 * b + 3 * i + j] = jac[(br[b] + i) * 15 + bc[b] + j];
     double a[225], inv[225];
-    status[f] = sqrt_information(c + 242, o + 62, a, inv);
+    status[f] = sqrt_information(c + 242, o + 62, a, inv, c[467], c[468]);
+    o[287] = (c[467] >= 0.0 && c[468] >= 0.0) ? 1.0 : 0.0;     // ImuInitError variant
 }
 
 // ------------------------------------------------------------------ K1 eval kernels (parity / roofline)
 // TwoFrame: 308 algorithmic bytes per block (40 const + 12 idx + 16 r + 240 J); output staged through
 // shared memory so that the 240 B Jacobian record leaves the SM as full 128 B lines.
-__global__ void __launch_bounds__(TPB) ba_eval_two_frame_kernel(BaDev d, double* __restrict__ r_out, double* __restrict__ J_out) {
+template <int STAGE, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) ba_eval_two_frame_kernel(BaDev d, double* __restrict__ r_out, double* __restrict__ J_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_J = reinterpret_cast<double*>(smem_raw);          // TPB x 31
-    double* s_poses = s_J + TPB * 31;                            // TPB*31*8 = 31744 B, a multiple of 16
+    double* s_J = reinterpret_cast<double*>(smem_raw);          // TPB x 31 (STAGE) -- the 240 B record leaves the SM as full lines
+    double* s_poses = s_J + (STAGE ? TPB * 31 : 0);              // TPB*31*8 = 31744 B, a multiple of 16
     __shared__ __align__(8) uint64_t bar;
     const double* poses = stage_poses(d, d.poses, s_poses, &bar);
     const int n = d.n[0];
@@ -180,19 +182,31 @@ __global__ void __launch_bounds__(TPB) ba_eval_two_frame_kernel(BaDev d, double*
         TwoFrameLin o; UQ u1, u2;
         two_frame_lin(d.cams, fo_x, fo_y, ob_x, ob_y, w, d.rho[il], poses + 7 * i1, poses + 7 * i2, o, &u1, &u2);
         if (r_out) reinterpret_cast<double2*>(r_out)[f] = make_double2(o.r[0], o.r[1]);
-        double* row = s_J + threadIdx.x * 31;
-        row[0] = o.Jrho[0]; row[15] = o.Jrho[1];
-        pose_block_to_ambient(u1, o.J1, 2, row + 1, 15);
-        pose_block_to_ambient(u2, o.J2, 2, row + 8, 15);
+        if (STAGE) {
+            double* row = s_J + threadIdx.x * 31;
+            row[0] = o.Jrho[0]; row[15] = o.Jrho[1];
+            pose_block_to_ambient(u1, o.J1, 2, row + 1, 15);
+            pose_block_to_ambient(u2, o.J2, 2, row + 8, 15);
+        } else if (J_out) {
+            double row[30];
+            row[0] = o.Jrho[0]; row[15] = o.Jrho[1];
+            pose_block_to_ambient(u1, o.J1, 2, row + 1, 15);
+            pose_block_to_ambient(u2, o.J2, 2, row + 8, 15);
+            double2* out = reinterpret_cast<double2*>(J_out + (size_t)f * 30);
+#pragma unroll
+            for (int k = 0; k < 15; ++k) out[k] = make_double2(row[2 * k], row[2 * k + 1]);
+        }
     }
-    __syncthreads();
-    if (J_out) {
-        const int first = blockIdx.x * TPB;
-        const int cnt = min(TPB, n - first) * 15;                // double2 elements
-        double2* out = reinterpret_cast<double2*>(J_out + (size_t)first * 30);
-        for (int e = threadIdx.x; e < cnt; e += TPB) {
-            const int t = e / 15, k = (e - t * 15) * 2;
-            out[e] = make_double2(s_J[t * 31 + k], s_J[t * 31 + k + 1]);
+    if (STAGE) {
+        __syncthreads();
+        if (J_out) {
+            const int first = blockIdx.x * TPB;
+            const int cnt = min(TPB, n - first) * 15;                // double2 elements
+            double2* out = reinterpret_cast<double2*>(J_out + (size_t)first * 30);
+            for (int e = threadIdx.x; e < cnt; e += TPB) {
+                const int t = e / 15, k = (e - t * 15) * 2;
+                out[e] = make_double2(s_J[t * 31 + k], s_J[t * 31 + k + 1]);
+            }
         }
     }
 }
@@ -231,9 +245,11 @@ __device__ void imu_warp_eval(const BaDev& d, int f, const double* P, const doub
     if (lane < 9) {   // lanes 0..7: one Jacobian block each (disjoint columns), lane 8: the residual
         const ImuConst k = load_imu_const(c);
         const double* Ti = P + 7 * ix[f]; const double* Vi = V + 3 * ix[n + f]; const double* Bai = V + 3 * ix[2 * n + f]; const double* Bgi = V + 3 * ix[3 * n + f];
-        const double* Tj = P + 7 * ix[4 * n + f]; const double* Vj = V + 3 * ix[5 * n + f]; const double* Baj = V + 3 * ix[6 * n + f]; const double* Bgj = V + 3 * ix[7 * n + f];
+        const double zero3[3] = {0.0, 0.0, 0.0};         // ImuInitError: Baj = Bgj = 0 (imu_error.hpp:141-142), idx = -1
+        const int i6 = ix[6 * n + f], i7 = ix[7 * n + f];
+        const double* Tj = P + 7 * ix[4 * n + f]; const double* Vj = V + 3 * ix[5 * n + f]; const double* Baj = i6 < 0 ? zero3 : V + 3 * i6; const double* Bgj = i7 < 0 ? zero3 : V + 3 * i7;
         if (lane == 8) imu_raw_residual(k, Ti, Vi, Bai, Bgi, Tj, Vj, Baj, Bgj, s_r);
-        else if (with_jac) imu_raw_jacobian_block(k, lane, Ti, Vi, Bgi, Tj, Vj, s_raw);
+        else if (with_jac && !(lane >= 6 && c[287] != 0.0)) imu_raw_jacobian_block(k, lane, Ti, Vi, Bgi, Tj, Vj, s_raw);
     }
     __syncwarp();
     const double* U = c + 62;
@@ -458,7 +474,7 @@ __global__ void __launch_bounds__(TPB) ba_linearize_other_kernel(BaDev d, BlockR
                     if (lane < 6) { blk = 0; loc = lane; } else if (lane < 15) { blk = 1 + (lane - 6) / 3; loc = (lane - 6) % 3; }
                     else if (lane < 21) { blk = 4; loc = lane - 15; } else { blk = 5 + (lane - 21) / 3; loc = (lane - 21) % 3; }
                     const int id = ix[(size_t)blk * n + f];
-                    const int off = (blk == 0 || blk == 4) ? d.pose_off[id] : d.vec3_off[id];
+                    const int off = id < 0 ? -1 : ((blk == 0 || blk == 4) ? d.pose_off[id] : d.vec3_off[id]);
                     gidx[lane] = off < 0 ? -1 : off + loc;
                 }
                 __syncwarp();
@@ -1112,7 +1128,10 @@ static int init_tables() {
     LVB_CUDA(cudaMemcpyToSymbol(c_tri_a, a, sizeof(a)));
     LVB_CUDA(cudaMemcpyToSymbol(c_tri_b, b, sizeof(b)));
     LVB_CUDA(cudaFuncSetAttribute(ba_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * 33 + (MAX_DIMC + 34) + (MAX_DIMC + 2) * 34) * 8));
-    LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (TPB * 31 + MAX_STAGE_POSES * 7 + 2) * 8));
+    LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (TPB * 31 + MAX_STAGE_POSES * 7 + 2) * 8));
+    LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (TPB * 31 + MAX_STAGE_POSES * 7 + 2) * 8));
+    LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel<0, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (MAX_STAGE_POSES * 7 + 2) * 8));
+    LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel<0, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (MAX_STAGE_POSES * 7 + 2) * 8));
     LVB_CUDA(cudaFuncSetAttribute(ba_linearize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     LVB_CUDA(cudaFuncSetAttribute(ba_linearize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     LVB_CUDA(cudaFuncSetAttribute(ba_schur_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_CHUNKS * TC_CHUNK_BYTES));
@@ -1193,6 +1212,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
         int lim = np;
         if ((k == 0 && j == 0) || k == 2) lim = nr;
         if (k == 3 && j != 0 && j != 4) lim = nv;
+        if (k == 3 && (j == 6 || j == 7) && v == -1 && ba->h_fc[3][(size_t)f * IMU_RAW + 467] >= 0.0) continue;     // ImuInitError has no j-side bias blocks
         if (v < 0 || v >= lim) { set_error("factor kind %d block %d: index %d out of range [0,%d)", k, f, v, lim); return LVB_ERR_INVALID; }
     }
     // slots / offsets.  Unknowns of the reduced camera system are ordered keyframe by keyframe
@@ -1211,7 +1231,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
         std::vector<long long> vkey(nv, -1);
         for (int f = 0; f < ba->n[3]; ++f) {
             const int32_t* ix = &ba->h_fi[3][8 * (size_t)f];
-            for (int b = 1; b < 8; ++b) { if (b == 4) continue; const int v = ix[b]; const int p = ix[b < 4 ? 0 : 4]; if (vkey[v] < 0) vkey[v] = (long long)p * 8 + (b & 3); }
+            for (int b = 1; b < 8; ++b) { if (b == 4) continue; const int v = ix[b]; if (v < 0) continue; const int p = ix[b < 4 ? 0 : 4]; if (vkey[v] < 0) vkey[v] = (long long)p * 8 + (b & 3); }
         }
         for (int i = 0; i < np; ++i) if (!ba->h_pose_const[i]) blks.push_back({(long long)i * 8, 0, i, 6});
         for (int i = 0; i < nv; ++i) if (!ba->h_vec3_const[i]) blks.push_back({vkey[i] >= 0 ? vkey[i] : (long long)np * 8 + i, 1, i, 3});
@@ -1326,7 +1346,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
         for (int f = 0; f < ba->n[3]; ++f) {
             const int32_t* ix = &ba->h_fi[3][8 * (size_t)f];
             int offs[8];
-            for (int b = 0; b < 8; ++b) offs[b] = (b == 0 || b == 4) ? pose_off[ix[b]] : vec3_off[ix[b]];
+            for (int b = 0; b < 8; ++b) offs[b] = ix[b] < 0 ? -1 : ((b == 0 || b == 4) ? pose_off[ix[b]] : vec3_off[ix[b]]);
             for (int a = 0; a < 8; ++a) for (int b = 0; b < a; ++b) couple(offs[a], offs[b]);
         }
         for (int f = 0; f < ba->n[4]; ++f) couple(pose_off[ba->h_fi[4][2 * (size_t)f]], pose_off[ba->h_fi[4][2 * (size_t)f + 1]]);
@@ -1485,8 +1505,13 @@ static int launch_eval(lvb_ba* ba, int kind, double* r_dev, double* J_dev) {
     BaDev& d = ba->dev;
     switch (kind) {
     case 0: {
-        const size_t smem = (size_t)(TPB * 31) * 8 + (d.stage_poses ? (size_t)d.n_poses * 56 + 16 : 0);
-        LAUNCH(ba, ba_eval_two_frame_kernel, nblk(n, TPB), TPB, smem, d, r_dev, J_dev); break; }
+        const size_t pose_b = d.stage_poses ? (size_t)d.n_poses * 56 + 16 : 0;
+        const int v = ba->ctx->eval_variant;       // LVB_EVAL_VARIANT: 0 staged/5 CTAs, 1 staged/6, 2 direct/5, 3 direct/6
+        if (v == 1) LAUNCH(ba, (ba_eval_two_frame_kernel<1, 6>), nblk(n, TPB), TPB, (size_t)(TPB * 31) * 8 + pose_b, d, r_dev, J_dev);
+        else if (v == 2) LAUNCH(ba, (ba_eval_two_frame_kernel<0, 5>), nblk(n, TPB), TPB, pose_b, d, r_dev, J_dev);
+        else if (v == 3) LAUNCH(ba, (ba_eval_two_frame_kernel<0, 6>), nblk(n, TPB), TPB, pose_b, d, r_dev, J_dev);
+        else LAUNCH(ba, (ba_eval_two_frame_kernel<1, 5>), nblk(n, TPB), TPB, (size_t)(TPB * 31) * 8 + pose_b, d, r_dev, J_dev);
+        break; }
     case 1: LAUNCH(ba, ba_eval_pose_only_kernel, nblk(n, TPB), TPB, 0, d, r_dev, J_dev); break;
     case 2: LAUNCH(ba, ba_eval_two_camera_kernel, nblk(n, TPB), TPB, 0, d, r_dev, J_dev); break;
     case 3: LAUNCH(ba, ba_eval_imu_kernel, nblk(n, 4), TPB, 0, d, r_dev, J_dev); break;

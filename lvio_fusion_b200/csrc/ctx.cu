@@ -110,6 +110,8 @@ int lvb_ctx_create(int device, void* cuda_stream, lvb_ctx** out) {
     c->use_tma = !(no_tma && no_tma[0] == '1');
     const char* no_graph = getenv("LVB_NO_GRAPH");
     c->use_graph = !(no_graph && no_graph[0] == '1');
+    const char* ev = getenv("LVB_EVAL_VARIANT");
+    if (ev) c->eval_variant = atoi(ev);
     const char* ce = getenv("LVB_CHECK_EVERY");
     if (ce && atoi(ce) > 0) c->check_every = atoi(ce);
     *out = c;

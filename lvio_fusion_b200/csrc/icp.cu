@@ -172,6 +172,20 @@ __device__ __forceinline__ float3 transform_f32(const float* tf, float3 p) {
     return make_float3(__fadd_rn(rx, tf[4]), __fadd_rn(ry, tf[5]), __fadd_rn(rz, tf[6]));
 }
 
+// Mapping::MergeScan (mapping.cpp:193-203): world cloud = float32 SE3 transform of the robot-frame cloud; the other
+// fields of each record (intensity, padding) are carried over unchanged.
+__global__ void icp_transform_cloud_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int n, int stride, const float* __restrict__ tf7) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float tf[7];
+    for (int k = 0; k < 7; ++k) tf[k] = tf7[k];
+    const float* src = reinterpret_cast<const float*>(in + (size_t)i * stride);
+    float* dst = reinterpret_cast<float*>(out + (size_t)i * stride);
+    const float3 q = transform_f32(tf, make_float3(src[0], src[1], src[2]));
+    dst[0] = q.x; dst[1] = q.y; dst[2] = q.z;
+    for (int k = 3; k < stride / 4; ++k) dst[k] = src[k];
+}
+
 struct Best3 { float d[3]; int i[3]; int p[3]; };   // d2, original index, position in the sorted array
 __device__ __forceinline__ void best_insert(Best3& b, float d, int i, int p) {
     if (d > b.d[2] || (d == b.d[2] && i > b.i[2])) return;
@@ -527,6 +541,21 @@ int lvb_icp_set_map(lvb_icp* h, const void* points, int n, int stride, float cel
     LVB_TRY(icheck("set_map"));
     LVB_CUDA(cudaStreamSynchronize(s));
     h->grid = g; h->P = n; h->cell_size = cell_size; h->have_map = true;
+    return LVB_OK;
+}
+
+int lvb_icp_transform_cloud(lvb_icp* h, const void* points, int n, int stride, const double pose[7], void* out) {
+    if (n < 0 || stride < 12 || (stride & 3) || (n && (!points || !out))) { set_error("bad cloud arguments"); return LVB_ERR_INVALID; }
+    if (n == 0) return LVB_OK;
+    LVB_CUDA(cudaSetDevice(h->ctx->device)); lvb::g_alloc_stream = h->ctx->stream;
+    cudaStream_t s = h->ctx->stream;
+    DevBuf<unsigned char> d_in, d_out; DevBuf<float> d_tf;
+    float tf[7]; for (int i = 0; i < 7; ++i) tf[i] = (float)pose[i];      // Twc.cast<float>()
+    LVB_TRY(d_in.upload((const unsigned char*)points, (size_t)n * stride, s)); LVB_TRY(d_out.ensure((size_t)n * stride)); LVB_TRY(d_tf.upload(tf, 7, s));
+    ILAUNCH(h, icp_transform_cloud_kernel, inblk(n, 256), 256, d_in.p, d_out.p, n, stride, d_tf.p);
+    LVB_TRY(icheck("transform_cloud"));
+    LVB_TRY(d_out.download((unsigned char*)out, (size_t)n * stride, s));
+    LVB_CUDA(cudaStreamSynchronize(s));
     return LVB_OK;
 }
 

@@ -27,6 +27,7 @@ struct lvb_ctx {
     int sm_count = 148;
     bool use_tma = true;          // cp.async.bulk staging of the pose array (env LVB_NO_TMA=1 disables)
     bool use_graph = true;        // replay the LM pass as a CUDA graph (env LVB_NO_GRAPH=1 disables)
+    int eval_variant = 0;         // A/B switch of the Jacobian-eval kernel (env LVB_EVAL_VARIANT)
     int check_every = 4;          // LM passes between host looks at the device state (env LVB_CHECK_EVERY)
     // NCCL (resolved at run time through dlopen, see comm.cu)
     void* comm = nullptr;

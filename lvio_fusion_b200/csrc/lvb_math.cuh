@@ -439,7 +439,7 @@ LVB_HD void imu_raw_jacobian(const ImuConst& c, const double* Ti, const double* 
 
 // sqrt_info = LLT(cov^-1).matrixL()^T (imu_error.hpp:32): partial-pivot LU inverse, then Cholesky.
 // Same operation order as the oracle so that the two agree to rounding.  Returns 0 on success.
-LVB_HD int sqrt_information(const double* cov /*225*/, double* U /*225*/, double* a /*225 scratch*/, double* inv /*225 scratch*/) {
+LVB_HD int sqrt_information(const double* cov /*225*/, double* U /*225*/, double* a /*225 scratch*/, double* inv /*225 scratch*/, double prior_a = -1.0, double prior_g = -1.0) {
     const int n = 15;
     int piv[15];
     for (int i = 0; i < 225; ++i) a[i] = cov[i];
@@ -456,6 +456,8 @@ LVB_HD int sqrt_information(const double* cov /*225*/, double* U /*225*/, double
         for (int i = 0; i < n; ++i) { double s = (piv[i] == c) ? 1.0 : 0.0; for (int k = 0; k < i; ++k) s -= a[i * n + k] * y[k]; y[i] = s; }
         for (int i = n - 1; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < n; ++k) s -= a[i * n + k] * inv[k * n + c]; inv[i * n + c] = s / a[i * n + i]; }
     }
+    if (prior_a >= 0.0 && prior_g >= 0.0)      // ImuInitError (imu_error.hpp:147-149): bias blocks of cov^-1 replaced by the priors
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { inv[(9 + i) * n + 9 + j] = (i == j) ? prior_a : 0.0; inv[(12 + i) * n + 12 + j] = (i == j) ? prior_g : 0.0; }
     for (int i = 0; i < 225; ++i) a[i] = 0.0;   // a := L
     for (int j = 0; j < n; ++j) {
         double d = inv[j * n + j];

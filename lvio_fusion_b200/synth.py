@@ -157,7 +157,7 @@ def preintegrate_batch(dt, acc, gyr, ba, bg, noise4=IMU_NOISE):
     """Midpoint preintegration of F factors at once (preintegration.cpp:30-127 semantics).
 
     acc, gyr: [F, S+1, 3] (sample 0 is the seed acc0/gyr0); ba, bg: [F,3].
-    Returns the LVB_IMU const records [F, 467].
+    Returns the LVB_IMU const records [F, 469] (prior_a = prior_g = -1: plain ImuError).
     """
     F, S1, _ = acc.shape
     dp = np.zeros((F, 3)); dv = np.zeros((F, 3)); dq = np.tile(np.array([0, 0, 0, 1.0]), (F, 1))
@@ -212,7 +212,8 @@ def preintegrate_batch(dt, acc, gyr, ba, bg, noise4=IMU_NOISE):
         dp, dv = ndp, ndv
         dq = rq / np.linalg.norm(rq, axis=1, keepdims=True)
         sum_dt += dt
-    out = np.zeros((F, 467))
+    out = np.zeros((F, 469))
+    out[:, 467:] = -1.0
     out[:, 0:3] = dp; out[:, 3:7] = dq; out[:, 7:10] = dv; out[:, 10:13] = ba; out[:, 13:16] = bg; out[:, 16] = sum_dt
     out[:, 17:242] = jac.reshape(F, 225); out[:, 242:467] = cov.reshape(F, 225)
     return out
@@ -322,6 +323,32 @@ def make_ba_problem(n_kf, n_landmarks, with_imu=True, seed=SEED, track_len=4, po
         factors[5] = (np.concatenate([P0[0], [100.0, 0.0]])[None, :], np.zeros((1, 1), dtype=np.int32))
     return dict(cameras=cams, poses=P0, poses_true=P_true, vec3=vec3, vec3_true=vec3_true, rho=rho0, rho_true=rho_true,
                 factors=factors, loss=loss, n_kf=N, n_landmarks=M)
+
+
+def make_fullba_problem(n_kf, n_landmarks, prior_a=1e8, prior_g=1e8, seed=SEED):
+    """imu::FullBA (tools.cpp:92-171): the visual factor mix of the window plus ImuInitError factors
+    (imu_error.hpp:124-229) that all share ONE accelerometer-bias and ONE gyroscope-bias block.
+
+    The reference calls it with prior_a = 1e4, prior_g = 1e2 (initializer.cpp:67); with the kitti.yaml IMU noise
+    those values make the patched cov^-1 indefinite (the bias cross-covariance of the preintegration is not
+    negligible) -- Eigen's LLT then returns NaN silently, this backend reports LVB_ERR_NUMERIC.  The synthetic
+    case therefore uses priors large enough to keep the matrix positive definite."""
+    d = make_ba_problem(n_kf, n_landmarks, with_imu=True, seed=seed)
+    N = n_kf
+    consts, _ = d["factors"][3]
+    consts = consts.copy()
+    consts[:, 467] = prior_a
+    consts[:, 468] = prior_g
+    vel = d["vec3"][0::3]
+    vec3 = np.concatenate([vel, d["vec3"][1:3]], axis=0)            # v_0..v_{N-1}, ba, bg
+    i = np.arange(N - 1); j = i + 1
+    idx = np.stack([i, i, np.full(N - 1, N), np.full(N - 1, N + 1), j, j, np.full(N - 1, -1), np.full(N - 1, -1)], axis=1).astype(np.int32)
+    d = dict(d)
+    d["factors"] = dict(d["factors"])
+    d["factors"][3] = (consts, idx)
+    d["vec3"] = vec3
+    d["vec3_true"] = np.concatenate([d["vec3_true"][0::3], d["vec3_true"][1:3]], axis=0)
+    return d
 
 
 def count_rows(d):

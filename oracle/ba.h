@@ -167,12 +167,14 @@ struct BaProblem {
         case K_POSE_PRIOR: pose_prior_eval(c, P + 7 * ix[0], r, J); return true;
         case K_IMU: {
             const Preint pre = load_preint(c);
+            static const double zero3[3] = {0.0, 0.0, 0.0};     // ImuInitError: Baj = Bgj = 0 (imu_error.hpp:141-142)
             const double* prm[8] = {P + 7 * ix[0], V + 3 * ix[1], V + 3 * ix[2], V + 3 * ix[3],
-                                    P + 7 * ix[4], V + 3 * ix[5], V + 3 * ix[6], V + 3 * ix[7]};
+                                    P + 7 * ix[4], V + 3 * ix[5], ix[6] < 0 ? zero3 : V + 3 * ix[6], ix[7] < 0 ? zero3 : V + 3 * ix[7]};
             if (!J) return imu_error_evaluate(pre, prm, r, nullptr);
             double jb[8][15 * 7];
             double* jp[8]; for (int k = 0; k < 8; ++k) jp[k] = jb[k];
             if (!imu_error_evaluate(pre, prm, r, jp)) return false;
+            if (pre.is_init()) { std::memset(jb[6], 0, sizeof(jb[6])); std::memset(jb[7], 0, sizeof(jb[7])); }
             static const int w[8] = {7, 3, 3, 3, 7, 3, 3, 3};
             int off = 0;
             for (int k = 0; k < 8; ++k) { for (int i = 0; i < 15; ++i) for (int j = 0; j < w[k]; ++j) J[i * 32 + off + j] = jb[k][i * w[k] + j]; off += w[k]; }
@@ -286,7 +288,7 @@ struct BaProblem {
                         for (int b = 0; b < 8; ++b) {
                             jt[b] = Jb[b];
                             if (b == 0 || b == 4) { pose_to_tangent(J + col0[b], 15, 32, P + 7 * ix[b], Jb[b]); offs[b] = pose_off(ix[b]); wid[b] = 6; }
-                            else { for (int k = 0; k < 15; ++k) for (int c = 0; c < 3; ++c) Jb[b][k * 3 + c] = J[k * 32 + col0[b] + c]; offs[b] = vec3_off(ix[b]); wid[b] = 3; }
+                            else { for (int k = 0; k < 15; ++k) for (int c = 0; c < 3; ++c) Jb[b][k * 3 + c] = J[k * 32 + col0[b] + c]; offs[b] = ix[b] < 0 ? -1 : vec3_off(ix[b]); wid[b] = 3; }
                         }
                         accumulate(15, 8, offs, wid, jt, r);
                     }

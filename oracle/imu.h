@@ -19,8 +19,10 @@ namespace oracle {
 static const double kGravity[3] = {0.0, 0.0, 9.81007};
 
 // Preintegrated measurement as the C ABI ships it (467 doubles):
-//   delta_p[3] delta_q[4 xyzw] delta_v[3] lin_ba[3] lin_bg[3] sum_dt jacobian[225 rm] covariance[225 rm]
-enum { kImuConsts = 17 + 225 + 225 };
+//   delta_p[3] delta_q[4 xyzw] delta_v[3] lin_ba[3] lin_bg[3] sum_dt jacobian[225 rm] covariance[225 rm] prior_a prior_g
+// prior_a, prior_g < 0: ImuError (imu_error.hpp:12-122).  >= 0: ImuInitError (imu_error.hpp:124-229) -- the j-side biases
+// are the constant zero vector, blocks (9,9) and (12,12) of the inverse covariance are replaced by prior * I.
+enum { kImuConsts = 17 + 225 + 225 + 2 };
 
 struct Preint {
     V3d dp, dv, lin_ba, lin_bg;
@@ -28,6 +30,8 @@ struct Preint {
     double sum_dt;
     double jac[15][15];
     double cov[15][15];
+    double prior_a = -1.0, prior_g = -1.0;
+    bool is_init() const { return prior_a >= 0.0 && prior_g >= 0.0; }
 };
 inline Preint load_preint(const double* c) {
     Preint p;
@@ -39,6 +43,7 @@ inline Preint load_preint(const double* c) {
     p.sum_dt = c[16];
     std::memcpy(p.jac, c + 17, sizeof(p.jac));
     std::memcpy(p.cov, c + 17 + 225, sizeof(p.cov));
+    p.prior_a = c[467]; p.prior_g = c[468];
     return p;
 }
 inline void store_preint(const Preint& p, double* c) {
@@ -50,6 +55,7 @@ inline void store_preint(const Preint& p, double* c) {
     c[16] = p.sum_dt;
     std::memcpy(c + 17, p.jac, sizeof(p.jac));
     std::memcpy(c + 17 + 225, p.cov, sizeof(p.cov));
+    c[467] = p.prior_a; c[468] = p.prior_g;
 }
 
 inline Mat3 block3(const double (*m)[15], int r, int c) {
@@ -193,7 +199,7 @@ inline void preint_append(PreintState& s, double dt, const V3d& acc, const V3d& 
 // LLT = Cholesky, lower.  Both restated in their plain unblocked forms.
 // Returns false if the inverse is not SPD (Eigen would return garbage silently).
 // ---------------------------------------------------------------------------------------
-inline bool sqrt_information(const double cov[15][15], double U[15][15]) {
+inline bool sqrt_information(const double cov[15][15], double U[15][15], double prior_a = -1.0, double prior_g = -1.0) {
     const int n = 15;
     double a[15][15], inv[15][15];
     std::memcpy(a, cov, sizeof(a));
@@ -214,6 +220,9 @@ inline bool sqrt_information(const double cov[15][15], double U[15][15]) {
         double y[15];
         for (int i = 0; i < n; ++i) { double s = (piv[i] == c) ? 1.0 : 0.0; for (int k = 0; k < i; ++k) s -= a[i][k] * y[k]; y[i] = s; }
         for (int i = n - 1; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < n; ++k) s -= a[i][k] * inv[k][c]; inv[i][c] = s / a[i][i]; }
+    }
+    if (prior_a >= 0.0 && prior_g >= 0.0) {   // imu_error.hpp:147-149
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { inv[9 + i][9 + j] = (i == j) ? prior_a : 0.0; inv[12 + i][12 + j] = (i == j) ? prior_g : 0.0; }
     }
     double L[15][15];
     std::memset(L, 0, sizeof(L));
@@ -267,7 +276,7 @@ inline bool imu_error_evaluate(const Preint& pre, const double* const* prm, doub
     double raw[15];
     imu_raw_residual(pre, Pi, Qi, Vi, Bai, Bgi, Pj, Qj, Vj, Baj, Bgj, raw);
     double U[15][15];
-    if (!sqrt_information(pre.cov, U)) return false;
+    if (!sqrt_information(pre.cov, U, pre.prior_a, pre.prior_g)) return false;
     for (int i = 0; i < 15; ++i) { double s = 0; for (int k = 0; k < 15; ++k) s += U[i][k] * raw[k]; res[i] = s; }
     if (!J) return true;
 

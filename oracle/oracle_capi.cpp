@@ -88,6 +88,7 @@ int orc_ba_finalize(orc_ba* b) {
             int lim = np;
             if ((k == K_TWO_FRAME && j == 0) || k == K_TWO_CAMERA) lim = nr;
             if (k == K_IMU && j != 0 && j != 4) lim = nv;
+            if (k == K_IMU && (j == 6 || j == 7) && v == -1 && g.consts[(size_t)f * kConstStride[k] + 467] >= 0.0) continue;   // ImuInitError
             if (v < 0 || v >= lim) return fail(LVB_ERR_INVALID, "factor index out of range");
         }
     }
@@ -196,6 +197,12 @@ static Knn3 query_limited(const orc_icp* h, const Pt& q, float max_d2) {
     Knn3 k = h->brute ? knn3_brute(h->map.data(), (int)h->map.size(), q) : h->tree.query(q);
     for (int j = 0; j < 3; ++j) if (!(k.d2[j] <= max_d2)) { k.idx[j] = -1; k.d2[j] = std::numeric_limits<float>::infinity(); }
     return k;
+}
+// Mapping::MergeScan (mapping.cpp:193-203)
+int orc_icp_transform_cloud(orc_icp*, const void* pts, int n, int stride, const double* pose, void* out) {
+    std::memcpy(out, pts, (size_t)n * stride);
+    for (int i = 0; i < n; ++i) { const Pt q = transform_f32(pose, load_pt(pts, i, stride)); float* f = (float*)((char*)out + (size_t)i * stride); f[0] = q.x; f[1] = q.y; f[2] = q.z; }
+    return LVB_OK;
 }
 int orc_icp_knn3(orc_icp* h, const void* scan, int n, int stride, const double* pose, float max_d2, int32_t* idx, float* d2) {
     const int T = std::max(1, h->num_threads);

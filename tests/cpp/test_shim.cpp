@@ -28,7 +28,7 @@ static int run_ba(const char* in, const char* out) {
     std::vector<int32_t> h = ri(f, 10);          // np nv nr n0..n5 max_iter
     const int np = h[0], nv = h[1], nr = h[2];
     std::vector<double> cam = rd(f, 22), P = rd(f, 7 * (size_t)np), V = rd(f, 3 * (size_t)nv), R = rd(f, nr);
-    static const int cs[6] = {5, 6, 5, 467, 8, 9}, is[6] = {3, 1, 1, 8, 2, 1};
+    static const int cs[6] = {5, 6, 5, 469, 8, 9}, is[6] = {3, 1, 1, 8, 2, 1};
     std::vector<double> C[6]; std::vector<int32_t> I[6];
     for (int k = 0; k < 6; ++k) { C[k] = rd(f, (size_t)h[3 + k] * cs[k]); I[k] = ri(f, (size_t)h[3 + k] * is[k]); }
     fclose(f);
@@ -60,7 +60,7 @@ static int run_ba(const char* in, const char* out) {
         problem.AddResidualBlock(lvio_fusion::TwoCameraReprojectionError::Create(Vector2d(c[0], c[1]), Vector2d(c[2], c[3]), cam0, cam1, c[4]), loss, &lms[I[2][f2]].inv_depth);
     }
     for (int f2 = 0; f2 < h[6]; ++f2) {                                                       // backend.cpp:143-162
-        const double* c = &C[3][467 * (size_t)f2]; const int32_t* ix = &I[3][8 * (size_t)f2];
+        const double* c = &C[3][469 * (size_t)f2]; const int32_t* ix = &I[3][8 * (size_t)f2];
         std::shared_ptr<Preintegration> pre(new Preintegration());
         pre->delta_p = Vector3d(c[0], c[1], c[2]); for (int k = 0; k < 4; ++k) pre->delta_q.c.v[k] = c[3 + k];
         pre->delta_v = Vector3d(c[7], c[8], c[9]); pre->linearized_ba = Vector3d(c[10], c[11], c[12]); pre->linearized_bg = Vector3d(c[13], c[14], c[15]); pre->sum_dt = c[16];

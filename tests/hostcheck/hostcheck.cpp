@@ -43,7 +43,7 @@ int hc_imu(const double* c467, const double* Ti, const double* Vi, const double*
     auto blk = [&](int r0, int c0) { M3 b; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) b.m[3 * i + j] = jac[(r0 + i) * 15 + c0 + j]; return b; };
     c.dp_dba = blk(0, 9); c.dp_dbg = blk(0, 12); c.dq_dbg = blk(3, 12); c.dv_dba = blk(6, 9); c.dv_dbg = blk(6, 12);
     double U[225], a[225], inv[225];
-    const int rc = sqrt_information(c467 + 242, U, a, inv);
+    const int rc = sqrt_information(c467 + 242, U, a, inv, c467[467], c467[468]);
     if (rc) return rc;
     double raw[15], Jr[15 * 32];
     imu_raw_residual(c, Ti, Vi, Bai, Bgi, Tj, Vj, Baj, Bgj, raw);

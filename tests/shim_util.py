@@ -20,7 +20,7 @@ def build_shim_binary():
 
 
 def dump_ba(path, d, max_iter):
-    strides = [5, 6, 5, 467, 8, 9]
+    strides = [5, 6, 5, 469, 8, 9]
     with open(path, "wb") as f:
         n = [len(d["factors"].get(k, (np.zeros((0, strides[k])),))[0]) for k in range(6)]
         np.array([len(d["poses"]), len(d["vec3"]), len(d["rho"])] + n + [max_iter], dtype=np.int32).tofile(f)

@@ -130,3 +130,20 @@ def test_errors_are_loud(lvb_ctx):
     d["factors"][TWO_FRAME][1][0, 1] = 99   # pose index out of range
     with pytest.raises(RuntimeError):
         backend.Problem.from_dict(lvb_ctx, d)
+
+
+def test_full_ba_with_imu_init_error(lvb_ctx, orc_ctx):
+    """imu::FullBA (tools.cpp:92-171): ImuInitError factors (imu_error.hpp:124-229) sharing one ba and one bg block."""
+    d = synth.make_fullba_problem(6, 600, seed=23)
+    pg, po = backend.Problem.from_dict(lvb_ctx, d), backend.Problem.from_dict(orc_ctx, d)
+    rg, Jg = pg.evaluate(IMU)
+    ro, Jo = po.evaluate(IMU)
+    assert _rel(rg, ro) < 1e-8 and _rel(Jg, Jo) < 1e-8
+    assert np.all(Jo[:, :, 26:] == 0) and np.all(Jg[:, :, 26:] == 0)        # no ba_j / bg_j blocks
+    Sg, bg, cg = pg.reduced_system(1e4)
+    So, bo, co = po.reduced_system(1e4)
+    assert abs(cg - co) < 1e-10 * co and _rel(Sg, So) < 1e-9 and _rel(bg, bo) < 1e-9
+    sg, so = pg.solve(max_num_iterations=30), po.solve(max_num_iterations=30, num_threads=2)
+    assert abs(sg.final_cost - so.final_cost) < 1e-6 * so.final_cost
+    assert np.max(np.abs(pg.poses() - po.poses())) < 1e-6
+    assert np.max(np.abs(pg.vec3() - po.vec3())) < 1e-5

@@ -85,3 +85,15 @@ def test_empty_and_unmatched_scans(lvb_ctx, scene):
     assert (idx == -1).all() and np.isinf(d2).all()
     idx, d2 = fg.knn3(np.zeros((0, 4), dtype=np.float32), scene["frame_pose"], 1.0)
     assert idx.shape == (0, 3)
+
+
+def test_merge_scan_transform_bit_exact(lvb_ctx, orc_ctx):
+    """Mapping::MergeScan / ToWorld (mapping.cpp:193-220): float32 transform of 32-byte PointXYZI records."""
+    sc = synth.make_icp_problem(5000, 2000, seed=9, kind="surf", stride_floats=8)
+    sc["scan"][:, 4] = np.arange(len(sc["scan"]), dtype=np.float32)          # intensity must survive
+    fg, fo = backend.FeatureAssociation(lvb_ctx), backend.FeatureAssociation(orc_ctx)
+    wg, wo = fg.transform_cloud(sc["scan"], sc["true_pose"]), fo.transform_cloud(sc["scan"], sc["true_pose"])
+    assert np.array_equal(wg.view(np.uint32), wo.view(np.uint32))
+    assert np.array_equal(wg[:, 4], sc["scan"][:, 4])
+    ref = synth.se3_apply(np.broadcast_to(sc["true_pose"], (len(wg), 7)), sc["scan"][:, :3].astype(np.float64))
+    assert np.max(np.abs(wg[:, :3] - ref)) < 1e-4

@@ -147,12 +147,12 @@ def test_preintegration_producers_agree(orc, small):
     ba = rng.normal(0, 0.01, (1, 3)); bg = rng.normal(0, 0.001, (1, 3))
     a = synth.preintegrate_batch(0.01, acc, gyr, ba, bg)[0]
     samples = np.concatenate([np.full((S, 1), 0.01), acc[0, 1:], gyr[0, 1:]], axis=1).copy()
-    out = np.zeros(467)
+    out = np.zeros(469)
     orc.preintegrate(S, _dp(samples), _dp(acc[0, 0].copy()), _dp(gyr[0, 0].copy()), _dp(ba[0].copy()), _dp(bg[0].copy()),
                      _dp(synth.IMU_NOISE.copy()), _dp(out))
     assert np.allclose(a[:17], out[:17], rtol=0, atol=1e-7)
     assert np.allclose(a[17:242], out[17:242], rtol=1e-6, atol=1e-8)
-    assert np.allclose(a[242:], out[242:], rtol=1e-5, atol=1e-14)
+    assert np.allclose(a[242:467], out[242:467], rtol=1e-5, atol=1e-14)
 
 
 def test_pose_plus_is_left_multiplication(orc):
@@ -164,3 +164,22 @@ def test_pose_plus_is_left_multiplication(orc):
     dq = np.concatenate([np.sin(n) / n * d[:3], [np.cos(n)]])
     assert np.allclose(out[:4], synth.quat_mul(dq[None], x[None, :4])[0], atol=1e-15)
     assert np.allclose(out[4:], x[4:] + d[3:])
+
+
+def test_imu_init_error_variant(orc_ctx):
+    """ImuInitError (imu_error.hpp:124-229): Baj = Bgj = 0, priors replace the bias blocks of cov^-1."""
+    d = synth.make_fullba_problem(4, 40, seed=3)
+    p = backend.Problem.from_dict(orc_ctx, d)
+    r, J = p.evaluate(IMU)
+    assert np.all(J[:, :, 26:] == 0)
+    # residual rows 9..14 are sqrt_info-mixed (-Bai, -Bgi); check through the un-whitened relation with U
+    c = d["factors"][IMU][0][0]
+    U = np.zeros((15, 15))
+    cov_inv = np.linalg.inv(c[242:467].reshape(15, 15))
+    cov_inv[9:12, 9:12] = c[467] * np.eye(3); cov_inv[12:15, 12:15] = c[468] * np.eye(3)
+    L = np.linalg.cholesky(cov_inv)
+    raw = np.linalg.solve(L.T, r[0])
+    ba, bg = d["vec3"][4], d["vec3"][5]
+    assert np.allclose(raw[9:12], -ba, atol=1e-9) and np.allclose(raw[12:15], -bg, atol=1e-9)
+    s = p.solve(max_num_iterations=20)
+    assert s.final_cost < s.initial_cost
