@@ -36,6 +36,9 @@ __device__ unsigned char c_tri_b[465];   // the index differs per lane and would
 
 struct BaDev {
     int n_poses, n_vec3, n_rho, dimc, n_pose_free;
+    // lower-triangular storage of Hpp and S: element (i, j), i >= j, lives at i * srow + j + soff.
+    // dense: srow = dimc, soff = 0 ; banded (half bandwidth B, dimc > MAX_DIMC): srow = B, soff = B (row-major n x (B+1)).
+    long long srow, soff; size_t nS;
     double *poses, *vec3, *rho, *c_poses, *c_vec3, *c_rho;
     const int *pose_off, *vec3_off, *rho_slot;
     int n[6];
@@ -60,6 +63,7 @@ struct BaDev {
     Cams cams;
 };
 
+#define SIDX(d_, i_, j_) ((size_t)(i_) * (size_t)(d_).srow + (size_t)(j_) + (size_t)(d_).soff)
 struct BlockRanges { int b[7]; };   // cumulative block starts per kind, b[6] = total
 
 // ------------------------------------------------------------------ small device helpers
@@ -119,20 +123,20 @@ __device__ __forceinline__ void block_add(double v, double* target, double* s_re
 }
 
 // H(lower) += JA^T JB for two distinct blocks; offsets are global camera-system offsets (>= 0)
-__device__ __forceinline__ void add_cross(double* H, int dimc, int offA, const double* JA, int wa, int offB, const double* JB, int wb, int rows) {
+__device__ __forceinline__ void add_cross(double* H, const BaDev& d, int offA, const double* JA, int wa, int offB, const double* JB, int wb, int rows) {
     for (int i = 0; i < wa; ++i) for (int j = 0; j < wb; ++j) {
         double s = 0; for (int k = 0; k < rows; ++k) s += JA[k * wa + i] * JB[k * wb + j];
         const int ra = offA + i, cb = offB + j;
-        if (ra > cb) atomicAdd(&H[(size_t)ra * dimc + cb], s); else atomicAdd(&H[(size_t)cb * dimc + ra], s);
+        if (ra > cb) atomicAdd(&H[SIDX(d, ra, cb)], s); else atomicAdd(&H[SIDX(d, cb, ra)], s);
     }
 }
-__device__ __forceinline__ void add_diag(double* H, double* g, int dimc, int off, const double* J, int w, int rows, const double* r) {
+__device__ __forceinline__ void add_diag(double* H, double* g, const BaDev& d, int off, const double* J, int w, int rows, const double* r) {
     for (int i = 0; i < w; ++i) {
         double gi = 0; for (int k = 0; k < rows; ++k) gi += J[k * w + i] * r[k];
         atomicAdd(&g[off + i], gi);
         for (int j = 0; j <= i; ++j) {
             double s = 0; for (int k = 0; k < rows; ++k) s += J[k * w + i] * J[k * w + j];
-            atomicAdd(&H[(size_t)(off + i) * dimc + off + j], s);
+            atomicAdd(&H[SIDX(d, off + i, off + j)], s);
         }
     }
 }
@@ -308,7 +312,7 @@ __device__ __forceinline__ void warp_syrk_flush(const BaDev& d, const double* A 
         if (a == ncol - 1) { atomicAdd(&d.gc[gb], v); continue; }
         const int ga = (ncol == 13) ? (a < 6 ? (off1 < 0 ? -1 : off1 + a) : (off2 < 0 ? -1 : off2 + a - 6)) : (off1 < 0 ? -1 : off1 + a);
         if (ga < 0) continue;
-        if (ga >= gb) atomicAdd(&d.Hpp[(size_t)ga * d.dimc + gb], v); else atomicAdd(&d.Hpp[(size_t)gb * d.dimc + ga], v);
+        if (ga >= gb) atomicAdd(&d.Hpp[SIDX(d, ga, gb)], v); else atomicAdd(&d.Hpp[SIDX(d, gb, ga)], v);
     }
 }
 
@@ -362,19 +366,28 @@ __global__ void __launch_bounds__(TPB) ba_linearize_kernel(BaDev d, BlockRanges 
             }
         }
         if (MODE == 0) {
-            const int k1 = __shfl_sync(0xffffffffu, i1, 0), k2 = __shfl_sync(0xffffffffu, i2, 0);
-            const bool uniform = d.warp_syrk && __all_sync(0xffffffffu, valid && i1 == k1 && i2 == k2 && i1 != i2);
-            if (uniform) {
+            // blocks are sorted by (pose_1, pose_2): a warp holds one key (padded layout) or a few key segments
+            unsigned todo = d.warp_syrk ? __ballot_sync(0xffffffffu, valid && i1 != i2) : 0u;
+            const bool direct = valid && (!d.warp_syrk || i1 == i2);
+            while (todo) {
+                const int leader = __ffs(todo) - 1;
+                const int k1 = __shfl_sync(0xffffffffu, i1, leader), k2 = __shfl_sync(0xffffffffu, i2, leader);
+                const int o1 = __shfl_sync(0xffffffffu, off1, leader), o2 = __shfl_sync(0xffffffffu, off2, leader);
+                const bool mine = valid && i1 == k1 && i2 == k2;
                 double* row0 = A + (2 * lane) * SYRK_LD; double* row1 = row0 + SYRK_LD;
-                for (int k = 0; k < 6; ++k) { row0[k] = o.J1[k]; row1[k] = o.J1[6 + k]; row0[6 + k] = o.J2[k]; row1[6 + k] = o.J2[6 + k]; }
-                row0[12] = o.r[0]; row1[12] = o.r[1];
+                if (mine) {
+                    for (int k = 0; k < 6; ++k) { row0[k] = o.J1[k]; row1[k] = o.J1[6 + k]; row0[6 + k] = o.J2[k]; row1[6 + k] = o.J2[6 + k]; }
+                    row0[12] = o.r[0]; row1[12] = o.r[1];
+                } else for (int k = 0; k < 13; ++k) { row0[k] = 0.0; row1[k] = 0.0; }
                 __syncwarp();
-                warp_syrk_flush(d, A, 13, off1, off2);
+                warp_syrk_flush(d, A, 13, o1, o2);
                 __syncwarp();
-            } else if (valid) {
-                if (off1 >= 0) add_diag(d.Hpp, d.gc, d.dimc, off1, o.J1, 6, 2, o.r);
-                if (off2 >= 0) add_diag(d.Hpp, d.gc, d.dimc, off2, o.J2, 6, 2, o.r);
-                if (off1 >= 0 && off2 >= 0) add_cross(d.Hpp, d.dimc, off1, o.J1, 6, off2, o.J2, 6, 2);
+                todo &= ~__ballot_sync(0xffffffffu, mine);
+            }
+            if (direct) {
+                if (off1 >= 0) add_diag(d.Hpp, d.gc, d, off1, o.J1, 6, 2, o.r);
+                if (off2 >= 0) add_diag(d.Hpp, d.gc, d, off2, o.J2, 6, 2, o.r);
+                if (off1 >= 0 && off2 >= 0) add_cross(d.Hpp, d, off1, o.J1, 6, off2, o.J2, 6, 2);
             }
         }
     } else if (b < R.b[2]) {     // ---- a2 PoseOnlyReprojectionError
@@ -393,16 +406,22 @@ __global__ void __launch_bounds__(TPB) ba_linearize_kernel(BaDev d, BlockRanges 
             if (MODE == 0) { off = d.pose_off[ip]; o.r[0] *= sr; o.r[1] *= sr; for (int k = 0; k < 12; ++k) o.J[k] *= sr; }
         }
         if (MODE == 0) {
-            const int k1 = __shfl_sync(0xffffffffu, ip, 0);
-            const bool uniform = d.warp_syrk && __all_sync(0xffffffffu, valid && ip == k1);
-            if (uniform) {
+            unsigned todo = d.warp_syrk ? __ballot_sync(0xffffffffu, valid) : 0u;
+            while (todo) {
+                const int leader = __ffs(todo) - 1;
+                const int k1 = __shfl_sync(0xffffffffu, ip, leader), o1 = __shfl_sync(0xffffffffu, off, leader);
+                const bool mine = valid && ip == k1;
                 double* row0 = A + (2 * lane) * SYRK_LD; double* row1 = row0 + SYRK_LD;
-                for (int k = 0; k < 6; ++k) { row0[k] = o.J[k]; row1[k] = o.J[6 + k]; }
-                row0[6] = o.r[0]; row1[6] = o.r[1];
+                if (mine) {
+                    for (int k = 0; k < 6; ++k) { row0[k] = o.J[k]; row1[k] = o.J[6 + k]; }
+                    row0[6] = o.r[0]; row1[6] = o.r[1];
+                } else for (int k = 0; k < 7; ++k) { row0[k] = 0.0; row1[k] = 0.0; }
                 __syncwarp();
-                warp_syrk_flush(d, A, 7, off, -1);
+                warp_syrk_flush(d, A, 7, o1, -1);
                 __syncwarp();
-            } else if (valid && off >= 0) add_diag(d.Hpp, d.gc, d.dimc, off, o.J, 6, 2, o.r);
+                todo &= ~__ballot_sync(0xffffffffu, mine);
+            }
+            if (!d.warp_syrk && valid && off >= 0) add_diag(d.Hpp, d.gc, d, off, o.J, 6, 2, o.r);
         }
     } else {                     // ---- a3 TwoCameraReprojectionError
         const int n = d.n[2];
@@ -487,7 +506,7 @@ __global__ void __launch_bounds__(TPB) ba_linearize_other_kernel(BaDev d, BlockR
                     const int ga = gidx[a], gb = gidx[bb];
                     if (ga < 0 || gb < 0) continue;
                     double h = 0; for (int i = 0; i < 15; ++i) h += raw[30 * i + a] * raw[30 * i + bb];
-                    if (ga >= gb) atomicAdd(&d.Hpp[(size_t)ga * d.dimc + gb], h); else atomicAdd(&d.Hpp[(size_t)gb * d.dimc + ga], h);
+                    if (ga >= gb) atomicAdd(&d.Hpp[SIDX(d, ga, gb)], h); else atomicAdd(&d.Hpp[SIDX(d, gb, ga)], h);
                 }
             }
         }
@@ -519,9 +538,9 @@ __global__ void __launch_bounds__(TPB) ba_linearize_other_kernel(BaDev d, BlockR
                 }
                 for (int k = 0; k < 36; ++k) { J1[k] *= sr; J2[k] *= sr; }
                 const int off1 = d.pose_off[i1], off2 = kind == 4 ? d.pose_off[i2] : -1;
-                if (off1 >= 0) add_diag(d.Hpp, d.gc, d.dimc, off1, J1, 6, 6, r);
-                if (off2 >= 0) add_diag(d.Hpp, d.gc, d.dimc, off2, J2, 6, 6, r);
-                if (off1 >= 0 && off2 >= 0 && off1 != off2) add_cross(d.Hpp, d.dimc, off1, J1, 6, off2, J2, 6, 6);
+                if (off1 >= 0) add_diag(d.Hpp, d.gc, d, off1, J1, 6, 6, r);
+                if (off2 >= 0) add_diag(d.Hpp, d.gc, d, off2, J2, 6, 6, r);
+                if (off1 >= 0 && off2 >= 0 && off1 != off2) add_cross(d.Hpp, d, off1, J1, 6, off2, J2, 6, 6);
             }
         }
     }
@@ -532,7 +551,7 @@ __global__ void __launch_bounds__(TPB) ba_linearize_other_kernel(BaDev d, BlockR
 __global__ void ba_zero_kernel(BaDev d) {
     const LmState* st = d.st;
     if (st->done || !st->need_linearize) return;
-    const size_t nH = (size_t)d.dimc * d.dimc;
+    const size_t nH = d.nS;
     const size_t total = nH + d.dimc + 2 * (size_t)d.n_rho;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         if (i < nH) d.Hpp[i] = 0.0;
@@ -564,15 +583,10 @@ __global__ void ba_prepare_landmark_kernel(BaDev d) {
 // S <- lower(Hpp), rhs <- -gc, gcr <- gc, diagH <- diag(Hpp), scalars <- 0
 __global__ void ba_build_S_kernel(BaDev d) {
     if (d.st->done) return;
-    const size_t nH = (size_t)d.dimc * d.dimc;
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     if (gid < 16) d.scal[gid] = 0.0;
-    for (size_t i = gid; i < nH; i += (size_t)gridDim.x * blockDim.x) {
-        const int r = (int)(i / d.dimc), c = (int)(i - (size_t)r * d.dimc);
-        const double v = d.Hpp[i];
-        d.S[i] = (c <= r) ? v : 0.0;
-        if (c == r) { d.diagH[r] = v; d.rhs[r] = -d.gc[r]; d.gcr[r] = d.gc[r]; }
-    }
+    for (size_t i = gid; i < d.nS; i += stride) d.S[i] = d.Hpp[i];          // only the lower triangle / band is ever written
+    for (size_t r = gid; r < (size_t)d.dimc; r += stride) { d.diagH[r] = d.Hpp[SIDX(d, r, r)]; d.rhs[r] = -d.gc[r]; d.gcr[r] = d.gc[r]; }
 }
 
 // K5: eliminate the inverse depths.  One warp per 32 landmarks that share their set of pose offsets
@@ -660,7 +674,7 @@ __global__ void __launch_bounds__(TPB) ba_schur_kernel(BaDev d, int cols_max) {
         const int gb = offs[b / 6] + b % 6;
         if (a == ncol - 1) { atomicAdd(&d.rhs[gb], v); continue; }
         const int ga = offs[a / 6] + a % 6;
-        if (ga >= gb) atomicAdd(&d.S[(size_t)ga * d.dimc + gb], -v); else atomicAdd(&d.S[(size_t)gb * d.dimc + ga], -v);
+        if (ga >= gb) atomicAdd(&d.S[SIDX(d, ga, gb)], -v); else atomicAdd(&d.S[SIDX(d, gb, ga)], -v);
     }
 }
 
@@ -741,7 +755,7 @@ __global__ void __launch_bounds__(128) ba_schur_tc_kernel(BaDev d, int n_chunks)
                 const float f = __uint_as_float(v[j]);
                 if (f == 0.0f) continue;
                 const int gb = d.tc_off[b];
-                if (ga >= gb) atomicAdd(&d.S[(size_t)ga * d.dimc + gb], -(double)f); else atomicAdd(&d.S[(size_t)gb * d.dimc + ga], -(double)f);
+                if (ga >= gb) atomicAdd(&d.S[SIDX(d, ga, gb)], -(double)f); else atomicAdd(&d.S[SIDX(d, gb, ga)], -(double)f);
             }
         }
     }
@@ -781,7 +795,7 @@ __global__ void ba_prepare_camera_kernel(BaDev d) {
         const double s = d.scale_c[off + k], s2 = s * s;
         const double lam = fmin(fmax(s2 * h, st->min_diag), st->max_diag) / (st->radius * s2);
         d.lam_c[off + k] = lam;
-        d.S[(size_t)(off + k) * d.dimc + off + k] += lam;
+        d.S[SIDX(d, off + k, off + k)] += lam;
     }
     if (st->need_linearize) {
         double gm = 0.0;
@@ -803,14 +817,16 @@ __global__ void lm_control_post_kernel(LmState* st) { lm_control_post(*st); if (
 // Right-looking blocked (32) factorisation of the lower triangle of S (n x n, row-major, in L2/HBM) with
 // the right-hand side carried along as an extra row (so the forward substitution is free), then a
 // blocked backward substitution.  Result: rhs <- S^-1 rhs.
-__global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict__ S, double* __restrict__ rhs, int n, LmState* st, int run_control_pre,
+#define SA(i_, j_) S[(size_t)(i_) * (size_t)srow + (size_t)(j_) + (size_t)soff]
+__global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict__ S, double* __restrict__ rhs, int n, long long srow, long long soff,
+                                                                  double* __restrict__ invd_g, LmState* st, int run_control_pre,
                                                                   const int* __restrict__ env_rmax, const int* __restrict__ env_cmin) {
     if (run_control_pre) { if (threadIdx.x == 0) lm_control_pre(*st); __syncthreads(); }
     if (st->done) return;
     extern __shared__ __align__(16) double sm[];
     double* D = sm;                    // 32 x 33   diagonal block of L
-    double* invd = sm + 32 * 33;       // n (+32)   reciprocals of diag(L)
-    double* P = invd + ((n + 32 + 1) & ~1);   // rows x 34 panel (16 B aligned rows for broadcast double2 loads)
+    double* invd = sm + 32 * 33;       // 32        reciprocals of diag(L) of the current block (all of them: invd_g)
+    double* P = invd + 32;             // rows x 34 panel (16 B aligned rows for broadcast double2 loads)
     __shared__ int fail;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     if (tid == 0) fail = 0;
@@ -829,13 +845,13 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
             m = env_rmax[kb >> 5] - (kb + bs) + 1 + 1;
             for (int rr = tid; rr < m; rr += nt) {
                 const bool is_rhs = (rr == m - 1);
-                double* src = is_rhs ? (rhs + kb) : (S + (size_t)(kb + bs + rr) * n + kb);
+                double* src = is_rhs ? (rhs + kb) : &SA(kb + bs + rr, kb);
                 double a[32];
     #pragma unroll
                 for (int j = 0; j < 32; ++j) a[j] = (j < bs) ? src[j] : 0.0;
     #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    a[j] *= invd[kb + j];
+                    a[j] *= invd[j];
     #pragma unroll
                     for (int k = 0; k < 32; ++k) if (k > j) a[k] -= a[j] * D[k * 33 + j];
                 }
@@ -884,7 +900,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
     #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int ip = min(r0 + 8 * i, m - 1);
-                    const double* src = (ip == m - 1) ? (rhs + kb + bs) : (S + (size_t)(kb + bs + ip) * n + kb + bs);
+                    const double* src = (ip == m - 1) ? (rhs + kb + bs) : &SA(kb + bs + ip, kb + bs);
     #pragma unroll
                     for (int j = 0; j < 8; ++j) { const int jp = c0 + 4 * j; cur[i][j] = (r0 + 8 * i < m && jp < m - 1 && jp <= ip) ? src[jp] : 0.0; }
                 }
@@ -892,7 +908,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
                 for (int i = 0; i < 4; ++i) {
                     const int ip = r0 + 8 * i;
                     if (ip >= m) continue;
-                    double* dst = (ip == m - 1) ? (rhs + kb + bs) : (S + (size_t)(kb + bs + ip) * n + kb + bs);
+                    double* dst = (ip == m - 1) ? (rhs + kb + bs) : &SA(kb + bs + ip, kb + bs);
     #pragma unroll
                     for (int j = 0; j < 8; ++j) { const int jp = c0 + 4 * j; if (jp < m - 1 && jp <= ip) dst[jp] = cur[i][j] - acc[i][j]; }
                 }
@@ -905,7 +921,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
             if (warp == 0) {
                 double a[32];
     #pragma unroll
-                for (int j = 0; j < 32; ++j) a[j] = (lane < bn && j <= lane) ? S[(size_t)(kn + lane) * n + kn + j] : ((j == lane) ? 1.0 : 0.0);
+                for (int j = 0; j < 32; ++j) a[j] = (lane < bn && j <= lane) ? SA(kn + lane, kn + j) : ((j == lane) ? 1.0 : 0.0);
                 int bad = 0;
                 double d0 = __shfl_sync(0xffffffffu, a[0], 0);
                 if (!(d0 > 0.0)) { bad = 1; d0 = 1.0; }
@@ -913,7 +929,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
     #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     if (lane >= j) a[j] *= inv;                       // l_ij (lane j: sqrt(d_jj))
-                    if (lane == j) invd[kn + j] = inv;
+                    if (lane == j) { invd[j] = inv; invd_g[kn + j] = inv; }
                     // update column j+1 first and start the next pivot's rsqrt: its latency overlaps the rest of the update
                     double inv_next = 1.0;
                     if (j + 1 < 32) {
@@ -935,7 +951,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
     #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     D[lane * 33 + j] = (j <= lane) ? a[j] : 0.0;
-                    if (lane < bn && j <= lane && j < bn) S[(size_t)(kn + lane) * n + kn + j] = a[j];
+                    if (lane < bn && j <= lane && j < bn) SA(kn + lane, kn + j) = a[j];
                 }
                 if (bad && lane == 0) fail = 1;
             }
@@ -952,9 +968,9 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
         if (warp == 0) {
             double col[32];                           // column `lane` of the block:  col[i] = L[kb+i][kb+lane], i >= lane
 #pragma unroll
-            for (int i = 0; i < 32; ++i) col[i] = (i < bs && lane < bs && i >= lane) ? S[(size_t)(kb + i) * n + kb + lane] : 0.0;
+            for (int i = 0; i < 32; ++i) col[i] = (i < bs && lane < bs && i >= lane) ? SA(kb + i, kb + lane) : 0.0;
             double t = (lane < bs) ? rhs[kb + lane] : 0.0;
-            const double my_inv = (lane < bs) ? invd[kb + lane] : 1.0;
+            const double my_inv = (lane < bs) ? invd_g[kb + lane] : 1.0;
 #pragma unroll
             for (int j = 31; j >= 0; --j) {
                 const double xj = __shfl_sync(0xffffffffu, t * my_inv, j);     // lane j's t is final here
@@ -967,7 +983,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
         for (int j = env_cmin[kb >> 5] + tid; j < kb; j += nt) {
             double acc = 0.0;
 #pragma unroll 8
-            for (int i = 0; i < 32; ++i) if (i < bs) acc += S[(size_t)(kb + i) * n + j] * xs[i];
+            for (int i = 0; i < 32; ++i) if (i < bs) acc += SA(kb + i, j) * xs[i];
             rhs[j] -= acc;
         }
         __syncthreads();
@@ -1035,7 +1051,7 @@ __global__ void __launch_bounds__(TPB) ba_update_kernel(BaDev d) {
 
 // One CTA closes the iteration: LM decision (thread 0), then -- if the step was accepted -- candidate -> x and the
 // accumulators of the next linearisation are cleared (problems on the dense-solver path are small: < 1 MB).
-__global__ void __launch_bounds__(1024) ba_post_kernel(BaDev d) {
+__global__ void __launch_bounds__(1024) ba_post_kernel(BaDev d, int decide_only) {
     LmState* st = d.st;
     __shared__ int s_accept, s_zero;
     if (threadIdx.x == 0) {
@@ -1045,6 +1061,7 @@ __global__ void __launch_bounds__(1024) ba_post_kernel(BaDev d) {
         s_zero = (!st->done && st->need_linearize) ? 1 : 0;
     }
     __syncthreads();
+    if (decide_only) return;
     if (s_accept) {
         const size_t np = (size_t)d.n_poses * 7, nv = (size_t)d.n_vec3 * 3, nr = d.n_rho;
         for (size_t i = threadIdx.x; i < np + nv + nr; i += blockDim.x) {
@@ -1054,12 +1071,35 @@ __global__ void __launch_bounds__(1024) ba_post_kernel(BaDev d) {
         }
     }
     if (s_zero) {
-        const size_t nH = (size_t)d.dimc * d.dimc;
+        const size_t nH = d.nS;
         double2* H2 = reinterpret_cast<double2*>(d.Hpp);
         for (size_t i = threadIdx.x; i < nH / 2; i += blockDim.x) H2[i] = make_double2(0.0, 0.0);
         if ((nH & 1) && threadIdx.x == 0) d.Hpp[nH - 1] = 0.0;
         for (size_t i = threadIdx.x; i < (size_t)d.dimc; i += blockDim.x) d.gc[i] = 0.0;
         for (size_t i = threadIdx.x; i < (size_t)d.n_rho; i += blockDim.x) { d.Hll[i] = 0.0; d.gl[i] = 0.0; }
+    }
+}
+
+// Large problems (banded storage): the same accept + clear spread over the whole grid.  `accept` may be stale when the
+// solve finished in an earlier pass; the copy is idempotent then (the candidate has not been rewritten).
+__global__ void ba_post_wide_kernel(BaDev d) {
+    const LmState* st = d.st;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    if (st->accept) {
+        const size_t np = (size_t)d.n_poses * 7, nv = (size_t)d.n_vec3 * 3, nr = d.n_rho;
+        for (size_t i = gid; i < np + nv + nr; i += stride) {
+            if (i < np) d.poses[i] = d.c_poses[i];
+            else if (i < np + nv) d.vec3[i - np] = d.c_vec3[i - np];
+            else d.rho[i - np - nv] = d.c_rho[i - np - nv];
+        }
+    }
+    if (!st->done && st->need_linearize) {
+        const size_t nH = d.nS;
+        double2* H2 = reinterpret_cast<double2*>(d.Hpp);
+        for (size_t i = gid; i < nH / 2; i += stride) H2[i] = make_double2(0.0, 0.0);
+        if ((nH & 1) && gid == 0) d.Hpp[nH - 1] = 0.0;
+        for (size_t i = gid; i < (size_t)d.dimc; i += stride) d.gc[i] = 0.0;
+        for (size_t i = gid; i < (size_t)d.n_rho; i += stride) { d.Hll[i] = 0.0; d.gl[i] = 0.0; }
     }
 }
 
@@ -1078,6 +1118,9 @@ __global__ void ba_reproj_error_kernel(BaDev d, int n, const double* __restrict_
 struct lvb_ba {
     lvb_ctx* ctx = nullptr;
     bool finalized = false, solvable = false;
+    const char* unsolvable_why = "the problem has no free camera parameter";
+    long long srow = 0, soff = 0; size_t nS = 1, chol_smem = 0; int band = 0, panel_rows = 2;
+    DevBuf<double> chol_invd;
     double cam[22];
     bool have_cam = false;
     std::vector<double> h_poses, h_vec3, h_rho;
@@ -1127,7 +1170,7 @@ static int init_tables() {
     for (int i = 0; i < 30; ++i) for (int j = 0; j <= i; ++j) { a[e] = (unsigned char)i; b[e] = (unsigned char)j; ++e; }
     LVB_CUDA(cudaMemcpyToSymbol(c_tri_a, a, sizeof(a)));
     LVB_CUDA(cudaMemcpyToSymbol(c_tri_b, b, sizeof(b)));
-    LVB_CUDA(cudaFuncSetAttribute(ba_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * 33 + (MAX_DIMC + 34) + (MAX_DIMC + 2) * 34) * 8));
+    LVB_CUDA(cudaFuncSetAttribute(ba_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
     LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (TPB * 31 + MAX_STAGE_POSES * 7 + 2) * 8));
     LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (TPB * 31 + MAX_STAGE_POSES * 7 + 2) * 8));
     LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel<0, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (MAX_STAGE_POSES * 7 + 2) * 8));
@@ -1253,11 +1296,14 @@ int lvb_ba_finalize(lvb_ba* ba) {
         }
         blk_start[blks.size()] = off;
     }
-    // larger camera systems can still be evaluated (lvb_ba_eval*); the dense reduced solve is capped
-    ba->solvable = ba->dimc <= MAX_DIMC && ba->dimc > 0;
-    // ---- device order of the blocks.  Solvable problems: TwoFrame blocks sorted by (pose_1, pose_2), PoseOnly
-    // blocks by pose, every key run padded to a multiple of 32 with weight-0 copies, so that each warp of the
-    // linearize kernel owns one key and can reduce its J^T J in shared memory before touching HBM.
+    // camera systems up to MAX_DIMC use dense lower-triangular storage, larger ones banded storage (decided below)
+    const bool dense_layout = ba->dimc <= MAX_DIMC;
+    ba->solvable = ba->dimc > 0;
+    // ---- device order of the blocks.  TwoFrame blocks sorted by (pose_1, pose_2), PoseOnly blocks by pose, so that
+    // a warp of the linearize kernel owns one key (or a few key segments) and can reduce its J^T J in shared memory
+    // before touching HBM.  Dense-layout (window-sized) problems also pad every key run to a multiple of 32 with
+    // weight-0 copies: one segment per warp.  Large problems stay unpadded (their runs are short, padding would
+    // inflate the block arrays).
     for (int k = 0; k < 6; ++k) {
         std::vector<int>& ord = ba->order[k];
         ord.clear();
@@ -1273,7 +1319,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
             for (int i = 0; i < n;) {
                 int j = i; while (j < n && key(ids[j]) == key(ids[i])) ++j;
                 for (int t = i; t < j; ++t) ord.push_back(ids[t]);
-                while (ord.size() % 32) ord.push_back(-1 - ids[i]);     // padding: encoded source block
+                while (dense_layout && ord.size() % 32) ord.push_back(-1 - ids[i]);     // padding: encoded source block
                 i = j;
             }
         } else { ord.resize(n); for (int f = 0; f < n; ++f) ord[f] = f; }
@@ -1331,6 +1377,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
     ba->n_schur_warps = (int)sw_group.size(); ba->schur_cols_max = cols_max;
     // ---- envelope of S: first structurally non-zero column per row, from every coupling the assembly can create
     std::vector<int> chol_rmax(ba->dimc / 32 + 2, 0), chol_cmin(ba->dimc / 32 + 2, 0);
+    int band = 0, panel_rows = 2;
     if (ba->solvable) {
         std::vector<int> first(ba->dimc);
         std::vector<int> fb(blks.size());
@@ -1350,17 +1397,44 @@ int lvb_ba_finalize(lvb_ba* ba) {
             for (int a = 0; a < 8; ++a) for (int b = 0; b < a; ++b) couple(offs[a], offs[b]);
         }
         for (int f = 0; f < ba->n[4]; ++f) couple(pose_off[ba->h_fi[4][2 * (size_t)f]], pose_off[ba->h_fi[4][2 * (size_t)f + 1]]);
+        // sharded problems: the other ranks' couplings arrive with the all-reduce, so the envelope must be the global one
+        if (ctx->world > 1) {
+            DevBuf<int> tmp;
+            LVB_TRY(tmp.upload(fb.data(), fb.size(), s));
+            LVB_TRY(comm_allreduce_min_i32(ctx, tmp.p, fb.size()));
+            LVB_CUDA(cudaMemcpyAsync(fb.data(), tmp.p, fb.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+            LVB_CUDA(cudaStreamSynchronize(s));
+        }
         for (int r = 0; r < ba->dimc; ++r) first[r] = fb[blk_of_off[r]];
-        for (int kb = 0, step = 0; kb < ba->dimc; kb += 32, ++step) {
-            const int bs = std::min(32, ba->dimc - kb);
-            int rmax = kb + bs - 1, cmin = kb;
-            for (int r = kb + bs; r < ba->dimc; ++r) if (first[r] < kb + bs) rmax = r;
-            for (int r = kb; r < kb + bs; ++r) cmin = std::min(cmin, first[r]);
-            // sharded problems: the other ranks' couplings arrive with the all-reduce, so no local envelope is valid
-            if (ctx->world > 1) { rmax = ba->dimc - 1; cmin = 0; }
-            chol_rmax[step] = rmax; chol_cmin[step] = cmin;
+        // rmax per 32-column step by a backward sweep: rows whose first column lies left of the end of the step
+        {
+            const int nstep = (ba->dimc + 31) / 32;
+            std::vector<int> last_row_of_col(ba->dimc, 0);      // largest row r with first[r] <= c, via prefix max over c
+            for (int c = 0; c < ba->dimc; ++c) last_row_of_col[c] = c;
+            for (int r = 0; r < ba->dimc; ++r) last_row_of_col[first[r]] = std::max(last_row_of_col[first[r]], r);
+            for (int c = 1; c < ba->dimc; ++c) last_row_of_col[c] = std::max(last_row_of_col[c], last_row_of_col[c - 1]);
+            for (int step = 0; step < nstep; ++step) {
+                const int kb = step * 32, bs = std::min(32, ba->dimc - kb);
+                int cmin = kb;
+                for (int r = kb; r < kb + bs; ++r) cmin = std::min(cmin, first[r]);
+                const int rmax = std::max(kb + bs - 1, last_row_of_col[kb + bs - 1]);
+                chol_rmax[step] = rmax; chol_cmin[step] = cmin;
+                band = std::max(band, std::max(rmax - kb, kb + bs - 1 - cmin));
+                panel_rows = std::max(panel_rows, rmax - (kb + bs) + 2);
+            }
         }
     }
+    // ---- storage of Hpp / S
+    band = std::min(std::max(band, 31), std::max(31, ba->dimc - 1));
+    if (dense_layout) { ba->srow = ba->dimc; ba->soff = 0; ba->nS = (size_t)ba->dimc * ba->dimc; }
+    else              { ba->srow = band; ba->soff = band; ba->nS = (size_t)ba->dimc * (size_t)(band + 1); }
+    ba->band = band; ba->panel_rows = panel_rows;
+    ba->chol_smem = (size_t)(32 * 33 + 32 + (panel_rows + 2) * 34) * 8;
+    if (ba->solvable && (ba->chol_smem > 227 * 1024 - 256 || ba->nS > ((size_t)3 << 30))) {
+        ba->solvable = false;
+        ba->unsolvable_why = "the envelope of the reduced camera system is too wide for the direct solver of this build";
+    }
+    if (!ba->solvable) ba->nS = 1;
     if (sw_group.empty()) { sw_group.push_back(0); sw_lm.assign(32, -1); }
     if (grp_ns.empty()) { grp_ns.push_back(0); grp_off.assign(MAX_TRACK, -1); }
 
@@ -1383,7 +1457,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
     LVB_TRY(ba->chol_rmax.upload(chol_rmax.data(), chol_rmax.size(), s));
     LVB_TRY(ba->chol_cmin.upload(chol_cmin.data(), chol_cmin.size(), s));
     // tensor-core Schur operands: compact pose dimensions (<= 128) and the zero-initialised split-bf16 U^T tiles
-    ba->tc_ok = ba->solvable && 6 * npf <= 128 && npf > 0 && ctx->world == 1;
+    ba->tc_ok = ba->solvable && dense_layout && 6 * npf <= 128 && npf > 0 && ctx->world == 1;
     {
         std::vector<int> cdim(std::max(1, ba->dimc), -1), coff(128, -1);
         int c = 0;
@@ -1426,7 +1500,8 @@ int lvb_ba_finalize(lvb_ba* ba) {
     }
     LVB_CUDA(cudaStreamSynchronize(s));
 
-    const size_t nH = ba->solvable ? (size_t)ba->dimc * ba->dimc : 1;
+    const size_t nH = ba->nS;
+    LVB_TRY(ba->chol_invd.ensure(ba->dimc + 32));
     LVB_TRY(ba->Hpp.ensure(nH)); LVB_TRY(ba->gc.ensure(ba->dimc));
     LVB_TRY(ba->Hll.ensure(std::max(1, nr))); LVB_TRY(ba->gl.ensure(std::max(1, nr)));
     LVB_TRY(ba->tf_w.ensure((size_t)std::max(1, ba->nd[0]) * 12));
@@ -1437,12 +1512,13 @@ int lvb_ba_finalize(lvb_ba* ba) {
 
     BaDev& d = ba->dev;
     d.n_poses = np; d.n_vec3 = nv; d.n_rho = nr; d.dimc = ba->dimc; d.n_pose_free = npf;
+    d.srow = ba->srow; d.soff = ba->soff; d.nS = ba->nS;
     d.poses = ba->poses.p; d.vec3 = ba->vec3.p; d.rho = ba->rho.p; d.c_poses = ba->c_poses.p; d.c_vec3 = ba->c_vec3.p; d.c_rho = ba->c_rho.p;
     d.pose_off = ba->pose_off.p; d.vec3_off = ba->vec3_off.p; d.rho_slot = ba->rho_slot.p;
     for (int k = 0; k < 6; ++k) { d.n[k] = ba->nd[k]; d.fc[k] = ba->fc[k].p; d.fi[k] = ba->fi[k].p; d.huber[k] = ba->huber[k]; }
     d.lm_start = ba->lm_start.p; d.lm_fac = ba->lm_fac.p;
     d.tf_slot = ba->tf_slot.p; d.sw_group = ba->sw_group.p; d.sw_lm = ba->sw_lm.p; d.grp_ns = ba->grp_ns.p; d.grp_off = ba->grp_off.p;
-    d.n_schur_warps = ba->n_schur_warps; d.warp_syrk = ba->solvable ? 1 : 0;
+    d.n_schur_warps = ba->n_schur_warps; d.warp_syrk = 1;
     d.tc_mode = 0; d.tc_u = ba->tc_u.p; d.tc_cdim = ba->tc_cdim.p; d.tc_off = ba->tc_off.p; d.tc_ndim = 6 * npf;
     d.Hpp = ba->Hpp.p; d.gc = ba->gc.p; d.Hll = ba->Hll.p; d.gl = ba->gl.p; d.tf_w = ba->tf_w.p;
     d.S = ba->arena.p; d.rhs = d.S + nH; d.gcr = d.rhs + ba->dimc; d.diagH = d.gcr + ba->dimc; d.scal = d.diagH + ba->dimc;
@@ -1572,7 +1648,7 @@ int lvb_ba_eval_device(lvb_ba* ba, int kind) {
 static int launch_linearize_and_reduce(lvb_ba* ba, bool standalone) {
     BaDev& d = ba->dev;
     lvb_ctx* ctx = ba->ctx;
-    const size_t nH = (size_t)d.dimc * d.dimc;
+    const size_t nH = d.nS;
     LAUNCH(ba, ba_linearize_kernel<0>, ba->ranges.b[3], TPB, ba->lin_smem, d, ba->ranges);
     LAUNCH(ba, ba_linearize_other_kernel<0>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
     LAUNCH(ba, ba_build_S_kernel, std::min(1024, nblk(nH, 256)), 256, 0, d);
@@ -1591,19 +1667,20 @@ static int launch_linearize_and_reduce(lvb_ba* ba, bool standalone) {
 static int launch_step(lvb_ba* ba) {
     BaDev& d = ba->dev;
     lvb_ctx* ctx = ba->ctx;
-    const size_t chol_smem = (size_t)(32 * 33 + (d.dimc + 34) + (d.dimc + 2) * 34) * 8;
-    LAUNCH(ba, ba_cholesky_kernel, 1, CHOL_T, chol_smem, d.S, d.rhs, d.dimc, d.st, 1, ba->chol_rmax.p, ba->chol_cmin.p);
+    LAUNCH(ba, ba_cholesky_kernel, 1, CHOL_T, ba->chol_smem, d.S, d.rhs, d.dimc, d.srow, d.soff, ba->chol_invd.p, d.st, 1, ba->chol_rmax.p, ba->chol_cmin.p);
     LAUNCH(ba, ba_update_kernel, nblk((size_t)d.n_poses + d.n_vec3 + d.n_rho, TPB), TPB, 0, d);
     LAUNCH(ba, ba_linearize_kernel<1>, ba->ranges.b[3], TPB, ba->lin_smem, d, ba->ranges);
     LAUNCH(ba, ba_linearize_other_kernel<1>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
     if (ctx->world > 1) LVB_TRY(comm_allreduce_sum_f64(ctx, &d.st->cand_cost_acc, 5));
-    LAUNCH(ba, ba_post_kernel, 1, 1024, 0, d);
+    const bool wide = d.nS > ((size_t)1 << 20) || (size_t)d.n_poses * 7 + (size_t)d.n_vec3 * 3 + d.n_rho > ((size_t)1 << 17);
+    LAUNCH(ba, ba_post_kernel, 1, wide ? 32 : 1024, 0, d, wide ? 1 : 0);
+    if (wide) LAUNCH(ba, ba_post_wide_kernel, 4 * ba->ctx->sm_count, 256, 0, d);
     return check_launch("step");
 }
 
 static int launch_clear(lvb_ba* ba) {
     BaDev& d = ba->dev;
-    const size_t nH = (size_t)d.dimc * d.dimc;
+    const size_t nH = d.nS;
     LAUNCH(ba, ba_zero_kernel, std::min(1024, nblk(nH + d.dimc + 2 * (size_t)d.n_rho, 256)), 256, 0, d);
     return check_launch("clear");
 }
@@ -1628,7 +1705,7 @@ static void apply_schur_mode(lvb_ba* ba, int mode) {
 
 static int require_solvable(lvb_ba* ba) {
     if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
-    if (!ba->solvable) { set_error("camera system dimension %d is outside the dense solver range (1..%d) of this build", ba->dimc, (int)MAX_DIMC); return LVB_ERR_UNSUPPORTED; }
+    if (!ba->solvable) { set_error("camera system of dimension %d cannot be solved: %s", ba->dimc, ba->unsolvable_why); return LVB_ERR_UNSUPPORTED; }
     return check_imu_status(ba);
 }
 
@@ -1640,7 +1717,10 @@ int lvb_ba_reduced_system(lvb_ba* ba, double radius, double* S, double* b, doubl
     LVB_TRY(launch_clear(ba));
     LVB_TRY(launch_linearize_and_reduce(ba, true));
     const int n = ba->dimc;
-    std::vector<double> hS((size_t)n * n);
+    if ((size_t)n > 8192) { set_error("lvb_ba_reduced_system: dimension %d is too large for a dense download", n); return LVB_ERR_UNSUPPORTED; }
+    std::vector<double> hS(ba->nS);
+    const size_t srow = (size_t)ba->srow, soff = (size_t)ba->soff; const int band = (ba->soff == 0) ? n : ba->band;
+    auto at = [&](int i, int j) { return (i - j <= band) ? hS[(size_t)i * srow + j + soff] : 0.0; };   // i >= j
     LmState h;
     cudaStream_t s = ba->ctx->stream;
     LVB_CUDA(cudaMemcpyAsync(hS.data(), ba->dev.S, hS.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1649,7 +1729,7 @@ int lvb_ba_reduced_system(lvb_ba* ba, double radius, double* S, double* b, doubl
     LVB_CUDA(cudaStreamSynchronize(s));
     // hand the system back in the caller-visible order (all poses, then all vec3 blocks)
     const std::vector<int>& cn = ba->canon;
-    if (S) for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) S[(size_t)cn[i] * n + cn[j]] = (j <= i) ? hS[(size_t)i * n + j] : hS[(size_t)j * n + i];
+    if (S) for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) S[(size_t)cn[i] * n + cn[j]] = (j <= i) ? at(i, j) : at(j, i);
     if (b) { std::vector<double> hb(b, b + n); for (int i = 0; i < n; ++i) b[cn[i]] = hb[i]; }
     if (cost) *cost = h.x_cost;
     return LVB_OK;

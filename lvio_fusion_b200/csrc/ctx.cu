@@ -68,6 +68,13 @@ int comm_allreduce_sum_f64(lvb_ctx* ctx, double* buf, size_t count) {
     return LVB_OK;
 }
 
+int comm_allreduce_min_i32(lvb_ctx* ctx, int* buf, size_t count) {
+    if (ctx->world <= 1 || count == 0) return LVB_OK;
+    const int rc = g_nccl.all_reduce(buf, buf, count, /*ncclInt32*/ 2, /*ncclMin*/ 3, ctx->comm, ctx->stream);
+    if (rc != 0) return nccl_fail(rc, "ncclAllReduce(min)");
+    return LVB_OK;
+}
+
 }  // namespace lvb
 
 using namespace lvb;

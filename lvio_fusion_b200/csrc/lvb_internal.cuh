@@ -37,6 +37,7 @@ struct lvb_ctx {
 namespace lvb {
 
 int comm_allreduce_sum_f64(lvb_ctx* ctx, double* buf, size_t count);   // no-op when world == 1
+int comm_allreduce_min_i32(lvb_ctx* ctx, int* buf, size_t count);      // device buffer, no-op when world == 1
 
 // Minimal owning device buffer on the stream-ordered allocator: a problem object allocates ~40 arrays, and
 // cudaMalloc (a device-wide synchronising call, ~0.1 ms each) would dominate the end-to-end time of a solve that

@@ -147,3 +147,29 @@ def test_full_ba_with_imu_init_error(lvb_ctx, orc_ctx):
     assert abs(sg.final_cost - so.final_cost) < 1e-6 * so.final_cost
     assert np.max(np.abs(pg.poses() - po.poses())) < 1e-6
     assert np.max(np.abs(pg.vec3() - po.vec3())) < 1e-5
+
+
+@pytest.mark.parametrize("n_kf,n_lm,imu", [(80, 3000, True), (150, 3000, False)])
+def test_banded_storage_matches_oracle(lvb_ctx, orc_ctx, n_kf, n_lm, imu):
+    """Camera systems above the dense cap (736) use banded storage of H_pp / S and the envelope Cholesky; the oracle
+    stays dense.  Covers the map-scale BA of backend.cpp:343-370 (imu::FullBA / global BA over all keyframes)."""
+    d = synth.make_ba_problem(n_kf, n_lm, with_imu=imu, seed=11)
+    if not imu:
+        d = dict(d); d["factors"] = dict(d["factors"])
+        d["factors"][POSE_PRIOR] = (np.concatenate([d["poses"][0], [100.0, 0.0]])[None], np.zeros((1, 1), dtype=np.int32))
+    pg, po = backend.Problem.from_dict(lvb_ctx, d), backend.Problem.from_dict(orc_ctx, d)
+    assert pg.dims() == po.dims() and pg.dims()[0] > 736
+    Sg, bg, cg = pg.reduced_system(1e4)
+    So, bo, co = po.reduced_system(1e4)
+    assert abs(cg - co) < 1e-10 * co
+    assert _rel(Sg, So) < 1e-9 and _rel(bg, bo) < 1e-9
+    sg = pg.solve(max_num_iterations=12)
+    so = po.solve(max_num_iterations=12, num_threads=4)
+    assert sg.termination_type == so.termination_type
+    assert sg.num_iterations == so.num_iterations
+    assert abs(sg.final_cost - so.final_cost) < 1e-6 * so.final_cost
+    assert sg.final_cost < 0.2 * sg.initial_cost
+    Pg, Po = pg.poses(), po.poses()
+    assert np.max(np.abs(Pg[:, 4:] - Po[:, 4:])) < 1e-5
+    assert np.max(np.abs(Pg[:, :4] - Po[:, :4])) < 1e-6
+    assert np.max(np.abs(pg.inv_depths() - po.inv_depths())) < 1e-5
