@@ -35,6 +35,11 @@ def main():
     P, V = p.poses(), p.vec3()
     rho = torch.from_numpy(np.where(np.arange(len(d["rho"])) % world == rank, p.inv_depths(), 0.0)).cuda()
     dist.all_reduce(rho)                                   # every rank owns the depths l % world == rank
+    # a map-scale problem: banded storage, the envelope is the min over ranks of the local envelopes
+    db = synth.make_ba_problem(60, 2500, with_imu=True, seed=33)
+    pb = backend.Problem.from_dict(ctx, synth.shard_ba_problem(db, rank, world))
+    sb = pb.solve(max_num_iterations=10)
+    Pb = pb.poses()
     sc = synth.make_icp_problem(4000, 50000, seed=32, kind="ground")
     fa = backend.FeatureAssociation(ctx)
     fa.set_map(sc["map"], sc["cell_size"])
@@ -51,7 +56,12 @@ def main():
         fo = backend.FeatureAssociation(octx)
         fo.set_map(sc["map"], sc["cell_size"])
         eo, sio = fo.scan_to_map(sc["mode"], sc["scan"], sc["frame_pose"], sc["map_pose"], e0, sc["weight"], -1.0, sc["huber_a"], sc["thr"])
+        pbo = backend.Problem.from_dict(octx, db)
+        sbo = pbo.solve(max_num_iterations=10, num_threads=4)
         checks = {
+            "banded_cost": abs(sb.final_cost - sbo.final_cost) < 1e-6 * sbo.final_cost,
+            "banded_iterations": sb.num_iterations == sbo.num_iterations,
+            "banded_poses": np.max(np.abs(Pb - pbo.poses())) < 1e-5,
             "final_cost": abs(s.final_cost - so.final_cost) < 1e-6 * so.final_cost,
             "iterations": s.num_iterations == so.num_iterations,
             "poses": np.max(np.abs(P - po.poses())) < 1e-6,
