@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--skip-icp", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
+    ap.add_argument("--skip-global", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -252,6 +253,28 @@ def main():
                                 "kernel": "ba_eval_two_frame_kernel", "blocks": nb, "bytes_per_block": BYTES_TWO_FRAME,
                                 "us_per_launch": t_avg * 1e3, "peak_source": src, "workload": "configs[4]-scale: %d keyframes, %d landmarks" % (EVAL_KF, EVAL_LM)}
             pb.close()
+
+        # ---------------- configs[4]: map-scale global BA (banded reduced system), landmarks sharded over the ranks
+        if not args.skip_global:
+            g_full = synth.make_ba_problem(EVAL_KF, EVAL_LM, with_imu=True, seed=synth.SEED + 1)
+            g_rows = synth.count_rows(g_full)
+            gd = synth.shard_ba_problem(g_full, rank, world) if world > 1 else g_full
+            del g_full
+            gp = backend.Problem.from_dict(ctx, gd)
+            gp.solve(bench_options(lvb, 3))
+            gp.update_params(gd["poses"], gd["vec3"], gd["rho"])
+            barrier()
+            e0.record(stream)
+            gs = gp.solve(bench_options(lvb, 5))
+            e1.record(stream)
+            barrier()
+            g_ms = max_over_ranks(e0.elapsed_time(e1)) / max(1, gs.num_iterations)
+            line["global_ba"] = {"metric": "ba_residual_jacobian_rows_per_s", "value": g_rows / (g_ms * 1e-3), "unit": "rows/s", "ms_per_iteration": g_ms,
+                                 "iterations": gs.num_iterations, "rows": g_rows, "camera_dims": gp.dims()[0], "scaling": "strong",
+                                 "cost": [gs.initial_cost, gs.final_cost],
+                                 "workload": "configs[4]-scale: %d keyframes + IMU, %d landmarks, sharded by landmark; banded reduced camera system, envelope Cholesky" % (EVAL_KF, EVAL_LM)}
+            gp.close()
+            del gd
 
         # ---------------- ICP (configs[2]): points/s through scan_to_map, map resident vs e2e with set_map
         if not args.skip_icp:
