@@ -32,6 +32,9 @@ from lvio_fusion_b200 import backend, synth  # noqa: E402
 N_KF, N_LM = 10, 4000                # configs[1]
 ICP_K, ICP_P = 120000, 1000000       # configs[2]
 EVAL_KF, EVAL_LM = 5000, 500000      # configs[4] scale for the eval-kernel roofline
+# dram__bytes_read.sum + dram__bytes_write.sum of one ba_eval_two_frame_kernel launch at that scale, from the
+# `ncu --set full` capture summarised in profiles/eval_r1_v3_summary.txt (75.19 MB + 293.14 MB)
+EVAL_DRAM_BYTES_PER_LAUNCH = 368.33e6
 BYTES_TWO_FRAME = 308                # 40 const + 12 idx + 16 r + 240 J
 
 
@@ -249,7 +252,7 @@ def main():
             t_avg = sum(times) / reps
             peak, src = peaks()
             ach = nb * BYTES_TWO_FRAME / (t_avg * 1e-3) / 1e9
-            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": EVAL_DRAM_BYTES_PER_LAUNCH,
                                 "kernel": "ba_eval_two_frame_kernel", "blocks": nb, "bytes_per_block": BYTES_TWO_FRAME,
                                 "us_per_launch": t_avg * 1e3, "peak_source": src, "workload": "configs[4]-scale: %d keyframes, %d landmarks" % (EVAL_KF, EVAL_LM)}
             pb.close()
