@@ -171,6 +171,18 @@ LVB_API int lvb_ba_get_inv_depths(lvb_ba* ba, double* rho);
  * (backend.cpp:185-190, outlier pass :229-245): err[i] = |pi(pw_i, pose_i) - ob_i|, weight 1. */
 LVB_API int lvb_ba_reprojection_errors(lvb_ba* ba, int n, const double* ob_pw /* n x 5 */, const int32_t* pose_idx, double* err);
 
+/* ---- IMU preintegration, the producer of the LVB_IMU constants.
+ * Stands behind Preintegration::Append / Propagate / MidPointIntegration (imu/preintegration.h:27-40,
+ * src/preintegration.cpp:30-127) for a batch of n keyframe intervals, and behind Preintegration::Repropagate
+ * (src/preintegration.cpp:129-142, called from tools.cpp:87 when the biases move): the same call with the new biases.
+ * Interval i owns the samples first[i] .. first[i+1]-1, each `dt acc[3] gyr[3]`; acc0/gyr0 seed the midpoint rule
+ * (the measurement at the first keyframe); noise = {ACC_N, GYR_N, ACC_W, GYR_W} (imu/imu.h, kitti.yaml:48-51).
+ * consts receives n records of 469 doubles in the LVB_IMU layout (prior_a = prior_g = -1: plain ImuError). */
+LVB_API int lvb_imu_preintegrate(lvb_ctx* ctx, int n, const int32_t* first /* n+1 */, const double* samples /* first[n] x 7 */,
+                                 const double* acc0 /* n x 3 */, const double* gyr0 /* n x 3 */,
+                                 const double* ba /* n x 3 */, const double* bg /* n x 3 */, const double noise[4],
+                                 double* consts /* n x 469 */);
+
 /* ---- lidar scan-to-map: stands behind pcl::KdTreeFLANN + FeatureAssociation::ScanToMapWith*
  * (association.cpp:270-384) and the two Solve calls of Mapping::Optimize (mapping.cpp:139-191) */
 LVB_API int lvb_icp_create(lvb_ctx* ctx, lvb_icp** out);

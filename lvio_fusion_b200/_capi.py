@@ -81,6 +81,7 @@ _SIGS = {
     "ba_get_vec3": (C.c_int, [VP, c_double_p]),
     "ba_get_inv_depths": (C.c_int, [VP, c_double_p]),
     "ba_reprojection_errors": (C.c_int, [VP, C.c_int, c_double_p, c_int32_p, c_double_p]),
+    "imu_preintegrate": (C.c_int, [VP, C.c_int, c_int32_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "icp_create": (C.c_int, [VP, C.POINTER(VP)]),
     "icp_destroy": (None, [VP]),
     "icp_set_map": (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_float]),

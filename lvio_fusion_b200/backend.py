@@ -85,6 +85,19 @@ def default_options(api, **kw):
     return o
 
 
+def preintegrate(ctx, first, samples, acc0, gyr0, ba, bg, noise4):
+    """Batched Preintegration::Append/Propagate (preintegration.cpp:30-127); re-running it with new biases is
+    Repropagate (:129-142).  Interval i owns samples[first[i]:first[i+1]] (rows `dt acc[3] gyr[3]`).
+    Returns the LVB_IMU constant records [n, 469]."""
+    first = np.ascontiguousarray(first, dtype=np.int32)
+    n = len(first) - 1
+    samples, acc0, gyr0, ba, bg, noise4 = (_f64(a) for a in (samples, acc0, gyr0, ba, bg, noise4))
+    assert samples.shape == (int(first[-1]), 7) and acc0.shape == gyr0.shape == ba.shape == bg.shape == (n, 3) and noise4.shape == (4,)
+    out = np.empty((n, CONST_STRIDE[IMU]), dtype=np.float64)
+    ctx.api.check(ctx.api.imu_preintegrate(ctx.h, n, _ip(first), _dp(samples), _dp(acc0), _dp(gyr0), _dp(ba), _dp(bg), _dp(noise4), _dp(out)), "imu_preintegrate")
+    return out
+
+
 class Problem:
     """adapt::Problem analogue: parameter blocks by index, residual blocks by kind."""
 

@@ -284,6 +284,16 @@ int orc_preintegrate(int n, const double* samples7, const double* acc0, const do
     }
     store_preint(s.p, out); return LVB_OK;
 }
+// batch form with the product's signature (lvb_imu_preintegrate): interval i owns samples first[i]..first[i+1]-1
+int orc_imu_preintegrate(void* /*ctx*/, int n, const int32_t* first, const double* samples7, const double* acc0, const double* gyr0,
+                         const double* ba, const double* bg, const double* noise4, double* out) {
+    if (n < 0 || (n && (!first || !acc0 || !gyr0 || !ba || !bg || !noise4 || !out))) return fail(LVB_ERR_INVALID, "orc_imu_preintegrate: bad arguments");
+    for (int i = 0; i < n; ++i) {
+        if (first[i + 1] < first[i]) return fail(LVB_ERR_INVALID, "orc_imu_preintegrate: first[] must be non-decreasing");
+        orc_preintegrate(first[i + 1] - first[i], samples7 + 7 * (size_t)first[i], acc0 + 3 * i, gyr0 + 3 * i, ba + 3 * i, bg + 3 * i, noise4, out + (size_t)kImuConsts * i);
+    }
+    return LVB_OK;
+}
 int orc_sqrt_information(const double* cov225, double* U225) {
     double c[15][15], U[15][15]; std::memcpy(c, cov225, sizeof(c));
     if (!sqrt_information(c, U)) return fail(LVB_ERR_NUMERIC, "covariance inverse not SPD");

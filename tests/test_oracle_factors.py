@@ -183,3 +183,22 @@ def test_imu_init_error_variant(orc_ctx):
     assert np.allclose(raw[9:12], -ba, atol=1e-9) and np.allclose(raw[12:15], -bg, atol=1e-9)
     s = p.solve(max_num_iterations=20)
     assert s.final_cost < s.initial_cost
+
+
+def test_batched_preintegration_agrees_with_numpy_producer(orc_ctx):
+    """Two independent producers of the LVB_IMU records: the oracle's C++ restatement (batch ABI form) and
+    synth.preintegrate_batch (numpy).  They differ only by the O(|w dt|^2) un-normalised-quaternion detail noted there."""
+    from lvio_fusion_b200 import backend, synth
+    rng = np.random.default_rng(3)
+    F, S = 12, 10
+    acc = rng.normal(0, 1.0, (F, S + 1, 3)) + [0, 0, 9.81]
+    gyr = rng.normal(0, 0.2, (F, S + 1, 3))
+    ba = rng.normal(0, 0.02, (F, 3)); bg = rng.normal(0, 0.005, (F, 3))
+    ref = synth.preintegrate_batch(0.01, acc, gyr, ba, bg)
+    first = (np.arange(F + 1) * S).astype(np.int32)
+    samples = np.concatenate([np.full((F, S, 1), 0.01), acc[:, 1:], gyr[:, 1:]], axis=2).reshape(F * S, 7)
+    out = backend.preintegrate(orc_ctx, first, samples, acc[:, 0], gyr[:, 0], ba, bg, np.array(synth.IMU_NOISE))
+    assert out.shape == ref.shape
+    assert np.max(np.abs(out[:, :17] - ref[:, :17])) < 1e-6
+    assert np.max(np.abs(out[:, 17:242] - ref[:, 17:242])) < 1e-6
+    assert np.max(np.abs(out[:, 242:467] - ref[:, 242:467])) < 1e-6 * np.abs(ref[:, 242:467]).max()
