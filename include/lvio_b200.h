@@ -218,6 +218,37 @@ LVB_API int lvb_icp_scan_to_map(lvb_icp* icp, int mode, const void* scan, int n,
                         double weight, double prior_weight, double huber_a, double dist_thr,
                         const lvb_solve_options* options, lvb_solve_summary* summary);
 
+/* ---- lidar feature pipeline, the producer of the scan-to-map inputs.
+ * Stands behind FeatureAssociation::Process (association.cpp:88-268: Preprocess, AdjustDistortion, CalculateSmoothness,
+ * ExtractFeatures, SegmentGround, Sensor2Robot) and ImageProjection::Process (projection.cpp:26-320: range-image
+ * projection, ground removal, segmentation), plus the three PCL filters they call (VoxelGrid, RadiusOutlierRemoval,
+ * SACSegmentation plane RANSAC).  Clouds are arrays of `x y z intensity` float32 (pcl::PointXYZI without padding) unless
+ * a stride is given. */
+typedef struct lvb_lidar_config {
+    int32_t num_scans, horizon_scan;         /* kitti.yaml:35-36 */
+    double ang_res_y, ang_bottom;            /* :37-38 */
+    int32_t ground_rows, reserved;           /* :39 */
+    double cycle_time, min_range, max_range; /* :40-42 */
+    double resolution;                       /* :45, Lidar::resolution */
+    double extrinsic[7];                     /* T_body_lidar, Sophus layout (estimator.cpp:133-141) */
+} lvb_lidar_config;
+LVB_API void lvb_lidar_default_config(lvb_lidar_config* cfg);   /* the kitti.yaml values, identity extrinsic */
+/* Preprocess + ImageProjection::Process + AdjustDistortion + CalculateSmoothness.  Outputs have capacity
+ * num_scans * horizon_scan; orientation = {start, end, diff}; any output pointer may be NULL. */
+LVB_API int lvb_lidar_segment(lvb_ctx* ctx, const lvb_lidar_config* cfg, const void* points, int n, int stride_bytes,
+                              float* seg_xyzi, float* seg_range, uint8_t* seg_ground, int32_t* seg_col, float* seg_curvature,
+                              int32_t* start_ring /* num_scans */, int32_t* end_ring /* num_scans */, float orientation[3], int32_t* n_seg);
+/* pcl::VoxelGrid (cubic leaf, all fields averaged, output ordered by voxel index); out capacity n */
+LVB_API int lvb_lidar_voxel_grid(lvb_ctx* ctx, const float* xyzi, int n, float leaf, float* out_xyzi, int32_t* n_out);
+/* pcl::RadiusOutlierRemoval: keeps points with >= min_neighbors points (itself included) closer than radius */
+LVB_API int lvb_lidar_radius_outlier_removal(lvb_ctx* ctx, const float* xyzi, int n, double radius, int min_neighbors, float* out_xyzi, int32_t* n_out);
+/* FeatureAssociation::SegmentGround (association.cpp:254-268): inliers of the RANSAC plane (100 iterations, p = 0.99) */
+LVB_API int lvb_lidar_segment_ground(lvb_ctx* ctx, const float* xyzi, int n, double distance_threshold, float* out_xyzi, int32_t* n_out);
+/* FeatureAssociation::Process: raw scan -> frame->feature_lidar {points_ground, points_surf} in the robot frame.
+ * Output capacity num_scans * horizon_scan points each. */
+LVB_API int lvb_lidar_extract_features(lvb_ctx* ctx, const lvb_lidar_config* cfg, const void* points, int n, int stride_bytes,
+                                       float* ground_xyzi, int32_t* n_ground, float* surf_xyzi, int32_t* n_surf);
+
 #ifdef __cplusplus
 }
 #endif

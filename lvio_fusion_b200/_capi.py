@@ -53,6 +53,18 @@ class SolveSummary(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class LidarConfig(C.Structure):
+    """lvb_lidar_config (include/lvio_b200.h): kitti.yaml:35-45 + the lidar extrinsic."""
+    _fields_ = [
+        ("num_scans", C.c_int32), ("horizon_scan", C.c_int32),
+        ("ang_res_y", C.c_double), ("ang_bottom", C.c_double),
+        ("ground_rows", C.c_int32), ("reserved", C.c_int32),
+        ("cycle_time", C.c_double), ("min_range", C.c_double), ("max_range", C.c_double),
+        ("resolution", C.c_double),
+        ("extrinsic", C.c_double * 7),
+    ]
+
+
 VP = C.c_void_p
 _SIGS = {
     "version": (C.c_int, []),
@@ -82,6 +94,13 @@ _SIGS = {
     "ba_get_inv_depths": (C.c_int, [VP, c_double_p]),
     "ba_reprojection_errors": (C.c_int, [VP, C.c_int, c_double_p, c_int32_p, c_double_p]),
     "imu_preintegrate": (C.c_int, [VP, C.c_int, c_int32_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "lidar_default_config": (None, [C.POINTER(LidarConfig)]),
+    "lidar_segment": (C.c_int, [VP, C.POINTER(LidarConfig), VP, C.c_int, C.c_int, c_float_p, c_float_p, c_uint8_p, c_int32_p, c_float_p,
+                                c_int32_p, c_int32_p, c_float_p, c_int32_p]),
+    "lidar_voxel_grid": (C.c_int, [VP, c_float_p, C.c_int, C.c_float, c_float_p, c_int32_p]),
+    "lidar_radius_outlier_removal": (C.c_int, [VP, c_float_p, C.c_int, C.c_double, C.c_int, c_float_p, c_int32_p]),
+    "lidar_segment_ground": (C.c_int, [VP, c_float_p, C.c_int, C.c_double, c_float_p, c_int32_p]),
+    "lidar_extract_features": (C.c_int, [VP, C.POINTER(LidarConfig), VP, C.c_int, C.c_int, c_float_p, c_int32_p, c_float_p, c_int32_p]),
     "icp_create": (C.c_int, [VP, C.POINTER(VP)]),
     "icp_destroy": (None, [VP]),
     "icp_set_map": (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_float]),

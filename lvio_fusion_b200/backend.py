@@ -312,3 +312,72 @@ class FeatureAssociation:
                                                 float(weight), float(prior_weight), float(huber_a), float(dist_thr),
                                                 C.byref(o), C.byref(s)), "icp_scan_to_map")
         return e, s
+
+
+def _fp(a):
+    return None if a is None else a.ctypes.data_as(_capi.c_float_p)
+
+
+class LidarFeatures:
+    """Lidar feature pipeline (FeatureAssociation::Process + ImageProjection::Process, association.cpp:88-268,
+    projection.cpp:26-320): raw scan -> ground / surf feature clouds.  Clouds are float32 [n, 4] (x, y, z, intensity)."""
+
+    def __init__(self, ctx, **overrides):
+        self.ctx = ctx
+        self.cfg = _capi.LidarConfig()
+        ctx.api.lidar_default_config(C.byref(self.cfg))
+        for k, v in overrides.items():
+            if k == "extrinsic":
+                for i in range(7):
+                    self.cfg.extrinsic[i] = float(v[i])
+            else:
+                setattr(self.cfg, k, v)
+
+    @property
+    def capacity(self):
+        return int(self.cfg.num_scans) * int(self.cfg.horizon_scan)
+
+    @staticmethod
+    def _raw(points):
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        assert pts.ndim == 2 and pts.shape[1] >= 3
+        return pts, pts.shape[0], pts.shape[1] * 4
+
+    def segment(self, points):
+        """Preprocess + range-image projection + ground removal + segmentation + relative time + smoothness."""
+        pts, n, stride = self._raw(points)
+        cap, R = self.capacity, int(self.cfg.num_scans)
+        seg = np.empty((cap, 4), np.float32); rng = np.empty(cap, np.float32); gnd = np.empty(cap, np.uint8)
+        col = np.empty(cap, np.int32); curv = np.empty(cap, np.float32)
+        sr = np.empty(R, np.int32); er = np.empty(R, np.int32); ori = np.empty(3, np.float32); m = np.zeros(1, np.int32)
+        a = self.ctx.api
+        a.check(a.lidar_segment(self.ctx.h, C.byref(self.cfg), pts.ctypes.data_as(C.c_void_p), n, stride, _fp(seg), _fp(rng), _bp(gnd), _ip(col), _fp(curv),
+                                _ip(sr), _ip(er), _fp(ori), _ip(m)), "lidar_segment")
+        k = int(m[0])
+        return {"points": seg[:k].copy(), "range": rng[:k].copy(), "ground": gnd[:k].copy(), "col": col[:k].copy(), "curvature": curv[:k].copy(),
+                "start_ring": sr, "end_ring": er, "orientation": ori}
+
+    def _filter(self, fn, name, cloud, *args):
+        cloud = np.ascontiguousarray(cloud, dtype=np.float32).reshape(-1, 4)
+        out = np.empty_like(cloud) if len(cloud) else np.empty((1, 4), np.float32)
+        m = np.zeros(1, np.int32)
+        self.ctx.api.check(fn(self.ctx.h, _fp(cloud), len(cloud), *args, _fp(out), _ip(m)), name)
+        return out[:int(m[0])].copy()
+
+    def voxel_grid(self, cloud, leaf):
+        return self._filter(self.ctx.api.lidar_voxel_grid, "lidar_voxel_grid", cloud, C.c_float(leaf))
+
+    def radius_outlier_removal(self, cloud, radius, min_neighbors):
+        return self._filter(self.ctx.api.lidar_radius_outlier_removal, "lidar_radius_outlier_removal", cloud, C.c_double(radius), int(min_neighbors))
+
+    def segment_ground(self, cloud, threshold):
+        return self._filter(self.ctx.api.lidar_segment_ground, "lidar_segment_ground", cloud, C.c_double(threshold))
+
+    def extract(self, points):
+        """FeatureAssociation::Process: returns (points_ground, points_surf) in the robot frame."""
+        pts, n, stride = self._raw(points)
+        cap = self.capacity
+        g = np.empty((cap, 4), np.float32); s = np.empty((cap, 4), np.float32); ng = np.zeros(1, np.int32); ns = np.zeros(1, np.int32)
+        a = self.ctx.api
+        a.check(a.lidar_extract_features(self.ctx.h, C.byref(self.cfg), pts.ctypes.data_as(C.c_void_p), n, stride, _fp(g), _ip(ng), _fp(s), _ip(ns)), "lidar_extract_features")
+        return g[:int(ng[0])].copy(), s[:int(ns[0])].copy()

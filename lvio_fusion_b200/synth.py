@@ -443,3 +443,49 @@ def relative_rpyxyz(map_pose, frame_pose):
     pitch = np.arcsin(2 * (q0 * q2 - q1 * q3))
     roll = np.arctan2(2 * (q2 * q3 + q0 * q1), 1 - 2 * (q1 * q1 + q2 * q2))
     return np.array([yaw, pitch, roll, t[0], t[1], t[2]])
+
+
+def make_lidar_scan(seed=SEED, num_scans=64, horizon_scan=1800, ang_res_y=0.427, ang_bottom=24.9, sensor_height=1.73,
+                    sigma=0.01, dropout=0.02, n_boxes=14):
+    """One revolution of a KITTI-like 64-beam spinning lidar (kitti.yaml:35-42) in the sensor frame (z up).
+
+    Scene: ground plane, a 44 m x 26 m walled yard, axis-aligned boxes (cars / poles) on the ground.  Rays are fired column by
+    column (all beams of one azimuth, azimuth decreasing so that the reference's orientation -atan2(y, x) increases through
+    the sweep), range noise sigma, a fraction of returns dropped (NaN, as the driver reports no-returns) and everything
+    outside the walls missing.  Returns float32 [n, 4] (x, y, z, 0) = pcl::PointXYZ records with a 16-byte stride.
+    """
+    rng = _rng(seed, 7)
+    az0 = rng.uniform(-np.pi, np.pi)
+    az = az0 - 2 * np.pi * (np.arange(horizon_scan) + rng.uniform(-0.2, 0.2, horizon_scan)) / horizon_scan
+    el = np.deg2rad(-ang_bottom + ang_res_y * (np.arange(num_scans) + 0.5))
+    A, E = np.meshgrid(az, el, indexing="ij")            # column-major firing order
+    d = np.stack([np.cos(E) * np.cos(A), np.cos(E) * np.sin(A), np.sin(E)], axis=-1).reshape(-1, 3)
+    t_best = np.full(len(d), np.inf)
+    # ground z = -h
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = -sensor_height / d[:, 2]
+        t_best = np.where((t > 0) & (t < t_best), t, t_best)
+        # walls
+        for axis, val in ((0, 22.0), (0, -22.0), (1, 13.0), (1, -13.0)):
+            t = val / d[:, axis]
+            t_best = np.where((t > 0) & (t < t_best), t, t_best)
+        # boxes: slab test
+        for _ in range(n_boxes):
+            c = np.array([rng.uniform(-18, 18), rng.uniform(-10, 10)])
+            if np.linalg.norm(c) < 6.0:
+                c = c / max(np.linalg.norm(c), 1e-3) * 7.0
+            half = np.array([rng.uniform(0.15, 2.2), rng.uniform(0.15, 1.0)])
+            height = rng.uniform(1.2, 2.5)
+            lo = np.array([c[0] - half[0], c[1] - half[1], -sensor_height])
+            hi = np.array([c[0] + half[0], c[1] + half[1], -sensor_height + height])
+            t1, t2 = lo / d, hi / d
+            tn = np.minimum(t1, t2).max(axis=1); tf = np.maximum(t1, t2).min(axis=1)
+            hit = (tn > 0) & (tn <= tf)
+            t_best = np.where(hit & (tn < t_best), tn, t_best)
+    t_best = t_best + rng.normal(0, sigma, len(d))
+    pts = d * t_best[:, None]
+    drop = rng.uniform(size=len(d)) < dropout
+    pts[drop | ~np.isfinite(t_best)] = np.nan
+    out = np.zeros((len(d), 4), dtype=np.float32)
+    out[:, :3] = pts
+    return out

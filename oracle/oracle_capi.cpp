@@ -12,6 +12,7 @@
 #include "../include/lvio_b200.h"
 #include "ba.h"
 #include "icp.h"
+#include "lidar.h"
 
 using namespace oracle;
 
@@ -307,6 +308,70 @@ int orc_se3_compose(const double* a, const double* b, double* out) { store_rigid
 int orc_se3_inverse(const double* a, double* out) { store_rigid(inverse(load_rigid<double>(a)), out); return LVB_OK; }
 int orc_transform_f32(const double* pose, int n, const float* in3, float* out3) {
     for (int i = 0; i < n; ++i) { const Pt q = transform_f32(pose, Pt{in3[3 * i], in3[3 * i + 1], in3[3 * i + 2]}); out3[3 * i] = q.x; out3[3 * i + 1] = q.y; out3[3 * i + 2] = q.z; }
+    return LVB_OK;
+}
+
+
+// ---- lidar feature pipeline (lidar.h), same signatures as lvb_lidar_*
+static LidarConfig to_cfg(const lvb_lidar_config* c) {
+    LidarConfig k;
+    k.num_scans = c->num_scans; k.horizon_scan = c->horizon_scan; k.ang_res_y = c->ang_res_y; k.ang_bottom = c->ang_bottom;
+    k.ground_rows = c->ground_rows; k.cycle_time = c->cycle_time; k.min_range = c->min_range; k.max_range = c->max_range; k.resolution = c->resolution;
+    std::memcpy(k.extrinsic, c->extrinsic, sizeof(k.extrinsic));
+    return k;
+}
+static int bad_cfg(const lvb_lidar_config* c) {
+    return !c || c->num_scans <= 0 || c->horizon_scan <= 0 || c->num_scans > 1024 || c->horizon_scan > 16384 || !(c->ang_res_y > 0) || c->ground_rows < 0 || !(c->resolution > 0);
+}
+static std::vector<PointI> to_cloud(const float* xyzi, int n) {
+    std::vector<PointI> v(n);
+    for (int i = 0; i < n; ++i) v[i] = PointI{xyzi[4 * i], xyzi[4 * i + 1], xyzi[4 * i + 2], xyzi[4 * i + 3]};
+    return v;
+}
+static void from_cloud(const std::vector<PointI>& v, float* out, int32_t* n_out) {
+    if (out) for (size_t i = 0; i < v.size(); ++i) { out[4 * i] = v[i].x; out[4 * i + 1] = v[i].y; out[4 * i + 2] = v[i].z; out[4 * i + 3] = v[i].intensity; }
+    if (n_out) *n_out = (int32_t)v.size();
+}
+void orc_lidar_default_config(lvb_lidar_config* c) {
+    std::memset(c, 0, sizeof(*c));
+    c->num_scans = 64; c->horizon_scan = 1800; c->ang_res_y = 0.427; c->ang_bottom = 24.9; c->ground_rows = 60;
+    c->cycle_time = 0.1036; c->min_range = 5; c->max_range = 30; c->resolution = 0.2; c->extrinsic[3] = 1.0;
+}
+int orc_lidar_segment(void*, const lvb_lidar_config* cfg, const void* points, int n, int stride, float* seg_xyzi, float* seg_range, uint8_t* seg_ground,
+                      int32_t* seg_col, float* seg_curv, int32_t* start_ring, int32_t* end_ring, float* orientation, int32_t* n_seg) {
+    if (bad_cfg(cfg) || n < 0 || (n && !points) || stride < 12 || (stride & 3)) return fail(LVB_ERR_INVALID, "orc_lidar_segment: bad arguments");
+    const LidarConfig c = to_cfg(cfg);
+    Segmented s = lidar_project_and_segment(c, lidar_preprocess(c, (const unsigned char*)points, n, stride));
+    lidar_adjust_distortion(c, s);
+    lidar_smoothness(s);
+    from_cloud(s.pts, seg_xyzi, n_seg);
+    for (size_t i = 0; i < s.pts.size(); ++i) {
+        if (seg_range) seg_range[i] = s.range[i];
+        if (seg_ground) seg_ground[i] = s.ground[i];
+        if (seg_col) seg_col[i] = s.col[i];
+        if (seg_curv) seg_curv[i] = s.curvature[i];
+    }
+    for (int i = 0; i < c.num_scans; ++i) { if (start_ring) start_ring[i] = s.start_ring[i]; if (end_ring) end_ring[i] = s.end_ring[i]; }
+    if (orientation) { orientation[0] = s.start_orientation; orientation[1] = s.end_orientation; orientation[2] = s.orientation_diff; }
+    return LVB_OK;
+}
+int orc_lidar_voxel_grid(void*, const float* xyzi, int n, float leaf, float* out, int32_t* n_out) {
+    if (n < 0 || (n && !xyzi) || !(leaf > 0.0f)) return fail(LVB_ERR_INVALID, "orc_lidar_voxel_grid: bad arguments");
+    from_cloud(voxel_grid(to_cloud(xyzi, n), leaf), out, n_out); return LVB_OK;
+}
+int orc_lidar_radius_outlier_removal(void*, const float* xyzi, int n, double radius, int min_neighbors, float* out, int32_t* n_out) {
+    if (n < 0 || (n && !xyzi) || !(radius > 0.0)) return fail(LVB_ERR_INVALID, "orc_lidar_radius_outlier_removal: bad arguments");
+    from_cloud(radius_outlier_removal(to_cloud(xyzi, n), radius, min_neighbors), out, n_out); return LVB_OK;
+}
+int orc_lidar_segment_ground(void*, const float* xyzi, int n, double thr, float* out, int32_t* n_out) {
+    if (n < 0 || (n && !xyzi) || !(thr > 0.0)) return fail(LVB_ERR_INVALID, "orc_lidar_segment_ground: bad arguments");
+    from_cloud(segment_ground(to_cloud(xyzi, n), thr), out, n_out); return LVB_OK;
+}
+int orc_lidar_extract_features(void*, const lvb_lidar_config* cfg, const void* points, int n, int stride, float* ground, int32_t* n_ground, float* surf, int32_t* n_surf) {
+    if (bad_cfg(cfg) || n < 0 || (n && !points) || stride < 12 || (stride & 3)) return fail(LVB_ERR_INVALID, "orc_lidar_extract_features: bad arguments");
+    std::vector<PointI> g, sf;
+    lidar_extract_features(to_cfg(cfg), (const unsigned char*)points, n, stride, g, sf);
+    from_cloud(g, ground, n_ground); from_cloud(sf, surf, n_surf);
     return LVB_OK;
 }
 
