@@ -69,17 +69,18 @@ inline Segmented lidar_project_and_segment(const LidarConfig& c, const std::vect
     const int R = c.num_scans, W = c.horizon_scan;
     Segmented s;
     s.start_ring.assign(R, 0); s.end_ring.assign(R, 0);
-    if (points.empty()) return s;
     const float ang_res_x = (float)(360.0 / (double)(float)W);      // projection.h:38  360.0 / float(horizon_scan)
     const float ang_res_y = (float)c.ang_res_y, ang_bottom = (float)c.ang_bottom;
     const float alpha_x = (float)((double)ang_res_x / 180.0 * M_PI), alpha_y = (float)((double)ang_res_y / 180.0 * M_PI);
     const float theta = (float)(60.0 / 180.0 * M_PI);
-    // FindStartEndAngle :42-55
-    s.start_orientation = (float)(-std::atan2((double)points.front().y, (double)points.front().x));
-    s.end_orientation = (float)(-std::atan2((double)points.back().y, (double)points.back().x) + 2 * M_PI);
-    if ((double)(s.end_orientation - s.start_orientation) > 3 * M_PI) s.end_orientation = (float)((double)s.end_orientation - 2 * M_PI);
-    else if ((double)(s.end_orientation - s.start_orientation) < M_PI) s.end_orientation = (float)((double)s.end_orientation + 2 * M_PI);
-    s.orientation_diff = s.end_orientation - s.start_orientation;
+    // FindStartEndAngle :42-55 (an empty cloud is undefined behaviour in the reference; defined here as orientation 0)
+    if (!points.empty()) {
+        s.start_orientation = (float)(-std::atan2((double)points.front().y, (double)points.front().x));
+        s.end_orientation = (float)(-std::atan2((double)points.back().y, (double)points.back().x) + 2 * M_PI);
+        if ((double)(s.end_orientation - s.start_orientation) > 3 * M_PI) s.end_orientation = (float)((double)s.end_orientation - 2 * M_PI);
+        else if ((double)(s.end_orientation - s.start_orientation) < M_PI) s.end_orientation = (float)((double)s.end_orientation + 2 * M_PI);
+        s.orientation_diff = s.end_orientation - s.start_orientation;
+    }
     // ProjectPointCloud :57-101
     std::vector<float> range_mat((size_t)R * W, FLT_MAX);
     std::vector<PointI> full((size_t)R * W, PointI{std::numeric_limits<float>::quiet_NaN(), std::numeric_limits<float>::quiet_NaN(), std::numeric_limits<float>::quiet_NaN(), -1.0f});

@@ -33,7 +33,7 @@ def test_segment_edge_cases(pipes):
     sparse = (rng.normal(0, 8, (300, 4))).astype(np.float32)                       # few scattered returns: tiny segments
     for cloud in (empty, nan, near, sparse):
         sg, so = g.segment(cloud), o.segment(cloud)
-        for k in ("points", "range", "ground", "col", "curvature", "start_ring", "end_ring"):
+        for k in ("points", "range", "ground", "col", "curvature", "start_ring", "end_ring", "orientation"):
             assert np.array_equal(sg[k], so[k]), k
     # a 32-byte record stride (pcl::PointXYZI with padding) gives the same result as the packed one
     scan = synth.make_lidar_scan(seed=13, horizon_scan=900)
@@ -85,6 +85,6 @@ def test_extract_features_bit_exact(lvb_ctx, orc_ctx, seed):
     assert np.array_equal(gs, os_)
     # the features feed the scan-to-map entry point unchanged (x y z intensity, 16-byte records)
     fa = backend.FeatureAssociation(lvb_ctx)
-    fa.set_map(gs, 0.4)
+    fa.set_map(gs, 2.0)
     idx, d2 = fa.knn3(gs[:100], np.array([0, 0, 0, 1, 0, 0, 0.0]), 4.0)
     assert np.array_equal(idx[:, 0], np.arange(100)) and np.all(d2[:, 0] == 0)
