@@ -309,6 +309,21 @@ def main():
                                    "note": "map upload + voxel build + scan upload + association + 4 LM iterations"},
                            "workload": "configs[2]: %d-point scan vs %d-point map, surf gate, Huber 0.1" % (ICP_K, ICP_P)}
 
+        # ---------------- lidar feature pipeline: raw 64 x 1800 sweep -> ground / surf features, host buffers in and out
+        if rank == 0 and not args.skip_icp:
+            sweep = synth.make_lidar_scan(seed=synth.SEED)
+            lf = backend.LidarFeatures(ctx)
+            for _ in range(3):
+                gcl, scl = lf.extract(sweep)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                lf.extract(sweep)
+            lf_ms = (time.perf_counter() - t0) * 1e3 / 10
+            line["lidar_features"] = {"metric": "lidar_raw_points_per_s", "value": len(sweep) / (lf_ms * 1e-3), "unit": "points/s", "ms_per_sweep": lf_ms,
+                                      "ground_points": int(len(gcl)), "surf_points": int(len(scl)),
+                                      "workload": "FeatureAssociation::Process on a synthetic %d-point sweep (64 x 1800), e2e with H2D/D2H" % len(sweep)}
+
         sampler.stop_flag = True
         sampler.join(timeout=2)
         line["clocks"] = sampler.summary()
@@ -327,6 +342,12 @@ def main():
             dtc = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": synth.count_rows(dc) * itc / dtc, "unit": "rows/s", "cores": T, "kind": "port",
                                     "sample": "%d LM iterations of the configs[1] window on the oracle restatement (%d threads of %d cores)" % (itc, T, os.cpu_count() or 1)}
+            if "lidar_features" in line:
+                olf = backend.LidarFeatures(octx)
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    olf.extract(sweep)
+                line["lidar_features"]["cpu_port_points_per_s"] = len(sweep) / ((time.perf_counter() - t0) / 5)
             print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
