@@ -152,18 +152,90 @@ __device__ __forceinline__ ImuConst load_imu_const(const double* c) {
 
 // ------------------------------------------------------------------ IMU prepare (once per finalize)
 // raw 467 -> packed 287 (scalars, five sub-blocks, U); status[f] != 0 when cov^-1 is not SPD
-__global__ void imu_prepare_kernel(const double* raw, double* packed, int n, int* status) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per factor.  Same arithmetic per element as lvb_math.cuh::sqrt_information (partial-pivot LU inverse, then
+// Cholesky; the oracle's order), with the independent elements of every step spread over the lanes.
+__device__ int sqrt_information_warp(const double* __restrict__ cov, double* __restrict__ U, double* a, double* inv, double prior_a, double prior_g) {
+    const int n = 15, lane = threadIdx.x & 31;
+    __shared__ int s_piv[4][16];
+    int* piv = s_piv[(threadIdx.x >> 5) & 3];
+    for (int e = lane; e < 225; e += 32) a[e] = cov[e];
+    if (lane < n) piv[lane] = lane;
+    __syncwarp();
+    for (int k = 0; k < n; ++k) {
+        // pivot: largest |a[i][k]|, i >= k, first index on ties
+        double bv = (lane >= k && lane < n) ? fabs(a[lane * n + k]) : -1.0;
+        int best = lane;
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+            if (ov > bv || (ov == bv && ob < best)) { bv = ov; best = ob; }
+        }
+        if (bv == 0.0) return 1;
+        if (best != k) {
+            if (lane < n) { const double t = a[k * n + lane]; a[k * n + lane] = a[best * n + lane]; a[best * n + lane] = t; }
+            if (lane == 0) { const int t = piv[k]; piv[k] = piv[best]; piv[best] = t; }
+        }
+        __syncwarp();
+        if (lane > k && lane < n) a[lane * n + k] /= a[k * n + k];
+        __syncwarp();
+        const int m = n - 1 - k;
+        for (int e = lane; e < m * m; e += 32) { const int i = k + 1 + e / m, j = k + 1 + e % m; a[i * n + j] -= a[i * n + k] * a[k * n + j]; }
+        __syncwarp();
+    }
+    if (lane < n) {                       // column `lane` of the inverse: forward / backward substitution
+        const int c = lane;
+        double y[15];
+#pragma unroll
+        for (int i = 0; i < 15; ++i) {
+            double sacc = (piv[i] == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < 15; ++k) if (k < i) sacc -= a[i * n + k] * y[k];
+            y[i] = sacc;
+        }
+#pragma unroll
+        for (int i = 14; i >= 0; --i) {
+            double sacc = y[i];
+#pragma unroll
+            for (int k = 0; k < 15; ++k) if (k > i) sacc -= a[i * n + k] * inv[k * n + c];
+            inv[i * n + c] = sacc / a[i * n + i];
+        }
+    }
+    __syncwarp();
+    if (prior_a >= 0.0 && prior_g >= 0.0 && lane < 9) {      // ImuInitError (imu_error.hpp:147-149)
+        const int i = lane / 3, j = lane % 3;
+        inv[(9 + i) * n + 9 + j] = (i == j) ? prior_a : 0.0; inv[(12 + i) * n + 12 + j] = (i == j) ? prior_g : 0.0;
+    }
+    for (int e = lane; e < 225; e += 32) a[e] = 0.0;          // a := L
+    __syncwarp();
+    for (int j = 0; j < n; ++j) {
+        double d = inv[j * n + j];
+        for (int k = 0; k < j; ++k) d -= a[j * n + k] * a[j * n + k];
+        if (!(d > 0.0)) return 2;
+        const double ljj = sqrt(d);
+        if (lane == 0) a[j * n + j] = ljj;
+        if (lane > j && lane < n) { double sacc = inv[lane * n + j]; for (int k = 0; k < j; ++k) sacc -= a[lane * n + k] * a[j * n + k]; a[lane * n + j] = sacc / ljj; }
+        __syncwarp();
+    }
+    for (int e = lane; e < 225; e += 32) { const int i = e / n, j = e - n * i; U[e] = a[j * n + i]; }
+    return 0;
+}
+
+__global__ void __launch_bounds__(128) imu_prepare_kernel(const double* raw, double* packed, int n, int* status) {
+    __shared__ double s_work[4][450];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * 4 + warp;
     if (f >= n) return;
     const double* c = raw + (size_t)f * IMU_RAW;
     double* o = packed + (size_t)f * IMU_STRIDE;
-    for (int i = 0; i < 17; ++i) o[i] = c[i];
+    if (lane < 17) o[lane] = c[lane];
     const double* jac = c + 17;
-    const int br[5] = {0, 0, 3, 6, 6}, bc[5] = {9, 12, 12, 9, 12};
-    for (int b = 0; b < 5; ++b) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o[17 + 9 * b + 3 * i + j] = jac[(br[b] + i) * 15 + bc[b] + j];
-    double a[225], inv[225];
-    status[f] = sqrt_information(c + 242, o + 62, a, inv, c[467], c[468]);
-    o[287] = (c[467] >= 0.0 && c[468] >= 0.0) ? 1.0 : 0.0;     // ImuInitError variant
+    for (int e = lane; e < 45; e += 32) {
+        const int br[5] = {0, 0, 3, 6, 6}, bc[5] = {9, 12, 12, 9, 12};
+        const int b = e / 9, i = (e % 9) / 3, j = e % 3;
+        o[17 + e] = jac[(br[b] + i) * 15 + bc[b] + j];
+    }
+    const int st = sqrt_information_warp(c + 242, o + 62, s_work[warp], s_work[warp] + 225, c[467], c[468]);
+    if (lane == 0) { status[f] = st; o[287] = (c[467] >= 0.0 && c[468] >= 0.0) ? 1.0 : 0.0; }     // ImuInitError variant
 }
 
 // ------------------------------------------------------------------ K1 eval kernels (parity / roofline)
@@ -1244,6 +1316,9 @@ int lvb_ba_set_loss(lvb_ba* ba, int kind, double a) {
 }
 
 int lvb_ba_finalize(lvb_ba* ba) {
+    static const bool prof_on = getenv("LVB_PROFILE") != nullptr;
+    auto prof_t = std::chrono::steady_clock::now();
+#define PROF(name) do { if (prof_on) { const auto t_ = std::chrono::steady_clock::now(); fprintf(stderr, "[finalize] %-28s %8.1f us\n", name, std::chrono::duration<double, std::micro>(t_ - prof_t).count()); prof_t = t_; } } while (0)
     lvb_ctx* ctx = ba->ctx;
     LVB_CUDA(cudaSetDevice(ctx->device)); lvb::g_alloc_stream = ctx->stream;
     cudaStream_t s = ctx->stream;
@@ -1258,6 +1333,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
         if (k == 3 && (j == 6 || j == 7) && v == -1 && ba->h_fc[3][(size_t)f * IMU_RAW + 467] >= 0.0) continue;     // ImuInitError has no j-side bias blocks
         if (v < 0 || v >= lim) { set_error("factor kind %d block %d: index %d out of range [0,%d)", k, f, v, lim); return LVB_ERR_INVALID; }
     }
+    PROF("validate");
     // slots / offsets.  Unknowns of the reduced camera system are ordered keyframe by keyframe
     // (pose_i, then the velocity / bias blocks an ImuError ties to pose_i): co-visibility and the IMU chain only
     // couple neighbouring keyframes, so S is block-banded and the Cholesky works inside its envelope.
@@ -1296,6 +1372,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
         }
         blk_start[blks.size()] = off;
     }
+    PROF("block order");
     // camera systems up to MAX_DIMC use dense lower-triangular storage, larger ones banded storage (decided below)
     const bool dense_layout = ba->dimc <= MAX_DIMC;
     ba->solvable = ba->dimc > 0;
@@ -1309,15 +1386,25 @@ int lvb_ba_finalize(lvb_ba* ba) {
         ord.clear();
         const int n = ba->n[k];
         if (ba->solvable && (k == 0 || k == 1) && n > 0) {
+            // stable order by key: counting sort when the key space is small (window-sized problems), else a pair sort
+            std::vector<long long> keys(n);
+            const long long key_space = (k == 0) ? (long long)np * np : (long long)np;
+            for (int f = 0; f < n; ++f) keys[f] = (k == 0) ? (long long)ba->h_fi[0][3 * (size_t)f + 1] * np + ba->h_fi[0][3 * (size_t)f + 2] : (long long)ba->h_fi[1][f];
             std::vector<int> ids(n);
-            for (int f = 0; f < n; ++f) ids[f] = f;
-            auto key = [&](int f) -> long long {
-                if (k == 0) return (long long)ba->h_fi[0][3 * (size_t)f + 1] * np + ba->h_fi[0][3 * (size_t)f + 2];
-                return ba->h_fi[1][f];
-            };
-            std::stable_sort(ids.begin(), ids.end(), [&](int x, int y) { return key(x) < key(y); });
+            if (key_space <= (1 << 16)) {
+                std::vector<int> start((size_t)key_space + 1, 0);
+                for (int f = 0; f < n; ++f) start[keys[f] + 1]++;
+                for (long long c = 0; c < key_space; ++c) start[c + 1] += start[c];
+                for (int f = 0; f < n; ++f) ids[start[keys[f]]++] = f;
+            } else {
+                std::vector<std::pair<long long, int>> kv(n);
+                for (int f = 0; f < n; ++f) kv[f] = {keys[f], f};
+                std::sort(kv.begin(), kv.end());
+                for (int f = 0; f < n; ++f) ids[f] = kv[f].second;
+            }
+            ord.reserve((size_t)n + 32 * 64);
             for (int i = 0; i < n;) {
-                int j = i; while (j < n && key(ids[j]) == key(ids[i])) ++j;
+                int j = i; while (j < n && keys[ids[j]] == keys[ids[i]]) ++j;
                 for (int t = i; t < j; ++t) ord.push_back(ids[t]);
                 while (dense_layout && ord.size() % 32) ord.push_back(-1 - ids[i]);     // padding: encoded source block
                 i = j;
@@ -1325,6 +1412,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
         } else { ord.resize(n); for (int f = 0; f < n; ++f) ord[f] = f; }
         ba->nd[k] = (int)ord.size();
     }
+    PROF("factor sort + pad");
     const int n_tf = ba->nd[0];
     auto tf_src = [&](int i) { const int o = ba->order[0][i]; return o >= 0 ? o : -1 - o; };
     // landmark CSR over device positions: TwoFrame i -> i, TwoCamera f -> -(f+1); padding is skipped
@@ -1336,33 +1424,74 @@ int lvb_ba_finalize(lvb_ba* ba) {
     for (int i = 0; i < n_tf; ++i) if (ba->order[0][i] >= 0) lm_fac[fill[ba->h_fi[0][3 * (size_t)ba->order[0][i]]]++] = i;
     for (int f = 0; f < ba->n[2]; ++f) lm_fac[fill[ba->h_fi[2][f]]++] = -(f + 1);
 
+    PROF("landmark CSR");
     // ---- Schur groups: landmarks with the same sorted set of free pose offsets share a warp-sized work item
     std::vector<int> tf_slot((size_t)std::max(1, n_tf) * 2, -1), sw_group, sw_lm, grp_ns, grp_off;
     int cols_max = 0;
     {
-        std::map<std::vector<int>, int> gid;
+        // signature = sorted set of free pose offsets of a landmark; groups found through an open-addressing hash table
+        // over the signatures (no per-landmark heap traffic), numbered in order of first appearance
         std::vector<std::vector<int>> members;
+        size_t tsize = 64; while (tsize < 4 * (size_t)std::max(1, nrf)) tsize <<= 1;
+        if (tsize > ((size_t)1 << 20)) tsize = (size_t)1 << 20;
+        std::vector<int> table(tsize, -1);
         for (int l = 0; l < nr; ++l) {
             if (rho_slot[l] < 0) continue;
-            std::vector<int> sig;
+            int sig[MAX_TRACK + 1], ns = 0;
             for (int e = lm_start[l]; e < lm_start[l + 1]; ++e) {
                 const int i = lm_fac[e]; if (i < 0) continue;
                 const int f = tf_src(i);
-                for (int side = 1; side <= 2; ++side) { const int off = pose_off[ba->h_fi[0][3 * (size_t)f + side]]; if (off >= 0) sig.push_back(off); }
+                for (int side = 1; side <= 2; ++side) {
+                    const int off = pose_off[ba->h_fi[0][3 * (size_t)f + side]];
+                    if (off < 0) continue;
+                    int p = 0; while (p < ns && sig[p] < off) ++p;
+                    if (p < ns && sig[p] == off) continue;
+                    if (ns == MAX_TRACK) { set_error("landmark %d is observed from more than %d keyframes", l, (int)MAX_TRACK); return LVB_ERR_UNSUPPORTED; }
+                    for (int q = ns; q > p; --q) sig[q] = sig[q - 1];
+                    sig[p] = off; ++ns;
+                }
             }
-            std::sort(sig.begin(), sig.end()); sig.erase(std::unique(sig.begin(), sig.end()), sig.end());
-            if ((int)sig.size() > MAX_TRACK) { set_error("landmark %d is observed from more than %d keyframes", l, (int)MAX_TRACK); return LVB_ERR_UNSUPPORTED; }
-            auto it = gid.find(sig);
-            int g;
-            if (it == gid.end()) { g = (int)members.size(); gid.emplace(sig, g); members.emplace_back(); grp_ns.push_back((int)sig.size()); for (int k2 = 0; k2 < MAX_TRACK; ++k2) grp_off.push_back(k2 < (int)sig.size() ? sig[k2] : -1); }
-            else g = it->second;
+            unsigned long long h = 1469598103934665603ull ^ (unsigned long long)ns;
+            for (int q = 0; q < ns; ++q) { h ^= (unsigned long long)(unsigned)sig[q]; h *= 1099511628211ull; }
+            size_t slot = (size_t)(h ^ (h >> 29)) & (tsize - 1);
+            int g = -1;
+            for (;;) {
+                const int cand = table[slot];
+                if (cand < 0) break;
+                if (grp_ns[cand] == ns) {
+                    bool same = true;
+                    for (int q = 0; q < ns && same; ++q) same = grp_off[(size_t)cand * MAX_TRACK + q] == sig[q];
+                    if (same) { g = cand; break; }
+                }
+                slot = (slot + 1) & (tsize - 1);
+            }
+            if (g < 0) {
+                g = (int)members.size();
+                if ((size_t)g * 2 >= tsize) {      // keep the load factor below 1/2: rebuild a larger table
+                    tsize <<= 1; table.assign(tsize, -1);
+                    for (int c = 0; c < g; ++c) {
+                        unsigned long long hc = 1469598103934665603ull ^ (unsigned long long)grp_ns[c];
+                        for (int q = 0; q < grp_ns[c]; ++q) { hc ^= (unsigned long long)(unsigned)grp_off[(size_t)c * MAX_TRACK + q]; hc *= 1099511628211ull; }
+                        size_t sc = (size_t)(hc ^ (hc >> 29)) & (tsize - 1);
+                        while (table[sc] >= 0) sc = (sc + 1) & (tsize - 1);
+                        table[sc] = c;
+                    }
+                    slot = (size_t)(h ^ (h >> 29)) & (tsize - 1);
+                    while (table[slot] >= 0) slot = (slot + 1) & (tsize - 1);
+                }
+                table[slot] = g;
+                members.emplace_back(); grp_ns.push_back(ns);
+                for (int k2 = 0; k2 < MAX_TRACK; ++k2) grp_off.push_back(k2 < ns ? sig[k2] : -1);
+            }
             members[g].push_back(l);
             for (int e = lm_start[l]; e < lm_start[l + 1]; ++e) {
                 const int i = lm_fac[e]; if (i < 0) continue;
                 const int f = tf_src(i);
                 for (int side = 1; side <= 2; ++side) {
                     const int off = pose_off[ba->h_fi[0][3 * (size_t)f + side]];
-                    if (off >= 0) tf_slot[(size_t)(side - 1) * n_tf + i] = (int)(std::lower_bound(sig.begin(), sig.end(), off) - sig.begin());
+                    if (off < 0) continue;
+                    int p = 0; while (sig[p] != off) ++p;
+                    tf_slot[(size_t)(side - 1) * n_tf + i] = p;
                 }
             }
         }
@@ -1375,6 +1504,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
         }
     }
     ba->n_schur_warps = (int)sw_group.size(); ba->schur_cols_max = cols_max;
+    PROF("schur groups");
     // ---- envelope of S: first structurally non-zero column per row, from every coupling the assembly can create
     std::vector<int> chol_rmax(ba->dimc / 32 + 2, 0), chol_cmin(ba->dimc / 32 + 2, 0);
     int band = 0, panel_rows = 2;
@@ -1438,6 +1568,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
     if (sw_group.empty()) { sw_group.push_back(0); sw_lm.assign(32, -1); }
     if (grp_ns.empty()) { grp_ns.push_back(0); grp_off.assign(MAX_TRACK, -1); }
 
+    PROF("envelope");
     LVB_TRY(ba->poses.upload(ba->h_poses.data(), ba->h_poses.size(), s));
     LVB_TRY(ba->vec3.upload(ba->h_vec3.data(), ba->h_vec3.size(), s));
     LVB_TRY(ba->rho.upload(ba->h_rho.data(), ba->h_rho.size(), s));
@@ -1469,36 +1600,45 @@ int lvb_ba_finalize(lvb_ba* ba) {
         LVB_CUDA(cudaMemsetAsync(ba->tc_u.p, 0, (size_t)std::max(1, ba->n_tc_chunks) * 3 * 2048 * sizeof(unsigned short), s));
     }
 
-    // factor planes in device order (AoS -> SoA transpose on the host; IMU stays AoS and is packed on the device)
-    std::vector<double> planes_k[6]; std::vector<int> iplanes_k[6];      // kept alive until the single sync below
-    for (int k = 0; k < 6; ++k) {
-        std::vector<double>& planes = planes_k[k]; std::vector<int>& iplanes = iplanes_k[k];
-        const int n = ba->nd[k];
-        const std::vector<int>& ord = ba->order[k];
-        iplanes.assign((size_t)std::max(1, n) * kIdxStride[k], 0);
-        for (int i = 0; i < n; ++i) { const int f = ord[i] >= 0 ? ord[i] : -1 - ord[i]; for (int j = 0; j < kIdxStride[k]; ++j) iplanes[(size_t)j * n + i] = ba->h_fi[k][(size_t)f * kIdxStride[k] + j]; }
-        LVB_TRY(ba->fi[k].upload(iplanes.data(), iplanes.size(), s));
-        if (k == 3) {
-            LVB_TRY(ba->imu_raw.upload(ba->h_fc[3].data(), ba->h_fc[3].size(), s));
-            LVB_TRY(ba->fc[3].ensure((size_t)std::max(1, n) * IMU_STRIDE));
-            LVB_TRY(ba->imu_status.ensure(std::max(1, n)));
-            if (n) {
-                imu_prepare_kernel<<<nblk(n, 64), 64, 0, s>>>(ba->imu_raw.p, ba->fc[3].p, n, ba->imu_status.p);
-                ctx->launches++;
-                LVB_TRY(check_launch("imu_prepare"));
-                ba->imu_checked = false;      // status is read back with the first solve / eval (no extra round trip here)
+    PROF("uploads (params, structure)");
+    // factor planes in device order (AoS -> SoA transpose on the host; IMU stays AoS and is packed on the device).
+    // cudaMemcpyAsync from pageable memory returns once the source has been staged, so the host vectors can go out of
+    // scope without a stream synchronisation; the IMU kernel is launched last because a pageable copy waits for the
+    // work queued before it.
+    {
+        std::vector<double> planes; std::vector<int> iplanes;
+        for (int k = 0; k < 6; ++k) {
+            const int n = ba->nd[k];
+            const std::vector<int>& ord = ba->order[k];
+            const int is = kIdxStride[k];
+            iplanes.assign((size_t)std::max(1, n) * is, 0);
+            const int32_t* hi = ba->h_fi[k].data();
+            for (int j = 0; j < is; ++j) { int* dst = iplanes.data() + (size_t)j * n; for (int i = 0; i < n; ++i) { const int f = ord[i] >= 0 ? ord[i] : -1 - ord[i]; dst[i] = hi[(size_t)f * is + j]; } }
+            LVB_TRY(ba->fi[k].upload(iplanes.data(), iplanes.size(), s));
+            if (k == 3) continue;
+            const int cs = kConstStride[k];
+            planes.assign((size_t)std::max(1, n) * cs, 0.0);
+            const int wcol = (k == 0) ? 4 : (k == 1 ? 5 : -1);     // weight column, zeroed on padding
+            const double* hc = ba->h_fc[k].data();
+            for (int j = 0; j < cs; ++j) {
+                double* dst = planes.data() + (size_t)j * n;
+                if (j == wcol) for (int i = 0; i < n; ++i) dst[i] = ord[i] < 0 ? 0.0 : hc[(size_t)ord[i] * cs + j];
+                else for (int i = 0; i < n; ++i) { const int f = ord[i] >= 0 ? ord[i] : -1 - ord[i]; dst[i] = hc[(size_t)f * cs + j]; }
             }
-            continue;
+            LVB_TRY(ba->fc[k].upload(planes.data(), planes.size(), s));
         }
-        planes.assign((size_t)std::max(1, n) * kConstStride[k], 0.0);
-        const int wcol = (k == 0) ? 4 : (k == 1 ? 5 : -1);     // weight column, zeroed on padding
-        for (int i = 0; i < n; ++i) {
-            const bool pad = ord[i] < 0; const int f = pad ? -1 - ord[i] : ord[i];
-            for (int j = 0; j < kConstStride[k]; ++j) planes[(size_t)j * n + i] = (pad && j == wcol) ? 0.0 : ba->h_fc[k][(size_t)f * kConstStride[k] + j];
+        const int n = ba->nd[3];
+        LVB_TRY(ba->imu_raw.upload(ba->h_fc[3].data(), ba->h_fc[3].size(), s));
+        LVB_TRY(ba->fc[3].ensure((size_t)std::max(1, n) * IMU_STRIDE));
+        LVB_TRY(ba->imu_status.ensure(std::max(1, n)));
+        if (n) {
+            imu_prepare_kernel<<<nblk(n, 4), 128, 0, s>>>(ba->imu_raw.p, ba->fc[3].p, n, ba->imu_status.p);
+            ctx->launches++;
+            LVB_TRY(check_launch("imu_prepare"));
+            ba->imu_checked = false;      // status is read back with the first solve / eval (no extra round trip here)
         }
-        LVB_TRY(ba->fc[k].upload(planes.data(), planes.size(), s));
     }
-    LVB_CUDA(cudaStreamSynchronize(s));
+    PROF("planes + uploads");
 
     const size_t nH = ba->nS;
     LVB_TRY(ba->chol_invd.ensure(ba->dimc + 32));
@@ -1510,6 +1650,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
     LVB_TRY(ba->scale_l.ensure(std::max(1, nr))); LVB_TRY(ba->lam_l.ensure(std::max(1, nr)));
     LVB_TRY(ba->st.ensure(1));
 
+    PROF("sync + alloc");
     BaDev& d = ba->dev;
     d.n_poses = np; d.n_vec3 = nv; d.n_rho = nr; d.dimc = ba->dimc; d.n_pose_free = npf;
     d.srow = ba->srow; d.soff = ba->soff; d.nS = ba->nS;
@@ -1542,6 +1683,8 @@ int lvb_ba_finalize(lvb_ba* ba) {
     ba->pose_smem = smem_pose; ba->imu_smem = smem_imu;
     ba->lin_smem = ((smem_pose + 15) & ~(size_t)15) + (size_t)(TPB / 32) * SYRK_ROWS * SYRK_LD * 8;
     ba->schur_smem = (size_t)(TPB / 32) * 32 * (size_t)std::max(1, cols_max) * 8;
+    PROF("tail");
+#undef PROF
     ba->finalized = true;
     return LVB_OK;
 }
