@@ -852,11 +852,8 @@ __global__ void ba_unpack_scalars_kernel(BaDev d) {
 }
 
 // camera blocks: Jacobi scale, damping added to diag(S), gradient max-norm ||x - Plus(x,-g)||_inf
-__global__ void ba_prepare_camera_kernel(BaDev d) {
+__device__ __forceinline__ void prepare_camera_block(const BaDev& d, int i) {
     LmState* st = d.st;
-    if (st->done) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.n_poses + d.n_vec3) return;
     const bool is_pose = i < d.n_poses;
     const int off = is_pose ? d.pose_off[i] : d.vec3_off[i - d.n_poses];
     if (off < 0) return;
@@ -880,6 +877,12 @@ __global__ void ba_prepare_camera_kernel(BaDev d) {
         } else for (int k = 0; k < 3; ++k) { const double df = fabs(d.gcr[off + k]); gm = (df == df) ? fmax(gm, df) : INFINITY; }
         atomic_max_nonneg(&st->grad_max_bits, gm);
     }
+}
+
+__global__ void ba_prepare_camera_kernel(BaDev d) {
+    if (d.st->done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d.n_poses + d.n_vec3) prepare_camera_block(d, i);
 }
 
 __global__ void lm_control_pre_kernel(LmState* st) { lm_control_pre(*st); }
@@ -1213,6 +1216,7 @@ struct lvb_ba {
     int n_schur_warps = 0, schur_cols_max = 0;
     size_t schur_smem = 0, lin_smem = 0;
     cudaGraphExec_t pass_graph = nullptr;
+    int pass_launches = 0;
     bool imu_checked = true;
     // tensor-core Schur (schur_mode 1)
     bool tc_ok = false; int schur_mode = 0, graph_mode = -1, n_tc_chunks = 0;
@@ -1257,6 +1261,8 @@ static int init_tables() {
 
 static inline int nblk(size_t n, int per) { return (int)((n + per - 1) / per); }
 static void mark(struct lvb_ba* ba, const char* name);
+#define LAUNCH_ON(ba, stream_, kernel, grid, block, smem, ...)                             \
+    do { if ((grid) > 0) { kernel<<<(grid), (block), (smem), (stream_)>>>(__VA_ARGS__); (ba)->ctx->launches++; } } while (0)
 #define LAUNCH(ba, kernel, grid, block, smem, ...)                                        \
     do { if ((grid) > 0) { kernel<<<(grid), (block), (smem), (ba)->ctx->stream>>>(__VA_ARGS__); (ba)->ctx->launches++; mark(ba, #kernel); } } while (0)
 
@@ -1785,15 +1791,26 @@ int lvb_ba_eval_device(lvb_ba* ba, int kind) {
     return launch_eval(ba, kind, ba->eval_r.p, ba->eval_J.p);
 }
 
-// one pass = one LM iteration attempt (all decisions on the device), 10 launches:
+static bool use_side_branch(lvb_ba* ba) {
+    return ba->ctx->use_side && ba->ctx->side && !g_timing && ba->ranges.b[3] > 0 && ba->ranges.b[6] > ba->ranges.b[3];
+}
+
+// one pass = one LM iteration attempt (all decisions on the device), 10 launches (the two linearise kernels and the two
+// cost kernels run as parallel branches on a second stream):
 //   linearize (visual) | linearize (IMU + priors) | build S | Schur | camera damping | Cholesky (+ LM pre-check)
 //   | back-substitution + candidate | cost (visual) | cost (IMU + priors) | LM decision + accept + clear
 static int launch_linearize_and_reduce(lvb_ba* ba, bool standalone) {
     BaDev& d = ba->dev;
     lvb_ctx* ctx = ba->ctx;
     const size_t nH = d.nS;
+    // the visual and the IMU / prior linearisations are independent (both only add into the accumulators): two branches
+    const bool fork = use_side_branch(ba);
+    if (fork) { LVB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream)); LVB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0)); }
     LAUNCH(ba, ba_linearize_kernel<0>, ba->ranges.b[3], TPB, ba->lin_smem, d, ba->ranges);
-    LAUNCH(ba, ba_linearize_other_kernel<0>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
+    if (fork) {
+        LAUNCH_ON(ba, ctx->side, ba_linearize_other_kernel<0>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
+        LVB_CUDA(cudaEventRecord(ctx->ev_join, ctx->side)); LVB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    } else LAUNCH(ba, ba_linearize_other_kernel<0>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
     LAUNCH(ba, ba_build_S_kernel, std::min(1024, nblk(nH, 256)), 256, 0, d);
     LAUNCH(ba, ba_schur_kernel, nblk(d.n_schur_warps, TPB / 32), TPB, ba->schur_smem, d, std::max(1, ba->schur_cols_max));
     if (d.tc_mode) LAUNCH(ba, ba_schur_tc_kernel, ba->n_tc_chunks / TC_CHUNKS, 128, (size_t)TC_CHUNKS * TC_CHUNK_BYTES, d, ba->n_tc_chunks);
@@ -1802,6 +1819,7 @@ static int launch_linearize_and_reduce(lvb_ba* ba, bool standalone) {
         LVB_TRY(comm_allreduce_sum_f64(ctx, d.S, nH + 3 * (size_t)d.dimc + 16));
         LAUNCH(ba, ba_unpack_scalars_kernel, 1, 1, 0, d);
     }
+    // (fusing this into the Cholesky prologue was measured: it perturbs that kernel's register allocation and is slower)
     LAUNCH(ba, ba_prepare_camera_kernel, nblk(d.n_poses + d.n_vec3, 128), 128, 0, d);
     if (standalone) LAUNCH(ba, lm_control_pre_kernel, 1, 1, 0, d.st);
     return check_launch("linearize");
@@ -1812,8 +1830,13 @@ static int launch_step(lvb_ba* ba) {
     lvb_ctx* ctx = ba->ctx;
     LAUNCH(ba, ba_cholesky_kernel, 1, CHOL_T, ba->chol_smem, d.S, d.rhs, d.dimc, d.srow, d.soff, ba->chol_invd.p, d.st, 1, ba->chol_rmax.p, ba->chol_cmin.p);
     LAUNCH(ba, ba_update_kernel, nblk((size_t)d.n_poses + d.n_vec3 + d.n_rho, TPB), TPB, 0, d);
+    const bool fork = use_side_branch(ba);
+    if (fork) { LVB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream)); LVB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0)); }
     LAUNCH(ba, ba_linearize_kernel<1>, ba->ranges.b[3], TPB, ba->lin_smem, d, ba->ranges);
-    LAUNCH(ba, ba_linearize_other_kernel<1>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
+    if (fork) {
+        LAUNCH_ON(ba, ctx->side, ba_linearize_other_kernel<1>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
+        LVB_CUDA(cudaEventRecord(ctx->ev_join, ctx->side)); LVB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    } else LAUNCH(ba, ba_linearize_other_kernel<1>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
     if (ctx->world > 1) LVB_TRY(comm_allreduce_sum_f64(ctx, &d.st->cand_cost_acc, 5));
     const bool wide = d.nS > ((size_t)1 << 20) || (size_t)d.n_poses * 7 + (size_t)d.n_vec3 * 3 + d.n_rho > ((size_t)1 << 17);
     LAUNCH(ba, ba_post_kernel, 1, wide ? 32 : 1024, 0, d, wide ? 1 : 0);
@@ -1907,6 +1930,7 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
         const bool use_graph = graph_ok && (ba->pass_graph || (pass >= 8 && opt.max_num_iterations - pass >= 16) || ba->solves_done >= 1);
         if (use_graph && !ba->pass_graph) {
             cudaGraph_t g = nullptr;
+            const long long before = ba->ctx->launches;
             LVB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
             int rc = launch_linearize_and_reduce(ba, false);
             if (rc == LVB_OK) rc = launch_step(ba);
@@ -1916,10 +1940,11 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
             ce = cudaGraphInstantiate(&ba->pass_graph, g, 0);
             cudaGraphDestroy(g);
             LVB_CUDA(ce);
-            ba->ctx->launches -= 10 + ba->dev.tc_mode;      // capture is not execution
+            ba->pass_launches = (int)(ba->ctx->launches - before);
+            ba->ctx->launches = before;                     // capture is not execution
         }
         for (int c = 0; c < chunk; ++c) {
-            if (use_graph) { LVB_CUDA(cudaGraphLaunch(ba->pass_graph, s)); ba->ctx->launches += 10 + ba->dev.tc_mode; }
+            if (use_graph) { LVB_CUDA(cudaGraphLaunch(ba->pass_graph, s)); ba->ctx->launches += ba->pass_launches; }
             else { LVB_TRY(launch_linearize_and_reduce(ba, false)); LVB_TRY(launch_step(ba)); }
         }
         pass += chunk;

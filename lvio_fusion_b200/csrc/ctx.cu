@@ -113,6 +113,11 @@ int lvb_ctx_create(int device, void* cuda_stream, lvb_ctx** out) {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { unsigned long long thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
     }
+    LVB_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    LVB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    LVB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    const char* no_side = getenv("LVB_NO_SIDE");
+    c->use_side = !(no_side && no_side[0] == '1');
     const char* no_tma = getenv("LVB_NO_TMA");
     c->use_tma = !(no_tma && no_tma[0] == '1');
     const char* no_graph = getenv("LVB_NO_GRAPH");
@@ -128,6 +133,9 @@ int lvb_ctx_create(int device, void* cuda_stream, lvb_ctx** out) {
 void lvb_ctx_destroy(lvb_ctx* ctx) {
     if (!ctx) return;
     if (ctx->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(ctx->comm);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -23,6 +23,9 @@ struct lvb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side = nullptr;        // second stream: independent kernels of an LM pass run as parallel branches
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool use_side = true;               // env LVB_NO_SIDE=1 disables
     long long launches = 0;
     int sm_count = 148;
     bool use_tma = true;          // cp.async.bulk staging of the pose array (env LVB_NO_TMA=1 disables)
@@ -112,7 +115,7 @@ __device__ inline void lm_control_pre(LmState& s) {
     if (s.done) return;
     if (s.need_linearize) { s.x_cost = s.cost_acc; if (s.iter == 0 && s.num_successful == 0 && s.scale_valid == 0) s.initial_cost = s.x_cost; }
     s.scale_valid = 1;
-    const double gmax = __longlong_as_double((long long)s.grad_max_bits);
+    const double gmax = __longlong_as_double((long long)*(volatile unsigned long long*)&s.grad_max_bits);   // written with atomics: read at L2
     if ((s.iter == 0 || s.last_successful) && gmax <= s.g_tol) { s.done = 1; s.termination = 0; return; }
     if (s.iter >= s.max_iter) { s.done = 1; return; }
     if (s.radius <= s.min_radius) { s.done = 1; s.termination = 0; return; }
