@@ -901,7 +901,8 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
     extern __shared__ __align__(16) double sm[];
     double* D = sm;                    // 32 x 33   diagonal block of L
     double* invd = sm + 32 * 33;       // 32        reciprocals of diag(L) of the current block (all of them: invd_g)
-    double* P = invd + 32;             // rows x 34 panel (16 B aligned rows for broadcast double2 loads)
+    double* Lc = invd + 32;            // 2 x 64    column of the diagonal block being factored (double buffered broadcast)
+    double* P = Lc + 128;              // rows x 34 panel (16 B aligned rows for broadcast double2 loads)
     __shared__ int fail;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     if (tid == 0) fail = 0;
@@ -994,6 +995,12 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
         if (kn < n) {
             __syncwarp();
             if (warp == 0) {
+                const long long t_d0 = clock64();
+                // Registers hold row `lane` of the block.  The 32 columns are processed in 4 groups of 8: inside a group the
+                // code is unrolled (register indices are compile-time), between groups the row is shifted left by 8, so the
+                // loop body exists once (the fully unrolled form is ~4000 instructions and starves the instruction cache).
+                // Column j goes through shared memory: the other columns read L[k][j] as broadcast LDS.128 (two columns per
+                // load) instead of two shuffles per column.
                 double a[32];
     #pragma unroll
                 for (int j = 0; j < 32; ++j) a[j] = (lane < bn && j <= lane) ? SA(kn + lane, kn + j) : ((j == lane) ? 1.0 : 0.0);
@@ -1001,65 +1008,87 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
                 double d0 = __shfl_sync(0xffffffffu, a[0], 0);
                 if (!(d0 > 0.0)) { bad = 1; d0 = 1.0; }
                 double inv = rsqrt(d0);
+    #pragma unroll 1
+                for (int c0 = 0; c0 < 32; c0 += 8) {
+                    const int rel = lane - c0;                    // register index of this lane's diagonal entry
     #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (lane >= j) a[j] *= inv;                       // l_ij (lane j: sqrt(d_jj))
-                    if (lane == j) { invd[j] = inv; invd_g[kn + j] = inv; }
-                    // update column j+1 first and start the next pivot's rsqrt: its latency overlaps the rest of the update
-                    double inv_next = 1.0;
-                    if (j + 1 < 32) {
-                        const double l1 = __shfl_sync(0xffffffffu, a[j], j + 1);
-                        if (lane >= j + 1) a[j + 1] -= a[j] * l1;
-                        double dn = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
-                        if (!(dn > 0.0)) { bad = 1; dn = 1.0; }
-                        inv_next = rsqrt(dn);
-                    }
-    #pragma unroll
-                    for (int k = 0; k < 32; ++k) {                    // constant trip count keeps a[] in registers
-                        if (k > j + 1) {
-                            const double lkj = __shfl_sync(0xffffffffu, a[j], k);
-                            if (lane >= k) a[k] -= a[j] * lkj;
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int j = c0 + jj;
+                        if (rel >= jj) a[jj] *= inv;                  // l_ij (lane j: sqrt(d_jj))
+                        if (rel == jj) { invd[j] = inv; invd_g[kn + j] = inv; }
+                        const double lj = (rel >= jj) ? a[jj] : 0.0;
+                        D[lane * 33 + j] = lj;
+                        if (lane < bn && rel >= jj && j < bn) SA(kn + lane, kn + j) = lj;
+                        double* buf = Lc + (jj & 1) * 64;
+                        buf[lane] = a[jj];
+                        // next pivot first: lane j+1 owns everything its diagonal entry needs, its rsqrt overlaps the update
+                        double inv_next = 1.0;
+                        if (j + 1 < 32) {
+                            double dn = __shfl_sync(0xffffffffu, a[jj + 1] - a[jj] * a[jj], j + 1);
+                            if (!(dn > 0.0)) { bad = 1; dn = 1.0; }
+                            inv_next = rsqrt(dn);
                         }
-                    }
-                    inv = inv_next;
-                }
+                        __syncwarp();
+                        const double2* bp = reinterpret_cast<const double2*>(buf + c0);
     #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    D[lane * 33 + j] = (j <= lane) ? a[j] : 0.0;
-                    if (lane < bn && j <= lane && j < bn) SA(kn + lane, kn + j) = a[j];
+                        for (int p = 0; p < 16; ++p) {                // register pair (2p, 2p+1) = columns c0 + 2p, c0 + 2p + 1
+                            if (2 * p + 1 > jj) {
+                                const double2 v = bp[p];             // entries beyond column 31 are never used (rel < their index)
+                                if (2 * p > jj && rel >= 2 * p) a[2 * p] -= a[jj] * v.x;
+                                if (rel >= 2 * p + 1) a[2 * p + 1] -= a[jj] * v.y;
+                            }
+                        }
+                        inv = inv_next;
+                    }
+    #pragma unroll
+                    for (int r = 0; r < 24; ++r) a[r] = a[r + 8];
+    #pragma unroll
+                    for (int r = 24; r < 32; ++r) a[r] = 0.0;
                 }
+                t_diag += clock64() - t_d0;
                 if (bad && lane == 0) fail = 1;
             }
         }
         __syncthreads();
         tA = clock64(); t_trail += tA - t0; t0 = tA;
     }
-    // ---- backward substitution  L^T x = y  (y is in rhs), right-looking: solve the 32 unknowns of a block with
-    // shuffles in warp 0, then every thread j < kb applies  y_j -= sum_i L[i][j] x_i  with coalesced row reads.
+    // ---- backward substitution  L^T x = y  (y is in rhs), left-looking per 32-column block:
+    //   x_k = D_k^-T (y_k - sum_{r below} L[r][k-block]^T x_r)
+    // the sum is a GEMV over the envelope rows spread over all warps (independent coalesced loads, one L2 round trip per
+    // batch), then warp 0 solves the 32 unknowns of the block with shuffles.  x overwrites rhs.
     const int last = ((n - 1) / 32) * 32;
-    double* xs = P;                                   // 32 solved unknowns of the current block
+    double* part = P;                                 // nw x 32 partial sums
     for (int kb = last; kb >= 0; kb -= 32) {
         const int bs = min(32, n - kb);
+        const int rend = env_rmax[kb >> 5];
+        double col[32];                               // warp 0: column `lane` of the diagonal block, col[i] = L[kb+i][kb+lane], i >= lane
+        double t = 0.0, my_inv = 1.0;
         if (warp == 0) {
-            double col[32];                           // column `lane` of the block:  col[i] = L[kb+i][kb+lane], i >= lane
 #pragma unroll
             for (int i = 0; i < 32; ++i) col[i] = (i < bs && lane < bs && i >= lane) ? SA(kb + i, kb + lane) : 0.0;
-            double t = (lane < bs) ? rhs[kb + lane] : 0.0;
-            const double my_inv = (lane < bs) ? invd_g[kb + lane] : 1.0;
+            if (lane < bs) { t = rhs[kb + lane]; my_inv = invd_g[kb + lane]; }
+        }
+        double acc = 0.0;
+        if (lane < bs) {
+            for (int r0 = kb + bs + warp; r0 <= rend; r0 += 16 * nw) {
+                double lv[16], xv[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) { const int r = r0 + u * nw; const bool ok = r <= rend; lv[u] = ok ? SA(r, kb + lane) : 0.0; xv[u] = ok ? rhs[r] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) acc += lv[u] * xv[u];
+            }
+        }
+        part[warp * 32 + lane] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            for (int w = 0; w < nw; ++w) t -= part[w * 32 + lane];
 #pragma unroll
             for (int j = 31; j >= 0; --j) {
                 const double xj = __shfl_sync(0xffffffffu, t * my_inv, j);     // lane j's t is final here
                 if (lane == j) t = xj;
                 else if (lane < j) t -= col[j] * xj;
             }
-            if (lane < bs) { rhs[kb + lane] = t; xs[lane] = t; } else xs[lane] = 0.0;
-        }
-        __syncthreads();
-        for (int j = env_cmin[kb >> 5] + tid; j < kb; j += nt) {
-            double acc = 0.0;
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) if (i < bs) acc += SA(kb + i, j) * xs[i];
-            rhs[j] -= acc;
+            if (lane < bs) rhs[kb + lane] = t;
         }
         __syncthreads();
     }
@@ -1565,7 +1594,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
     if (dense_layout) { ba->srow = ba->dimc; ba->soff = 0; ba->nS = (size_t)ba->dimc * ba->dimc; }
     else              { ba->srow = band; ba->soff = band; ba->nS = (size_t)ba->dimc * (size_t)(band + 1); }
     ba->band = band; ba->panel_rows = panel_rows;
-    ba->chol_smem = (size_t)(32 * 33 + 32 + (panel_rows + 2) * 34) * 8;
+    ba->chol_smem = (size_t)(32 * 33 + 32 + 128 + std::max((panel_rows + 2) * 34, (CHOL_T / 32) * 32)) * 8;      // panel, later the backward partial sums
     if (ba->solvable && (ba->chol_smem > 227 * 1024 - 256 || ba->nS > ((size_t)3 << 30))) {
         ba->solvable = false;
         ba->unsolvable_why = "the envelope of the reduced camera system is too wide for the direct solver of this build";
