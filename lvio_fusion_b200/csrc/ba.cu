@@ -1382,13 +1382,23 @@ int lvb_ba_finalize(lvb_ba* ba) {
     struct Blk { long long key; int type, idx, width; };
     std::vector<Blk> blks;
     {
-        std::vector<long long> vkey(nv, -1);
+        std::vector<int> vkey(nv, -1);
+        if ((long long)np * 8 >= (1ll << 31)) { set_error("too many poses"); return LVB_ERR_UNSUPPORTED; }
         for (int f = 0; f < ba->n[3]; ++f) {
             const int32_t* ix = &ba->h_fi[3][8 * (size_t)f];
-            for (int b = 1; b < 8; ++b) { if (b == 4) continue; const int v = ix[b]; if (v < 0) continue; const int p = ix[b < 4 ? 0 : 4]; if (vkey[v] < 0) vkey[v] = (long long)p * 8 + (b & 3); }
+            for (int b = 1; b < 8; ++b) { if (b == 4) continue; const int v = ix[b]; if (v < 0) continue; const int p = ix[b < 4 ? 0 : 4]; if (vkey[v] < 0) vkey[v] = p * 8 + (b & 3); }
+        }
+        // sharded problems: a rank only sees the IMU factors it owns, but the order of the unknowns (= the layout of the
+        // all-reduced system) must be the same on every rank: take the key any rank found (collective, like the envelope)
+        if (ctx->world > 1 && nv > 0) {
+            DevBuf<int> tmp;
+            LVB_TRY(tmp.upload(vkey.data(), vkey.size(), s));
+            LVB_TRY(comm_allreduce_max_i32(ctx, tmp.p, vkey.size()));
+            LVB_CUDA(cudaMemcpyAsync(vkey.data(), tmp.p, vkey.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+            LVB_CUDA(cudaStreamSynchronize(s));
         }
         for (int i = 0; i < np; ++i) if (!ba->h_pose_const[i]) blks.push_back({(long long)i * 8, 0, i, 6});
-        for (int i = 0; i < nv; ++i) if (!ba->h_vec3_const[i]) blks.push_back({vkey[i] >= 0 ? vkey[i] : (long long)np * 8 + i, 1, i, 3});
+        for (int i = 0; i < nv; ++i) if (!ba->h_vec3_const[i]) blks.push_back({vkey[i] >= 0 ? (long long)vkey[i] : (long long)np * 8 + i, 1, i, 3});
         std::stable_sort(blks.begin(), blks.end(), [](const Blk& a, const Blk& b) { return a.key < b.key; });
     }
     std::vector<int> blk_of_off(ba->dimc, 0), blk_start(blks.size() + 1, 0);
@@ -1945,7 +1955,7 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
     // The pass is a fixed sequence of launches whose kernels all read their control flags from the device state,
     // so it is captured once into a CUDA graph and replayed; the host looks at the state only every
     // `check_every` passes (kernels of a finished solve return immediately).
-    const bool graph_ok = ba->ctx->world == 1 && ba->ctx->use_graph && !g_timing;
+    const bool graph_ok = comm_graph_safe(ba->ctx, ba->nS + 3 * (size_t)ba->dimc + 16) && ba->ctx->use_graph && !g_timing;
     const int check_every = std::max(1, ba->ctx->check_every);
     const bool capped = opt.max_solver_time_in_seconds < 1e8;
     int pass = 0;

@@ -7,6 +7,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <vector>
 #include "lvb_internal.cuh"
 
 namespace lvb {
@@ -29,6 +31,7 @@ struct NcclId { char internal[128]; };
 typedef int (*fn_get_unique_id)(NcclId*);
 typedef int (*fn_comm_init_rank)(void**, int, NcclId, int);
 typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_all_gather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*fn_comm_destroy)(void*);
 typedef const char* (*fn_get_error_string)(int);
 
@@ -37,6 +40,7 @@ static struct {
     fn_get_unique_id get_unique_id = nullptr;
     fn_comm_init_rank comm_init_rank = nullptr;
     fn_all_reduce all_reduce = nullptr;
+    fn_all_gather all_gather = nullptr;
     fn_comm_destroy comm_destroy = nullptr;
     fn_get_error_string get_error_string = nullptr;
 } g_nccl;
@@ -50,6 +54,7 @@ static int nccl_load() {
     g_nccl.get_unique_id = (fn_get_unique_id)dlsym(h, "ncclGetUniqueId");
     g_nccl.comm_init_rank = (fn_comm_init_rank)dlsym(h, "ncclCommInitRank");
     g_nccl.all_reduce = (fn_all_reduce)dlsym(h, "ncclAllReduce");
+    g_nccl.all_gather = (fn_all_gather)dlsym(h, "ncclAllGather");
     g_nccl.comm_destroy = (fn_comm_destroy)dlsym(h, "ncclCommDestroy");
     g_nccl.get_error_string = (fn_get_error_string)dlsym(h, "ncclGetErrorString");
     if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.all_reduce) { set_error("NCCL symbols missing"); return LVB_ERR_COMM; }
@@ -61,10 +66,122 @@ static int nccl_fail(int rc, const char* what) {
     return LVB_ERR_COMM;
 }
 
+// ---- in-kernel all-reduce over peer memory (NVLink / NVSwitch) ---------------------------------------------------------
+// The reduced system of a window is ~0.2 MB: an NCCL call costs more in launch + protocol latency than the transfer.  Each
+// rank owns an exchange buffer (cudaMalloc + CUDA IPC, mapped by every peer).  One kernel per all-reduce:
+//   1. every CTA copies its slice of the local contribution into the local exchange buffer (phase = epoch parity),
+//   2. release-stores the epoch into the flag slot (phase, CTA, my rank) of every peer,
+//   3. acquire-spins on its own flag slots until all peers have published the same epoch,
+//   4. sums the slice over the ranks IN RANK ORDER with loads from the peers' buffers (bitwise identical result on every
+//      rank, which the redundant solves rely on) and writes it back in place.
+// The phase double-buffers the data: a rank can only reach epoch e+2 after every peer has published e+1, i.e. after they
+// finished reading e.  The epoch lives on the device and is advanced by the kernel, so the launch can sit in a CUDA graph.
+enum { XB_BLOCKS = 64, XB_DATA = 1 << 20, XB_FLAGS = 2 * XB_BLOCKS * 8 * 4, XB_CTRL = 256, XB_TOTAL = XB_FLAGS + XB_CTRL + 2 * XB_DATA };
+struct P2PArgs { unsigned char* peer[8]; int rank, world; };
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) { unsigned int v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+__global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2PArgs a, double* __restrict__ buf, int count) {
+    unsigned char* mine = a.peer[a.rank];
+    unsigned int* ctrl = reinterpret_cast<unsigned int*>(mine + XB_FLAGS);          // [0] epoch, [1] finished CTAs
+    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(ctrl) + 1u;
+    const int phase = (int)(epoch & 1u);
+    double* my_data = reinterpret_cast<double*>(mine + XB_FLAGS + XB_CTRL + (size_t)phase * XB_DATA);
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) my_data[i] = buf[i];
+    __syncthreads();
+    const size_t slot = ((size_t)phase * XB_BLOCKS + blockIdx.x) * 8;
+    if (threadIdx.x < a.world) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned int*>(a.peer[threadIdx.x]) + slot + a.rank, epoch);
+        const unsigned int* f = reinterpret_cast<const unsigned int*>(mine) + slot + threadIdx.x;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (ld_acquire_sys(f) != epoch) {                         // a lost peer must not hang the GPU: give up after 20 s
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 20000000000ull) __trap();
+        }
+    }
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        double s = 0.0;
+        for (int r = 0; r < a.world; ++r) s += __ldcv(reinterpret_cast<const double*>(a.peer[r] + XB_FLAGS + XB_CTRL + (size_t)phase * XB_DATA) + i);
+        buf[i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&ctrl[1], 1u) == gridDim.x - 1) { ctrl[1] = 0u; __threadfence(); *reinterpret_cast<volatile unsigned int*>(ctrl) = epoch; }
+    }
+}
+
+static int p2p_setup(lvb_ctx* ctx) {
+    // every step is collective; a failure on any rank disables the path on all of them (min all-reduce of the ok flag)
+    int ok = 1;
+    const char* off = getenv("LVB_NO_P2P");
+    if ((off && off[0] == '1') || ctx->world > 8 || !g_nccl.all_gather) ok = 0;
+    cudaIpcMemHandle_t mine; memset(&mine, 0, sizeof(mine));
+    if (ok) {
+        if (cudaMalloc((void**)&ctx->xbuf, XB_TOTAL) != cudaSuccess) { ok = 0; ctx->xbuf = nullptr; cudaGetLastError(); }
+        else if (cudaMemset(ctx->xbuf, 0, XB_TOTAL) != cudaSuccess || cudaIpcGetMemHandle(&mine, ctx->xbuf) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    }
+    unsigned char* d_all = nullptr;
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    LVB_CUDA(cudaMalloc((void**)&d_all, hb * ctx->world + 16));
+    LVB_CUDA(cudaMemcpy(d_all + hb * ctx->rank, &mine, hb, cudaMemcpyHostToDevice));
+    int* d_ok = reinterpret_cast<int*>(d_all + hb * ctx->world);
+    if (g_nccl.all_gather) {
+        const int rc = g_nccl.all_gather(d_all + hb * ctx->rank, d_all, hb, /*ncclChar*/ 0, ctx->comm, ctx->stream);
+        if (rc != 0) { cudaFree(d_all); return nccl_fail(rc, "ncclAllGather"); }
+    }
+    LVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<cudaIpcMemHandle_t> all(ctx->world);
+    LVB_CUDA(cudaMemcpy(all.data(), d_all, hb * ctx->world, cudaMemcpyDeviceToHost));
+    if (ok) {
+        for (int r = 0; r < ctx->world && ok; ++r) {
+            if (r == ctx->rank) { ctx->xpeer[r] = ctx->xbuf; continue; }
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+            ctx->xpeer[r] = (unsigned char*)p;
+        }
+    }
+    LVB_CUDA(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    const int rc = g_nccl.all_reduce(d_ok, d_ok, 1, /*ncclInt32*/ 2, /*ncclMin*/ 3, ctx->comm, ctx->stream);
+    if (rc != 0) { cudaFree(d_all); return nccl_fail(rc, "ncclAllReduce(p2p ok)"); }
+    LVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    LVB_CUDA(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+    ctx->p2p_ok = ok != 0;
+    return LVB_OK;
+}
+
+bool comm_graph_safe(const lvb_ctx* ctx, size_t max_count) {
+    return ctx->world <= 1 || (ctx->p2p_ok && max_count * sizeof(double) <= (size_t)XB_DATA);
+}
+
 int comm_allreduce_sum_f64(lvb_ctx* ctx, double* buf, size_t count) {
     if (ctx->world <= 1 || !ctx->comm) return LVB_OK;
+    if (ctx->p2p_ok && count * sizeof(double) <= (size_t)XB_DATA) {
+        P2PArgs a;
+        for (int r = 0; r < 8; ++r) a.peer[r] = ctx->xpeer[r];
+        a.rank = ctx->rank; a.world = ctx->world;
+        const int blocks = (int)std::min<size_t>(XB_BLOCKS, (count + 255) / 256);
+        p2p_allreduce_kernel<<<std::max(1, blocks), 256, 0, ctx->stream>>>(a, buf, (int)count);
+        ctx->launches++;
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("p2p all-reduce launch failed: %s", cudaGetErrorString(e)); return LVB_ERR_CUDA; }
+        return LVB_OK;
+    }
     const int rc = g_nccl.all_reduce(buf, buf, count, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->comm, ctx->stream);
     if (rc != 0) return nccl_fail(rc, "ncclAllReduce");
+    return LVB_OK;
+}
+
+int comm_allreduce_max_i32(lvb_ctx* ctx, int* buf, size_t count) {
+    if (ctx->world <= 1 || count == 0) return LVB_OK;
+    const int rc = g_nccl.all_reduce(buf, buf, count, /*ncclInt32*/ 2, /*ncclMax*/ 2, ctx->comm, ctx->stream);
+    if (rc != 0) return nccl_fail(rc, "ncclAllReduce(max)");
     return LVB_OK;
 }
 
@@ -132,6 +249,8 @@ int lvb_ctx_create(int device, void* cuda_stream, lvb_ctx** out) {
 
 void lvb_ctx_destroy(lvb_ctx* ctx) {
     if (!ctx) return;
+    for (int r = 0; r < 8; ++r) if (ctx->xpeer[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->xpeer[r]);
+    if (ctx->xbuf) cudaFree(ctx->xbuf);
     if (ctx->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(ctx->comm);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -167,7 +286,7 @@ int lvb_comm_init(lvb_ctx* ctx, int rank, int world_size, const char id[128]) {
     const int rc = g_nccl.comm_init_rank(&comm, world_size, u, rank);
     if (rc != 0) return nccl_fail(rc, "ncclCommInitRank");
     ctx->comm = comm; ctx->rank = rank; ctx->world = world_size;
-    return LVB_OK;
+    return p2p_setup(ctx);
 }
 
 }  // extern "C"

@@ -35,12 +35,18 @@ struct lvb_ctx {
     // NCCL (resolved at run time through dlopen, see comm.cu)
     void* comm = nullptr;
     int rank = 0, world = 1;
+    // peer-memory exchange for the in-kernel all-reduce over NVLink (ctx.cu); peer[rank] == own buffer
+    unsigned char* xbuf = nullptr;
+    unsigned char* xpeer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool p2p_ok = false;
 };
 
 namespace lvb {
 
 int comm_allreduce_sum_f64(lvb_ctx* ctx, double* buf, size_t count);   // no-op when world == 1
+bool comm_graph_safe(const lvb_ctx* ctx, size_t max_count);          // every all-reduce of <= max_count doubles is a capturable kernel
 int comm_allreduce_min_i32(lvb_ctx* ctx, int* buf, size_t count);      // device buffer, no-op when world == 1
+int comm_allreduce_max_i32(lvb_ctx* ctx, int* buf, size_t count);
 
 // Minimal owning device buffer on the stream-ordered allocator: a problem object allocates ~40 arrays, and
 // cudaMalloc (a device-wide synchronising call, ~0.1 ms each) would dominate the end-to-end time of a solve that
