@@ -33,6 +33,21 @@ def icp_case(kind):
     return synth.make_icp_problem(300, 4000, seed=102, kind=kind)
 
 
+def lidar_case():
+    return synth.make_lidar_scan(seed=103, horizon_scan=450, n_boxes=8)
+
+
+def imu_case():
+    rng = np.random.default_rng(104)
+    counts = np.array([0, 7, 12, 1, 9])
+    first = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    m = int(first[-1])
+    samples = np.concatenate([rng.uniform(0.004, 0.012, (m, 1)), rng.normal(0, 1.5, (m, 3)) + [0, 0, 9.81], rng.normal(0, 0.3, (m, 3))], axis=1)
+    n = len(counts)
+    return (first, samples, rng.normal(0, 1.5, (n, 3)) + [0, 0, 9.81], rng.normal(0, 0.3, (n, 3)), rng.normal(0, 0.05, (n, 3)), rng.normal(0, 0.01, (n, 3)),
+            np.array(synth.IMU_NOISE, dtype=np.float64))
+
+
 def main():
     orc = binding.load()
     ctx = backend.Context(orc)
@@ -58,6 +73,14 @@ def main():
         e, s = fa.scan_to_map(sc["mode"], sc["scan"], sc["frame_pose"], sc["map_pose"], e0, sc["weight"], -1.0, sc["huber_a"], sc["thr"])
         np.savez_compressed(os.path.join(HERE, "icp_%s.npz" % kind), idx=idx, d2=d2, acc=acc, r=r, J=J, e0=e0, e=e,
                             final_cost=np.array(s.final_cost), blocks=np.array(s.num_residual_blocks))
+    lf = backend.LidarFeatures(ctx, horizon_scan=450, extrinsic=[0.0, 0.0, 0.0, 1.0, 0.27, 0.0, 0.08])
+    scan = lidar_case()
+    seg = lf.segment(scan)
+    ground, surf = lf.extract(scan)
+    np.savez_compressed(os.path.join(HERE, "lidar_small.npz"), seg_points=seg["points"], seg_range=seg["range"], seg_ground=seg["ground"], seg_col=seg["col"],
+                        seg_curvature=seg["curvature"], start_ring=seg["start_ring"], end_ring=seg["end_ring"], orientation=seg["orientation"],
+                        ground=ground, surf=surf)
+    np.savez_compressed(os.path.join(HERE, "imu_small.npz"), consts=backend.preintegrate(ctx, *imu_case()))
     print("golden fixtures written to", HERE)
 
 

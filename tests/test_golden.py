@@ -68,3 +68,35 @@ def test_cuda_reproduces_golden_ba(lvb_ctx):
 @pytest.mark.parametrize("kind", ["ground", "surf"])
 def test_cuda_reproduces_golden_icp(lvb_ctx, kind):
     _check_icp(lvb_ctx, kind, brute=False)
+
+
+def _check_lidar(ctx):
+    g = np.load(os.path.join(HERE, "golden", "lidar_small.npz"))
+    lf = backend.LidarFeatures(ctx, horizon_scan=450, extrinsic=[0.0, 0.0, 0.0, 1.0, 0.27, 0.0, 0.08])
+    scan = make_golden.lidar_case()
+    seg = lf.segment(scan)
+    for k, gk in (("points", "seg_points"), ("range", "seg_range"), ("ground", "seg_ground"), ("col", "seg_col"), ("curvature", "seg_curvature"),
+                  ("start_ring", "start_ring"), ("end_ring", "end_ring"), ("orientation", "orientation")):
+        assert np.array_equal(seg[k], g[gk]), k                       # float32 / integer path: bit-exact
+    ground, surf = lf.extract(scan)
+    assert len(g["ground"]) > 100 and len(g["surf"]) > 100
+    assert np.array_equal(ground, g["ground"]) and np.array_equal(surf, g["surf"])
+
+
+def _check_imu(ctx, tol):
+    g = np.load(os.path.join(HERE, "golden", "imu_small.npz"))["consts"]
+    c = backend.preintegrate(ctx, *make_golden.imu_case())
+    assert c.shape == g.shape
+    for lo, hi in ((0, 17), (17, 242), (242, 467), (467, 469)):
+        assert np.max(np.abs(c[:, lo:hi] - g[:, lo:hi])) <= tol * max(1e-300, np.abs(g[:, lo:hi]).max())
+
+
+def test_oracle_reproduces_golden_lidar_and_imu(orc_ctx):
+    _check_lidar(orc_ctx)
+    _check_imu(orc_ctx, 1e-15)
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_golden_lidar_and_imu(lvb_ctx):
+    _check_lidar(lvb_ctx)
+    _check_imu(lvb_ctx, 1e-12)
