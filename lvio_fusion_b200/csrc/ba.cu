@@ -1246,6 +1246,7 @@ struct lvb_ba {
     size_t schur_smem = 0, lin_smem = 0;
     cudaGraphExec_t pass_graph = nullptr;
     int pass_launches = 0;
+    bool capturing = false;
     bool imu_checked = true;
     // tensor-core Schur (schur_mode 1)
     bool tc_ok = false; int schur_mode = 0, graph_mode = -1, n_tc_chunks = 0;
@@ -1831,7 +1832,9 @@ int lvb_ba_eval_device(lvb_ba* ba, int kind) {
 }
 
 static bool use_side_branch(lvb_ba* ba) {
-    return ba->ctx->use_side && ba->ctx->side && !g_timing && ba->ranges.b[3] > 0 && ba->ranges.b[6] > ba->ranges.b[3];
+    // not inside a captured graph: replaying a graph with parallel branches was measured to be erratic (0.19 - 0.9 ms per
+    // pass on the same build), a linear graph is stable
+    return ba->ctx->use_side && ba->ctx->side && !g_timing && !ba->capturing && ba->ranges.b[3] > 0 && ba->ranges.b[6] > ba->ranges.b[3];
 }
 
 // one pass = one LM iteration attempt (all decisions on the device), 10 launches (the two linearise kernels and the two
@@ -1971,8 +1974,10 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
             cudaGraph_t g = nullptr;
             const long long before = ba->ctx->launches;
             LVB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            ba->capturing = true;
             int rc = launch_linearize_and_reduce(ba, false);
             if (rc == LVB_OK) rc = launch_step(ba);
+            ba->capturing = false;
             cudaError_t ce = cudaStreamEndCapture(s, &g);
             if (rc != LVB_OK) { if (g) cudaGraphDestroy(g); return rc; }
             LVB_CUDA(ce);
