@@ -224,7 +224,7 @@ def main():
         line = {
             "metric": "ba_residual_jacobian_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": iters, "warmup": args.warmup,
             "ms_per_step": ms / iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: KITTI-shaped stereo+IMU 10-keyframe window, %d landmarks per GPU (sharded by landmark, one NCCL all-reduce of the reduced system per iteration), %d residual rows total; step = one LM iteration" % (N_LM, total_rows),
+            "config": {"workload": "configs[1]: KITTI-shaped stereo+IMU 10-keyframe window, %d landmarks per GPU (sharded by landmark, one in-kernel all-reduce of the reduced system over NVLink peer memory per iteration), %d residual rows total; step = one LM iteration" % (N_LM, total_rows),
                        "blocks": synth.count_blocks(full), "iters_per_solve": per,
                        "l2": "BA working set (~3 MB) is L2-resident by design; the roofline leg streams 394 MB per launch (> 126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": int(h2d / per), "d2h_bytes_per_step": int(d2h / per),
