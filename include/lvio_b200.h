@@ -113,7 +113,11 @@ LVB_API int lvb_ctx_synchronize(lvb_ctx* ctx);
 /* Multi-GPU: one process per GPU; the id is produced on rank 0 and shipped to
  * the other ranks by the caller (torch.distributed broadcast in bench.py). After init every
  * lvb_ba_solve / lvb_icp_scan_to_map on this context all-reduces its reduced normal
- * equations (one ncclAllReduce(sum,f64) per LM iteration). */
+ * equations once per LM iteration: messages up to 1 MB through an in-kernel all-reduce over NVLink peer
+ * memory (CUDA IPC exchange buffers set up here; LVB_NO_P2P=1 disables), larger ones through
+ * ncclAllReduce(sum, f64).  lvb_comm_init is collective, and so are lvb_ba_finalize / lvb_ba_solve /
+ * lvb_ba_reduced_system / lvb_icp_scan_to_map on a context with world_size > 1: every rank must make the
+ * same calls in the same order. */
 LVB_API int lvb_comm_unique_id(char id[128]);
 LVB_API int lvb_comm_init(lvb_ctx* ctx, int rank, int world_size, const char id[128]);
 
@@ -137,7 +141,8 @@ LVB_API int lvb_ba_add_factors(lvb_ba* ba, int kind, int n, const double* consts
 /* ceres::HuberLoss(a) for every block of `kind` (backend.cpp:98 uses 1.0 on the visual kinds);
  * a <= 0 means NULL / TrivialLoss. */
 LVB_API int lvb_ba_set_loss(lvb_ba* ba, int kind, double huber_a);
-/* Freeze the structure, sort/transpose to the device layout, upload.  */
+/* Freeze the structure, sort/transpose to the device layout, upload.  Collective when world_size > 1 (the order of
+ * the unknowns and the envelope of the reduced system are agreed on across the ranks). */
 LVB_API int lvb_ba_finalize(lvb_ba* ba);
 LVB_API int lvb_ba_dims(lvb_ba* ba, int* dim_camera, int* n_inv_depth_free, int* n_residual_rows);
 /* Re-upload parameter values only (same structure) -- used between solves / by the bench. */

@@ -638,19 +638,6 @@ __device__ __forceinline__ void atomic_max_nonneg(unsigned long long* p, double 
     else atomicMax(p, 0x7ff0000000000000ull);   // NaN -> +inf so the tolerance test fails
 }
 
-// landmarks: Jacobi scale (first pass), LM damping, gradient max-norm contribution
-__global__ void ba_prepare_landmark_kernel(BaDev d) {
-    LmState* st = d.st;
-    if (st->done) return;
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= d.n_rho) return;
-    if (d.rho_slot[l] < 0) { d.lam_l[l] = 0.0; return; }
-    const double h = d.Hll[l];
-    if (!st->scale_valid) d.scale_l[l] = st->jacobi ? 1.0 / (1.0 + sqrt(h)) : 1.0;
-    const double s = d.scale_l[l], s2 = s * s;
-    d.lam_l[l] = fmin(fmax(s2 * h, st->min_diag), st->max_diag) / (st->radius * s2);
-    if (st->need_linearize && d.lm_start[l + 1] > d.lm_start[l]) atomic_max_nonneg(&st->grad_max_bits, d.gl[l]);
-}
 
 // S <- lower(Hpp), rhs <- -gc, gcr <- gc, diagH <- diag(Hpp), scalars <- 0
 __global__ void ba_build_S_kernel(BaDev d) {
@@ -772,7 +759,7 @@ __global__ void __launch_bounds__(128) ba_schur_tc_kernel(BaDev d, int n_chunks)
     __shared__ __align__(8) uint64_t bar_load, bar_mma;
     __shared__ uint32_t tmem_base_slot;
     if (d.st->done) return;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int c0 = blockIdx.x * TC_CHUNKS;
     const int nc = min(TC_CHUNKS, n_chunks - c0);
     if (tid == 0) { mbar_init(&bar_load, 1); mbar_init(&bar_mma, 1); }
@@ -886,7 +873,6 @@ __global__ void ba_prepare_camera_kernel(BaDev d) {
 }
 
 __global__ void lm_control_pre_kernel(LmState* st) { lm_control_pre(*st); }
-__global__ void lm_control_post_kernel(LmState* st) { lm_control_post(*st); if (st->accept) st->x_cost = st->cand_cost_acc; }
 
 // ------------------------------------------------------------------ K6 dense Cholesky, one CTA
 // Right-looking blocked (32) factorisation of the lower triangle of S (n x n, row-major, in L2/HBM) with
