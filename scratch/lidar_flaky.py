@@ -1,0 +1,22 @@
+import sys, os
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lvio_fusion_b200 import _capi, backend, synth
+from oracle import binding
+g = backend.LidarFeatures(backend.Context(_capi.load())); o = backend.LidarFeatures(backend.Context(binding.load()))
+reps = int(sys.argv[1])
+bad = {"ground": 0, "surf": 0, "seg": 0, "vox": 0, "ror": 0, "sac": 0}
+for seed in (11, 14, 15):
+    scan = synth.make_lidar_scan(seed=seed)
+    og, os_ = o.extract(scan)
+    so = o.segment(scan)
+    vo = o.voxel_grid(so["points"], 0.4); ro = o.radius_outlier_removal(vo, 0.8, 4); sa = o.segment_ground(vo, 0.02)
+    for _ in range(reps):
+        gg, gs = g.extract(scan)
+        bad["ground"] += not np.array_equal(gg, og); bad["surf"] += not np.array_equal(gs, os_)
+        sg = g.segment(scan)
+        bad["seg"] += not all(np.array_equal(sg[k], so[k]) for k in ("points", "curvature", "ground"))
+        bad["vox"] += not np.array_equal(g.voxel_grid(so["points"], 0.4), vo)
+        bad["ror"] += not np.array_equal(g.radius_outlier_removal(vo, 0.8, 4), ro)
+        bad["sac"] += not np.array_equal(g.segment_ground(vo, 0.02), sa)
+print("SAFE" if os.environ.get("LVB_LIDAR_SAFE") else "FAST", "reps", reps, "mismatches", bad)
