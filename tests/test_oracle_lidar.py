@@ -116,3 +116,128 @@ def test_extract_features_outputs(olf, scan):
     lf2 = backend.LidarFeatures(olf.ctx, extrinsic=[0, 0, 0, 1, 0.5, -0.25, 1.0])
     g2, s2 = lf2.extract(scan)
     assert np.allclose(g2[:, :3], ground[:, :3] + np.float32([0.5, -0.25, 1.0]), atol=1e-6) and np.array_equal(s2[:, 3], surf[:, 3])
+
+
+def _numpy_segmentation(scan, cfg):
+    """Independent vectorised derivation of projection.cpp:57-320: range image (last writer wins), ground flags (closed form
+    of the bottom-up pair walk), segmentation as connected components (scipy) of the symmetric neighbour criterion with
+    the BFS feasibility rule.  Returns the kept (row, col, is_ground) triples in raster order."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    R, W = int(cfg.num_scans), int(cfg.horizon_scan)
+    p = scan[:, :3].astype(np.float32)
+    ok = np.isfinite(p).all(1)
+    d = (p[:, 0] * p[:, 0] + p[:, 1] * p[:, 1]) + p[:, 2] * p[:, 2]
+    ok &= (d.astype(np.float64) > cfg.min_range ** 2) & (d.astype(np.float64) < cfg.max_range ** 2)
+    p = p[ok]
+    ang_res_x = np.float32(360.0 / np.float32(W)); ang_res_y = np.float32(cfg.ang_res_y); ang_bottom = np.float32(cfg.ang_bottom)
+    xy2 = p[:, 0] * p[:, 0] + p[:, 1] * p[:, 1]
+    va = (np.arctan2(p[:, 2].astype(np.float64), np.sqrt(xy2.astype(np.float64))) * 180 / np.pi).astype(np.float32)
+    row = np.trunc((va + ang_bottom) / ang_res_y).astype(np.int64)
+    ha = (np.arctan2(p[:, 0].astype(np.float64), p[:, 1].astype(np.float64)) * 180 / np.pi).astype(np.float32)
+    q = (ha.astype(np.float64) - 90.0) / np.float64(ang_res_x)
+    rnd = np.where(q >= 0, np.floor(q + 0.5), np.ceil(q - 0.5))                 # C round(): half away from zero
+    col = np.trunc(-rnd + W // 2).astype(np.int64)
+    col = np.where(col >= W, col - W, col)
+    valid = (row >= 0) & (row < R) & (col >= 0) & (col < W)
+    rng_img = np.full((R, W), np.inf, np.float32); pts = np.full((R, W, 3), np.nan, np.float32)
+    idx = np.flatnonzero(valid)
+    cell = row[idx] * W + col[idx]
+    order = np.argsort(cell, kind="stable")                                    # last occurrence of each cell wins
+    last = np.r_[cell[order][1:] != cell[order][:-1], True]
+    win = idx[order][last]
+    r2 = xy2[win] + p[win, 2] * p[win, 2]
+    rng_img[row[win], col[win]] = np.sqrt(r2.astype(np.float64)).astype(np.float32)
+    pts[row[win], col[win]] = p[win]
+    have = np.isfinite(rng_img)
+    # ground: pair (i, i+1) flat / invalid
+    rows = min(int(cfg.ground_rows), R - 1)
+    lo, up = pts[:rows], pts[1:rows + 1]
+    pair_valid = have[:rows] & have[1:rows + 1]
+    dx, dy, dz = up[..., 0] - lo[..., 0], up[..., 1] - lo[..., 1], up[..., 2] - lo[..., 2]
+    with np.errstate(invalid="ignore"):
+        ang = (np.arctan2(dz.astype(np.float64), np.sqrt((dx * dx + dy * dy).astype(np.float64))) * 180 / np.pi).astype(np.float32)
+        flat = pair_valid & (np.abs(ang) <= 10)
+    ground = np.zeros((R, W), bool)
+    ground[1:rows + 1] |= flat                                  # flag from the pair below
+    g_own = np.zeros((R, W), bool); g_own[:rows] = flat
+    inval_own = np.zeros((R, W), bool); inval_own[:rows] = ~pair_valid
+    ground = np.where(inval_own, False, ground | g_own)
+    # components over valid, non-ground cells
+    node = have & ~ground
+    ids = -np.ones((R, W), np.int64); ids[node] = np.arange(node.sum())
+    theta = np.float32(60.0 / 180.0 * np.pi)
+    ax = np.float32(np.float64(ang_res_x) / 180.0 * np.pi); ay = np.float32(np.float64(ang_res_y) / 180.0 * np.pi)
+
+    def edges(a_ids, b_ids, ra, rb, alpha):
+        both = (a_ids >= 0) & (b_ids >= 0)
+        with np.errstate(invalid="ignore"):
+            d1 = np.maximum(ra, rb).astype(np.float64); d2 = np.minimum(ra, rb).astype(np.float64)
+            angle = np.arctan2(d2 * np.sin(np.float64(alpha)), d1 - d2 * np.cos(np.float64(alpha))).astype(np.float32)
+        e = both & (angle > theta)
+        return a_ids[e], b_ids[e]
+    e1 = edges(ids, np.roll(ids, -1, axis=1), rng_img, np.roll(rng_img, -1, axis=1), ax)       # right neighbour with wrap
+    e2 = edges(ids[:-1], ids[1:], rng_img[:-1], rng_img[1:], ay)                                # row above
+    n = int(node.sum())
+    ei = np.concatenate([e1[0], e2[0]]); ej = np.concatenate([e1[1], e2[1]])
+    ncomp, lab = connected_components(coo_matrix((np.ones(len(ei)), (ei, ej)), shape=(n, n)), directed=False)
+    rr, cc = np.nonzero(node)
+    size = np.bincount(lab, minlength=ncomp)
+    seed = np.full(ncomp, n, np.int64); np.minimum.at(seed, lab, np.arange(n))                 # raster-first cell = BFS seed
+    nonseed = np.arange(n) != seed[lab]
+    rowsets = np.zeros((ncomp, R), bool); rowsets[lab[nonseed], rr[nonseed]] = True            # rows of pushed cells
+    feasible = (size >= 30) | ((size >= 5) & (rowsets.sum(1) >= 3))
+    keep = ground.copy(); keep[rr, cc] |= feasible[lab]
+    kr, kc = np.nonzero(keep)
+    return kr, kc, ground[kr, kc], pts[kr, kc], rng_img[kr, kc]
+
+
+def test_segmentation_matches_independent_numpy_derivation(olf, scan):
+    s = olf.segment(scan)
+    kr, kc, kg, kp, krng = _numpy_segmentation(scan, olf.cfg)
+    ring = s["points"][:, 3].astype(np.int64)
+    a = set(zip(ring.tolist(), s["col"].tolist())); b = set(zip(kr.tolist(), kc.tolist()))
+    # libm vs numpy transcendental rounding may move a point across a bin / threshold edge: allow a handful of cells
+    assert len(a ^ b) <= max(5, len(a) // 5000), (len(a), len(b), len(a ^ b))
+    both = {rc: i for i, rc in enumerate(zip(ring.tolist(), s["col"].tolist()))}
+    sel = [(both[rc], j) for j, rc in enumerate(zip(kr.tolist(), kc.tolist())) if rc in both]
+    io, ij = np.array([x[0] for x in sel]), np.array([x[1] for x in sel])
+    assert np.all(np.diff(io) > 0)                                        # same raster order
+    assert (s["ground"][io].astype(bool) != kg[ij]).sum() <= 5
+    assert np.array_equal(s["points"][io, :3], kp[ij]) and np.array_equal(s["range"][io], krng[ij])
+
+
+def test_smoothness_and_relative_time_closed_forms(olf, scan):
+    """The vectorised forms the CUDA kernels use (stencil for association.cpp:151-166; "index > first index whose first-branch
+    angle passes pi" for the sequential half_passed flag of :113-149) against the oracle's literal loops."""
+    s = olf.segment(scan)
+    r = s["range"]; n = len(r)
+    i = np.arange(5, n - 5)
+    base = r[i - 5]
+    dr = (r[i + 5] - base) / np.float32(10)
+    acc = None
+    for k in range(9):
+        e = r[i + 4 - k] - base - np.float32(9 - k) * dr
+        acc = e * e if acc is None else acc + e * e
+    curv = np.zeros(n, np.float32)
+    curv[i] = (acc / np.float32(9)) * np.float32(10) / r[i]
+    assert np.array_equal(curv, s["curvature"])
+    so, eo, diff = (np.float32(v) for v in s["orientation"])
+    p = s["points"]
+    ori0 = (-np.arctan2(p[:, 1].astype(np.float64), p[:, 0].astype(np.float64))).astype(np.float32)
+    first = ori0.copy()
+    lo = first.astype(np.float64) < np.float64(so) - np.pi / 2
+    hi = ~lo & (first.astype(np.float64) > np.float64(so) + np.pi * 3 / 2)
+    first = np.where(lo, (first.astype(np.float64) + 2 * np.pi).astype(np.float32), np.where(hi, (first.astype(np.float64) - 2 * np.pi).astype(np.float32), first))
+    trip = np.flatnonzero((first - so).astype(np.float64) > np.pi)
+    m = trip[0] if len(trip) else n
+    second = (ori0.astype(np.float64) + 2 * np.pi).astype(np.float32)
+    lo2 = second.astype(np.float64) < np.float64(eo) - np.pi * 3 / 2
+    hi2 = ~lo2 & (second.astype(np.float64) > np.float64(eo) + np.pi / 2)
+    second = np.where(lo2, (second.astype(np.float64) + 2 * np.pi).astype(np.float32), np.where(hi2, (second.astype(np.float64) - 2 * np.pi).astype(np.float32), second))
+    ori = np.where(np.arange(n) <= m, first, second)
+    rel = (ori - so) / diff
+    ring = np.trunc(p[:, 3]).astype(np.int64)                 # int(intensity) survives the update (fraction < 1)
+    expect = (ring.astype(np.float64) + olf.cfg.cycle_time * rel.astype(np.float64)).astype(np.float32)
+    bad = np.flatnonzero(expect != p[:, 3])
+    assert len(bad) <= 3, (len(bad), n)                       # numpy vs libm atan2 rounding
