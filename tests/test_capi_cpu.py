@@ -56,3 +56,15 @@ def test_shim_compiles_and_reports_failure_without_a_device(tmp_path):
     shim_util.dump_ba(tmp_path / "in.bin", d, 3)
     p = subprocess.run([exe, "ba", str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
     assert p.returncode == 3 and "no device" in p.stderr      # ceres::Solve reports FAILURE through the Summary
+
+
+def test_lidar_and_imu_host_header_builds_and_fails_loudly(tmp_path):
+    """include/lvio_b200/lidar_features.h against a pcl::PointXYZI-shaped record; without a device the calls return
+    false (no CPU fallback), with one they run (empty inputs)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "lvio_fusion_b200", "csrc")
+    exe = str(tmp_path / "lidar_header")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(root, "include"), "-o", exe,
+                           os.path.join(root, "tests", "cpp", "compile_lidar_header.cpp"), "-L" + lib_dir, "-llvio_b200", "-Wl,-rpath," + lib_dir])
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == (0 if _has_gpu() else 3)
