@@ -117,6 +117,8 @@ _LVB_ONLY = {
     "comm_unique_id": (C.c_int, [C.c_char_p]),
     "comm_init": (C.c_int, [VP, C.c_int, C.c_int, C.c_char_p]),
     "ba_set_schur_mode": (C.c_int, [VP, C.c_int]),
+    "debug_timing": (C.c_int, [C.c_int]),
+    "debug_cholesky_clocks": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
 }
 
 EXPORTED_SYMBOLS = ["lvb_" + k for k in list(_SIGS) + list(_LVB_ONLY)]
