@@ -15,12 +15,15 @@
 // each a lvb::DeviceCost carrying its factor kind and constant record.  Problem records pointers exactly
 // like Ceres (pointer identity = block identity, memory owned by the caller's Frame / Landmark objects),
 // Solve() packs them into the flat arrays of lvb_ba_*, runs the LM on the device and writes the
-// parameters back IN PLACE.  Blocks of any other cost type make Solve() report FAILURE with a message --
-// the off-path tiny problems of the reference (navsat, pose graph, relocation) keep using a
-// host solver and are out of scope here.  There is no CPU fallback behind this header.
+// parameters back IN PLACE.  There is no CPU fallback for these: without a device Solve() reports FAILURE.
+// Problems made only of generic functors (ceres_autodiff.h: the off-path tiny solves of the reference --
+// navsat, section pose graph, relocation), optionally with PoseGraphError / PoseError blocks, are
+// solved by the small dense host LM in host_solver.h; mixing them with hot-path factor kinds is an error.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <memory>
 #include <set>
@@ -82,14 +85,66 @@ class LossFunction { public: virtual ~LossFunction() {} virtual double huber_a()
 class TrivialLoss : public LossFunction {};
 class HuberLoss : public LossFunction { public: explicit HuberLoss(double a) : a_(a) {} double huber_a() const override { return a_; } private: double a_; };
 
-class LocalParameterization { public: virtual ~LocalParameterization() {} virtual int GlobalSize() const = 0; virtual int LocalSize() const = 0; };
-class EigenQuaternionParameterization : public LocalParameterization { public: int GlobalSize() const override { return 4; } int LocalSize() const override { return 3; } };
-class IdentityParameterization : public LocalParameterization { public: explicit IdentityParameterization(int n) : n_(n) {} int GlobalSize() const override { return n_; } int LocalSize() const override { return n_; } private: int n_; };
+// Plus / ComputeJacobian are only exercised by the host solver of the off-path small solves (host_solver.h); on the device
+// path the 7-double pose block always carries the quaternion (x) identity product (backend.cpp:99-101).
+class LocalParameterization {
+public:
+    virtual ~LocalParameterization() {}
+    virtual int GlobalSize() const = 0;
+    virtual int LocalSize() const = 0;
+    virtual bool Plus(const double* x, const double* delta, double* x_plus_delta) const = 0;
+    virtual bool ComputeJacobian(const double* x, double* jacobian /* GlobalSize x LocalSize, row-major */) const = 0;
+};
+// [upstream] ceres::EigenQuaternionParameterization: storage x y z w, q' = q_delta (x) q with q_delta = (sin|d|/|d| d, cos|d|)
+class EigenQuaternionParameterization : public LocalParameterization {
+public:
+    int GlobalSize() const override { return 4; }
+    int LocalSize() const override { return 3; }
+    bool Plus(const double* x, const double* d, double* out) const override {
+        const double n = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        if (n == 0.0) { for (int i = 0; i < 4; ++i) out[i] = x[i]; return true; }
+        const double k = std::sin(n) / n, qx = k * d[0], qy = k * d[1], qz = k * d[2], qw = std::cos(n);
+        out[0] = qw * x[0] + qx * x[3] + qy * x[2] - qz * x[1];
+        out[1] = qw * x[1] - qx * x[2] + qy * x[3] + qz * x[0];
+        out[2] = qw * x[2] + qx * x[1] - qy * x[0] + qz * x[3];
+        out[3] = qw * x[3] - qx * x[0] - qy * x[1] - qz * x[2];
+        return true;
+    }
+    bool ComputeJacobian(const double* x, double* j) const override {
+        j[0] = x[3]; j[1] = x[2]; j[2] = -x[1];
+        j[3] = -x[2]; j[4] = x[3]; j[5] = x[0];
+        j[6] = x[1]; j[7] = -x[0]; j[8] = x[3];
+        j[9] = -x[0]; j[10] = -x[1]; j[11] = -x[2];
+        return true;
+    }
+};
+class IdentityParameterization : public LocalParameterization {
+public:
+    explicit IdentityParameterization(int n) : n_(n) {}
+    int GlobalSize() const override { return n_; }
+    int LocalSize() const override { return n_; }
+    bool Plus(const double* x, const double* d, double* out) const override { for (int i = 0; i < n_; ++i) out[i] = x[i] + d[i]; return true; }
+    bool ComputeJacobian(const double*, double* j) const override { for (int i = 0; i < n_ * n_; ++i) j[i] = 0.0; for (int i = 0; i < n_; ++i) j[i * n_ + i] = 1.0; return true; }
+private:
+    int n_;
+};
 class ProductParameterization : public LocalParameterization {
 public:
     ProductParameterization(LocalParameterization* a, LocalParameterization* b) : a_(a), b_(b) {}
     int GlobalSize() const override { return a_->GlobalSize() + b_->GlobalSize(); }
     int LocalSize() const override { return a_->LocalSize() + b_->LocalSize(); }
+    bool Plus(const double* x, const double* d, double* out) const override {
+        return a_->Plus(x, d, out) && b_->Plus(x + a_->GlobalSize(), d + a_->LocalSize(), out + a_->GlobalSize());
+    }
+    bool ComputeJacobian(const double* x, double* j) const override {
+        const int ga = a_->GlobalSize(), la = a_->LocalSize(), gb = b_->GlobalSize(), lb = b_->LocalSize(), l = la + lb;
+        std::vector<double> ja((size_t)ga * la), jb((size_t)gb * lb);
+        if (!a_->ComputeJacobian(x, ja.data()) || !b_->ComputeJacobian(x + ga, jb.data())) return false;
+        for (int i = 0; i < (ga + gb) * l; ++i) j[i] = 0.0;
+        for (int r = 0; r < ga; ++r) for (int c = 0; c < la; ++c) j[r * l + c] = ja[(size_t)r * la + c];
+        for (int r = 0; r < gb; ++r) for (int c = 0; c < lb; ++c) j[(ga + r) * l + la + c] = jb[(size_t)r * lb + c];
+        return true;
+    }
 private:
     std::unique_ptr<LocalParameterization> a_, b_;
 };
@@ -111,10 +166,15 @@ public:
     const std::vector<double>& consts() const { return consts_; }
     // Host-side single-block evaluation is not part of the device path; callers that need residuals of many
     // blocks use lvb_ba_eval / lvb_ba_reprojection_errors (compute_reprojection_error, backend.cpp:185-190).
-    bool Evaluate(double const* const*, double*, double**) const override { return false; }
+    // Kinds that also occur in the off-path host solves (PoseGraphError / PoseError in navsat.cpp:294-301,
+    // pose_graph.cpp) carry a host evaluator (factors.h attaches it); the hot-path kinds do not.
+    bool Evaluate(double const* const* p, double* r, double** j) const override { return host_ ? host_->Evaluate(p, r, j) : false; }
+    void set_host_evaluator(ceres::CostFunction* f) { host_.reset(f); }
+    bool has_host_evaluator() const { return (bool)host_; }
 private:
     int kind_;
     std::vector<double> consts_;
+    std::unique_ptr<ceres::CostFunction> host_;
 };
 
 // One whole ScanToMapWith{Ground,Segmented} association expressed as a single residual "block group":
@@ -177,7 +237,7 @@ public:
     Problem& operator=(const Problem&) = delete;
 
     void AddParameterBlock(double* values, int size) { add_block(values, size); }
-    void AddParameterBlock(double* values, int size, LocalParameterization* p) { add_block(values, size); if (p) params_owned_.insert(p); }
+    void AddParameterBlock(double* values, int size, LocalParameterization* p) { add_block(values, size); if (p) { params_owned_.insert(p); param_of_[values] = p; } }
 
     template <typename... Ts>
     ResidualBlockId AddResidualBlock(CostFunction* cost, LossFunction* loss, double* x0, Ts*... xs) {
@@ -194,6 +254,12 @@ public:
     void GetResidualBlocksForParameterBlock(const double* v, std::vector<ResidualBlockId>* out) const {
         out->clear(); auto it = by_block_.find(const_cast<double*>(v)); if (it != by_block_.end()) *out = it->second;
     }
+    // navsat.cpp:245-246 (only honoured by the host solver; the device path has no bounded blocks)
+    void SetParameterLowerBound(double* v, int i, double b) { bound(lower_, v, -std::numeric_limits<double>::infinity())[i] = b; }
+    void SetParameterUpperBound(double* v, int i, double b) { bound(upper_, v, std::numeric_limits<double>::infinity())[i] = b; }
+    const LocalParameterization* parameterization_of(double* v) const { auto it = param_of_.find(v); return it == param_of_.end() ? nullptr : it->second; }
+    const double* lower_bounds_of(double* v) const { auto it = lower_.find(v); return it == lower_.end() ? nullptr : it->second.data(); }
+    const double* upper_bounds_of(double* v) const { auto it = upper_.find(v); return it == upper_.end() ? nullptr : it->second.data(); }
     int NumResidualBlocks() const { return (int)residuals_.size(); }
     int NumParameterBlocks() const { return (int)blocks_.size(); }
 
@@ -209,7 +275,20 @@ private:
     std::unordered_map<double*, std::vector<ResidualBlockId>> by_block_;
     std::set<double*> constant_;
     std::set<LocalParameterization*> params_owned_;
+    std::unordered_map<double*, LocalParameterization*> param_of_;
+    std::unordered_map<double*, std::vector<double>> lower_, upper_;
+    std::vector<double>& bound(std::unordered_map<double*, std::vector<double>>& m, double* v, double init) {
+        auto it = m.find(v);
+        if (it == m.end()) { int size = 1; auto ix = index_.find(v); if (ix != index_.end()) size = blocks_[ix->second].second; it = m.emplace(v, std::vector<double>((size_t)size, init)).first; }
+        return it->second;
+    }
 };
+
+}  // namespace ceres
+
+namespace lvb { namespace host { inline void solve(const ceres::Solver::Options&, ceres::Problem*, ceres::Solver::Summary*); } }   // host_solver.h
+
+namespace ceres {
 
 inline void fill_options(const Solver::Options& o, lvb_solve_options* out) {
     lvb_default_options(out);
@@ -232,20 +311,27 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
     *summary = Solver::Summary();
     lvb::Runtime& rt = lvb::Runtime::get();
     auto fail = [&](const std::string& m) { summary->termination_type = FAILURE; summary->message = m; };
-    if (!rt.ensure()) return fail("no device: " + rt.error);
-    lvb_solve_options opt; fill_options(options, &opt);
-    lvb_solve_summary sum; std::memset(&sum, 0, sizeof(sum));
 
     // ---- scan-to-map problems (Mapping::Optimize): one ScanToMapCost (+ optional IcpPriorCost)
     const lvb::ScanToMapCost* scan = nullptr; const lvb::IcpPriorCost* prior = nullptr; const LossFunction* scan_loss = nullptr;
-    bool has_device = false, has_other = false;
+    bool has_device = false, has_other = false, has_hostable = false;
     for (auto& rb : problem->residual_blocks()) {
         if (auto* s = dynamic_cast<const lvb::ScanToMapCost*>(rb->cost)) { scan = s; scan_loss = rb->loss; }
         else if (auto* p = dynamic_cast<const lvb::IcpPriorCost*>(rb->cost)) prior = p;
-        else if (dynamic_cast<const lvb::DeviceCost*>(rb->cost)) has_device = true;
+        else if (auto* dc = dynamic_cast<const lvb::DeviceCost*>(rb->cost)) { if (dc->has_host_evaluator()) has_hostable = true; else has_device = true; }
         else has_other = true;
     }
-    if (has_other) return fail("a cost function outside the device factor set was added (generic functors are not on the B200 path)");
+    // Off-path small solves (navsat, section pose graph, relocation: generic AutoDiff functors, possibly together with
+    // PoseGraphError / PoseError): dense LM on the host, host_solver.h.  A problem with any reprojection / IMU / scan-to-map
+    // block never goes there.
+    if (has_other) {
+        if (has_device || scan) return fail("generic cost functions cannot be mixed with the device factor kinds of the B200 path");
+        return lvb::host::solve(options, problem, summary);
+    }
+    (void)has_hostable;
+    if (!rt.ensure()) return fail("no device: " + rt.error);
+    lvb_solve_options opt; fill_options(options, &opt);
+    lvb_solve_summary sum; std::memset(&sum, 0, sizeof(sum));
     if (scan) {
         if (has_device) return fail("scan-to-map blocks cannot be mixed with BA blocks");
         const double huber = scan_loss ? scan_loss->huber_a() : 0.0;
@@ -312,3 +398,5 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
 }
 
 }  // namespace ceres
+
+#include "host_solver.h"

@@ -9,6 +9,7 @@
 // the rig actually used on the device is the one registered with lvb::Runtime::set_cameras (Camera::Get(0/1)).
 #pragma once
 #include "ceres_shim.h"
+#include "ceres_autodiff.h"
 
 namespace lvio_fusion {
 
@@ -89,7 +90,21 @@ public:
     template <class SE3>
     static ceres::CostFunction* Create(const SE3& last_pose, const SE3& pose, double weight = 1, double v = 1) {
         double e[6]; relative_rpyxyz(detail::ptr(last_pose), detail::ptr(pose), e);
-        return new lvb::DeviceCost(LVB_POSE_GRAPH, 6, {7, 7}, {e[0], e[1], e[2], e[3], e[4], e[5], weight, v});
+        return make(e, weight, v);
+    }
+    // second constructor of the reference (pose_error.hpp:20-23, navsat.cpp:300): the relative pose is given
+    template <class SE3>
+    static ceres::CostFunction* Create(const SE3& relative_i_j, double weight = 1, double v = 1) {
+        double e[6]; lvb::host::se3_to_rpyxyz(detail::ptr(relative_i_j), e);
+        return make(e, weight, v);
+    }
+    static ceres::CostFunction* make(const double* e, double weight, double v) {
+        lvb::DeviceCost* c = new lvb::DeviceCost(LVB_POSE_GRAPH, 6, {7, 7}, {e[0], e[1], e[2], e[3], e[4], e[5], weight, v});
+        lvb::host::PoseGraphFunctor* f = new lvb::host::PoseGraphFunctor();      // host evaluator: only the off-path solves use it
+        for (int i = 0; i < 6; ++i) f->e[i] = e[i];
+        f->w = weight; f->v = v;
+        c->set_host_evaluator(new ceres::AutoDiffCostFunction<lvb::host::PoseGraphFunctor, 6, 7, 7>(f));
+        return c;
     }
     // base.hpp:40-55,70-77,94-141 on doubles (unit quaternions assumed for the stored poses)
     static void relative_rpyxyz(const double* a, const double* b, double* e);
@@ -101,7 +116,12 @@ public:
     template <class SE3>
     static ceres::CostFunction* Create(const SE3& pose, double weight = 1, double v = 1) {
         const double* p = detail::ptr(pose);
-        return new lvb::DeviceCost(LVB_POSE_PRIOR, 6, {7}, {p[0], p[1], p[2], p[3], p[4], p[5], p[6], weight, v});
+        lvb::DeviceCost* c = new lvb::DeviceCost(LVB_POSE_PRIOR, 6, {7}, {p[0], p[1], p[2], p[3], p[4], p[5], p[6], weight, v});
+        lvb::host::PoseFunctor* f = new lvb::host::PoseFunctor();
+        for (int i = 0; i < 7; ++i) f->pose[i] = p[i];
+        f->w = weight; f->v = v;
+        c->set_host_evaluator(new ceres::AutoDiffCostFunction<lvb::host::PoseFunctor, 6, 7>(f));
+        return c;
     }
 };
 
