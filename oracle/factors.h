@@ -1,5 +1,7 @@
 // oracle/factors.h -- CPU restatement of the reference's autodiff cost functors
-// (TEST INFRASTRUCTURE ONLY; parity unpinned -- the reference has no golden vectors).
+// (TEST INFRASTRUCTURE ONLY).  The reference has no golden vectors; the visual, lidar-plane and pose factors of this file
+// are pinned against the reference's own functor headers compiled in place (oracle/ref_harness.cpp, oracle/ref_compat,
+// tests/golden/ref_factors.npz, tests/test_ref_golden.py); everything else in oracle/ stays "parity unpinned".
 //
 // Every functor below is templated on the scalar so that it can be run on doubles (the
 // residual) or oracle::Dual<N> (the Jacobian an AutoDiffCostFunction would return).

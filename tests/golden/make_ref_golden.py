@@ -1,0 +1,93 @@
+"""Generate tests/golden/ref_factors.npz by running the REFERENCE's own factor functors.
+
+`make -C oracle ref` compiles /root/reference/src/lvio_fusion/include/lvio_fusion/ceres/{visual,lidar,pose}_error.hpp (in
+place, never copied) against the stand-in third-party headers in oracle/ref_compat and the oracle's dual numbers; this script
+feeds it seeded KITTI-shaped inputs and stores inputs + residuals + Jacobians.  The oracle (tests/test_ref_golden.py, CPU)
+and the CUDA path (same file, -m gpu) must reproduce them.  Only runs where /root/reference is mounted.
+
+    python tests/golden/make_ref_golden.py
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from lvio_fusion_b200 import synth  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+N = 24
+
+
+def _unit_pose(rng, P, sigma_q=0.01, sigma_t=0.05, scale=1.0):
+    q = P[:4] + rng.normal(0, sigma_q, 4)
+    return np.concatenate([q / np.linalg.norm(q) * scale, P[4:] + rng.normal(0, sigma_t, 3)])
+
+
+def build_cases(seed=synth.SEED):
+    rng = np.random.default_rng(seed)
+    d = synth.make_ba_problem(6, 120, with_imu=False, seed=seed)
+    P = d["poses"]
+    c0, i0 = d["factors"][0]; c1, i1 = d["factors"][1]; c2, i2 = d["factors"][2]
+    cases = {"cameras": np.asarray(d["cameras"], dtype=np.float64)}
+    # a1: consts (first_ob, ob, w), params rho, T1, T2 -- one pose pair with a non-unit quaternion (QuaternionRotatePoint normalises)
+    sel = rng.choice(len(c0), N, replace=False)
+    T1 = np.stack([_unit_pose(rng, P[i0[s, 1]], scale=1.0 + 0.01 * (k % 3)) for k, s in enumerate(sel)])
+    T2 = np.stack([_unit_pose(rng, P[i0[s, 2]]) for s in sel])
+    cases["tf_c"] = c0[sel]; cases["tf_x"] = np.concatenate([d["rho"][i0[sel, 0]][:, None], T1, T2], axis=1)
+    sel = rng.choice(len(c1), N, replace=False)
+    cases["po_c"] = c1[sel]; cases["po_x"] = np.stack([_unit_pose(rng, P[i1[s, 0]]) for s in sel])
+    sel = rng.choice(len(c2), N, replace=False)
+    cases["tc_c"] = c2[sel]; cases["tc_x"] = d["rho"][i2[sel, 0]][:, None] * rng.uniform(0.9, 1.1, (N, 1))
+    # a5: mode, p, pa, pb, pc, Twc1, rpyxyz, w
+    lid = []
+    for k in range(N):
+        pa = rng.normal(0, 8, 3); pb = pa + rng.normal(0, 0.4, 3); pc = pa + rng.normal(0, 0.4, 3)
+        p = rng.normal(0, 8, 3)
+        T = _unit_pose(rng, P[k % len(P)], sigma_q=0.05, sigma_t=1.0)
+        e = np.concatenate([rng.normal(0, 0.05, 3), rng.normal(0, 0.3, 3)])
+        lid.append(np.concatenate([[k % 2], p, pa, pb, pc, T, e, [rng.uniform(0.01, 1.0)]]))
+    cases["lidar"] = np.asarray(lid)
+    # a6
+    pg, pe, pr = [], [], []
+    for k in range(N):
+        a, b = _unit_pose(rng, P[k % 5]), _unit_pose(rng, P[k % 5 + 1])
+        x1, x2 = _unit_pose(rng, P[k % 5], 0.02, 0.1, 1.0 + 0.005 * (k % 2)), _unit_pose(rng, P[k % 5 + 1], 0.02, 0.1)
+        pg.append(np.concatenate([a, b, [rng.uniform(1, 100), rng.uniform(0, 2)], x1, x2]))
+        pe.append(np.concatenate([a, [rng.uniform(1, 100), rng.uniform(0, 2)], x1]))
+        pr.append(np.concatenate([[k % 2], rng.normal(0, 0.3, 6), [rng.uniform(1, 100)], rng.normal(0, 0.3, 3)]))
+    cases["pg"] = np.asarray(pg); cases["pe"] = np.asarray(pe); cases["pr"] = np.asarray(pr)
+    return cases
+
+
+def run_reference(cases):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    flat = [cases["cameras"], np.array([N] * 7, dtype=np.float64)]
+    flat += [np.concatenate([cases["tf_c"], cases["tf_x"]], axis=1).ravel(), np.concatenate([cases["po_c"], cases["po_x"]], axis=1).ravel(),
+             np.concatenate([cases["tc_c"], cases["tc_x"]], axis=1).ravel(), cases["lidar"].ravel(), cases["pg"].ravel(), cases["pe"].ravel(), cases["pr"].ravel()]
+    with tempfile.TemporaryDirectory() as td:
+        np.concatenate(flat).astype(np.float64).tofile(os.path.join(td, "cases.bin"))
+        subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "ref_factors"), os.path.join(td, "cases.bin"), os.path.join(td, "out.bin")])
+        o = np.fromfile(os.path.join(td, "out.bin"), dtype=np.float64)
+    out, pos = {}, 0
+    for name, R, C in (("tf", 2, 15), ("po", 2, 7), ("tc", 2, 1), ("lidar", 1, 3), ("pg", 6, 14), ("pe", 6, 7), ("pr", 3, 3)):
+        blk = o[pos:pos + N * (R + R * C)].reshape(N, R + R * C); pos += N * (R + R * C)
+        out[name + "_r"] = blk[:, :R].copy(); out[name + "_J"] = blk[:, R:].reshape(N, R, C).copy()
+    assert pos == len(o)
+    return out
+
+
+def main():
+    if not os.path.isdir("/root/reference"):
+        raise SystemExit("the reference tree is not mounted here; the committed fixture stays as it is")
+    cases = build_cases()
+    out = run_reference(cases)
+    np.savez_compressed(os.path.join(HERE, "ref_factors.npz"), **cases, **out)
+    print("reference golden written:", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()
