@@ -1,5 +1,7 @@
-// oracle/imu.h -- IMU preintegration + ImuError restatement (TEST INFRASTRUCTURE ONLY,
-// parity unpinned).
+// oracle/imu.h -- IMU preintegration + ImuError restatement (TEST INFRASTRUCTURE ONLY).
+// Pinned against the reference's own src/preintegration.cpp and ceres/imu_error.hpp compiled in place against a mini-Eigen
+// (oracle/ref_harness.cpp, oracle/ref_compat/mini_eigen.h, tests/golden/ref_factors.npz, tests/test_ref_golden.py):
+// preintegration record 1e-12, whitened residual / Jacobians 1e-8.  ImuInitError (the FullBA variant) is not in the fixture.
 //
 //   producer : /root/reference/src/lvio_fusion/src/preintegration.cpp:11-127 (midpoint propagate)
 //   residual : /root/reference/src/lvio_fusion/src/preintegration.cpp:144-165 (Evaluate)

@@ -13,8 +13,22 @@ namespace ceres {
 using std::abs; using std::asin; using std::atan2; using std::cos; using std::sin; using std::sqrt;
 // the oracle's dual-number math lives in namespace oracle and is found by argument-dependent lookup
 
-class CostFunction { public: virtual ~CostFunction() {} };
+class CostFunction {
+public:
+    virtual ~CostFunction() {}
+    virtual bool Evaluate(double const* const*, double*, double**) const { return false; }
+};
+template <int kNumResiduals, int... Ns> class SizedCostFunction : public CostFunction {};      // imu_error.hpp:12,124 derive from it
 enum Ownership { DO_NOT_TAKE_OWNERSHIP, TAKE_OWNERSHIP };
+enum NumericDiffMethodType { CENTRAL, FORWARD, RIDDERS };
+template <typename Functor, NumericDiffMethodType kMethod, int kNumResiduals, int... Ns>
+class NumericDiffCostFunction : public CostFunction {                                            // named by imu_error.hpp:265 only
+public:
+    explicit NumericDiffCostFunction(Functor* f) : functor_(f) {}
+    ~NumericDiffCostFunction() override { delete functor_; }
+private:
+    Functor* functor_;
+};
 template <typename Functor, int kNumResiduals, int... Ns>
 class AutoDiffCostFunction : public CostFunction {
 public:

@@ -12,10 +12,12 @@
 #include "lvio_fusion/ceres/visual_error.hpp"
 #include "lvio_fusion/ceres/lidar_error.hpp"
 #include "lvio_fusion/ceres/pose_error.hpp"
+#include "lvio_fusion/ceres/imu_error.hpp"
 
 namespace lvio_fusion {
 std::vector<Camera::Ptr> Camera::devices_;      // defined in the reference's src/visual/camera.cpp, which is not compiled here
 double Camera::baseline = 1;
+std::vector<Imu::Ptr> Imu::devices_;            // src/imu/imu.cpp, not compiled here
 }
 using namespace lvio_fusion;
 using oracle::Dual;
@@ -50,7 +52,7 @@ int main(int argc, char** argv) {
     double cam[22]; take(cam, 22);
     for (int c = 0; c < 2; ++c) Camera::Create(cam[11 * c], cam[11 * c + 1], cam[11 * c + 2], cam[11 * c + 3], SE3d(cam + 11 * c + 4));
     Camera::Ptr left = Camera::Get(0), right = Camera::Get(1);
-    const int n_tf = (int)next(), n_po = (int)next(), n_tc = (int)next(), n_lidar = (int)next(), n_pg = (int)next(), n_pe = (int)next(), n_pr = (int)next();
+    const int n_tf = (int)next(), n_po = (int)next(), n_tc = (int)next(), n_lidar = (int)next(), n_pg = (int)next(), n_pe = (int)next(), n_pr = (int)next(), n_imu = (int)next();
     for (int i = 0; i < n_tf; ++i) {           // a1: first_ob(2) ob(2) w | rho T1 T2
         double c[5], x[15]; take(c, 5); take(x, 15);
         TwoFrameReprojectionError f(Vector2d(c[0], c[1]), Vector2d(c[2], c[3]), left, right, c[4]);
@@ -96,6 +98,34 @@ int main(int argc, char** argv) {
         double e[6], x[3]; take(e, 6); const double w = next(); take(x, 3);
         if (mode == 0) { PoseErrorRPZ f(e, w); eval<3, 3>(f, x, [](const PoseErrorRPZ& g, const Dual<3>* X, Dual<3>* Y) { g(X, X + 1, X + 2, Y); }); }
         else { PoseErrorYXY f(e, w); eval<3, 3>(f, x, [](const PoseErrorYXY& g, const Dual<3>* X, Dual<3>* Y) { g(X, X + 1, X + 2, Y); }); }
+    }
+    // a4 ImuError (imu_error.hpp:12-122) on top of Preintegration::Append / Propagate (preintegration.h:27-40,
+    // src/preintegration.cpp:30-127, compiled in place): noise4 once, then per case  ba bg acc0 gyr0 n_samples (dt acc gyr)*
+    // and the 8 parameter blocks pose_i v_i ba_i bg_i pose_j v_j ba_j bg_j.  Emits the preintegration record (delta_p,
+    // delta_q xyzw, delta_v, linearized ba / bg, sum_dt, jacobian, covariance), then r[15] and the 8 row-major Jacobians.
+    if (n_imu > 0) {
+        double nz[4]; take(nz, 4);                     // ACC_N GYR_N ACC_W GYR_W
+        Imu::Create(SE3d(), nz[0], nz[2], nz[1], nz[3], 9.81007);
+    }
+    for (int i = 0; i < n_imu; ++i) {
+        double ba[3], bg[3], a0[3], g0[3]; take(ba, 3); take(bg, 3); take(a0, 3); take(g0, 3);
+        const int ns = (int)next();
+        imu::Preintegration::Ptr pre = imu::Preintegration::Create(Bias(Vector3d(ba[0], ba[1], ba[2]), Vector3d(bg[0], bg[1], bg[2])));
+        for (int k = 0; k < ns; ++k) {
+            double smp[7]; take(smp, 7);
+            pre->Append(smp[0], Vector3d(smp[1], smp[2], smp[3]), Vector3d(smp[4], smp[5], smp[6]), Vector3d(a0[0], a0[1], a0[2]), Vector3d(g0[0], g0[1], g0[2]));
+        }
+        double rec[17] = {pre->delta_p.x(), pre->delta_p.y(), pre->delta_p.z(), pre->delta_q.x(), pre->delta_q.y(), pre->delta_q.z(), pre->delta_q.w(),
+                          pre->delta_v.x(), pre->delta_v.y(), pre->delta_v.z(), pre->linearized_ba.x(), pre->linearized_ba.y(), pre->linearized_ba.z(),
+                          pre->linearized_bg.x(), pre->linearized_bg.y(), pre->linearized_bg.z(), pre->sum_dt};
+        put(rec, 17); put(pre->jacobian.data(), 225); put(pre->covariance.data(), 225);
+        double x[32]; take(x, 32);
+        const double* prm[8] = {x, x + 7, x + 10, x + 13, x + 16, x + 23, x + 26, x + 29};
+        double r[15], J0[105], J1[45], J2[45], J3[45], J4[105], J5[45], J6[45], J7[45];
+        double* J[8] = {J0, J1, J2, J3, J4, J5, J6, J7};
+        ImuError f(pre);
+        f.Evaluate(prm, r, J);
+        put(r, 15); put(J0, 105); put(J1, 45); put(J2, 45); put(J3, 45); put(J4, 105); put(J5, 45); put(J6, 45); put(J7, 45);
     }
     fclose(out);
     return 0;

@@ -20,6 +20,7 @@ from lvio_fusion_b200 import synth  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 N = 24
+N_IMU = 12
 
 
 def _unit_pose(rng, P, sigma_q=0.01, sigma_t=0.05, scale=1.0):
@@ -60,14 +61,36 @@ def build_cases(seed=synth.SEED):
         pe.append(np.concatenate([a, [rng.uniform(1, 100), rng.uniform(0, 2)], x1]))
         pr.append(np.concatenate([[k % 2], rng.normal(0, 0.3, 6), [rng.uniform(1, 100)], rng.normal(0, 0.3, 3)]))
     cases["pg"] = np.asarray(pg); cases["pe"] = np.asarray(pe); cases["pr"] = np.asarray(pr)
+    # a4: noise4, then per case: ba bg acc0 gyr0 n_samples samples[n][7] | pose_i v_i ba_i bg_i pose_j v_j ba_j bg_j
+    cases["imu_noise"] = np.array(synth.IMU_NOISE, dtype=np.float64)
+    imu = []
+    for k in range(N_IMU):
+        ns = 6 + (k % 7)
+        ba, bg = rng.normal(0, 0.05, 3), rng.normal(0, 0.01, 3)
+        acc = rng.normal(0, 0.8, (ns + 1, 3)) + [0.3, 0.1, 9.81]; gyr = rng.normal(0, 0.15, (ns + 1, 3))
+        dt = rng.uniform(0.008, 0.012, ns)
+        T = dt.sum()
+        pose_i = _unit_pose(rng, P[k % len(P)], 0.05, 0.5)
+        v_i = np.array([9.5, 0.3, -0.1]) + rng.normal(0, 0.3, 3)
+        pose_j = _unit_pose(rng, np.concatenate([pose_i[:4], pose_i[4:] + v_i * T]), 0.02, 0.03)
+        v_j = v_i + rng.normal(0, 0.2, 3)
+        x = np.concatenate([pose_i, v_i, ba + rng.normal(0, 0.01, 3), bg + rng.normal(0, 0.002, 3), pose_j, v_j, ba + rng.normal(0, 0.01, 3), bg + rng.normal(0, 0.002, 3)])
+        imu.append({"ba": ba, "bg": bg, "acc0": acc[0], "gyr0": gyr[0], "samples": np.concatenate([dt[:, None], acc[1:], gyr[1:]], axis=1), "x": x})
+    cases["imu_first"] = np.concatenate([[0], np.cumsum([len(c["samples"]) for c in imu])]).astype(np.int32)
+    cases["imu_samples"] = np.concatenate([c["samples"] for c in imu])
+    for key in ("ba", "bg", "acc0", "gyr0", "x"):
+        cases["imu_" + key] = np.stack([c[key] for c in imu])
     return cases
 
 
 def run_reference(cases):
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
-    flat = [cases["cameras"], np.array([N] * 7, dtype=np.float64)]
+    flat = [cases["cameras"], np.array([N] * 7 + [N_IMU], dtype=np.float64)]
     flat += [np.concatenate([cases["tf_c"], cases["tf_x"]], axis=1).ravel(), np.concatenate([cases["po_c"], cases["po_x"]], axis=1).ravel(),
-             np.concatenate([cases["tc_c"], cases["tc_x"]], axis=1).ravel(), cases["lidar"].ravel(), cases["pg"].ravel(), cases["pe"].ravel(), cases["pr"].ravel()]
+             np.concatenate([cases["tc_c"], cases["tc_x"]], axis=1).ravel(), cases["lidar"].ravel(), cases["pg"].ravel(), cases["pe"].ravel(), cases["pr"].ravel(), cases["imu_noise"]]
+    for k in range(N_IMU):
+        lo, hi = cases["imu_first"][k], cases["imu_first"][k + 1]
+        flat += [cases["imu_ba"][k], cases["imu_bg"][k], cases["imu_acc0"][k], cases["imu_gyr0"][k], np.array([hi - lo], dtype=np.float64), cases["imu_samples"][lo:hi].ravel(), cases["imu_x"][k]]
     with tempfile.TemporaryDirectory() as td:
         np.concatenate(flat).astype(np.float64).tofile(os.path.join(td, "cases.bin"))
         subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "ref_factors"), os.path.join(td, "cases.bin"), os.path.join(td, "out.bin")])
@@ -76,6 +99,14 @@ def run_reference(cases):
     for name, R, C in (("tf", 2, 15), ("po", 2, 7), ("tc", 2, 1), ("lidar", 1, 3), ("pg", 6, 14), ("pe", 6, 7), ("pr", 3, 3)):
         blk = o[pos:pos + N * (R + R * C)].reshape(N, R + R * C); pos += N * (R + R * C)
         out[name + "_r"] = blk[:, :R].copy(); out[name + "_J"] = blk[:, R:].reshape(N, R, C).copy()
+    per = 17 + 225 + 225 + 15 + 105 + 45 * 3 + 105 + 45 * 3
+    blk = o[pos:pos + N_IMU * per].reshape(N_IMU, per); pos += N_IMU * per
+    out["imu_record"] = blk[:, :467].copy()                      # LVB_IMU layout without the two prior slots
+    out["imu_r"] = blk[:, 467:482].copy()
+    sizes, q, Js = [7, 3, 3, 3, 7, 3, 3, 3], 482, []
+    for w in sizes:
+        Js.append(blk[:, q:q + 15 * w].reshape(N_IMU, 15, w)); q += 15 * w
+    out["imu_J"] = np.concatenate(Js, axis=2)                      # [n, 15, 32] in the block order of imu_error.hpp:12
     assert pos == len(o)
     return out
 
