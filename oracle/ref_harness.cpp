@@ -126,6 +126,12 @@ int main(int argc, char** argv) {
         ImuError f(pre);
         f.Evaluate(prm, r, J);
         put(r, 15); put(J0, 105); put(J1, 45); put(J2, 45); put(J3, 45); put(J4, 105); put(J5, 45); put(J6, 45); put(J7, 45);
+        // ImuInitError (imu_error.hpp:124-229, imu::FullBA): same preintegration, priors 1e8 / 1e8, blocks pose_i v_i ba_i bg_i pose_j v_j
+        ImuInitError fi(pre, 1e8, 1e8);
+        const double* prm6[6] = {x, x + 7, x + 10, x + 13, x + 16, x + 23};
+        double* J6b[6] = {J0, J1, J2, J3, J4, J5};
+        fi.Evaluate(prm6, r, J6b);
+        put(r, 15); put(J0, 105); put(J1, 45); put(J2, 45); put(J3, 45); put(J4, 105); put(J5, 45);
     }
     fclose(out);
     return 0;
