@@ -6,9 +6,16 @@
 //   ImageProjection::Process and helpers /root/reference/src/lvio_fusion/src/projection.cpp:26-320
 //   filter_points_by_distance            /root/reference/src/lvio_fusion/include/lvio_fusion/utility.h:70-96
 //
+// Pinned: lidar_preprocess + lidar_project_and_segment reproduce the reference's own filter_points_by_distance and
+// ImageProjection::Process (src/projection.cpp compiled in place, oracle/ref_lidar_harness.cpp, tests/golden/ref_lidar.npz)
+// bit for bit -- points, order, ranges, ground flags, columns, ring indices -- on the fixture and on four full 64 x 1800 sweeps.
+// Toolchain-dependent detail: the unqualified abs / atan2 / sqrt calls of projection.cpp resolve to the float overloads when
+// libstdc++'s <stdlib.h> / <math.h> wrappers are in scope (they are in the real build: Eigen -> <emmintrin.h> -> <mm_malloc.h>
+// -> <stdlib.h>); with only <cmath>/<cstdlib> in scope abs(float) would be C's int abs and ~0.06 % of the cells change their
+// ground flag.  The oracle (and the CUDA path) take abs as the float overload and evaluate atan2 / sqrt in *double*, rounded once
+// to float: that is reproducible across CPU and GPU, gives the same bins as the reference's float evaluation on all of the
+// above, and differs by at most one ulp in the sweep's start / end orientation.
 // [upstream] behaviours that are not in the reference tree and cannot be verified in this container:
-//   * unqualified math calls (atan2, sqrt, sin, cos, round) on float arguments are taken as the *double* overloads with
-//     the result rounded to float where the reference stores it in a float; `abs(angle)` is taken as the float overload;
 //   * pcl::VoxelGrid: keying ijk = floor(p * inverse_leaf) - min_b, idx = i + j*dx + k*dx*dy over the bounding box of the
 //     input, output sorted by idx, centroid of all fields accumulated in float32.  PCL sorts with std::sort (order inside a
 //     voxel unspecified); the oracle accumulates in ascending input index;

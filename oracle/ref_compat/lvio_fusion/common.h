@@ -4,7 +4,14 @@
 // reference's sensor.h, visual/camera.h, imu/imu.h, imu/preintegration.h, utility.h, the factor headers under ceres/ and
 // src/preintegration.cpp to compile unchanged.  The arithmetic of the functors is the reference's own code.
 #pragma once
+// The real common.h pulls Eigen/Core, which on x86-64 includes <emmintrin.h> -> <xmmintrin.h> -> <mm_malloc.h> -> <stdlib.h>:
+// in C++ that is libstdc++'s wrapper with `using std::abs;` (and OpenCV / PCL include <math.h>, whose wrapper exports the
+// float overloads of the math functions).  The unqualified abs(float) of src/projection.cpp:129 therefore resolves to the
+// floating-point overload in the real build; the same two C headers are included here so that it does in this one too.
+#include <math.h>
+#include <stdlib.h>
 #include <cassert>
+#include <cfloat>
 #include <chrono>
 #include <cmath>
 #include <map>
@@ -40,8 +47,27 @@ typedef Sophus::SE3d SE3d;
 typedef Sophus::SO3d SO3d;
 
 typedef unsigned char uchar;
+// OpenCV names: camera.h keeps two cv::Mat members filled through the comma initialiser (never read here);
+// src/projection.cpp uses cv::Mat(rows, cols, type, cv::Scalar::all(v)) and at<T>(i, j) for its range / label / ground images.
+#define CV_8S 1
+#define CV_32S 4
+#define CV_32F 5
 namespace cv {
-struct Mat {};
+struct Scalar { double v; static Scalar all(double x) { Scalar s; s.v = x; return s; } };
+struct Mat {
+    int rows = 0, cols = 0, type = 0;
+    std::vector<unsigned char> buf;
+    Mat() {}
+    Mat(int r, int c, int t, const Scalar& s) : rows(r), cols(c), type(t), buf((size_t)r * c * elem(t)) {
+        for (int i = 0; i < r * c; ++i) {
+            if (t == CV_32F) reinterpret_cast<float*>(buf.data())[i] = (float)s.v;
+            else if (t == CV_32S) reinterpret_cast<int*>(buf.data())[i] = (int)s.v;
+            else reinterpret_cast<signed char*>(buf.data())[i] = (signed char)s.v;
+        }
+    }
+    static int elem(int t) { return t == CV_8S ? 1 : 4; }
+    template <class T> T& at(int i, int j) { return reinterpret_cast<T*>(buf.data())[(size_t)i * cols + j]; }
+};
 template <class T> struct MatCommaInit { MatCommaInit& operator,(T) { return *this; } operator Mat() const { return Mat(); } };
 template <class T> struct Mat_ : Mat { Mat_(int, int) {} };
 template <class T> inline MatCommaInit<T> operator<<(const Mat_<T>&, T) { return MatCommaInit<T>(); }
@@ -49,6 +75,31 @@ struct Point2f { float x, y; Point2f(float x_ = 0, float y_ = 0) : x(x_), y(y_) 
 struct Point3f { float x, y, z; Point3f(float x_ = 0, float y_ = 0, float z_ = 0) : x(x_), y(y_), z(z_) {} };
 struct KeyPoint { Point2f pt; float size; KeyPoint() : size(0) {} KeyPoint(Point2f p, float s) : pt(p), size(s) {} };
 }  // namespace cv
-namespace pcl { template <class PointT> struct PointCloud; }
+// PCL names: point records and a cloud that is a vector with a header
+namespace pcl {
+struct PointXYZ { float x = 0, y = 0, z = 0, pad = 0; };
+struct PointXYZI { float x = 0, y = 0, z = 0, pad0 = 0, intensity = 0, pad1 = 0, pad2 = 0, pad3 = 0; };
+struct PointXYZRGB { float x = 0, y = 0, z = 0, pad0 = 0; unsigned int rgba = 0; float pad1 = 0, pad2 = 0, pad3 = 0; };
+struct PCLHeader { unsigned int seq = 0; unsigned long long stamp = 0; std::string frame_id; };
+template <class PointT> struct PointCloud {
+    PCLHeader header;
+    std::vector<PointT> points;
+    unsigned int width = 0, height = 0;
+    bool is_dense = true;
+    size_t size() const { return points.size(); }
+    void push_back(const PointT& p) { points.push_back(p); width = (unsigned int)points.size(); height = 1; }
+    void clear() { points.clear(); width = height = 0; }
+    PointT& operator[](size_t i) { return points[i]; }
+    const PointT& operator[](size_t i) const { return points[i]; }
+    typename std::vector<PointT>::iterator begin() { return points.begin(); }
+    typename std::vector<PointT>::iterator end() { return points.end(); }
+};
+}  // namespace pcl
+typedef pcl::PointXYZ Point3;
+typedef pcl::PointCloud<Point3> Point3Cloud;
+typedef pcl::PointXYZI PointI;
+typedef pcl::PointCloud<PointI> PointICloud;
+typedef pcl::PointXYZRGB PointRGB;
+typedef pcl::PointCloud<PointRGB> PointRGBCloud;
 
 class NotImplemented : public std::logic_error { public: NotImplemented() : std::logic_error("Function not yet implemented") {} };

@@ -117,6 +117,33 @@ def run_reference(cases):
     return out
 
 
+LIDAR_CFG = dict(num_scans=64, horizon_scan=450, ang_res_y=0.427, ang_bottom=24.9, ground_rows=60, min_range=5.0, max_range=30.0)
+
+
+def run_reference_lidar(scan):
+    """ImageProjection::Process (src/projection.cpp) + filter_points_by_distance (utility.h) of the reference on a raw sweep."""
+    c = LIDAR_CFG
+    with tempfile.TemporaryDirectory() as td:
+        with open(os.path.join(td, "in.bin"), "wb") as f:
+            np.array([c["num_scans"], c["horizon_scan"], c["ang_res_y"], c["ang_bottom"], c["ground_rows"], c["min_range"], c["max_range"]], dtype=np.float64).tofile(f)
+            np.array([len(scan)], dtype=np.int32).tofile(f)
+            np.ascontiguousarray(scan[:, :3], dtype=np.float32).tofile(f)
+        subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "ref_lidar"), os.path.join(td, "in.bin"), os.path.join(td, "out.bin")])
+        raw = open(os.path.join(td, "out.bin"), "rb").read()
+    m = int(np.frombuffer(raw[:4], dtype=np.int32)[0]); off = 4
+    R = c["num_scans"]
+    out = {}
+    out["points"] = np.frombuffer(raw[off:off + 16 * m], dtype=np.float32).reshape(m, 4).copy(); off += 16 * m
+    out["range"] = np.frombuffer(raw[off:off + 4 * m], dtype=np.float32).copy(); off += 4 * m
+    out["ground"] = np.frombuffer(raw[off:off + m], dtype=np.uint8).copy(); off += m
+    out["col"] = np.frombuffer(raw[off:off + 4 * m], dtype=np.int32).copy(); off += 4 * m
+    out["start_ring"] = np.frombuffer(raw[off:off + 4 * R], dtype=np.int32).copy(); off += 4 * R
+    out["end_ring"] = np.frombuffer(raw[off:off + 4 * R], dtype=np.int32).copy(); off += 4 * R
+    out["orientation"] = np.frombuffer(raw[off:off + 12], dtype=np.float32).copy(); off += 12
+    assert off == len(raw)
+    return out
+
+
 def main():
     if not os.path.isdir("/root/reference"):
         raise SystemExit("the reference tree is not mounted here; the committed fixture stays as it is")
@@ -124,6 +151,10 @@ def main():
     out = run_reference(cases)
     np.savez_compressed(os.path.join(HERE, "ref_factors.npz"), **cases, **out)
     print("reference golden written:", {k: v.shape for k, v in out.items()})
+    scan = synth.make_lidar_scan(seed=synth.SEED + 5, horizon_scan=LIDAR_CFG["horizon_scan"], n_boxes=10)
+    lid = run_reference_lidar(scan)
+    np.savez_compressed(os.path.join(HERE, "ref_lidar.npz"), scan=scan[:, :3].astype(np.float32), **lid)
+    print("reference lidar golden written:", len(lid["points"]), "segmented points of", len(scan))
 
 
 if __name__ == "__main__":
