@@ -1,5 +1,7 @@
-// oracle/icp.h -- scan-to-map association + point-to-plane ICP of the CPU oracle
-// (TEST INFRASTRUCTURE ONLY, parity unpinned).
+// oracle/icp.h -- scan-to-map association + point-to-plane ICP of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+// The association (gate, factor creation, loss, prior weight) and the plane factors are pinned against the reference's own
+// association.cpp / lidar_error.hpp compiled in place (oracle/ref_assoc_harness.cpp, tests/golden/ref_assoc.npz); the kd-tree
+// (FLANN tie order) and the LM schedule remain "parity unpinned".
 //
 //   association : /root/reference/src/lvio_fusion/src/association.cpp:270-384
 //   driver      : /root/reference/src/lvio_fusion/src/mapping.cpp:139-191

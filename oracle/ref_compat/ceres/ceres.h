@@ -6,6 +6,8 @@
 // functor (the harness differentiates by calling the functor with duals directly, which is what Ceres' autodiff does).
 #pragma once
 #include <cmath>
+#include <utility>
+#include <vector>
 #include "../../dual.h"
 
 namespace ceres {
@@ -38,5 +40,33 @@ public:
 private:
     Functor* functor_;
 };
+
+
+// ---- the problem-building surface src/association.cpp uses (adapt::Problem derives from ceres::Problem): recorded, not solved
+class LossFunction { public: virtual ~LossFunction() {} virtual double huber_a() const { return 0.0; } };
+class TrivialLoss : public LossFunction {};
+class HuberLoss : public LossFunction { public: explicit HuberLoss(double a) : a_(a) {} double huber_a() const override { return a_; } private: double a_; };
+class LocalParameterization { public: virtual ~LocalParameterization() {} };
+struct ResidualBlock { CostFunction* cost; LossFunction* loss; std::vector<double*> blocks; };
+typedef ResidualBlock* ResidualBlockId;
+enum LinearSolverType { DENSE_QR, SPARSE_NORMAL_CHOLESKY, SPARSE_SCHUR };
+class Solver { public: struct Options { LinearSolverType linear_solver_type; int max_num_iterations = 50; double max_solver_time_in_seconds = 1e9; int num_threads = 1; }; struct Summary { double final_cost = 0; int num_residual_blocks_reduced = 0; }; };
+class Problem {
+public:
+    ~Problem() { for (ResidualBlock* r : residual_blocks) delete r; }
+    void AddParameterBlock(double* v, int size) { parameter_blocks.push_back({v, size}); }
+    void AddParameterBlock(double* v, int size, LocalParameterization*) { parameter_blocks.push_back({v, size}); }
+    template <typename... Ts> ResidualBlockId AddResidualBlock(CostFunction* cost, LossFunction* loss, double* x0, Ts*... xs) {
+        residual_blocks.push_back(new ResidualBlock{cost, loss, {x0, xs...}});
+        return residual_blocks.back();
+    }
+    void GetResidualBlocksForParameterBlock(const double* v, std::vector<ResidualBlockId>* out) const {
+        out->clear();
+        for (ResidualBlock* r : residual_blocks) for (double* b : r->blocks) if (b == v) { out->push_back(r); break; }
+    }
+    std::vector<ResidualBlock*> residual_blocks;
+    std::vector<std::pair<double*, int>> parameter_blocks;
+};
+void Solve(const Solver::Options&, Problem*, Solver::Summary*);      // named by adapt::Solve, never called here
 
 }  // namespace ceres

@@ -26,6 +26,7 @@ using namespace Eigen;
 
 namespace Sophus {
 struct SO3d { static constexpr int num_parameters = 4; };
+struct SE3f { float d[7]; float* data() { return d; } const float* data() const { return d; } };
 // storage [qx qy qz qw tx ty tz], unit quaternion
 struct SE3d {
     static constexpr int num_parameters = 7;
@@ -41,6 +42,7 @@ struct SE3d {
     SE3d inverse() const { const Quaterniond qi = unit_quaternion().conjugate(); return SE3d(qi, Vector3d(qi * Vector3d(-translation()))); }
     SE3d operator*(const SE3d& b) const { return SE3d(unit_quaternion() * b.unit_quaternion(), Vector3d(unit_quaternion() * b.translation() + translation())); }
     Vector3d operator*(const Vector3d& p) const { return Vector3d(unit_quaternion() * p + translation()); }
+    template <class T> SE3f cast() const { SE3f r; for (int i = 0; i < 7; ++i) r.d[i] = (T)d[i]; return r; }      // frame->pose.cast<float>() (association.cpp:287)
 };
 }  // namespace Sophus
 typedef Sophus::SE3d SE3d;
@@ -78,10 +80,19 @@ struct KeyPoint { Point2f pt; float size; KeyPoint() : size(0) {} KeyPoint(Point
 // PCL names: point records and a cloud that is a vector with a header
 namespace pcl {
 struct PointXYZ { float x = 0, y = 0, z = 0, pad = 0; };
-struct PointXYZI { float x = 0, y = 0, z = 0, pad0 = 0, intensity = 0, pad1 = 0, pad2 = 0, pad3 = 0; };
+struct PointXYZI {                     // PCL layout: data[4] aliases x y z, then intensity in its own 16-byte lane
+    union { float data[4]; struct { float x, y, z; }; };
+    union { struct { float intensity; }; float data_c[4]; };
+    PointXYZI() { data[0] = data[1] = data[2] = 0; data[3] = 1; data_c[0] = data_c[1] = data_c[2] = data_c[3] = 0; }
+};
 struct PointXYZRGB { float x = 0, y = 0, z = 0, pad0 = 0; unsigned int rgba = 0; float pad1 = 0, pad2 = 0, pad3 = 0; };
 struct PCLHeader { unsigned int seq = 0; unsigned long long stamp = 0; std::string frame_id; };
+inline void copy_intensity(const PointXYZ&, PointXYZI&) {}
+inline void copy_intensity(const PointXYZI& p, PointXYZI& q) { q.intensity = p.intensity; }
+inline void copy_intensity(const PointXYZI&, PointXYZ&) {}
+inline void copy_intensity(const PointXYZ&, PointXYZ&) {}
 template <class PointT> struct PointCloud {
+    typedef std::shared_ptr<PointCloud<PointT>> Ptr;
     PCLHeader header;
     std::vector<PointT> points;
     unsigned int width = 0, height = 0;
@@ -93,6 +104,8 @@ template <class PointT> struct PointCloud {
     const PointT& operator[](size_t i) const { return points[i]; }
     typename std::vector<PointT>::iterator begin() { return points.begin(); }
     typename std::vector<PointT>::iterator end() { return points.end(); }
+    template <class It> void insert(typename std::vector<PointT>::iterator pos, It a, It b) { points.insert(pos, a, b); width = (unsigned int)points.size(); height = 1; }
+    PointCloud operator+(const PointCloud& o) const { PointCloud r = *this; r.points.insert(r.points.end(), o.points.begin(), o.points.end()); r.width = (unsigned int)r.points.size(); r.height = 1; return r; }
 };
 }  // namespace pcl
 typedef pcl::PointXYZ Point3;
@@ -101,5 +114,10 @@ typedef pcl::PointXYZI PointI;
 typedef pcl::PointCloud<PointI> PointICloud;
 typedef pcl::PointXYZRGB PointRGB;
 typedef pcl::PointCloud<PointRGB> PointRGBCloud;
+
+namespace boost { template <class T, class... A> inline std::shared_ptr<T> make_shared(A&&... a) { return std::make_shared<T>(std::forward<A>(a)...); } }
+
+extern const double epsilon;      // src/config.cpp in the reference
+extern const int num_threads;
 
 class NotImplemented : public std::logic_error { public: NotImplemented() : std::logic_error("Function not yet implemented") {} };

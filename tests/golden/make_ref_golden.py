@@ -144,6 +144,63 @@ def run_reference_lidar(scan):
     return out
 
 
+ASSOC_EXT = [0.01, -0.02, 0.005, 1.0, 0.27, 0.0, 0.08]
+W_VISUAL, N_FEATURES_LEFT = 71.8856, 120
+
+
+def _assoc_cfg(horizon, ext):
+    return np.array([64, horizon, 0.427, 24.9, 60, 0.1036, 5, 30, 0.2, 0], dtype=np.float64).tobytes() + np.asarray(ext, dtype=np.float64).tobytes()
+
+
+def _read_cloud(raw, off):
+    m = int(np.frombuffer(raw[off:off + 4], dtype=np.int32)[0]); off += 4
+    return np.frombuffer(raw[off:off + 16 * m], dtype=np.float32).reshape(m, 4).copy(), off + 16 * m
+
+
+def run_reference_extract(scan, horizon):
+    """FeatureAssociation::Preprocess .. ExtractFeatures (association.cpp:88-268) of the reference on a raw sweep."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_assoc")
+    with tempfile.TemporaryDirectory() as td:
+        with open(os.path.join(td, "in.bin"), "wb") as f:
+            f.write(_assoc_cfg(horizon, ASSOC_EXT)); np.array([len(scan)], dtype=np.int32).tofile(f); np.ascontiguousarray(scan[:, :3], dtype=np.float32).tofile(f)
+        subprocess.check_call([exe, "extract", os.path.join(td, "in.bin"), os.path.join(td, "out.bin")])
+        raw = open(os.path.join(td, "out.bin"), "rb").read()
+    seg, off = _read_cloud(raw, 0)
+    curv = np.frombuffer(raw[off:off + 4 * len(seg)], dtype=np.float32).copy(); off += 4 * len(seg)
+    ground, off = _read_cloud(raw, off); surf, off = _read_cloud(raw, off)
+    assert off == len(raw)
+    return {"seg": seg, "curvature": curv, "ground": ground, "surf": surf}
+
+
+def run_reference_scan2map(sc, mode, e0):
+    """FeatureAssociation::ScanToMapWithGround / ScanToMapWithSegmented (association.cpp:270-384) of the reference."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_assoc")
+    scan = np.ascontiguousarray(sc["scan"][:, :4], dtype=np.float32); mp = np.ascontiguousarray(sc["map"][:, :4], dtype=np.float32)
+    w = [W_VISUAL, sc["weight"] if mode == 0 else 1.0, sc["weight"] if mode == 1 else 0.01]
+    with tempfile.TemporaryDirectory() as td:
+        with open(os.path.join(td, "in.bin"), "wb") as f:
+            f.write(_assoc_cfg(1800, [0, 0, 0, 1, 0, 0, 0]))
+            np.array([mode], dtype=np.int32).tofile(f)
+            for a in (sc["frame_pose"], sc["map_pose"], e0, w):
+                np.asarray(a, dtype=np.float64).tofile(f)
+            np.array([N_FEATURES_LEFT, 0], dtype=np.int32).tofile(f)
+            np.array([len(scan)], dtype=np.int32).tofile(f); scan.tofile(f); np.array([len(mp)], dtype=np.int32).tofile(f); mp.tofile(f)
+        subprocess.check_call([exe, "scan2map", os.path.join(td, "in.bin"), os.path.join(td, "out.bin")])
+        o = np.fromfile(os.path.join(td, "out.bin"), dtype=np.float64)
+    return o[:4].copy(), o[4:].reshape(len(scan), 5).copy()
+
+
+def assoc_case(kind):
+    """Scan / map feature clouds with a share of scan points pushed away from every map surface, so that the gate rejects."""
+    sc = synth.make_icp_problem(1200, 9000, seed=synth.SEED + (7 if kind == "ground" else 8), kind=kind)
+    rng = np.random.default_rng(99)
+    scan = np.array(sc["scan"], dtype=np.float32, copy=True)
+    far = rng.choice(len(scan), len(scan) // 6, replace=False)
+    scan[far, :3] += rng.normal(0, 1.5, (len(far), 3)).astype(np.float32)
+    sc = dict(sc); sc["scan"] = scan
+    return sc
+
+
 def main():
     if not os.path.isdir("/root/reference"):
         raise SystemExit("the reference tree is not mounted here; the committed fixture stays as it is")
@@ -155,6 +212,15 @@ def main():
     lid = run_reference_lidar(scan)
     np.savez_compressed(os.path.join(HERE, "ref_lidar.npz"), scan=scan[:, :3].astype(np.float32), **lid)
     print("reference lidar golden written:", len(lid["points"]), "segmented points of", len(scan))
+    ext = run_reference_extract(scan, LIDAR_CFG["horizon_scan"])
+    out = {"scan": scan[:, :3].astype(np.float32), "ext_seg": ext["seg"], "ext_curvature": ext["curvature"], "ext_ground": ext["ground"], "ext_surf": ext["surf"]}
+    for kind, mode in (("ground", 0), ("surf", 1)):
+        sc = assoc_case(kind)
+        e0 = synth.relative_rpyxyz(sc["map_pose"], sc["frame_pose"])
+        head, tab = run_reference_scan2map(sc, mode, e0)
+        out.update({kind + "_head": head, kind + "_table": tab, kind + "_e0": np.asarray(e0)})
+        print("reference scan-to-map (%s): %d blocks of %d scan points, prior weight %.3f, huber %.2f" % (kind, int(head[0]), len(tab), head[2], head[3]))
+    np.savez_compressed(os.path.join(HERE, "ref_assoc.npz"), **out)
 
 
 if __name__ == "__main__":
