@@ -124,8 +124,43 @@ static int run_autodiff() {
     return 0;
 }
 
+// PoseGraphError / PoseError of factors.h evaluated on the host (the evaluators the off-path solves use) on the cases of the
+// reference fixture: n, then n x (last[7] pose[7] w v T1[7] T2[7]), then n x (pose[7] w v T[7]); writes r and J per case
+static int run_refcases(const char* in, const char* out) {
+    FILE* f = fopen(in, "rb"); if (!f) return 2;
+    int n; if (fread(&n, sizeof(int), 1, f) != 1) return 2;
+    std::vector<double> pg((size_t)n * 30), pe((size_t)n * 16);
+    if (fread(pg.data(), sizeof(double), pg.size(), f) != pg.size() || fread(pe.data(), sizeof(double), pe.size(), f) != pe.size()) return 2;
+    fclose(f);
+    FILE* o = fopen(out, "wb"); if (!o) return 2;
+    for (int i = 0; i < n; ++i) {
+        const double* c = &pg[(size_t)i * 30];
+        SE3 a, b; memcpy(a.d, c, 56); memcpy(b.d, c + 7, 56);
+        ceres::CostFunction* cost = lvio_fusion::PoseGraphError::Create(a, b, c[14], c[15]);
+        const double* p[2] = {c + 16, c + 23};
+        double r[6], J1[42], J2[42]; double* J[2] = {J1, J2};
+        if (!cost->Evaluate(p, r, J)) return 3;
+        fwrite(r, sizeof(double), 6, o);
+        for (int row = 0; row < 6; ++row) { fwrite(J1 + 7 * row, sizeof(double), 7, o); fwrite(J2 + 7 * row, sizeof(double), 7, o); }
+        delete cost;
+    }
+    for (int i = 0; i < n; ++i) {
+        const double* c = &pe[(size_t)i * 16];
+        SE3 a; memcpy(a.d, c, 56);
+        ceres::CostFunction* cost = lvio_fusion::PoseError::Create(a, c[7], c[8]);
+        const double* p[1] = {c + 9};
+        double r[6], J1[42]; double* J[1] = {J1};
+        if (!cost->Evaluate(p, r, J)) return 3;
+        fwrite(r, sizeof(double), 6, o); fwrite(J1, sizeof(double), 42, o);
+        delete cost;
+    }
+    fclose(o);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 4 && std::string(argv[1]) == "posegraph") return run_posegraph(argv[2], argv[3]);
+    if (argc >= 4 && std::string(argv[1]) == "refcases") return run_refcases(argv[2], argv[3]);
     if (argc >= 3 && std::string(argv[1]) == "navsat") return run_navsat((unsigned)atoi(argv[2]));
     if (argc >= 2 && std::string(argv[1]) == "autodiff") return run_autodiff();
     fprintf(stderr, "usage: test_host_solver posegraph in out | navsat seed | autodiff\n");

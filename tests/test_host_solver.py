@@ -85,3 +85,20 @@ def test_pose_graph_matches_oracle_lm(exe, orc, orc_ctx, tmp_path, huber):
     assert abs(res6[1] - so6.final_cost) < 1e-10 * so6.final_cost
     assert np.max(np.abs(res6[4:].reshape(n, 7) - po6.poses())) < 1e-9
     assert head[1] < 0.05 * head[0]
+
+
+def test_shim_pose_factors_reproduce_the_reference_functors(exe, tmp_path):
+    """PoseGraphError / PoseError as the shim evaluates them on the host (factors.h + ceres_autodiff.h) against the fixture
+    produced by the reference's own pose_error.hpp (tests/golden/ref_factors.npz)."""
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "ref_factors.npz"))
+    n = len(ref["pg"])
+    with open(tmp_path / "cases.bin", "wb") as f:
+        np.array([n], dtype=np.int32).tofile(f)
+        ref["pg"].astype(np.float64).tofile(f); ref["pe"].astype(np.float64).tofile(f)
+    subprocess.run([exe, "refcases", str(tmp_path / "cases.bin"), str(tmp_path / "out.bin")], check=True)
+    o = np.fromfile(tmp_path / "out.bin", dtype=np.float64)
+    pg = o[:n * 90].reshape(n, 90); pe = o[n * 90:].reshape(n, 48)
+    assert np.max(np.abs(pg[:, :6] - ref["pg_r"])) < 1e-12 * max(1.0, np.abs(ref["pg_r"]).max())
+    assert np.max(np.abs(pg[:, 6:].reshape(n, 6, 14) - ref["pg_J"])) < 1e-11 * max(1.0, np.abs(ref["pg_J"]).max())
+    assert np.max(np.abs(pe[:, :6] - ref["pe_r"])) < 1e-12 * max(1.0, np.abs(ref["pe_r"]).max())
+    assert np.max(np.abs(pe[:, 6:].reshape(n, 6, 7) - ref["pe_J"])) < 1e-11 * max(1.0, np.abs(ref["pe_J"]).max())
