@@ -102,3 +102,17 @@ def test_shim_pose_factors_reproduce_the_reference_functors(exe, tmp_path):
     assert np.max(np.abs(pg[:, 6:].reshape(n, 6, 14) - ref["pg_J"])) < 1e-11 * max(1.0, np.abs(ref["pg_J"]).max())
     assert np.max(np.abs(pe[:, :6] - ref["pe_r"])) < 1e-12 * max(1.0, np.abs(ref["pe_r"]).max())
     assert np.max(np.abs(pe[:, 6:].reshape(n, 6, 7) - ref["pe_J"])) < 1e-11 * max(1.0, np.abs(ref["pe_J"]).max())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/lvio_fusion/include"), reason="the reference tree is only mounted in the development container")
+def test_reference_navsat_functors_drop_onto_the_shim(tmp_path):
+    """The reference's navsat_error.hpp / base.hpp, compiled where they lie, against the PRODUCT shim (<ceres/ceres.h> resolves
+    to include/lvio_b200 through tests/cpp/compat_product): NavsatInitError::Create + the two-stage solve of navsat.cpp:104-129."""
+    lib_dir = os.path.join(ROOT, "lvio_fusion_b200", "csrc")
+    out = str(tmp_path / "ref_navsat")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "tests", "cpp", "compat_product"), "-I" + os.path.join(ROOT, "oracle", "ref_compat"),
+                           "-I" + os.path.join(ROOT, "include"), "-I/root/reference/src/lvio_fusion/include", "-o", out,
+                           os.path.join(ROOT, "tests", "cpp", "ref_navsat_dropin.cpp"), "-L" + lib_dir, "-llvio_b200", "-Wl,-rpath," + lib_dir])
+    p = subprocess.run([out], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "host LM" in p.stdout
