@@ -15,16 +15,49 @@ namespace lvio_fusion {
 
 namespace detail {
 template <class V> inline const double* ptr(const V& v) { return v.data(); }
+// ceres::QuaternionRotatePoint on a stored (x, y, z, w) quaternion: normalises first (base.hpp:26-31)
+inline void rotate_xyzw(const double* q, const double* p, double* out) {
+    const double s = 1.0 / std::sqrt(q[3] * q[3] + q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    const double x = q[0] * s, y = q[1] * s, z = q[2] * s, w = q[3] * s;
+    double u0 = y * p[2] - z * p[1], u1 = z * p[0] - x * p[2], u2 = x * p[1] - y * p[0];
+    u0 += u0; u1 += u1; u2 += u2;
+    out[0] = p[0] + w * u0 + (y * u2 - z * u1); out[1] = p[1] + w * u1 + (z * u0 - x * u2); out[2] = p[2] + w * u2 + (x * u1 - y * u0);
+}
+// SE3Inverse + SE3TransformPoint (base.hpp:40-55,70-77): p in the frame of T = [q | t]
+inline void inverse_transform(const double* T, const double* p, double* out) {
+    const double qi[4] = {-T[0], -T[1], -T[2], T[3]}, nt[3] = {-T[4], -T[5], -T[6]};
+    double ti[3], r[3];
+    rotate_xyzw(qi, nt, ti); rotate_xyzw(qi, p, r);
+    out[0] = r[0] + ti[0]; out[1] = r[1] + ti[1]; out[2] = r[2] + ti[2];
+}
 }  // namespace detail
 
 // visual_error.hpp:48-76   AutoDiffCostFunction<PoseOnlyReprojectionError, 2, 7>
 class PoseOnlyReprojectionError {
 public:
+    // The functor itself, as compute_reprojection_error builds and calls it on the host for the outlier test after the
+    // solve (backend.cpp:185-190,232: one scalar evaluation per feature; the batched form is lvb_ba_reprojection_errors).
+    template <class V2, class V3, class CameraPtr>
+    PoseOnlyReprojectionError(const V2& ob, const V3& pw, CameraPtr camera, double weight) : weight_(weight) {
+        const double* o = detail::ptr(ob); const double* p = detail::ptr(pw); const double* e = camera->extrinsic.data();
+        ob_[0] = o[0]; ob_[1] = o[1]; pw_[0] = p[0]; pw_[1] = p[1]; pw_[2] = p[2];
+        for (int i = 0; i < 7; ++i) ext_[i] = e[i];
+        fx_ = camera->fx; fy_ = camera->fy; cx_ = camera->cx; cy_ = camera->cy;
+    }
+    bool operator()(const double* Twc, double* residuals) const {       // Reprojection(), visual_error.hpp:10-24
+        double pb[3], pc[3];
+        detail::inverse_transform(Twc, pw_, pb); detail::inverse_transform(ext_, pb, pc);
+        residuals[0] = weight_ * (fx_ * (pc[0] / pc[2]) + cx_ - ob_[0]);
+        residuals[1] = weight_ * (fy_ * (pc[1] / pc[2]) + cy_ - ob_[1]);
+        return true;
+    }
     template <class V2, class V3, class CameraPtr>
     static ceres::CostFunction* Create(const V2& ob, const V3& pw, CameraPtr /*camera == Camera::Get(0)*/, double weight) {
         const double* o = detail::ptr(ob); const double* p = detail::ptr(pw);
         return new lvb::DeviceCost(LVB_POSE_ONLY, 2, {7}, {o[0], o[1], p[0], p[1], p[2], weight});
     }
+private:
+    double ob_[2], pw_[3], ext_[7], fx_, fy_, cx_, cy_, weight_;
 };
 
 // visual_error.hpp:78-107  AutoDiffCostFunction<TwoFrameReprojectionError, 2, 1, 7, 7>
@@ -126,13 +159,7 @@ public:
 };
 
 inline void PoseGraphError::relative_rpyxyz(const double* a, const double* b, double* e) {
-    auto rot = [](const double* q, const double* p, double* out) {   // normalising rotate, base.hpp:26-31
-        const double s = 1.0 / std::sqrt(q[3] * q[3] + q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
-        const double x = q[0] * s, y = q[1] * s, z = q[2] * s, w = q[3] * s;
-        double u0 = y * p[2] - z * p[1], u1 = z * p[0] - x * p[2], u2 = x * p[1] - y * p[0];
-        u0 += u0; u1 += u1; u2 += u2;
-        out[0] = p[0] + w * u0 + (y * u2 - z * u1); out[1] = p[1] + w * u1 + (z * u0 - x * u2); out[2] = p[2] + w * u2 + (x * u1 - y * u0);
-    };
+    auto rot = detail::rotate_xyzw;
     const double qi[4] = {-a[0], -a[1], -a[2], a[3]}, nt[3] = {-a[4], -a[5], -a[6]};
     double ti[3]; rot(qi, nt, ti);
     // q = qi (x) qb (Hamilton, stored xyzw), t = R(qi) tb + ti

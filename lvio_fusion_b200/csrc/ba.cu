@@ -151,7 +151,7 @@ __device__ __forceinline__ ImuConst load_imu_const(const double* c) {
 }
 
 // ------------------------------------------------------------------ IMU prepare (once per finalize)
-// raw 467 -> packed 287 (scalars, five sub-blocks, U); status[f] != 0 when cov^-1 is not SPD
+// raw 467 -> packed 287 (scalars, five sub-blocks, U); status[f] != 0 when the covariance is singular or a pivot is NaN
 // One warp per factor.  Same arithmetic per element as lvb_math.cuh::sqrt_information (partial-pivot LU inverse, then
 // Cholesky; the oracle's order), with the independent elements of every step spread over the lanes.
 __device__ int sqrt_information_warp(const double* __restrict__ cov, double* __restrict__ U, double* a, double* inv, double prior_a, double prior_g) {
@@ -210,7 +210,12 @@ __device__ int sqrt_information_warp(const double* __restrict__ cov, double* __r
     for (int j = 0; j < n; ++j) {
         double d = inv[j * n + j];
         for (int k = 0; k < j; ++k) d -= a[j * n + k] * a[j * n + k];
-        if (!(d > 0.0)) return 2;
+        if (d != d) return 2;
+        if (d <= 0.0) {      // warp-uniform.  Eigen's LLT stops here; matrixL() shows the untouched lower triangle from column j on
+            for (int e = lane; e < 225; e += 32) { const int i = e / n, c = e - n * i; if (c >= j && i >= c) a[e] = inv[e]; }
+            __syncwarp();
+            break;
+        }
         const double ljj = sqrt(d);
         if (lane == 0) a[j * n + j] = ljj;
         if (lane > j && lane < n) { double sacc = inv[lane * n + j]; for (int k = 0; k < j; ++k) sacc -= a[lane * n + k] * a[j * n + k]; a[lane * n + j] = sacc / ljj; }
@@ -1745,7 +1750,7 @@ static int check_imu_status(lvb_ba* ba) {
     std::vector<int> status(ba->nd[3]);
     LVB_TRY(ba->imu_status.download(status.data(), status.size(), ba->ctx->stream));
     LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream));
-    for (size_t f = 0; f < status.size(); ++f) if (status[f]) { set_error("ImuError %d: covariance inverse is not SPD (code %d)", (int)f, status[f]); return LVB_ERR_NUMERIC; }
+    for (size_t f = 0; f < status.size(); ++f) if (status[f]) { set_error("ImuError %d: covariance is singular or not finite (code %d)", (int)f, status[f]); return LVB_ERR_NUMERIC; }
     ba->imu_checked = true;
     return LVB_OK;
 }

@@ -462,7 +462,11 @@ LVB_HD int sqrt_information(const double* cov /*225*/, double* U /*225*/, double
     for (int j = 0; j < n; ++j) {
         double d = inv[j * n + j];
         for (int k = 0; k < j; ++k) d -= a[j * n + k] * a[j * n + k];
-        if (!(d > 0.0)) return 2;
+        if (d != d) return 2;
+        if (d <= 0.0) {      // Eigen's LLT stops here and matrixL() shows the untouched lower triangle from this column on (oracle/imu.h)
+            for (int c = j; c < n; ++c) for (int i = c; i < n; ++i) a[i * n + c] = inv[i * n + c];
+            break;
+        }
         a[j * n + j] = sqrt(d);
         for (int i = j + 1; i < n; ++i) { double s = inv[i * n + j]; for (int k = 0; k < j; ++k) s -= a[i * n + k] * a[j * n + k]; a[i * n + j] = s / a[j * n + j]; }
     }

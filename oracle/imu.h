@@ -199,7 +199,7 @@ inline void preint_append(PreintState& s, double dt, const V3d& acc, const V3d& 
 // sqrt_info = LLT(covariance.inverse()).matrixL().transpose()   imu_error.hpp:32
 // [upstream] Eigen: inverse() of a 15x15 = PartialPivLU solve against identity;
 // LLT = Cholesky, lower.  Both restated in their plain unblocked forms.
-// Returns false if the inverse is not SPD (Eigen would return garbage silently).
+// Returns false only if the covariance is singular or a pivot is NaN; a non-positive Cholesky pivot follows Eigen (below).
 // ---------------------------------------------------------------------------------------
 inline bool sqrt_information(const double cov[15][15], double U[15][15], double prior_a = -1.0, double prior_g = -1.0) {
     const int n = 15;
@@ -231,7 +231,14 @@ inline bool sqrt_information(const double cov[15][15], double U[15][15], double 
     for (int j = 0; j < n; ++j) {
         double d = inv[j][j];
         for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-        if (!(d > 0.0)) return false;
+        if (d != d) return false;
+        if (d <= 0.0) {
+            // Eigen's llt_inplace::unblocked returns here (info() = NumericalIssue, never read by the reference) and
+            // matrixL() shows the untouched lower triangle of the input from this column on.  ImuInitError gets here with
+            // the reference's own priors (initializer.cpp:62: 1e4 / 1e2 over the bias blocks make cov^-1 indefinite).
+            for (int c = j; c < n; ++c) for (int i = c; i < n; ++i) L[i][c] = inv[i][c];
+            break;
+        }
         L[j][j] = std::sqrt(d);
         for (int i = j + 1; i < n; ++i) {
             double s = inv[i][j];

@@ -19,8 +19,12 @@ class CostFunction {
 public:
     virtual ~CostFunction() {}
     virtual bool Evaluate(double const* const*, double*, double**) const { return false; }
+    virtual int num_residuals() const { return 0; }
 };
-template <int kNumResiduals, int... Ns> class SizedCostFunction : public CostFunction {};      // imu_error.hpp:12,124 derive from it
+template <int kNumResiduals, int... Ns> class SizedCostFunction : public CostFunction {       // imu_error.hpp:12,124 derive from it
+public:
+    int num_residuals() const override { return kNumResiduals; }
+};
 enum Ownership { DO_NOT_TAKE_OWNERSHIP, TAKE_OWNERSHIP };
 enum NumericDiffMethodType { CENTRAL, FORWARD, RIDDERS };
 template <typename Functor, NumericDiffMethodType kMethod, int kNumResiduals, int... Ns>
@@ -37,7 +41,11 @@ public:
     explicit AutoDiffCostFunction(Functor* f) : functor_(f) {}
     ~AutoDiffCostFunction() override { delete functor_; }
     const Functor& functor() const { return *functor_; }
+    int num_residuals() const override { return kNumResiduals; }
+    // residuals only (tests/cpp/ref_backend_dropin.cpp sums the cost of a recorded problem with the reference's functors)
+    bool Evaluate(double const* const* p, double* r, double** j) const override { return j ? false : call(p, r, std::make_index_sequence<sizeof...(Ns)>()); }
 private:
+    template <size_t... I> bool call(double const* const* p, double* r, std::index_sequence<I...>) const { return (*functor_)(p[I]..., r); }
     Functor* functor_;
 };
 
@@ -47,6 +55,15 @@ class LossFunction { public: virtual ~LossFunction() {} virtual double huber_a()
 class TrivialLoss : public LossFunction {};
 class HuberLoss : public LossFunction { public: explicit HuberLoss(double a) : a_(a) {} double huber_a() const override { return a_; } private: double a_; };
 class LocalParameterization { public: virtual ~LocalParameterization() {} };
+class EigenQuaternionParameterization : public LocalParameterization {};                         // backend.cpp:99-101: named, recorded only
+class IdentityParameterization : public LocalParameterization { public: explicit IdentityParameterization(int) {} };
+class ProductParameterization : public LocalParameterization {
+public:
+    ProductParameterization(LocalParameterization* a, LocalParameterization* b) : a_(a), b_(b) {}
+    ~ProductParameterization() override { delete a_; delete b_; }
+private:
+    LocalParameterization *a_, *b_;
+};
 struct ResidualBlock { CostFunction* cost; LossFunction* loss; std::vector<double*> blocks; };
 typedef ResidualBlock* ResidualBlockId;
 enum LinearSolverType { DENSE_QR, SPARSE_NORMAL_CHOLESKY, SPARSE_SCHUR };

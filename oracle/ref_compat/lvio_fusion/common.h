@@ -25,7 +25,14 @@
 using namespace Eigen;
 
 namespace Sophus {
-struct SO3d { static constexpr int num_parameters = 4; };
+struct SO3d {                                        // storage: the unit quaternion (x, y, z, w)
+    static constexpr int num_parameters = 4;
+    double d[4];
+    SO3d() : d{0, 0, 0, 1} {}
+    explicit SO3d(const Quaterniond& q) : d{q.x(), q.y(), q.z(), q.w()} {}
+    double* data() { return d; }
+    const double* data() const { return d; }
+};
 struct SE3f { float d[7]; float* data() { return d; } const float* data() const { return d; } };
 // storage [qx qy qz qw tx ty tz], unit quaternion
 struct SE3d {
@@ -54,6 +61,7 @@ typedef unsigned char uchar;
 #define CV_8S 1
 #define CV_32S 4
 #define CV_32F 5
+#define CV_32FC3 21
 namespace cv {
 struct Scalar { double v; static Scalar all(double x) { Scalar s; s.v = x; return s; } };
 struct Mat {
@@ -67,9 +75,16 @@ struct Mat {
             else reinterpret_cast<signed char*>(buf.data())[i] = (signed char)s.v;
         }
     }
-    static int elem(int t) { return t == CV_8S ? 1 : 4; }
+    static int elem(int t) { return t == CV_8S ? 1 : (t == CV_32FC3 ? 12 : 4); }
     template <class T> T& at(int i, int j) { return reinterpret_cast<T*>(buf.data())[(size_t)i * cols + j]; }
+    // Frame::GetObservation (src/frame.cpp:45-77, the reinforcement-learning observation; compiled, never run here)
+    static Mat zeros(int r, int c, int t) { return Mat(r, c, t, Scalar::all(0)); }
+    template <class T> T* begin() { return reinterpret_cast<T*>(buf.data()); }
+    template <class T> T* end() { return reinterpret_cast<T*>(buf.data() + buf.size()); }
+    Mat reshape(int, int) const { return *this; }
+    template <class T> operator std::vector<T>() const { const T* p = reinterpret_cast<const T*>(buf.data()); return std::vector<T>(p, p + buf.size() / sizeof(T)); }
 };
+struct Vec3f { float v[3]; float& operator[](int i) { return v[i]; } };
 template <class T> struct MatCommaInit { MatCommaInit& operator,(T) { return *this; } operator Mat() const { return Mat(); } };
 template <class T> struct Mat_ : Mat { Mat_(int, int) {} };
 template <class T> inline MatCommaInit<T> operator<<(const Mat_<T>&, T) { return MatCommaInit<T>(); }

@@ -4,7 +4,7 @@
 // files compile unchanged without Eigen installed: Matrix<S,R,C[,RowMajor]>, MatrixXd, block<>() / bottomRightCorner<>(),
 // the comma initialiser, Map<>, Quaternion<S>, LLT<>, inverse().  Everything is double, sizes are checked at run time.
 // [upstream] where the numerics matter: Quaternion * vector uses Eigen's  v + w t + u x t,  t = 2 u x v ; inverse() is a
-// partial-pivot LU solve against the identity; LLT is the unblocked lower Cholesky.
+// partial-pivot LU solve against the identity; LLT is the unblocked lower Cholesky with Eigen's early return on a non-positive pivot.
 #pragma once
 #include <cassert>
 #include <cmath>
@@ -80,8 +80,10 @@ class Matrix : public MatrixBase<Matrix<S, R, C, Opt>> {
 public:
     typedef S Scalar;
     enum { RowsAtCompileTime = R, ColsAtCompileTime = C, Options = Opt };
+    static constexpr bool kFixed2 = R != Dynamic && C != Dynamic && R * C == 2;
     Matrix() : MatrixBase<Matrix>(R == Dynamic ? 0 : R, C == Dynamic ? 0 : C) {}
-    Matrix(int rows, int cols) : MatrixBase<Matrix>(rows, cols) {}
+    // Eigen's rule: on a fixed-size 2-vector two integers are coefficients (Vector2d error(0, 0), backend.cpp:187), else sizes
+    Matrix(int rows, int cols) : MatrixBase<Matrix>(kFixed2 ? R : rows, kFixed2 ? C : cols) { if (kFixed2) this->a = {(double)rows, (double)cols}; }
     Matrix(const Dyn& o) : MatrixBase<Matrix>(o.r, o.c) { check(o); this->a = o.a; }                       // NOLINT implicit
     Matrix(double x, double y) : MatrixBase<Matrix>(R, C) { static_assert(R * C == 2, "2-vector"); this->a = {x, y}; }
     Matrix(double x, double y, double z) : MatrixBase<Matrix>(R, C) { static_assert(R * C == 3, "3-vector"); this->a = {x, y, z}; }
@@ -174,17 +176,23 @@ private:
 };
 template <class M> inline MatrixXd operator*(const Dyn& x, const Map<M>& y) { return x * static_cast<const Dyn&>(y.eval()); }
 
-// LLT<M>(A).matrixL().transpose()
+// LLT<M>(A).matrixL().transpose().  Eigen 3.3 Cholesky/LLT.h, llt_inplace<Scalar, Lower>::unblocked (what blocked() calls
+// below 32 rows), restated INCLUDING its failure path: the factorisation runs in place on a copy of A, reads the lower
+// triangle only, and on the first pivot x <= 0 returns at once -- LLT::info() turns NumericalIssue, which the reference
+// never looks at (imu_error.hpp:32,150,257) -- so matrixL() then shows the finished columns followed by the untouched lower
+// triangle of A.  ImuInitError reaches that path with the reference's own settings (priors 1e4 / 1e2 written over the
+// bias blocks of cov^-1, initializer.cpp:62, make the matrix indefinite), so it is part of the behaviour to reproduce.
 template <class M> class LLT {
 public:
     explicit LLT(const Dyn& A) : L_(A.r, A.c) {
         const int n = A.r;
-        for (int j = 0; j < n; ++j) {
-            double d = A(j, j);
-            for (int k = 0; k < j; ++k) d -= L_(j, k) * L_(j, k);
-            d = std::sqrt(d);
-            L_(j, j) = d;
-            for (int i = j + 1; i < n; ++i) { double s = A(i, j); for (int k = 0; k < j; ++k) s -= L_(i, k) * L_(j, k); L_(i, j) = s / d; }
+        for (int i = 0; i < n; ++i) for (int j = 0; j <= i; ++j) L_(i, j) = A(i, j);
+        for (int k = 0; k < n; ++k) {
+            double x = L_(k, k);
+            for (int j = 0; j < k; ++j) x -= L_(k, j) * L_(k, j);
+            if (x <= 0.0) break;
+            L_(k, k) = x = std::sqrt(x);
+            for (int i = k + 1; i < n; ++i) { double s = L_(i, k); for (int j = 0; j < k; ++j) s -= L_(i, j) * L_(k, j); L_(i, k) = s / x; }
         }
     }
     const MatrixXd& matrixL() const { return L_; }
@@ -217,12 +225,24 @@ public:
     }
     using QuaternionBase<Quaternion<S>>::w; using QuaternionBase<Quaternion<S>>::x; using QuaternionBase<Quaternion<S>>::y; using QuaternionBase<Quaternion<S>>::z;
     double& w() { return q[3]; } double& x() { return q[0]; } double& y() { return q[1]; } double& z() { return q[2]; }
+    struct Coeffs { double* p; double* data() { return p; } const double* data() const { return p; } double& operator[](int i) { return p[i]; } };      // (x, y, z, w), Eigen's storage order
+    Coeffs coeffs() { return Coeffs{q}; }
+    Coeffs coeffs() const { return Coeffs{const_cast<double*>(q)}; }
     static Quaternion Identity() { return Quaternion(); }
     void setIdentity() { q[0] = q[1] = q[2] = 0; q[3] = 1; }
     double squaredNorm() const { return q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]; }
     double norm() const { return std::sqrt(squaredNorm()); }
     void normalize() { const double n = norm(); for (double& v : q) v /= n; }
     Quaternion normalized() const { Quaternion o = *this; o.normalize(); return o; }
+    Quaternion slerp(double t, const Quaternion& o) const {          // Eigen/src/Geometry/Quaternion.h: QuaternionBase::slerp
+        const double one = 1.0 - 2.220446049250313e-16;
+        const double d = q[0] * o.q[0] + q[1] * o.q[1] + q[2] * o.q[2] + q[3] * o.q[3], ad = std::fabs(d);
+        double s0, s1;
+        if (ad >= one) { s0 = 1.0 - t; s1 = t; }
+        else { const double th = std::acos(ad), st = std::sin(th); s0 = std::sin((1.0 - t) * th) / st; s1 = std::sin(t * th) / st; }
+        if (d < 0) s1 = -s1;
+        return Quaternion(s0 * q[3] + s1 * o.q[3], s0 * q[0] + s1 * o.q[0], s0 * q[1] + s1 * o.q[1], s0 * q[2] + s1 * o.q[2]);
+    }
     Quaternion conjugate() const { return Quaternion(q[3], -q[0], -q[1], -q[2]); }
     Quaternion inverse() const { const double n2 = squaredNorm(); Quaternion c = conjugate(); for (double& v : c.q) v /= n2; return c; }
     Quaternion operator*(const Quaternion& b) const {

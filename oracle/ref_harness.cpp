@@ -132,6 +132,11 @@ int main(int argc, char** argv) {
         double* J6b[6] = {J0, J1, J2, J3, J4, J5};
         fi.Evaluate(prm6, r, J6b);
         put(r, 15); put(J0, 105); put(J1, 45); put(J2, 45); put(J3, 45); put(J4, 105); put(J5, 45);
+        // ... and with the priors Initializer::Initialize really passes (src/initializer.cpp:62: 1e4 / 1e2): written over the
+        // bias blocks they leave cov^-1 indefinite, so this is the LLT-returns-early path (see mini_eigen.h LLT)
+        ImuInitError fr(pre, 1e4, 1e2);
+        fr.Evaluate(prm6, r, J6b);
+        put(r, 15); put(J0, 105); put(J1, 45); put(J2, 45); put(J3, 45); put(J4, 105); put(J5, 45);
     }
     fclose(out);
     return 0;

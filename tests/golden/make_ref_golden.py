@@ -99,7 +99,7 @@ def run_reference(cases):
     for name, R, C in (("tf", 2, 15), ("po", 2, 7), ("tc", 2, 1), ("lidar", 1, 3), ("pg", 6, 14), ("pe", 6, 7), ("pr", 3, 3)):
         blk = o[pos:pos + N * (R + R * C)].reshape(N, R + R * C); pos += N * (R + R * C)
         out[name + "_r"] = blk[:, :R].copy(); out[name + "_J"] = blk[:, R:].reshape(N, R, C).copy()
-    per = 17 + 225 + 225 + 15 + 105 + 45 * 3 + 105 + 45 * 3 + 15 + 105 + 45 * 3 + 105 + 45
+    per = 17 + 225 + 225 + 15 + 105 + 45 * 3 + 105 + 45 * 3 + 2 * (15 + 105 + 45 * 3 + 105 + 45)
     blk = o[pos:pos + N_IMU * per].reshape(N_IMU, per); pos += N_IMU * per
     out["imu_record"] = blk[:, :467].copy()                      # LVB_IMU layout without the two prior slots
     out["imu_r"] = blk[:, 467:482].copy()
@@ -112,6 +112,11 @@ def run_reference(cases):
     for w in [7, 3, 3, 3, 7, 3]:
         Js.append(blk[:, q:q + 15 * w].reshape(N_IMU, 15, w)); q += 15 * w
     out["imuinit_J"] = np.concatenate(Js, axis=2)                  # [n, 15, 26], ImuInitError with priors 1e8 / 1e8
+    out["imuinit2_r"] = blk[:, q:q + 15].copy(); q += 15
+    Js = []
+    for w in [7, 3, 3, 3, 7, 3]:
+        Js.append(blk[:, q:q + 15 * w].reshape(N_IMU, 15, w)); q += 15 * w
+    out["imuinit2_J"] = np.concatenate(Js, axis=2)                 # the reference's real priors 1e4 / 1e2 (initializer.cpp:62): indefinite cov^-1
     assert q == per
     assert pos == len(o)
     return out

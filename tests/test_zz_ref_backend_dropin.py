@@ -1,0 +1,118 @@
+"""Drop-in proof for SURVEY 8(a1/a2/a9): the REFERENCE's own src/backend.cpp + src/tools.cpp (and frame / landmark / map /
+manager / preintegration), compiled where they lie, drive the product's header-only host side (include/lvio_b200/*.h).
+
+tests/cpp/ref_backend_dropin.cpp plays the frontend (fills the reference's Map through the reference's own classes) and then
+calls Backend::BuildProblem, adapt::Solve, imu::RecoverBias, imu::FullBA and compute_reprojection_error.  Three builds of it
+live in oracle/_ref/ (made by `make -C oracle ref` where /root/reference is mounted; the binaries travel to the GPU box):
+
+  ref_backend_truth   recording ceres + the reference's own factor headers: the cost the reference's functors assign
+  ref_backend_orc     product shim, C ABI served by the CPU oracle (lvb_* renamed to orc_*)
+  ref_backend_lvb     product shim bound to liblvio_b200.so: the CUDA path
+
+(The file sorts last on purpose: it is the only GPU test that runs prebuilt reference-derived binaries.)"""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+HAVE_REFERENCE = os.path.isdir("/root/reference/src/lvio_fusion/include")
+
+
+def _binary(name):
+    if HAVE_REFERENCE:
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    path = os.path.join(REF_DIR, name)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/%s is built only where the reference tree is mounted" % name)
+    return path
+
+
+def _run(name, mode, dump=None):
+    args = [_binary(name), str(mode)] + ([dump] if dump else [])
+    out = subprocess.run(args, check=True, capture_output=True, text=True, timeout=300).stdout
+    rec = {}
+    for line in out.splitlines():
+        tag, rest = line.split(" ", 1)
+        if tag in ("solve", "fullba") and "msg" in rest:
+            rest, rec["msg"] = rest.split(" msg ", 1)
+        toks = rest.split()
+        if tag in ("mode", "blocks"):                   # "mode 0 keyframes 10 ...": the tag is the first key
+            toks = [tag] + toks
+        if tag in ("before", "after", "solve", "reference", "types", "kinds", "mode", "blocks"):
+            for k, v in zip(toks[0::2], toks[1::2]):
+                rec[tag + "." + k] = float(v)
+        elif tag == "fullba" and toks[0] == "bias":
+            rec["fullba.bias"] = np.array([float(v) for v in toks[1:7]])
+    rec["stdout"] = out
+    return rec
+
+
+def _rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_reference_backend_builds_the_same_problem_on_the_shim(mode):
+    """Backend::BuildProblem (src/backend.cpp:96-183) run against the product's ceres::Problem / factors.h and against the
+    reference's own factors: same block census, and the cost the solver starts from (through the C ABI, oracle-served) is the
+    cost the reference's functors assign to that problem -- reprojection, IMU and weak-constraint blocks, Huber(1) included."""
+    t, o = _run("ref_backend_truth", mode), _run("ref_backend_orc", mode)
+    for k in ("types.visual", "types.weak", "types.imu", "types.other", "types.frames", "types.global_end", "mode.reproj_n", "mode.landmarks"):
+        assert t[k] == o[k], k
+    assert o["kinds.two_frame"] + o["kinds.pose_only"] == o["types.visual"] + o["types.weak"] > 500      # backend.cpp:114,128,138
+    assert o["kinds.two_camera"] + o["kinds.pose_graph"] + o["kinds.pose_prior"] == o["types.other"]       # :124,171,176
+    assert o["kinds.imu"] == o["types.imu"] == (7 if mode == 0 else 0)
+    assert o["kinds.pose_only"] > 100 and o["types.weak"] > 50                                               # landmarks born before the window; Far()
+    if mode == 1:
+        assert o["kinds.pose_graph"] == 2 and o["kinds.pose_prior"] == 0                                     # the two starved keyframes (:164-177)
+    assert t["reference.initial_cost"] > 1e5
+    assert _rel(o["solve.initial_cost"], t["reference.initial_cost"]) < 1e-12
+    # compute_reprojection_error (backend.cpp:185-190): the host form of PoseOnlyReprojectionError in factors.h vs the reference's functor
+    assert _rel(o["mode.reproj_sum"], t["mode.reproj_sum"]) < 1e-13
+    # and adapt::Solve does its job on it (parameters are written back into Frame::pose / Landmark::inv_depth in place)
+    assert o["solve.term"] == 0 and o["solve.final_cost"] < 0.25 * o["solve.initial_cost"]
+    assert o["after.rel_t"] < 0.6 * o["before.rel_t"] and o["after.rel_r"] < 0.2 * o["before.rel_r"]
+    assert o["after.reproj_sum"] < 0.25 * o["mode.reproj_sum"]
+
+
+def test_reference_fullba_runs_on_the_shim():
+    """imu::FullBA (src/tools.cpp:92-171) with the priors of Initializer::Initialize: ImuInitError blocks sharing one ba / bg
+    block, every keyframe free.  The absolute pose is a gauge (no anchor in that problem), the relative motion is not."""
+    o = _run("ref_backend_orc", 2)
+    assert o["after.rel_t"] < 0.05 * o["before.rel_t"] and o["after.rel_r"] < 0.05 * o["before.rel_r"]
+    assert np.max(np.abs(o["fullba.bias"])) < 1e-3            # the zero-mean bias prior of ImuInitError (Ba_j = Bg_j = 0) dominates
+
+
+def test_product_build_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    o = _run("ref_backend_lvb", 0)
+    assert o["solve.term"] == 2 and "no CPU fallback" in o["msg"]
+    assert o["after.rel_t"] == o["before.rel_t"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_reference_backend_drives_the_cuda_path(mode, tmp_path):
+    """The same binaries on the B200: the reference's Backend::BuildProblem / adapt::Solve / imu::FullBA through the shim on
+    liblvio_b200.so, against the oracle-served run of the identical problem."""
+    fo, fg = str(tmp_path / "orc.bin"), str(tmp_path / "lvb.bin")
+    o, g = _run("ref_backend_orc", mode, fo), _run("ref_backend_lvb", mode, fg)
+    so, sg = np.fromfile(fo), np.fromfile(fg)
+    assert so.shape == sg.shape and len(so) > 100
+    if mode < 2:
+        assert g["solve.term"] == 0, g["stdout"]
+        assert _rel(g["solve.initial_cost"], o["solve.initial_cost"]) < 1e-9
+        assert _rel(g["solve.final_cost"], o["solve.final_cost"]) < 1e-5
+        assert np.max(np.abs(so - sg)) < 1e-4
+    else:
+        # gauge-free problem: compare what is observable
+        assert g["after.rel_t"] < 0.05 * g["before.rel_t"] and g["after.rel_r"] < 0.05 * g["before.rel_r"]
+        assert abs(g["after.rel_t"] - o["after.rel_t"]) < 1e-4 and abs(g["after.rel_r"] - o["after.rel_r"]) < 1e-5
+        assert np.max(np.abs(g["fullba.bias"] - o["fullba.bias"])) < 1e-5
