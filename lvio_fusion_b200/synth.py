@@ -329,10 +329,10 @@ def make_fullba_problem(n_kf, n_landmarks, prior_a=1e8, prior_g=1e8, seed=SEED):
     """imu::FullBA (tools.cpp:92-171): the visual factor mix of the window plus ImuInitError factors
     (imu_error.hpp:124-229) that all share ONE accelerometer-bias and ONE gyroscope-bias block.
 
-    The reference calls it with prior_a = 1e4, prior_g = 1e2 (initializer.cpp:67); with the kitti.yaml IMU noise
-    those values make the patched cov^-1 indefinite (the bias cross-covariance of the preintegration is not
-    negligible) -- Eigen's LLT then returns NaN silently, this backend reports LVB_ERR_NUMERIC.  The synthetic
-    case therefore uses priors large enough to keep the matrix positive definite."""
+    The reference calls it with prior_a = 1e4, prior_g = 1e2 (initializer.cpp:62); with the kitti.yaml IMU noise
+    those values make the patched cov^-1 indefinite and Eigen's LLT returns early (the
+    backend reproduces that factor).  The default here keeps the matrix positive definite; pass the reference's
+    values to exercise the other path."""
     d = make_ba_problem(n_kf, n_landmarks, with_imu=True, seed=seed)
     N = n_kf
     consts, _ = d["factors"][3]
