@@ -13,6 +13,7 @@
 //   frame->weights.lidar_ground / lidar_surf / visual,  frame->features_left.size()
 #pragma once
 #include <cmath>
+#include <type_traits>
 #include "ceres_shim.h"
 
 // Inside the reference tree the class of the same name already exists (it also owns the feature extraction):
@@ -22,6 +23,23 @@
 #endif
 
 namespace lvio_fusion {
+
+namespace detail {
+// first record of a cloud: pcl::PointCloud keeps its records in the public vector `points` (every PCL version; PCL >= 1.11
+// also has data()); plain containers have data()
+template <class Cloud> inline auto cloud_data(const Cloud& c, int) -> decltype(c.points.data()) { return c.points.data(); }
+template <class Cloud> inline auto cloud_data(const Cloud& c, long) -> decltype(c.data()) { return c.data(); }
+// adapt::Problem (adapt/problem.h:37-47) hides ceres::Problem::AddResidualBlock behind an overload that takes the block's
+// ProblemType first and keeps a census of them; a plain ceres::Problem has no such census.  Use whichever the caller has:
+// `lidar` selects ProblemType::LidarError, otherwise ProblemType::Other (association.cpp:318,324).
+template <class P>
+inline auto add_block(P& p, int, bool lidar, ceres::CostFunction* c, ceres::LossFunction* l, double* x0, double* x1, double* x2) -> decltype(p.num_types, void()) {
+    typedef typename std::decay<decltype(p.num_types.begin()->first)>::type Type;
+    p.AddResidualBlock(lidar ? Type::LidarError : Type::Other, c, l, x0, x1, x2);
+}
+template <class P>
+inline void add_block(P& p, long, bool, ceres::CostFunction* c, ceres::LossFunction* l, double* x0, double* x1, double* x2) { p.AddResidualBlock(c, l, x0, x1, x2); }
+}  // namespace detail
 
 class LVB_ASSOCIATION_CLASS {
 public:
@@ -48,21 +66,21 @@ private:
         lvb::Runtime& rt = lvb::Runtime::get();
         if (!rt.ensure()) { delete loss; return false; }
         if (!icp && lvb_icp_create(rt.ctx, &icp) != LVB_OK) { delete loss; return false; }
-        const int stride = (int)sizeof(scan.data()[0]);
+        const int stride = (int)sizeof(detail::cloud_data(scan, 0)[0]);
         const float cell = std::nextafter((float)std::sqrt(thr), 1e30f) * 1.0001f;
-        if (lvb_icp_set_map(icp, map.data(), (int)map.size(), stride, cell) != LVB_OK) { delete loss; return false; }
+        if (lvb_icp_set_map(icp, detail::cloud_data(map, 0), (int)map.size(), stride, cell) != LVB_OK) { delete loss; return false; }
         if (mode == 0) { problem.AddParameterBlock(para + 1, 1); problem.AddParameterBlock(para + 2, 1); problem.AddParameterBlock(para + 5, 1); }
         else { problem.AddParameterBlock(para + 0, 1); problem.AddParameterBlock(para + 3, 1); problem.AddParameterBlock(para + 4, 1); }
         double* x0 = mode == 0 ? para + 1 : para + 0; double* x1 = mode == 0 ? para + 2 : para + 3; double* x2 = mode == 0 ? para + 5 : para + 4;
         lvb::ScanToMapCost* c = new lvb::ScanToMapCost();
-        c->mode = mode; c->icp = icp; c->scan = scan.data(); c->n = (int)scan.size(); c->stride = stride;
+        c->mode = mode; c->icp = icp; c->scan = detail::cloud_data(scan, 0); c->n = (int)scan.size(); c->stride = stride;
         std::memcpy(c->frame_pose, frame->pose.data(), sizeof(c->frame_pose)); std::memcpy(c->map_pose, map_frame->pose.data(), sizeof(c->map_pose));
         c->rpyxyz = para; c->weight = weight; c->dist_thr = thr;
-        problem.AddResidualBlock(c, loss, x0, x1, x2);
+        detail::add_block(problem, 0, true, c, loss, x0, x1, x2);
         if (!relocate) {
             lvb::IcpPriorCost* p = new lvb::IcpPriorCost();
             p->mode = mode; p->weight = (double)frame->features_left.size() * frame->weights.visual;   // association.cpp:323,381
-            problem.AddResidualBlock(p, nullptr, x0, x1, x2);
+            detail::add_block(problem, 0, false, p, nullptr, x0, x1, x2);
         }
         return true;
     }

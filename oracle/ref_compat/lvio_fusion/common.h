@@ -100,12 +100,18 @@ struct PointXYZI {                     // PCL layout: data[4] aliases x y z, the
     union { struct { float intensity; }; float data_c[4]; };
     PointXYZI() { data[0] = data[1] = data[2] = 0; data[3] = 1; data_c[0] = data_c[1] = data_c[2] = data_c[3] = 0; }
 };
-struct PointXYZRGB { float x = 0, y = 0, z = 0, pad0 = 0; unsigned int rgba = 0; float pad1 = 0, pad2 = 0, pad3 = 0; };
+struct PointXYZRGB {                   // PCL layout: x y z pad, then b g r a packed into one 32-bit word
+    float x = 0, y = 0, z = 0, pad0 = 0;
+    union { struct { unsigned char b, g, r, a; }; unsigned int rgba; };
+    float pad1 = 0, pad2 = 0, pad3 = 0;
+    PointXYZRGB() : rgba(0xff000000u) {}
+};
 struct PCLHeader { unsigned int seq = 0; unsigned long long stamp = 0; std::string frame_id; };
 inline void copy_intensity(const PointXYZ&, PointXYZI&) {}
 inline void copy_intensity(const PointXYZI& p, PointXYZI& q) { q.intensity = p.intensity; }
 inline void copy_intensity(const PointXYZI&, PointXYZ&) {}
 inline void copy_intensity(const PointXYZ&, PointXYZ&) {}
+inline void copy_intensity(const PointXYZRGB& p, PointXYZRGB& q) { q.rgba = p.rgba; }
 template <class PointT> struct PointCloud {
     typedef std::shared_ptr<PointCloud<PointT>> Ptr;
     PCLHeader header;
@@ -113,12 +119,16 @@ template <class PointT> struct PointCloud {
     unsigned int width = 0, height = 0;
     bool is_dense = true;
     size_t size() const { return points.size(); }
+    bool empty() const { return points.empty(); }
+    PointCloud& operator+=(const PointCloud& o) { points.insert(points.end(), o.points.begin(), o.points.end()); width = (unsigned int)points.size(); height = 1; return *this; }
     void push_back(const PointT& p) { points.push_back(p); width = (unsigned int)points.size(); height = 1; }
     void clear() { points.clear(); width = height = 0; }
     PointT& operator[](size_t i) { return points[i]; }
     const PointT& operator[](size_t i) const { return points[i]; }
     typename std::vector<PointT>::iterator begin() { return points.begin(); }
     typename std::vector<PointT>::iterator end() { return points.end(); }
+    typename std::vector<PointT>::const_iterator begin() const { return points.begin(); }
+    typename std::vector<PointT>::const_iterator end() const { return points.end(); }
     template <class It> void insert(typename std::vector<PointT>::iterator pos, It a, It b) { points.insert(pos, a, b); width = (unsigned int)points.size(); height = 1; }
     PointCloud operator+(const PointCloud& o) const { PointCloud r = *this; r.points.insert(r.points.end(), o.points.begin(), o.points.end()); r.width = (unsigned int)r.points.size(); r.height = 1; return r; }
 };

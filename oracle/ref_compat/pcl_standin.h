@@ -38,6 +38,15 @@ public:
 private:
     float leaf_ = 1; typename PointCloud<PointT>::Ptr in_;
 };
+// Mapping::GetGlobalMap (src/mapping.cpp:228-244) down-samples the coloured display cloud: visualisation, outside the path
+template <> class VoxelGrid<PointXYZRGB> {
+public:
+    void setLeafSize(float, float, float) {}
+    void setInputCloud(const PointCloud<PointXYZRGB>::Ptr& c) { in_ = c; }
+    void filter(PointCloud<PointXYZRGB>& out) { out = *in_; }
+private:
+    PointCloud<PointXYZRGB>::Ptr in_;
+};
 template <class PointT> class RadiusOutlierRemoval {
 public:
     void setRadiusSearch(double r) { r_ = r; }

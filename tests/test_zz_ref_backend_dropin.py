@@ -8,6 +8,7 @@ live in oracle/_ref/ (made by `make -C oracle ref` where /root/reference is moun
   ref_backend_truth   recording ceres + the reference's own factor headers: the cost the reference's functors assign
   ref_backend_orc     product shim, C ABI served by the CPU oracle (lvb_* renamed to orc_*)
   ref_backend_lvb     product shim bound to liblvio_b200.so: the CUDA path
+  ref_mapping_*       the same for src/mapping.cpp (tests/cpp/ref_mapping_dropin.cpp), see the mapping test below
 
 (The file sorts last on purpose: it is the only GPU test that runs prebuilt reference-derived binaries.)"""
 import os
@@ -95,6 +96,47 @@ def test_product_build_has_no_cpu_fallback():
     o = _run("ref_backend_lvb", 0)
     assert o["solve.term"] == 2 and "no CPU fallback" in o["msg"]
     assert o["after.rel_t"] == o["before.rel_t"]
+
+
+def _run_mapping(name, dump):
+    out = subprocess.run([_binary(name), dump], check=True, capture_output=True, text=True, timeout=300).stdout
+    rec = {"stdout": out}
+    for line in out.splitlines():
+        t = line.split()
+        if t[0] in ("before", "after"):
+            rec[(t[0], int(t[2]))] = (float(t[4]), float(t[6]))
+        elif t[0] == "map":
+            rec["clouds"], rec["forward_updates"] = int(t[2]), int(t[4])
+    return rec, np.fromfile(dump).reshape(3, 7)
+
+
+def test_reference_mapping_optimize_runs_on_the_shim(tmp_path):
+    """Mapping::Optimize (src/mapping.cpp:139-194, compiled in place): BuildMapFrame over the last three lidar keyframes,
+    ScanToMapWithGround / ScanToMapWithSegmented, adapt::Solve(DENSE_QR, 4 iterations), rpyxyz2se3, ToWorld -- three
+    keyframes in turn, each registered against a map that already holds its predecessor.
+
+    ref_mapping_orc     the two ScanToMap members forward to lvio_b200/association.h (one fused cost per call, C ABI served
+                        by the oracle); this is the INTEGRATION.md section 3 substitution
+    ref_mapping_hostlm  nothing substituted: the reference's own kd-tree loop and one LidarPlaneError AutoDiff block per accepted
+                        point plus the PoseErrorRPZ / YXY prior, solved by the shim's host LM
+    Same poses from both: the fused association + closed-form Jacobians + LM of the device API do what the reference's block-
+    per-point formulation does."""
+    o, po = _run_mapping("ref_mapping_orc", str(tmp_path / "o.bin"))
+    h, ph = _run_mapping("ref_mapping_hostlm", str(tmp_path / "h.bin"))
+    assert o["clouds"] == 6 and o["forward_updates"] == 3                        # ToWorld for every optimised keyframe, PoseGraph::ForwardUpdate each time
+    for k in (3, 4, 5):
+        assert o[("after", k)][0] < 0.15 * o[("before", k)][0] and o[("after", k)][1] < 0.05 * o[("before", k)][1]
+        assert o[("after", k)][0] < 0.025 and o[("after", k)][1] < 5e-4
+    assert np.max(np.abs(po - ph)) < 1e-9
+
+
+@pytest.mark.gpu
+def test_reference_mapping_optimize_drives_the_cuda_path(tmp_path):
+    o, po = _run_mapping("ref_mapping_orc", str(tmp_path / "o.bin"))
+    g, pg = _run_mapping("ref_mapping_lvb", str(tmp_path / "g.bin"))
+    assert g["clouds"] == 6 and g["forward_updates"] == 3, g["stdout"]
+    # three registrations in sequence, each map holding the previous result through a float32 transform: allow the cascade
+    assert np.max(np.abs(pg - po)) < 1e-5, g["stdout"]
 
 
 @pytest.mark.gpu
