@@ -24,7 +24,7 @@
 
 namespace lvio_fusion {
 
-namespace detail {
+namespace assoc_detail {
 // first record of a cloud: pcl::PointCloud keeps its records in the public vector `points` (every PCL version; PCL >= 1.11
 // also has data()); plain containers have data()
 template <class Cloud> inline auto cloud_data(const Cloud& c, int) -> decltype(c.points.data()) { return c.points.data(); }
@@ -39,7 +39,7 @@ inline auto add_block(P& p, int, bool lidar, ceres::CostFunction* c, ceres::Loss
 }
 template <class P>
 inline void add_block(P& p, long, bool, ceres::CostFunction* c, ceres::LossFunction* l, double* x0, double* x1, double* x2) { p.AddResidualBlock(c, l, x0, x1, x2); }
-}  // namespace detail
+}  // namespace assoc_detail
 
 class LVB_ASSOCIATION_CLASS {
 public:
@@ -66,21 +66,21 @@ private:
         lvb::Runtime& rt = lvb::Runtime::get();
         if (!rt.ensure()) { delete loss; return false; }
         if (!icp && lvb_icp_create(rt.ctx, &icp) != LVB_OK) { delete loss; return false; }
-        const int stride = (int)sizeof(detail::cloud_data(scan, 0)[0]);
+        const int stride = (int)sizeof(assoc_detail::cloud_data(scan, 0)[0]);
         const float cell = std::nextafter((float)std::sqrt(thr), 1e30f) * 1.0001f;
-        if (lvb_icp_set_map(icp, detail::cloud_data(map, 0), (int)map.size(), stride, cell) != LVB_OK) { delete loss; return false; }
+        if (lvb_icp_set_map(icp, assoc_detail::cloud_data(map, 0), (int)map.size(), stride, cell) != LVB_OK) { delete loss; return false; }
         if (mode == 0) { problem.AddParameterBlock(para + 1, 1); problem.AddParameterBlock(para + 2, 1); problem.AddParameterBlock(para + 5, 1); }
         else { problem.AddParameterBlock(para + 0, 1); problem.AddParameterBlock(para + 3, 1); problem.AddParameterBlock(para + 4, 1); }
         double* x0 = mode == 0 ? para + 1 : para + 0; double* x1 = mode == 0 ? para + 2 : para + 3; double* x2 = mode == 0 ? para + 5 : para + 4;
         lvb::ScanToMapCost* c = new lvb::ScanToMapCost();
-        c->mode = mode; c->icp = icp; c->scan = detail::cloud_data(scan, 0); c->n = (int)scan.size(); c->stride = stride;
+        c->mode = mode; c->icp = icp; c->scan = assoc_detail::cloud_data(scan, 0); c->n = (int)scan.size(); c->stride = stride;
         std::memcpy(c->frame_pose, frame->pose.data(), sizeof(c->frame_pose)); std::memcpy(c->map_pose, map_frame->pose.data(), sizeof(c->map_pose));
         c->rpyxyz = para; c->weight = weight; c->dist_thr = thr;
-        detail::add_block(problem, 0, true, c, loss, x0, x1, x2);
+        assoc_detail::add_block(problem, 0, true, c, loss, x0, x1, x2);
         if (!relocate) {
             lvb::IcpPriorCost* p = new lvb::IcpPriorCost();
             p->mode = mode; p->weight = (double)frame->features_left.size() * frame->weights.visual;   // association.cpp:323,381
-            detail::add_block(problem, 0, false, p, nullptr, x0, x1, x2);
+            assoc_detail::add_block(problem, 0, false, p, nullptr, x0, x1, x2);
         }
         return true;
     }

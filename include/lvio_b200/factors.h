@@ -12,6 +12,12 @@
 #include "ceres_autodiff.h"
 
 namespace lvio_fusion {
+// The classes below carry the reference's names but are different types from the functors in the reference's ceres/*.hpp,
+// and translation units that stay on those headers (pose_graph.cpp, navsat.cpp, relocator.cpp: off-path solves on the host
+// LM) end up in the same binary as the ones switched to this header.  The inline namespace keeps the two sets apart for
+// the linker (lvio_fusion::lvb_device::PoseGraphError vs lvio_fusion::PoseGraphError) while unqualified and
+// lvio_fusion::-qualified lookup in a translation unit that includes only this header still finds them.
+inline namespace lvb_device {
 
 namespace detail {
 template <class V> inline const double* ptr(const V& v) { return v.data(); }
@@ -173,4 +179,5 @@ inline void PoseGraphError::relative_rpyxyz(const double* a, const double* b, do
     e[3] = t[0] + ti[0]; e[4] = t[1] + ti[1]; e[5] = t[2] + ti[2];
 }
 
+}  // inline namespace lvb_device
 }  // namespace lvio_fusion

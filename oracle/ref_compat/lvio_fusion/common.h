@@ -32,6 +32,9 @@ struct SO3d {                                        // storage: the unit quater
     explicit SO3d(const Quaterniond& q) : d{q.x(), q.y(), q.z(), q.w()} {}
     double* data() { return d; }
     const double* data() const { return d; }
+    Vector3d operator*(const Vector3d& p) const { return Vector3d(Quaterniond(d[3], d[0], d[1], d[2]) * p); }
+    SO3d operator*(const SO3d& o) const { return SO3d(Quaterniond(d[3], d[0], d[1], d[2]) * Quaterniond(o.d[3], o.d[0], o.d[1], o.d[2])); }
+    SO3d inverse() const { return SO3d(Quaterniond(d[3], -d[0], -d[1], -d[2])); }
 };
 struct SE3f { float d[7]; float* data() { return d; } const float* data() const { return d; } };
 // storage [qx qy qz qw tx ty tz], unit quaternion
@@ -44,6 +47,7 @@ struct SE3d {
     double* data() { return d; }
     const double* data() const { return d; }
     Quaterniond unit_quaternion() const { return Quaterniond(d[3], d[0], d[1], d[2]); }
+    SO3d so3() const { return SO3d(unit_quaternion()); }
     Vector3d translation() const { return Vector3d(d[4], d[5], d[6]); }
     Matrix3d rotationMatrix() const { return unit_quaternion().toRotationMatrix(); }
     SE3d inverse() const { const Quaterniond qi = unit_quaternion().conjugate(); return SE3d(qi, Vector3d(qi * Vector3d(-translation()))); }

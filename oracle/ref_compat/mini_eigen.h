@@ -92,6 +92,9 @@ public:
     static Matrix Zero() { return Matrix(); }
     static Matrix Zero(int rows, int cols) { return Matrix(rows, cols); }
     static Matrix Identity() { Matrix m; m.setIdentity(); return m; }
+    static Matrix UnitX() { Matrix m; m.a[0] = 1.0; return m; }
+    static Matrix UnitY() { Matrix m; m.a[1] = 1.0; return m; }
+    static Matrix UnitZ() { Matrix m; m.a[2] = 1.0; return m; }
     static Matrix Identity(int rows, int cols) { Matrix m(rows, cols); m.setIdentity(); return m; }
     CommaInit operator<<(double first) { return CommaInit(*this, first); }
 private:
