@@ -8,7 +8,9 @@
 // [upstream] Forward-mode dual numbers give the exact derivative, so any correct implementation reproduces Ceres' Jacobians to
 // rounding; UnitQuaternionRotatePoint uses the "uv" form of Ceres 2.x.
 #pragma once
+#include <algorithm>
 #include <cmath>
+#include <limits>
 #include <utility>
 #include <vector>
 #include "ceres_shim.h"
@@ -147,6 +149,57 @@ public:
 private:
     template <typename T, size_t... I>
     bool call(T const* const* p, T* residuals, std::index_sequence<I...>) const { return (*functor_)(p[I]..., residuals); }
+    Functor* functor_;
+    Ownership ownership_;
+};
+
+// ---- NumericDiffCostFunction<Functor, method, kNumResiduals, N0, N1, ...> ------------------------------------------------
+// Named once by the reference: ImuInitGError (imu_error.hpp:263-266, FORWARD), the gravity-direction factor of
+// imu::InertialOptimization.  [upstream, restated from Ceres' internal/numeric_diff.h; parity unpinned]: one-sided difference
+// per coordinate with step  h_j = max(sqrt(DBL_EPSILON), |x_j| * 1e-6)  (NumericDiffOptions::relative_step_size), CENTRAL uses
+// the two-sided quotient with the same step.  RIDDERS is not provided.
+enum NumericDiffMethodType { CENTRAL, FORWARD, RIDDERS };
+
+template <typename Functor, NumericDiffMethodType kMethod, int kNumResiduals, int... Ns>
+class NumericDiffCostFunction : public SizedCostFunction<kNumResiduals, Ns...> {
+public:
+    explicit NumericDiffCostFunction(Functor* functor, Ownership ownership = TAKE_OWNERSHIP) : functor_(functor), ownership_(ownership) {
+        static_assert(kMethod != RIDDERS, "Ridders' method is not provided");
+        static_assert(kNumResiduals > 0, "dynamic residual counts are not used by the reference");
+    }
+    ~NumericDiffCostFunction() override { if (ownership_ == TAKE_OWNERSHIP) delete functor_; }
+    bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const override {
+        constexpr int kBlocks = sizeof...(Ns);
+        if (!call(parameters, residuals, std::make_index_sequence<kBlocks>())) return false;
+        if (!jacobians) return true;
+        const int sizes[kBlocks] = {Ns...};
+        // a private copy of the parameters: one coordinate is perturbed at a time
+        std::vector<std::vector<double>> copy(kBlocks);
+        const double* ptrs[kBlocks];
+        for (int b = 0; b < kBlocks; ++b) { copy[b].assign(parameters[b], parameters[b] + sizes[b]); ptrs[b] = copy[b].data(); }
+        const double min_step = std::sqrt(std::numeric_limits<double>::epsilon());
+        double plus[kNumResiduals], minus[kNumResiduals];
+        for (int b = 0; b < kBlocks; ++b) {
+            if (!jacobians[b]) continue;
+            for (int k = 0; k < sizes[b]; ++k) {
+                const double x = parameters[b][k], h = std::max(min_step, std::fabs(x) * 1e-6);
+                copy[b][k] = x + h;
+                if (!call(ptrs, plus, std::make_index_sequence<kBlocks>())) return false;
+                if (kMethod == CENTRAL) {
+                    copy[b][k] = x - h;
+                    if (!call(ptrs, minus, std::make_index_sequence<kBlocks>())) return false;
+                    for (int r = 0; r < kNumResiduals; ++r) jacobians[b][r * sizes[b] + k] = (plus[r] - minus[r]) / (2 * h);
+                } else {
+                    for (int r = 0; r < kNumResiduals; ++r) jacobians[b][r * sizes[b] + k] = (plus[r] - residuals[r]) / h;
+                }
+                copy[b][k] = x;
+            }
+        }
+        return true;
+    }
+private:
+    template <size_t... I>
+    bool call(double const* const* p, double* residuals, std::index_sequence<I...>) const { return (*functor_)(p[I]..., residuals); }
     Functor* functor_;
     Ownership ownership_;
 };

@@ -8,6 +8,7 @@
 // any pointer-like object with fx, fy, cx, cy and extrinsic.data() (include/lvio_fusion/visual/camera.h:79-80);
 // the rig actually used on the device is the one registered with lvb::Runtime::set_cameras (Camera::Get(0/1)).
 #pragma once
+#include <type_traits>
 #include "ceres_shim.h"
 #include "ceres_autodiff.h"
 
@@ -120,6 +121,48 @@ public:
         delete base;
         c[467] = prior_a; c[468] = prior_g;
         return new lvb::DeviceCost(LVB_IMU, 15, {7, 3, 3, 3, 7, 3}, std::move(c));
+    }
+};
+
+// imu_error.hpp:231-274    NumericDiffCostFunction<ImuInitGError, FORWARD, 15, 3, 3, 3, 3, 4>: the gravity-direction factor of
+// imu::InertialOptimization (tools.cpp:35-90) -- velocities, one shared bias pair and the quaternion Rwg, poses fixed.  An
+// off-path problem (3 + 3 + 4 + 3 N unknowns, DENSE_QR): evaluated on the host and solved by the host LM.  The raw residual is the
+// caller's own Preintegration::Evaluate(..., Rg) (preintegration.cpp:167-188); the whitening is the ImuInitError one.
+template <class PreintegrationPtr, class SE3>
+class ImuInitGFunctor {
+public:
+    ImuInitGFunctor(PreintegrationPtr pre, const SE3& current_pose, const SE3& last_pose, double prior_a, double prior_g)
+        : pre_(pre), current_pose_(current_pose), last_pose_(last_pose) {
+        double cov[225];
+        const double* C = pre->covariance.data();                       // Eigen: column-major
+        for (int i = 0; i < 15; ++i) for (int j = 0; j < 15; ++j) cov[i * 15 + j] = C[j * 15 + i];
+        ok_ = lvb::host::imu_sqrt_information(cov, prior_a, prior_g, U_);
+    }
+    bool operator()(const double* vi, const double* bai, const double* bgi, const double* vj, const double* rg, double* residuals) const {
+        if (!ok_) return false;
+        typedef typename std::decay<decltype(pre_->delta_p)>::type V3;
+        typedef typename std::decay<decltype(pre_->delta_q)>::type Q;
+        const Q Qi(last_pose_.rotationMatrix()), Qj(current_pose_.rotationMatrix());
+        const V3 Pi = last_pose_.translation(), Pj = current_pose_.translation();
+        const Q Rg(rg[3], rg[0], rg[1], rg[2]);
+        const auto raw = pre_->Evaluate(Pi, Qi, V3(vi[0], vi[1], vi[2]), V3(bai[0], bai[1], bai[2]), V3(bgi[0], bgi[1], bgi[2]),
+                                        Pj, Qj, V3(vj[0], vj[1], vj[2]), V3(0, 0, 0), V3(0, 0, 0), Rg);
+        const double* r = raw.data();
+        for (int i = 0; i < 15; ++i) { double s = 0; for (int k = 0; k < 15; ++k) s += U_[i * 15 + k] * r[k]; residuals[i] = s; }
+        return true;
+    }
+private:
+    PreintegrationPtr pre_;
+    SE3 current_pose_, last_pose_;
+    double U_[225];
+    bool ok_;
+};
+class ImuInitGError {
+public:
+    template <class PreintegrationPtr, class SE3>
+    static ceres::CostFunction* Create(PreintegrationPtr pre, const SE3& current_pose, const SE3& last_pose, double prior_a, double prior_g) {
+        typedef ImuInitGFunctor<PreintegrationPtr, SE3> F;
+        return new ceres::NumericDiffCostFunction<F, ceres::FORWARD, 15, 3, 3, 3, 3, 4>(new F(pre, current_pose, last_pose, prior_a, prior_g));
     }
 };
 

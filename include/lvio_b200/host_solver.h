@@ -263,5 +263,42 @@ inline void solve(const ceres::Solver::Options& options, ceres::Problem* problem
     summary->total_time_in_seconds = elapsed();
 }
 
+// sqrt_info = LLT(cov^-1 with the bias blocks overwritten by the priors).matrixL()^T  (imu_error.hpp:147-150,254-257), row-major
+// 15 x 15, for the host-evaluated ImuInitGError.  Same restatement as the device path's (lvio_fusion_b200/csrc/lvb_math.cuh ::
+// sqrt_information, oracle/imu.h): partial-pivot LU inverse, then the unblocked lower Cholesky with Eigen's early return on a
+// non-positive pivot (from that column on matrixL() shows the untouched lower triangle of the input).  False: singular / NaN.
+inline bool imu_sqrt_information(const double* cov, double prior_a, double prior_g, double* U) {
+    const int n = 15;
+    double a[225], inv[225], L[225];
+    int piv[15];
+    for (int i = 0; i < 225; ++i) a[i] = cov[i];
+    for (int i = 0; i < n; ++i) piv[i] = i;
+    for (int k = 0; k < n; ++k) {
+        int best = k; double bv = std::fabs(a[k * n + k]);
+        for (int i = k + 1; i < n; ++i) if (std::fabs(a[i * n + k]) > bv) { bv = std::fabs(a[i * n + k]); best = i; }
+        if (bv == 0.0) return false;
+        if (best != k) { for (int j = 0; j < n; ++j) std::swap(a[k * n + j], a[best * n + j]); std::swap(piv[k], piv[best]); }
+        for (int i = k + 1; i < n; ++i) { a[i * n + k] /= a[k * n + k]; const double f = a[i * n + k]; for (int j = k + 1; j < n; ++j) a[i * n + j] -= f * a[k * n + j]; }
+    }
+    for (int c = 0; c < n; ++c) {
+        double y[15];
+        for (int i = 0; i < n; ++i) { double s = (piv[i] == c) ? 1.0 : 0.0; for (int k = 0; k < i; ++k) s -= a[i * n + k] * y[k]; y[i] = s; }
+        for (int i = n - 1; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < n; ++k) s -= a[i * n + k] * inv[k * n + c]; inv[i * n + c] = s / a[i * n + i]; }
+    }
+    if (prior_a >= 0.0 && prior_g >= 0.0)
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { inv[(9 + i) * n + 9 + j] = (i == j) ? prior_a : 0.0; inv[(12 + i) * n + 12 + j] = (i == j) ? prior_g : 0.0; }
+    for (int i = 0; i < 225; ++i) L[i] = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double d = inv[j * n + j];
+        for (int k = 0; k < j; ++k) d -= L[j * n + k] * L[j * n + k];
+        if (d != d) return false;
+        if (d <= 0.0) { for (int c = j; c < n; ++c) for (int i = c; i < n; ++i) L[i * n + c] = inv[i * n + c]; break; }
+        L[j * n + j] = std::sqrt(d);
+        for (int i = j + 1; i < n; ++i) { double s = inv[i * n + j]; for (int k = 0; k < j; ++k) s -= L[i * n + k] * L[j * n + k]; L[i * n + j] = s / L[j * n + j]; }
+    }
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) U[i * n + j] = L[j * n + i];
+    return true;
+}
+
 }  // namespace host
 }  // namespace lvb

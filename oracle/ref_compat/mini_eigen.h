@@ -252,6 +252,7 @@ public:
         const double aw = q[3], ax = q[0], ay = q[1], az = q[2], bw = b.q[3], bx = b.q[0], by = b.q[1], bz = b.q[2];
         return Quaternion(aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz, aw * bz + az * bw + ax * by - ay * bx);
     }
+    Matrix<double, 3, 3> operator*(const Matrix<double, 3, 3>& m) const { return Matrix<double, 3, 3>(toRotationMatrix() * m); }      // RotationBase * matrix (map.cpp:112)
     Vector3d operator*(const Dyn& v) const {            // Eigen's _transformVector
         const Vector3d u(q[0], q[1], q[2]);
         const Vector3d t = 2.0 * u.cross(v);

@@ -34,6 +34,18 @@ namespace lvio_fusion {
 double compute_reprojection_error(Vector2d ob, Vector3d pw, SE3d pose, Camera::Ptr camera);      // src/backend.cpp:185
 // declared by the headers above, defined in translation units the harness does not link (never reached)
 Matrix3d normalize_R(const Matrix3d&) { std::abort(); }
+// src/utility.cpp (needs OpenCV as a whole): the rotation that takes the z axis onto `vec`, about z x vec -- what
+// Initializer::EstimateVelAndRwg / Initialize ask for (initializer.cpp:27,42).  Rodrigues' formula.
+Matrix3d get_R_from_vector(Vector3d vec) {
+    vec.normalize();
+    Vector3d axis = Vector3d::UnitZ().cross(vec);
+    const double s = axis.norm(), c = vec.z();
+    if (s < 1e-12) return Matrix3d::Identity();
+    axis = axis / s;
+    const double ang = std::atan2(s, c);
+    Matrix3d K; K << 0, -axis.z(), axis.y(), axis.z(), 0, -axis.x(), -axis.y(), axis.x(), 0;
+    return Matrix3d(Matrix3d::Identity() + std::sin(ang) * K + (1 - std::cos(ang)) * (K * K));
+}
 }  // namespace lvio_fusion
 #ifndef DROPIN_PRODUCT
 namespace ceres { void Solve(const Solver::Options&, Problem*, Solver::Summary*) {} }
@@ -79,7 +91,8 @@ static double recorded_cost(const ceres::Problem& problem) {
 
 struct Window { Frames all; Frames active; std::vector<SE3d> truth; double start = 0; };
 
-// mode: 0 visual + IMU (initialised), 1 visual only with two starved keyframes (the weak-constraint branch, backend.cpp:164-177)
+// mode: 0 visual + IMU (initialised), 1 visual only with two starved keyframes (the weak-constraint branch, backend.cpp:164-177),
+// 3 visual + IMU samples, IMU not initialised yet (biases unknown, set to zero)
 static Window make_window(int mode) {
     const double fx = 718.856, fy = 718.856, cx = 607.1928, cy = 185.2157, base = 0.537;
     Matrix3d Rbc; Rbc << 0, 0, 1, -1, 0, 0, 0, -1, 0;                 // camera z = body x
@@ -90,7 +103,8 @@ static Window make_window(int mode) {
     Camera::Create(fx, fy, cx, cy, SE3d(qe, t0));
     Camera::Create(fx, fy, cx, cy, SE3d(qe, Vector3d(t0 + qe * Vector3d(base, 0, 0))));
     Camera::baseline = base;
-    if (mode == 0) { Imu::Create(SE3d(), 0.08, 0.00004, 0.004, 2.0e-6, 9.81007); Imu::Get()->initialized = true; }
+    const bool with_imu = mode == 0 || mode == 3;
+    if (with_imu) { Imu::Create(SE3d(), 0.08, 0.00004, 0.004, 2.0e-6, 9.81007); Imu::Get()->initialized = mode == 0; }
 
     const int n_before = 2, n_active = 8;
     const double dt_kf = 0.4;
@@ -103,16 +117,17 @@ static Window make_window(int mode) {
         f->pose = traj_pose(f->time);
         f->last_keyframe = last;
         f->Vw = traj_v(f->time);
-        if (mode == 0) {
-            f->good_imu = true;
-            f->bias = Bias(0.02, -0.01, 0.015, 0.001, -0.002, 0.0015);
+        if (with_imu) {
+            const Bias true_bias(0.02, -0.01, 0.015, 0.001, -0.002, 0.0015);
+            f->good_imu = mode == 0;
+            f->bias = mode == 0 ? true_bias : Bias();                     // mode 3: nothing known yet, the initializer estimates it
             if (last) {                                                   // 100 Hz samples between the two keyframes
                 f->preintegration = imu::Preintegration::Create(f->bias);
                 const int ns = 40; const double h = dt_kf / ns;
                 auto meas = [&](double t, Vector3d& acc, Vector3d& gyr) {
                     const Quaterniond q = yaw_q(traj_yaw(t));
-                    acc = q.conjugate() * Vector3d(traj_a(t) + imu::g) + f->bias.linearized_ba + Vector3d(0.02 * nrand(), 0.02 * nrand(), 0.02 * nrand());
-                    gyr = Vector3d(0, 0, traj_yaw_rate(t)) + f->bias.linearized_bg + Vector3d(0.001 * nrand(), 0.001 * nrand(), 0.001 * nrand());
+                    acc = q.conjugate() * Vector3d(traj_a(t) + imu::g) + true_bias.linearized_ba + Vector3d(0.02 * nrand(), 0.02 * nrand(), 0.02 * nrand());
+                    gyr = Vector3d(0, 0, traj_yaw_rate(t)) + true_bias.linearized_bg + Vector3d(0.001 * nrand(), 0.001 * nrand(), 0.001 * nrand());
                 };
                 Vector3d acc0, gyr0; meas(last->time, acc0, gyr0);
                 for (int s = 1; s <= ns; ++s) { Vector3d acc, gyr; meas(last->time + h * s, acc, gyr); f->preintegration->Append(h, acc, gyr, acc0, gyr0); }
@@ -159,7 +174,7 @@ static Window make_window(int mode) {
     for (auto& f : frames) w.truth.push_back(f->pose);
     for (size_t i = 0; i < frames.size(); ++i) {
         frames[i]->pose = perturb(frames[i]->pose, i < (size_t)n_before ? 0.0 : 0.004, i < (size_t)n_before ? 0.0 : 0.06);
-        if (mode == 0) frames[i]->Vw = Vector3d(frames[i]->Vw + Vector3d(0.05 * nrand(), 0.05 * nrand(), 0.05 * nrand()));
+        if (with_imu) frames[i]->Vw = Vector3d(frames[i]->Vw + Vector3d(0.05 * nrand(), 0.05 * nrand(), 0.05 * nrand()));
     }
     for (auto& pl : lvio_fusion::Map::Instance().landmarks) pl.second->inv_depth *= 1.0 + 0.05 * nrand();
     w.all = lvio_fusion::Map::Instance().keyframes;
@@ -199,9 +214,15 @@ static double reprojection_sum(const Frames& kfs, int* count) {                 
 }
 
 int main(int argc, char** argv) {
-    const int mode = argc > 1 ? std::atoi(argv[1]) : 0;          // 0 window with IMU, 1 visual only (weak constraints), 2 imu::FullBA
+    const int mode = argc > 1 ? std::atoi(argv[1]) : 0;          // 0 window with IMU, 1 visual only (weak constraints), 2 imu::FullBA, 3 Initializer
     const char* dump = argc > 2 ? argv[2] : nullptr;
     Window w = make_window(mode == 2 ? 0 : mode);
+    if (mode == 3) {
+        // the visual-only map is not gravity aligned: tilt everything (poses and velocities; landmarks hang on their first keyframe)
+        const Quaterniond tilt = Quaterniond(std::cos(0.09), std::sin(0.09) * 0.8, std::sin(0.09) * 0.6, 0);        // 0.18 rad about (0.8, 0.6, 0)
+        lvio_fusion::Map::Instance().ApplyGravityRotation(tilt.toRotationMatrix());
+        w.all = lvio_fusion::Map::Instance().keyframes;
+    }
 #ifdef DROPIN_PRODUCT
     {   // Estimator would register the rig once
         double cam[2][11];
@@ -217,7 +238,28 @@ int main(int argc, char** argv) {
     printf("mode %d keyframes %zu active %zu landmarks %zu reproj_n %d reproj_sum %.12e\n", mode, w.all.size(), w.active.size(), lvio_fusion::Map::Instance().landmarks.size(), n_rep, rep0);
     print_state("before", w);
 
-    if (mode == 2) {
+    if (mode == 3) {
+        // Initializer::Initialize(frames, prior_a, prior_g) (src/initializer.cpp:32-55): velocities and gravity direction from the
+        // preintegrated velocities, imu::InertialOptimization (NumericDiff ImuInitGError on the host LM), the map rotated onto
+        // gravity, imu::FullBA (device path), Imu::initialized = true.  Every frame handed over has a predecessor and a preintegration.
+        auto gravity_tilt = [&]() {       // angle between the estimated and the true vertical, worst keyframe
+            double worst = 0; int i = 0;
+            for (auto& kv : w.all) { const Vector3d up = (kv.second->pose.unit_quaternion() * w.truth[i++].unit_quaternion().conjugate()) * Vector3d::UnitZ(); worst = std::max(worst, std::acos(std::min(1.0, up.z()))); }
+            return worst;
+        };
+#ifdef DROPIN_PRODUCT
+        Frames frames(++w.all.begin(), w.all.end());
+        printf("init tilt_before %.6e\n", gravity_tilt());
+        Initializer initializer;
+        const bool ok = initializer.Initialize(frames, 1e4, 1e2);
+        print_state("after", w);
+        const Bias b = frames.begin()->second->bias;
+        printf("init ok %d initialized %d tilt_after %.6e bias %.6e %.6e %.6e %.6e %.6e %.6e\n", (int)ok, (int)Imu::Get()->initialized, gravity_tilt(),
+               b.linearized_ba[0], b.linearized_ba[1], b.linearized_ba[2], b.linearized_bg[0], b.linearized_bg[1], b.linearized_bg[2]);
+#else
+        printf("initializer skipped in the recording build\n");
+#endif
+    } else if (mode == 2) {
         // imu::FullBA (src/tools.cpp:92-171): every keyframe of the map, ImuInitError with one shared ba / bg block
 #ifdef DROPIN_PRODUCT
         imu::FullBA(w.all, 1e4, 1e2);                     // the priors of Initializer::Initialize (src/initializer.cpp:62)

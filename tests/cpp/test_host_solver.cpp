@@ -121,6 +121,24 @@ static int run_autodiff() {
     double e1 = 0, e2 = 0, nrm = 0;
     for (int i = 0; i < 3; ++i) { e1 = std::fmax(e1, std::fabs(r1[i] - r2[i])); e2 = std::fmax(e2, std::fabs(r3[i] - r4[i])); nrm += r1[i] * r1[i]; }
     printf("rotation %.3e %.3e norm %.12f\n", e1, e2, std::sqrt(nrm));
+    // NumericDiffCostFunction (FORWARD as ImuInitGError uses it, and CENTRAL) against the AutoDiff Jacobian of the same functor
+    struct Plain {          // the non-template call operator NumericDiff wants, on top of the templated functor
+        lvb::host::PoseGraphFunctor f;
+        bool operator()(const double* x0, const double* x1, double* res) const { return f(x0, x1, res); }
+    };
+    Plain* pf = new Plain(); Plain* pc = new Plain();
+    for (int i = 0; i < 6; ++i) { pf->f.e[i] = e[i]; pc->f.e[i] = e[i]; } pf->f.w = pc->f.w = 3.0; pf->f.v = pc->f.v = 0.7;
+    ceres::NumericDiffCostFunction<Plain, ceres::FORWARD, 6, 7, 7> fwd(pf);
+    ceres::NumericDiffCostFunction<Plain, ceres::CENTRAL, 6, 7, 7> cen(pc);
+    double rn[6], Jfa[42], Jfb[42], Jca[42], Jcb[42]; double* Jf[2] = {Jfa, Jfb}; double* Jc[2] = {Jca, Jcb};
+    if (!fwd.Evaluate(p, rn, Jf) || !cen.Evaluate(p, rn, Jc)) return 3;
+    double wf = 0, wc = 0, wr = 0;
+    for (int i = 0; i < 6; ++i) wr = std::fmax(wr, std::fabs(rn[i] - r[i]));
+    for (int i = 0; i < 42; ++i) {
+        wf = std::fmax(wf, std::fmax(std::fabs(Jfa[i] - Ja[i]), std::fabs(Jfb[i] - Jb[i])));
+        wc = std::fmax(wc, std::fmax(std::fabs(Jca[i] - Ja[i]), std::fabs(Jcb[i] - Jb[i])));
+    }
+    printf("numericdiff %.3e %.3e %.3e\n", wf, wc, wr);
     return 0;
 }
 

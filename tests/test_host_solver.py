@@ -27,6 +27,8 @@ def test_autodiff_and_rotation_templates(exe):
     assert float(out[1]) < 1e-7                        # AutoDiffCostFunction vs central differences
     assert float(out[3]) < 1e-14 and float(out[4]) < 1e-14
     assert abs(float(out[6]) - np.linalg.norm([0.3, -1.2, 2.0])) < 1e-12     # rotation preserves length
+    # NumericDiffCostFunction: forward quotient (step ~1e-6 |x|, >= 1.5e-8) and central quotient against AutoDiff, same residuals
+    assert float(out[8]) < 1e-4 and float(out[9]) < 1e-6 and float(out[10]) == 0.0
 
 
 def test_navsat_shaped_two_stage_and_bounded_solve(exe):

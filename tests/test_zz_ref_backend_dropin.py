@@ -49,6 +49,11 @@ def _run(name, mode, dump=None):
                 rec[tag + "." + k] = float(v)
         elif tag == "fullba" and toks[0] == "bias":
             rec["fullba.bias"] = np.array([float(v) for v in toks[1:7]])
+        elif tag == "init" and toks[0] == "tilt_before":
+            rec["init.tilt_before"] = float(toks[1])
+        elif tag == "init" and toks[0] == "ok":
+            rec["init.ok"], rec["init.initialized"], rec["init.tilt_after"] = int(toks[1]), int(toks[3]), float(toks[5])
+            rec["init.bias"] = np.array([float(v) for v in toks[7:13]])
     rec["stdout"] = out
     return rec
 
@@ -87,6 +92,19 @@ def test_reference_fullba_runs_on_the_shim():
     o = _run("ref_backend_orc", 2)
     assert o["after.rel_t"] < 0.05 * o["before.rel_t"] and o["after.rel_r"] < 0.05 * o["before.rel_r"]
     assert np.max(np.abs(o["fullba.bias"])) < 1e-3            # the zero-mean bias prior of ImuInitError (Ba_j = Bg_j = 0) dominates
+
+
+def test_reference_initializer_runs_on_the_shim():
+    """SURVEY 8(f).1, "the unmodified Backend + Initializer run on the new solver": Initializer::Initialize(frames, 1e4, 1e2)
+    (src/initializer.cpp:32-55, compiled in place) on a tilted, not yet gravity-aligned visual map with unknown biases --
+    EstimateVelAndRwg, imu::InertialOptimization (the reference's loop over ImuInitGError::Create; factors.h builds it as a
+    NumericDiffCostFunction around the caller's Preintegration::Evaluate(..., Rg), solved by the host LM with the quaternion
+    parameterisation on Rwg), Map::ApplyGravityRotation, imu::FullBA (device path, oracle-served here)."""
+    o = _run("ref_backend_orc", 3)
+    assert o["init.ok"] == 1 and o["init.initialized"] == 1
+    assert o["init.tilt_before"] > 0.15 and o["init.tilt_after"] < 0.12 * o["init.tilt_before"]        # 0.188 rad -> 0.014 rad
+    assert o["after.rel_t"] < 0.12 * o["before.rel_t"] and o["after.rel_r"] < 0.05 * o["before.rel_r"]
+    assert np.max(np.abs(o["init.bias"])) < 0.1
 
 
 def test_product_build_has_no_cpu_fallback():
@@ -154,7 +172,7 @@ def test_reference_mapping_optimize_drives_the_cuda_path(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_reference_backend_drives_the_cuda_path(mode, tmp_path):
     """The same binaries on the B200: the reference's Backend::BuildProblem / adapt::Solve / imu::FullBA through the shim on
     liblvio_b200.so, against the oracle-served run of the identical problem."""
@@ -171,4 +189,7 @@ def test_reference_backend_drives_the_cuda_path(mode, tmp_path):
         # gauge-free problem: compare what is observable
         assert g["after.rel_t"] < 0.05 * g["before.rel_t"] and g["after.rel_r"] < 0.05 * g["before.rel_r"]
         assert abs(g["after.rel_t"] - o["after.rel_t"]) < 1e-4 and abs(g["after.rel_r"] - o["after.rel_r"]) < 1e-5
-        assert np.max(np.abs(g["fullba.bias"] - o["fullba.bias"])) < 1e-5
+        if mode == 2:
+            assert np.max(np.abs(g["fullba.bias"] - o["fullba.bias"])) < 1e-5
+        else:
+            assert g["init.ok"] == 1 and abs(g["init.tilt_after"] - o["init.tilt_after"]) < 1e-5 and np.max(np.abs(g["init.bias"] - o["init.bias"])) < 1e-5
