@@ -162,6 +162,20 @@ def test_reference_pose_graph_runs_on_the_host_lm():
     assert float(rec["rmse_after"]) < 0.5 * float(rec["rmse_before"]) and float(rec["moved_const"]) == 0.0
 
 
+def test_reference_navsat_runs_on_the_host_lm():
+    """SURVEY 8(f).4: src/navsat.cpp compiled in place with its own AutoDiff functors.  Navsat::AddPoint interpolates the fixes
+    onto the keyframes and fires Navsat::Initialize after the first 10 m (two-stage solve: yaw with x, y constant, then all three);
+    Navsat::Optimize(section) then removes a heading error picked up in a bend: OptimizeBC (scalar blocks, some constant, z
+    bounded, HuberLoss(0.1), a one-parameter roll pre-solve), OptimizeAB (PoseGraphError + TError, quaternion parameterisation),
+    the per-keyframe x corrections.  All on include/lvio_b200/host_solver.h."""
+    out = subprocess.run([_binary("ref_navsat")], capture_output=True, text=True, timeout=120, check=True).stdout.splitlines()
+    a, b = out[0].split(), out[1].split()
+    assert int(a[2]) == 1 and int(a[10]) >= 60                                           # initialised; nearly every keyframe got a fix
+    assert abs(float(a[4]) - 0.3) < 5e-3 and abs(float(a[6]) - 5.0) < 0.05 and abs(float(a[8]) + 3.0) < 0.1      # yaw, x, y of the extrinsic from 10 m of driving
+    rec = dict(zip(b[1::2], map(float, b[2::2])))
+    assert rec["rms_after"] < 0.3 * rec["rms_before"] and rec["yaw_after"] < 0.1 * rec["yaw_before"] and rec["ab_rms"] < 0.15
+
+
 @pytest.mark.gpu
 def test_reference_mapping_optimize_drives_the_cuda_path(tmp_path):
     o, po = _run_mapping("ref_mapping_orc", str(tmp_path / "o.bin"))
