@@ -84,7 +84,7 @@ def build_cases(seed=synth.SEED):
 
 
 def run_reference(cases):
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    subprocess.check_call(["make", "-s", "-j4", "-C", os.path.join(ROOT, "oracle"), "ref"])
     flat = [cases["cameras"], np.array([N] * 7 + [N_IMU], dtype=np.float64)]
     flat += [np.concatenate([cases["tf_c"], cases["tf_x"]], axis=1).ravel(), np.concatenate([cases["po_c"], cases["po_x"]], axis=1).ravel(),
              np.concatenate([cases["tc_c"], cases["tc_x"]], axis=1).ravel(), cases["lidar"].ravel(), cases["pg"].ravel(), cases["pe"].ravel(), cases["pr"].ravel(), cases["imu_noise"]]

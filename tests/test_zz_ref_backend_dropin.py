@@ -26,7 +26,7 @@ HAVE_REFERENCE = os.path.isdir("/root/reference/src/lvio_fusion/include")
 
 def _binary(name):
     if HAVE_REFERENCE:
-        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+        subprocess.check_call(["make", "-s", "-j4", "-C", os.path.join(ROOT, "oracle"), "ref"])
     path = os.path.join(REF_DIR, name)
     if not os.path.exists(path):
         pytest.skip("oracle/_ref/%s is built only where the reference tree is mounted" % name)
