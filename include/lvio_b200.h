@@ -254,7 +254,7 @@ LVB_API int lvb_lidar_segment_ground(lvb_ctx* ctx, const float* xyzi, int n, dou
 LVB_API int lvb_lidar_extract_features(lvb_ctx* ctx, const lvb_lidar_config* cfg, const void* points, int n, int stride_bytes,
                                        float* ground_xyzi, int32_t* n_ground, float* surf_xyzi, int32_t* n_surf);
 
-/* ---- profiling hooks (used by scratch/dbg_*.py; not part of the drop-in surface) */
+/* ---- profiling hooks (used by tools/kernel_timing*.py; not part of the drop-in surface) */
 /* enable != 0: record a CUDA event after every kernel of the BA pass (disables the graph); 0: print the per-kernel times */
 LVB_API int lvb_debug_timing(int enable);
 /* SM clock counters of ba_cholesky_kernel summed over calls: {diag, panel, trailing, backward, total, calls, -, -} */
