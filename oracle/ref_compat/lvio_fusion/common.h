@@ -44,6 +44,7 @@ struct SE3d {
     SE3d() : d{0, 0, 0, 1, 0, 0, 0} {}
     explicit SE3d(const double* p) { for (int i = 0; i < 7; ++i) d[i] = p[i]; }
     SE3d(const Quaterniond& q, const Vector3d& t) : d{q.x(), q.y(), q.z(), q.w(), t.x(), t.y(), t.z()} {}
+    SE3d(const SO3d& r, const Vector3d& t) : d{r.d[0], r.d[1], r.d[2], r.d[3], t.x(), t.y(), t.z()} {}
     double* data() { return d; }
     const double* data() const { return d; }
     Quaterniond unit_quaternion() const { return Quaterniond(d[3], d[0], d[1], d[2]); }

@@ -162,6 +162,15 @@ def test_reference_pose_graph_runs_on_the_host_lm():
     assert float(rec["rmse_after"]) < 0.5 * float(rec["rmse_before"]) and float(rec["moved_const"]) == 0.0
 
 
+def test_reference_relocator_submap_rotation_runs_on_the_host_lm():
+    """SURVEY 8(f).4: Relocator::UpdateNewSubmap (src/relocator.cpp:247-282, compiled in place): one bare quaternion block under
+    EigenQuaternionParameterization, a RelocateRError per keyframe of the new submap, DENSE_QR.  The harness re-evaluates the
+    objective with the reference's functor: the solved rotation beats the identity, the planted rotation and 2 000 perturbed
+    candidates (to Ceres' function tolerance), and every other keyframe moves by the same rigid transform."""
+    out = subprocess.run([_binary("ref_relocator")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout
+
+
 def test_reference_navsat_runs_on_the_host_lm():
     """SURVEY 8(f).4: src/navsat.cpp compiled in place with its own AutoDiff functors.  Navsat::AddPoint interpolates the fixes
     onto the keyframes and fires Navsat::Initialize after the first 10 m (two-stage solve: yaw with x, y constant, then all three);
