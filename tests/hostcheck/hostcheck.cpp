@@ -53,6 +53,7 @@ int hc_imu(const double* c467, const double* Ti, const double* Vi, const double*
     for (int i = 0; i < 15; ++i) for (int j = 0; j < 32; ++j) { double s = 0; for (int k = 0; k < 15; ++k) s += U[15 * i + k] * Jr[32 * k + j]; J[32 * i + j] = s; }
     return 0;
 }
+int hc_sqrt_information(const double* cov225, double* U225, double prior_a, double prior_g) { double a[225], inv[225]; return sqrt_information(cov225, U225, a, inv, prior_a, prior_g); }
 void hc_icp_point(int mode, const double* Twc1, const double* rpyxyz, const double* c10, double* r, double* J) {
     const IcpFrame f = icp_frame(mode, Twc1, rpyxyz);
     *r = icp_point(f, v3(c10[0], c10[1], c10[2]), v3(c10[3], c10[4], c10[5]), v3(c10[6], c10[7], c10[8]), c10[9], J);

@@ -145,3 +145,37 @@ def test_pose_plus(hc, orc):
         a = np.zeros(7); b = np.zeros(7)
         hc.hc_pose_plus(_dp(x), _dp(d), _dp(a)); orc.pose_plus(_dp(x), _dp(d), _dp(b))
         assert np.max(np.abs(a - b)) < 1e-15
+
+
+def test_warp_whitening_kernel_code_on_emulated_lanes(hc):
+    """lvb_imu_warp.cuh::sqrt_information_warp -- the code imu_prepare_kernel runs, one warp per IMU factor -- executed on the
+    CPU by 32 lock-step host threads (tests/hostcheck/warp_emul.cpp) against the scalar lvb_math.cuh::sqrt_information:
+    identical factor for SPD inputs, for ImuInitError priors that keep the matrix SPD, and for the reference's real priors
+    (1e4 / 1e2: indefinite, Eigen's LLT returns early), plus the two error codes."""
+    src = os.path.join(HERE, "hostcheck", "warp_emul.cpp")
+    lib = os.path.join(HERE, "hostcheck", "libwarp_emul.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", lib, src])
+    we = C.CDLL(lib)
+    for fn in (we.hc_sqrt_information_warp, hc.hc_sqrt_information):
+        fn.argtypes = [DP, DP, C.c_double, C.c_double]; fn.restype = C.c_int
+    ref = np.load(os.path.join(HERE, "golden", "ref_factors.npz"))
+    covs = [ref["imu_record"][k, 242:467].copy() for k in range(len(ref["imu_record"]))]
+    rng = np.random.default_rng(11)
+    for _ in range(4):                                        # well-conditioned random SPD matrices as well
+        m = rng.normal(size=(15, 15)); covs.append((m @ m.T + 15 * np.eye(15)).ravel())
+    early = 0
+    for cov in covs:
+        for pa, pg in ((-1.0, -1.0), (1e8, 1e8), (1e4, 1e2)):
+            Uw, Us = np.zeros(225), np.zeros(225)
+            sw = we.hc_sqrt_information_warp(_dp(cov), _dp(Uw), pa, pg)
+            ss = hc.hc_sqrt_information(_dp(cov), _dp(Us), pa, pg)
+            assert sw == ss == 0
+            assert np.array_equal(Uw, Us), (pa, pg)
+            L = Us.reshape(15, 15).T
+            # the early return leaves raw input entries on the diagonal from the failing column on (the prior itself, not a square root)
+            early += int((pa, pg) == (1e4, 1e2) and (L[11, 11] == pa or L[14, 14] == pg))
+    assert early >= len(ref["imu_record"])                     # every fixture covariance takes the early return with the real priors
+    U = np.zeros(225)
+    assert we.hc_sqrt_information_warp(_dp(np.zeros(225)), _dp(U), -1.0, -1.0) == 1 == hc.hc_sqrt_information(_dp(np.zeros(225)), _dp(U), -1.0, -1.0)
+    bad = covs[0].copy(); bad[0] = np.nan
+    assert we.hc_sqrt_information_warp(_dp(bad), _dp(U), -1.0, -1.0) != 0 and hc.hc_sqrt_information(_dp(bad), _dp(U), -1.0, -1.0) != 0
