@@ -1,7 +1,8 @@
 // oracle/icp.h -- scan-to-map association + point-to-plane ICP of the CPU oracle (TEST INFRASTRUCTURE ONLY).
 // The association (gate, factor creation, loss, prior weight) and the plane factors are pinned against the reference's own
-// association.cpp / lidar_error.hpp compiled in place (oracle/ref_assoc_harness.cpp, tests/golden/ref_assoc.npz); the kd-tree
-// (FLANN tie order) and the LM schedule remain "parity unpinned".
+// association.cpp / lidar_error.hpp compiled in place (oracle/ref_assoc_harness.cpp, tests/golden/ref_assoc.npz); the exact 3-NN is
+// pinned against FLANN's KDTreeSingleIndex as bundled with OpenCV (cv2.flann_Index, tests/test_flann_pin.py: same indices, bit-identical
+// float32 distances); the order of exact distance ties and the LM schedule remain "parity unpinned".
 //
 //   association : /root/reference/src/lvio_fusion/src/association.cpp:270-384
 //   driver      : /root/reference/src/lvio_fusion/src/mapping.cpp:139-191
@@ -11,7 +12,8 @@
 // The oracle defines the result as: exact 3 nearest neighbours under d2 = dx*dx + dy*dy + dz*dz
 // accumulated in float32 in that order WITHOUT fused multiply-add (compile with
 // -ffp-contract=off), ordered ascending by (d2, index).  FLANN's true tie order is traversal
-// dependent and unpinned; on tie-free inputs both definitions agree.
+// dependent and unpinned; on tie-free inputs both definitions agree -- checked against the FLANN copy that ships inside OpenCV's
+// Python module (PCL's own FLANN is not in the image; same index class, same search parameters).
 #pragma once
 #include <algorithm>
 #include <cstdint>
