@@ -46,8 +46,3 @@ def test_oracle_knn_matches_flann(orc_ctx, brute):
     _check(orc_ctx, brute, 3000, 60000, "surf", 21, FRAC)
     _check(orc_ctx, brute, 3000, 60000, "ground", 22, FRAC)
 
-
-@pytest.mark.gpu
-def test_cuda_knn_matches_flann(lvb_ctx):
-    _check(lvb_ctx, None, 20000, 300000, "surf", 23, FRAC)
-    _check(lvb_ctx, None, 20000, 300000, "ground", 24, FRAC)

@@ -40,3 +40,10 @@ def test_cuda_reproduces_the_reference_feature_extraction_and_association(lvb_ct
     R._check_extract(lvb_ctx)
     R._check_scan2map(lvb_ctx, brute=False)
 
+
+@pytest.mark.gpu
+def test_cuda_knn_matches_flann(lvb_ctx):
+    """tests/test_flann_pin.py on the device: the voxel-hash 3-NN against FLANN's KDTreeSingleIndex (OpenCV's bundled copy)."""
+    F = pytest.importorskip("test_flann_pin")
+    F._check(lvb_ctx, None, 20000, 300000, "surf", 23, F.FRAC)
+    F._check(lvb_ctx, None, 20000, 300000, "ground", 24, F.FRAC)
