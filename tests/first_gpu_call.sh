@@ -1,7 +1,7 @@
 #!/bin/bash
 # The first gpurun call of the next round: everything that was only cross-compiled at the end of
 # round 1 runs here, late-sorting files last so that a failure there cannot hide the verified tests.
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/first_gpu_call.sh r2_v0'
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tests/first_gpu_call.sh r2_v0'
 set -x
 V=${1:-r2_v0}
 O=gpurun_out
