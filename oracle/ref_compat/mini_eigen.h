@@ -103,6 +103,11 @@ private:
 typedef Matrix<double, 2, 1> Vector2d;
 typedef Matrix<double, 3, 1> Vector3d;
 typedef Matrix<double, 3, 3> Matrix3d;
+class VectorXd : public Matrix<double, Dynamic, 1> {           // environment.cpp:124: VectorXd v(3)
+public:
+    explicit VectorXd(int n) : Matrix<double, Dynamic, 1>(n, 1) {}
+    VectorXd(const Dyn& o) : Matrix<double, Dynamic, 1>(o) {}                                               // NOLINT implicit
+};
 
 inline MatrixXd operator+(const Dyn& x, const Dyn& y) { assert(x.r == y.r && x.c == y.c); MatrixXd o(x.r, x.c); for (size_t i = 0; i < x.a.size(); ++i) o.a[i] = x.a[i] + y.a[i]; return o; }
 inline MatrixXd operator-(const Dyn& x, const Dyn& y) { assert(x.r == y.r && x.c == y.c); MatrixXd o(x.r, x.c); for (size_t i = 0; i < x.a.size(); ++i) o.a[i] = x.a[i] - y.a[i]; return o; }
