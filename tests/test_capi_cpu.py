@@ -68,3 +68,10 @@ def test_lidar_and_imu_host_header_builds_and_fails_loudly(tmp_path):
                            os.path.join(root, "tests", "cpp", "compile_lidar_header.cpp"), "-L" + lib_dir, "-llvio_b200", "-Wl,-rpath," + lib_dir])
     p = subprocess.run([exe], capture_output=True, text=True)
     assert p.returncode == (0 if _has_gpu() else 3)
+
+
+def test_host_headers_are_cxx14():
+    """Ceres 2.x, which the reference builds against, needs C++14 and nothing newer: the header-only host side must not either."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for src in ("test_shim.cpp", "compile_lidar_header.cpp", "test_host_solver.cpp"):
+        subprocess.check_call(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp", src)])
