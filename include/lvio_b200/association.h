@@ -14,6 +14,7 @@
 #pragma once
 #include <cmath>
 #include <type_traits>
+#include <unordered_map>
 #include "ceres_shim.h"
 
 // Inside the reference tree the class of the same name already exists (it also owns the feature extraction):
@@ -44,19 +45,23 @@ inline void add_block(P& p, long, bool, ceres::CostFunction* c, ceres::LossFunct
 class LVB_ASSOCIATION_CLASS {
 public:
     explicit LVB_ASSOCIATION_CLASS(double lidar_resolution = 0.2) : resolution_(lidar_resolution) {}
-    ~LVB_ASSOCIATION_CLASS() { if (icp_ground_) lvb_icp_destroy(icp_ground_); if (icp_surf_) lvb_icp_destroy(icp_surf_); }
+    ~LVB_ASSOCIATION_CLASS() {                      // the calling thread's handles; another thread's go with that thread's context
+        auto& m = handles_of_thread();
+        auto it = m.find(this);
+        if (it != m.end()) { if (it->second.ground) lvb_icp_destroy(it->second.ground); if (it->second.surf) lvb_icp_destroy(it->second.surf); m.erase(it); }
+    }
 
     // association.cpp:270-326 : pitch/roll/z = para+1,+2,+5 ; gate d2 < 100 res^2 ; TrivialLoss ; PoseErrorRPZ prior
     template <class FramePtr, class Problem>
     bool ScanToMapWithGround(FramePtr frame, FramePtr map_frame, double* para, Problem& problem, bool relocate = false) {
         return add(0, frame, map_frame, frame->feature_lidar->points_ground, map_frame->feature_lidar->points_ground, para, problem, relocate,
-                   resolution_ * resolution_ * 100, frame->weights.lidar_ground, new ceres::TrivialLoss(), icp_ground_);
+                   resolution_ * resolution_ * 100, frame->weights.lidar_ground, new ceres::TrivialLoss(), handles_of_thread()[this].ground);
     }
     // association.cpp:328-384 : yaw/x/y = para+0,+3,+4 ; gate d2 < 25 res^2 ; HuberLoss(0.1) ; PoseErrorYXY prior
     template <class FramePtr, class Problem>
     bool ScanToMapWithSegmented(FramePtr frame, FramePtr map_frame, double* para, Problem& problem, bool relocate = false) {
         return add(1, frame, map_frame, frame->feature_lidar->points_surf, map_frame->feature_lidar->points_surf, para, problem, relocate,
-                   resolution_ * resolution_ * 25, frame->weights.lidar_surf, new ceres::HuberLoss(0.1), icp_surf_);
+                   resolution_ * resolution_ * 25, frame->weights.lidar_surf, new ceres::HuberLoss(0.1), handles_of_thread()[this].surf);
     }
 
 private:
@@ -84,9 +89,12 @@ private:
         }
         return true;
     }
+    // lvb_icp handles (voxel hash + scratch on one context's stream) are single-threaded and the context is per host thread
+    // (ceres_shim.h): Mapping::Optimize and Relocator::RelocateByPoints reach the same object from two threads without a lock
+    // (mapping.cpp:155-177, relocator.cpp:188-206), so every thread gets its own pair.
+    struct Handles { lvb_icp* ground = nullptr; lvb_icp* surf = nullptr; };
+    static std::unordered_map<const void*, Handles>& handles_of_thread() { static thread_local std::unordered_map<const void*, Handles> m; return m; }
     double resolution_;
-    lvb_icp* icp_ground_ = nullptr;
-    lvb_icp* icp_surf_ = nullptr;
 };
 
 }  // namespace lvio_fusion

@@ -34,13 +34,16 @@
 
 namespace lvb {
 
-// Process-wide device context + the stereo rig constants (Camera::Get(0/1) of the reference).
+// Device context + the stereo rig constants (Camera::Get(0/1) of the reference).
+// The reference solves from several host threads at once (Backend::BackendLoop, Backend::GlobalLoop, Relocator::DetectorLoop:
+// backend.cpp:19-20, relocator.cpp), so the context -- one CUDA stream, on which an LM pass may be under graph capture -- is per
+// host THREAD: kernels of one thread's solve never land in another thread's stream.  The rig is registered once for the process.
 struct Runtime {
     lvb_ctx* ctx = nullptr;
-    double cameras[22] = {0};
-    bool have_cameras = false;
     std::string error;
-    static Runtime& get() { static Runtime r; return r; }
+    double (&cameras)[22];
+    bool& have_cameras;
+    static Runtime& get() { static thread_local Runtime r; return r; }
     bool ensure(int device = 0) {
         if (ctx) return true;
         if (lvb_ctx_create(device, nullptr, &ctx) != LVB_OK) { error = lvb_last_error(); ctx = nullptr; return false; }
@@ -50,6 +53,12 @@ struct Runtime {
     void set_cameras(const double* cam0_11, const double* cam1_11) {
         std::memcpy(cameras, cam0_11, 11 * sizeof(double)); std::memcpy(cameras + 11, cam1_11, 11 * sizeof(double)); have_cameras = true;
     }
+    // (never destroyed: the solver threads of the reference live as long as the process, and tearing a context down from a
+    // thread_local destructor at process exit would call into a CUDA runtime that is already unloading)
+private:
+    struct Rig { double c[22] = {0}; bool have = false; };
+    static Rig& rig() { static Rig r; return r; }
+    Runtime() : cameras(rig().c), have_cameras(rig().have) {}
 };
 
 }  // namespace lvb

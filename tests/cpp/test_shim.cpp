@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <string>
+#include <thread>
 #include <vector>
 #include "lvio_b200/association.h"
 #include "lvio_b200/factors.h"
@@ -23,7 +25,7 @@ struct Quat { Coeffs c; const Coeffs& coeffs() const { return c; } };
 struct Mat15 { std::vector<double> v; const double* data() const { return v.data(); } };
 struct Preintegration { Vector3d delta_p, delta_v, linearized_ba, linearized_bg; Quat delta_q; double sum_dt; Mat15 jacobian, covariance; };
 
-static int run_ba(const char* in, const char* out) {
+static int run_ba(const char* in, const char* out, bool register_rig = true) {
     FILE* f = fopen(in, "rb"); if (!f) { perror(in); return 2; }
     std::vector<int32_t> h = ri(f, 10);          // np nv nr n0..n5 max_iter
     const int np = h[0], nv = h[1], nr = h[2];
@@ -32,7 +34,7 @@ static int run_ba(const char* in, const char* out) {
     std::vector<double> C[6]; std::vector<int32_t> I[6];
     for (int k = 0; k < 6; ++k) { C[k] = rd(f, (size_t)h[3 + k] * cs[k]); I[k] = ri(f, (size_t)h[3 + k] * is[k]); }
     fclose(f);
-    lvb::Runtime::get().set_cameras(cam.data(), cam.data() + 11);
+    if (register_rig) lvb::Runtime::get().set_cameras(cam.data(), cam.data() + 11);          // once per process (Estimator); the context itself is per thread
     std::vector<Frame> frames(np); std::vector<Landmark> lms(nr);
     std::vector<Vector3d> vecs(nv);
     for (int i = 0; i < np; ++i) for (int k = 0; k < 7; ++k) frames[i].pose.v[k] = P[7 * i + k];
@@ -129,7 +131,21 @@ static int run_icp(const char* in, const char* out) {
     return 0;
 }
 
+// Backend::BackendLoop, Backend::GlobalLoop and Relocator::DetectorLoop solve from their own threads (backend.cpp:19-20): N host
+// threads build and solve the same window at once, each through its own per-thread context (lvb::Runtime), results to out.<k>
+static int run_ba_threads(const char* in, const char* out, int n) {
+    { FILE* f = fopen(in, "rb"); if (!f) { perror(in); return 2; } std::vector<int32_t> h = ri(f, 10); std::vector<double> cam = rd(f, 22); fclose(f);
+      lvb::Runtime::get().set_cameras(cam.data(), cam.data() + 11); }
+    std::vector<int> rc(n, -1); std::vector<const void*> rt(n, nullptr);
+    std::vector<std::thread> th;
+    for (int k = 0; k < n; ++k) th.emplace_back([&, k] { const std::string o = std::string(out) + "." + std::to_string(k); rc[k] = run_ba(in, o.c_str(), false); rt[k] = &lvb::Runtime::get(); });
+    for (auto& t : th) t.join();
+    for (int k = 0; k < n; ++k) { if (rc[k]) return rc[k]; for (int j = 0; j < k; ++j) if (rt[j] == rt[k]) { fprintf(stderr, "two threads shared a runtime\n"); return 4; } }
+    return 0;
+}
+
 int main(int argc, char** argv) {
-    if (argc != 4) { fprintf(stderr, "usage: test_shim ba|icp in.bin out.bin\n"); return 1; }
+    if (argc == 5 && std::string(argv[1]) == "ba_threads") return run_ba_threads(argv[2], argv[3], std::atoi(argv[4]));
+    if (argc != 4) { fprintf(stderr, "usage: test_shim ba|icp in.bin out.bin | ba_threads in.bin out.bin n\n"); return 1; }
     return argv[1][0] == 'b' ? run_ba(argv[2], argv[3]) : run_icp(argv[2], argv[3]);
 }

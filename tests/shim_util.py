@@ -14,9 +14,21 @@ def build_shim_binary():
     if not os.path.exists(os.path.join(lib_dir, "liblvio_b200.so")):
         raise RuntimeError("liblvio_b200.so not built")
     if not os.path.exists(BIN) or os.path.getmtime(BIN) < os.path.getmtime(src):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-o", BIN, src,
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(ROOT, "include"), "-o", BIN, src,
                                "-L" + lib_dir, "-llvio_b200", "-Wl,-rpath," + lib_dir])
     return BIN
+
+
+def build_shim_binary_on_oracle():
+    """The same program with the C ABI served by the CPU oracle (lvb_* renamed to orc_*): host-side logic checks without a device."""
+    src = os.path.join(ROOT, "tests", "cpp", "test_shim.cpp")
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.check_call(["make", "-s", "-C", odir])
+    syms = subprocess.run(["nm", "-D", os.path.join(odir, "liboracle.so")], capture_output=True, text=True, check=True).stdout.split("\n")
+    defs = ["-Dlvb_%s=orc_%s" % (t.split()[2][4:], t.split()[2][4:]) for t in syms if len(t.split()) == 3 and t.split()[1] == "T" and t.split()[2].startswith("orc_")]
+    out = BIN + "_orc"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread"] + defs + ["-I" + os.path.join(ROOT, "include"), "-o", out, src, "-L" + odir, "-loracle", "-Wl,-rpath," + odir])
+    return out
 
 
 def dump_ba(path, d, max_iter):

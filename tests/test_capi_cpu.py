@@ -75,3 +75,21 @@ def test_host_headers_are_cxx14():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for src in ("test_shim.cpp", "compile_lidar_header.cpp", "test_host_solver.cpp"):
         subprocess.check_call(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp", src)])
+
+
+def test_shim_solves_from_several_threads_at_once(tmp_path):
+    """The reference solves from the backend, the global and the relocator thread concurrently: the shim's context is per host
+    thread (ceres_shim.h, lvb::Runtime).  Four threads build and solve the same window at once (C ABI served by the oracle here):
+    four distinct runtimes, four results identical to the single-threaded one."""
+    import numpy as np
+    import shim_util
+    from lvio_fusion_b200 import synth
+    exe = shim_util.build_shim_binary_on_oracle()
+    d = synth.make_ba_problem(4, 150, with_imu=True, seed=9)
+    shim_util.dump_ba(tmp_path / "in.bin", d, 6)
+    subprocess.check_call([exe, "ba", str(tmp_path / "in.bin"), str(tmp_path / "single.bin")])
+    subprocess.check_call([exe, "ba_threads", str(tmp_path / "in.bin"), str(tmp_path / "multi.bin"), "4"])
+    single = np.fromfile(tmp_path / "single.bin")
+    assert single[-3] < 0.5 * single[-4]                      # final < initial cost
+    for k in range(4):
+        assert np.array_equal(np.fromfile(str(tmp_path / "multi.bin") + ".%d" % k), single)

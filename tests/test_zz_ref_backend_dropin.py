@@ -218,3 +218,21 @@ def test_reference_backend_drives_the_cuda_path(mode, tmp_path):
             assert np.max(np.abs(g["fullba.bias"] - o["fullba.bias"])) < 5e-5
         else:
             assert g["init.ok"] == 1 and abs(g["init.tilt_after"] - o["init.tilt_after"]) < 1e-3 and np.max(np.abs(g["init.bias"] - o["init.bias"])) < 2e-3
+
+
+@pytest.mark.gpu
+def test_shim_solves_from_two_threads_on_the_device(tmp_path):
+    """tests/test_capi_cpu.py::test_shim_solves_from_several_threads_at_once on the B200: two host threads, each with its own
+    per-thread context and stream (graph capture is thread-local), solve the same window at once; both must equal the single-threaded
+    result.  Bounded by a timeout so that a wedged run cannot hold the box."""
+    import shim_util
+    from lvio_fusion_b200 import synth
+    exe = shim_util.build_shim_binary()
+    d = synth.make_ba_problem(4, 150, with_imu=True, seed=9)
+    shim_util.dump_ba(tmp_path / "in.bin", d, 6)
+    subprocess.run([exe, "ba", str(tmp_path / "in.bin"), str(tmp_path / "single.bin")], check=True, timeout=90)
+    subprocess.run([exe, "ba_threads", str(tmp_path / "in.bin"), str(tmp_path / "multi.bin"), "2"], check=True, timeout=90)
+    single = np.fromfile(tmp_path / "single.bin")
+    for k in range(2):
+        multi = np.fromfile(str(tmp_path / "multi.bin") + ".%d" % k)
+        assert multi.shape == single.shape and np.max(np.abs(multi[:-4] - single[:-4])) < 1e-9
