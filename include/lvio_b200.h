@@ -8,10 +8,11 @@
  *
  * Conventions: extern "C", int return (LVB_OK or a negative LVB_ERR_*; text via
  * lvb_last_error), no exceptions or STL across the boundary, the caller owns every host
- * buffer, the library owns the device buffers tied to a handle.  A handle is
- * single-threaded; different handles (each with its own stream) may be driven from
- * different host threads (Backend thread + Relocator thread, backend.cpp:32,
- * relocator.cpp:188-206).  There is NO CPU fallback: every compute entry point fails with
+ * buffer, the library owns the device buffers tied to a handle.  Threads: a context (lvb_ctx:
+ * one CUDA stream, on which an LM pass may be under thread-local graph capture) and the handles
+ * created from it belong to ONE host thread at a time; use one context per solving thread
+ * (Backend thread, global thread, Relocator thread: backend.cpp:19-20, relocator.cpp:188-206) --
+ * the C++ shim does (lvb::Runtime is thread_local).  There is NO CPU fallback: every compute entry point fails with
  * LVB_ERR_CUDA when no sm_100 device is usable.
  *
  * Layouts: pose = Sophus::SE3d::data() = [qx qy qz qw tx ty tz] (include/lvio_fusion/ceres/
