@@ -77,11 +77,13 @@ public:
         residual_blocks.push_back(new ResidualBlock{cost, loss, {x0, xs...}});
         return residual_blocks.back();
     }
+    void SetParameterBlockConstant(double* v) { constant_blocks.push_back(v); }          // environment.cpp:62-68: recorded only
     void GetResidualBlocksForParameterBlock(const double* v, std::vector<ResidualBlockId>* out) const {
         out->clear();
         for (ResidualBlock* r : residual_blocks) for (double* b : r->blocks) if (b == v) { out->push_back(r); break; }
     }
     std::vector<ResidualBlock*> residual_blocks;
+    std::vector<double*> constant_blocks;
     std::vector<std::pair<double*, int>> parameter_blocks;
 };
 void Solve(const Solver::Options&, Problem*, Solver::Summary*);      // named by adapt::Solve, never called here

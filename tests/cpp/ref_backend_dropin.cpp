@@ -19,6 +19,7 @@
 #include <cstring>
 #define private public
 #include "lvio_fusion/backend.h"
+#include "lvio_fusion/adapt/environment.h"
 #undef private
 #include "lvio_fusion/imu/tools.h"
 #include "lvio_fusion/manager.h"
@@ -214,9 +215,9 @@ static double reprojection_sum(const Frames& kfs, int* count) {                 
 }
 
 int main(int argc, char** argv) {
-    const int mode = argc > 1 ? std::atoi(argv[1]) : 0;          // 0 window with IMU, 1 visual only (weak constraints), 2 imu::FullBA, 3 Initializer
+    const int mode = argc > 1 ? std::atoi(argv[1]) : 0;          // 0 window with IMU, 1 visual only (weak constraints), 2 imu::FullBA, 3 Initializer, 4 Environment::Optimize
     const char* dump = argc > 2 ? argv[2] : nullptr;
-    Window w = make_window(mode == 2 ? 0 : mode);
+    Window w = make_window(mode == 2 || mode == 4 ? 0 : mode);
     if (mode == 3) {
         // the visual-only map is not gravity aligned: tilt everything (poses and velocities; landmarks hang on their first keyframe)
         const Quaterniond tilt = Quaterniond(std::cos(0.09), std::sin(0.09) * 0.8, std::sin(0.09) * 0.6, 0);        // 0.18 rad about (0.8, 0.6, 0)
@@ -238,7 +239,28 @@ int main(int argc, char** argv) {
     printf("mode %d keyframes %zu active %zu landmarks %zu reproj_n %d reproj_sum %.12e\n", mode, w.all.size(), w.active.size(), lvio_fusion::Map::Instance().landmarks.size(), n_rep, rep0);
     print_state("before", w);
 
-    if (mode == 3) {
+    if (mode == 4) {
+        // Environment::Optimize (src/environment.cpp:18-113; the weight-adaptation environment re-solves ONE keyframe): a copy of the
+        // frame, PoseOnlyReprojectionError for every left feature, one ImuError whose other seven blocks are constant, DENSE_QR.
+        // No estimator behind it here (mapping == nullptr: the lidar branch is skipped).
+#ifdef DROPIN_PRODUCT
+        alignas(Estimator) static unsigned char est_storage[sizeof(Estimator)] = {0};       // all-zero shared_ptr members are empty ones
+        Environment::estimator_ = Estimator::Ptr(reinterpret_cast<Estimator*>(est_storage), [](Estimator*) {});
+        Environment::u_ = std::uniform_real_distribution<double>(w.start, w.start + 1.0);
+        Environment* env = new Environment();
+        env->frames_ = w.active;
+        env->state_ = env->frames_.begin(); ++env->state_; ++env->state_; ++env->state_;     // the fourth active keyframe
+        Frame::Ptr frame = env->state_->second;
+        auto frame_reproj = [&](const SE3d& pose) { double s = 0; for (auto& pf : frame->features_left) s += compute_reprojection_error(cv2eigen(pf.second->keypoint.pt), pf.second->landmark.lock()->ToWorld(), pose, Camera::Get()); return s; };
+        const SE3d before = frame->pose;
+        const SE3d result = env->Optimize();
+        const SE3d moved = before.inverse() * result;
+        printf("env features %zu reproj_before %.9e reproj_after %.9e moved_t %.6e moved_r %.6e frame_untouched %d\n", frame->features_left.size(), frame_reproj(before), frame_reproj(result),
+               moved.translation().norm(), 2 * moved.unit_quaternion().vec().norm(), (int)(std::memcmp(frame->pose.data(), before.data(), 7 * sizeof(double)) == 0));
+#else
+        printf("environment skipped in the recording build\n");
+#endif
+    } else if (mode == 3) {
         // Initializer::Initialize(frames, prior_a, prior_g) (src/initializer.cpp:32-55): velocities and gravity direction from the
         // preintegrated velocities, imu::InertialOptimization (NumericDiff ImuInitGError on the host LM), the map rotated onto
         // gravity, imu::FullBA (device path), Imu::initialized = true.  Every frame handed over has a predecessor and a preintegration.

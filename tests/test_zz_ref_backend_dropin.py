@@ -107,6 +107,16 @@ def test_reference_initializer_runs_on_the_shim():
     assert np.max(np.abs(o["init.bias"])) < 0.1
 
 
+def test_reference_environment_single_frame_solve_runs_on_the_shim():
+    """Environment::Optimize (src/environment.cpp:18-113, compiled in place; the weight-adaptation module's use of the hot path): one
+    keyframe re-solved against fixed landmarks -- PoseOnlyReprojectionError for each of its features plus one ImuError whose other
+    seven parameter blocks are SetParameterBlockConstant -- through the shim (constant flags on pose / vec3 blocks, DENSE_QR)."""
+    out = _run("ref_backend_orc", 4)["stdout"].splitlines()[-1].split()
+    rec = dict(zip(out[1::2], out[2::2]))
+    assert int(rec["features"]) > 100 and int(rec["frame_untouched"]) == 1            # it works on a copy of the frame (:24-25)
+    assert float(rec["reproj_after"]) < 0.9 * float(rec["reproj_before"]) and 1e-3 < float(rec["moved_t"]) < 0.5
+
+
 def test_product_build_has_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
@@ -195,7 +205,7 @@ def test_reference_mapping_optimize_drives_the_cuda_path(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 def test_reference_backend_drives_the_cuda_path(mode, tmp_path):
     """The same binaries on the B200: the reference's Backend::BuildProblem / adapt::Solve / imu::FullBA through the shim on
     liblvio_b200.so, against the oracle-served run of the identical problem."""
@@ -203,7 +213,11 @@ def test_reference_backend_drives_the_cuda_path(mode, tmp_path):
     o, g = _run("ref_backend_orc", mode, fo), _run("ref_backend_lvb", mode, fg)
     so, sg = np.fromfile(fo), np.fromfile(fg)
     assert so.shape == sg.shape and len(so) > 100
-    if mode < 2:
+    if mode == 4:
+        a, b = g["stdout"].splitlines()[-1].split(), o["stdout"].splitlines()[-1].split()
+        ga, oa = dict(zip(a[1::2], map(float, a[2::2]))), dict(zip(b[1::2], map(float, b[2::2])))
+        assert abs(ga["reproj_after"] - oa["reproj_after"]) < 1e-6 * oa["reproj_after"] and abs(ga["moved_t"] - oa["moved_t"]) < 1e-7
+    elif mode < 2:
         assert g["solve.term"] == 0, g["stdout"]
         assert _rel(g["solve.initial_cost"], o["solve.initial_cost"]) < 1e-9
         assert _rel(g["solve.final_cost"], o["solve.final_cost"]) < 1e-5
