@@ -126,9 +126,23 @@ int main(int argc, char** argv) {
     report("after");
     printf("map clouds %zu forward_updates %d ground0 %zu surf0 %zu\n", mapping.pointclouds_surf.size(), g_forward_updates,
            frames[3]->feature_lidar->points_ground.size(), frames[3]->feature_lidar->points_surf.size());
+    // Mapping::Relocate (:246-300): the loop-closure registration -- four rounds of both scan-to-map solves without the prior
+    // (relocate = true), against the map frame around an OLD keyframe, scored from Summary::num_residual_blocks_reduced and
+    // Summary::final_cost (the only place the reference reads a Summary)
+    Frame::Ptr old_frame = frames[1], current = frames[4];
+    current->loop_closure = loop::LoopClosure::Ptr(new loop::LoopClosure());
+    current->loop_closure->frame_old = old_frame;
+    const SE3d true_rel = truth[1].inverse() * truth[4];
+    current->loop_closure->relative_o_c = SE3d(true_rel.unit_quaternion() * rpy_q(0.02, -0.004, 0.003), Vector3d(true_rel.translation() + Vector3d(0.15, -0.1, 0.04)));
+    SE3d relative_o_c;
+    const int score = mapping.Relocate(old_frame, current, relative_o_c);
+    const SE3d d_rel = (old_frame->pose * true_rel).inverse() * (old_frame->pose * relative_o_c);
+    printf("relocate score %d err_t %.9e err_r %.9e\n", score, d_rel.translation().norm(), 2 * d_rel.unit_quaternion().vec().norm());
     if (dump) {
         FILE* f = fopen(dump, "wb");
         for (int k = 3; k < 6; ++k) fwrite(frames[k]->pose.data(), sizeof(double), 7, f);
+        fwrite(relative_o_c.data(), sizeof(double), 7, f);
+        const double sc = score; fwrite(&sc, sizeof(double), 1, f);
         fclose(f);
     }
     return 0;

@@ -135,7 +135,9 @@ def _run_mapping(name, dump):
             rec[(t[0], int(t[2]))] = (float(t[4]), float(t[6]))
         elif t[0] == "map":
             rec["clouds"], rec["forward_updates"] = int(t[2]), int(t[4])
-    return rec, np.fromfile(dump).reshape(3, 7)
+        elif t[0] == "relocate":
+            rec["score"], rec["relocate_err"] = int(t[2]), (float(t[4]), float(t[6]))
+    return rec, np.fromfile(dump)           # three optimised poses, the relocated relative pose, the score
 
 
 def test_reference_mapping_optimize_runs_on_the_shim(tmp_path):
@@ -156,6 +158,10 @@ def test_reference_mapping_optimize_runs_on_the_shim(tmp_path):
         assert o[("after", k)][0] < 0.15 * o[("before", k)][0] and o[("after", k)][1] < 0.05 * o[("before", k)][1]
         assert o[("after", k)][0] < 0.025 and o[("after", k)][1] < 5e-4
     assert np.max(np.abs(po - ph)) < 1e-9
+    # Mapping::Relocate (:246-300): relocate = true (no prior), four rounds of both solves, scored from the Summary fields -- the
+    # one place the reference reads them (num_residual_blocks_reduced, final_cost): same score, same relative pose from both builds
+    assert o["score"] == h["score"] >= 40 and po[-1] == ph[-1] == o["score"]
+    assert o["relocate_err"][0] < 0.01 and o["relocate_err"][1] < 1e-3                     # from an 18 cm / 20 mrad initial guess
 
 
 def test_reference_pose_graph_runs_on_the_host_lm():
@@ -201,7 +207,8 @@ def test_reference_mapping_optimize_drives_the_cuda_path(tmp_path):
     g, pg = _run_mapping("ref_mapping_lvb", str(tmp_path / "g.bin"))
     assert g["clouds"] == 6 and g["forward_updates"] == 3, g["stdout"]
     # three registrations in sequence, each map holding the previous result through a float32 transform: allow the cascade
-    assert np.max(np.abs(pg - po)) < 1e-5, g["stdout"]
+    assert np.max(np.abs(pg[:-1] - po[:-1])) < 1e-5, g["stdout"]
+    assert abs(g["score"] - o["score"]) <= 1, g["stdout"]                                  # an integer cast of a sum of two scores
 
 
 @pytest.mark.gpu
