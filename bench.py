@@ -233,10 +233,13 @@ def main():
         }
 
         # ---------------- roofline of the dominant streaming kernel: TwoFrame Jacobian eval at configs[4] scale
+        # rank-0-only legs run on their own world-1 context: on the communicator-attached one Problem.from_dict is a collective
+        # (lvb_ba_finalize agrees on the unknown order and the envelope over the ranks) and would pair with nothing
+        ctx1 = backend.Context(lvb, device=local_rank, stream=stream.cuda_stream) if world > 1 else ctx
         if rank == 0 and not args.skip_roofline:
             big = synth.make_ba_problem(EVAL_KF, EVAL_LM, with_imu=False, seed=synth.SEED)
             big["factors"] = {0: big["factors"][0]}
-            pb = backend.Problem.from_dict(ctx, big)
+            pb = backend.Problem.from_dict(ctx1, big)
             nb = len(big["factors"][0][0])
             for _ in range(3):
                 pb.evaluate_device(0)
@@ -313,7 +316,7 @@ def main():
         # ---------------- lidar feature pipeline: raw 64 x 1800 sweep -> ground / surf features, host buffers in and out
         if rank == 0 and not args.skip_icp:
             sweep = synth.make_lidar_scan(seed=synth.SEED)
-            lf = backend.LidarFeatures(ctx)
+            lf = backend.LidarFeatures(ctx1)
             for _ in range(3):
                 gcl, scl = lf.extract(sweep)
             torch.cuda.synchronize()
@@ -361,6 +364,9 @@ def main():
                 line["lidar_features"]["cpu_port_points_per_s"] = len(sweep) / ((time.perf_counter() - t0) / 5)
             print(json.dumps(line))
     if world > 1:
+        dist.barrier()                  # rank 0 is still timing the CPU baseline: nobody tears the process group down under it
+        torch.cuda.synchronize()
+        ctx.close()
         dist.destroy_process_group()
 
 

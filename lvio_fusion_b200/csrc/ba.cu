@@ -1885,8 +1885,12 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
     int pass = 0;
     while (pass <= opt.max_num_iterations) {
         int chunk = std::min(check_every, opt.max_num_iterations + 1 - pass);
-        if (capped) {      // never overrun the wall-clock budget by more than about one pass
-            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (capped) {      // never overrun the wall-clock budget by more than about one pass (backend.cpp:208)
+            // sharded problems: every pass contains collectives, so all ranks must launch the same number of passes -- the decision
+            // is taken on the maximum elapsed time over the ranks (one small collective per look at the clock), never on a local clock
+            double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            LVB_TRY(comm_max_seconds(ba->ctx, &el));
+            if (pass > 0 && el >= opt.max_solver_time_in_seconds) break;
             chunk = pass == 0 ? 1 : std::max(1, std::min(chunk, (int)((opt.max_solver_time_in_seconds - el) / (el / pass))));
         }
         // instantiating a graph costs a few hundred microseconds: only worth it for a long solve or a reused problem
@@ -1915,9 +1919,8 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
         pass += chunk;
         LVB_CUDA(cudaMemcpyAsync(&h, ba->st.p, sizeof(h), cudaMemcpyDeviceToHost, s));
         LVB_CUDA(cudaStreamSynchronize(s));
-        if (h.done) break;
-        const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (el >= opt.max_solver_time_in_seconds) break;   // backend.cpp:208 wall-clock cap
+        LVB_TRY(comm_check(ba->ctx));
+        if (h.done) break;             // identical on every rank: the state is a function of bitwise-identical all-reduced sums
     }
     ba->solves_done++;
     if (summary) {

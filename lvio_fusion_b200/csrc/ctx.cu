@@ -77,14 +77,18 @@ static int nccl_fail(int rc, const char* what) {
 // The phase double-buffers the data: a rank can only reach epoch e+2 after every peer has published e+1, i.e. after they
 // finished reading e.  The epoch lives on the device and is advanced by the kernel, so the launch can sit in a CUDA graph.
 enum { XB_BLOCKS = 64, XB_DATA = 1 << 20, XB_FLAGS = 2 * XB_BLOCKS * 8 * 4, XB_CTRL = 256, XB_TOTAL = XB_FLAGS + XB_CTRL + 2 * XB_DATA };
-struct P2PArgs { unsigned char* peer[8]; int rank, world; };
+struct P2PArgs { unsigned char* peer[8]; int rank, world; unsigned long long timeout_ns; };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) { unsigned int v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 __global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2PArgs a, double* __restrict__ buf, int count) {
     unsigned char* mine = a.peer[a.rank];
-    unsigned int* ctrl = reinterpret_cast<unsigned int*>(mine + XB_FLAGS);          // [0] epoch, [1] finished CTAs
+    unsigned int* ctrl = reinterpret_cast<unsigned int*>(mine + XB_FLAGS);          // [0] epoch, [1] finished CTAs, [2] sticky error (1 + silent peer)
+    __shared__ int s_dead;
+    if (threadIdx.x == 0) s_dead = *reinterpret_cast<volatile unsigned int*>(ctrl + 2) != 0u;
+    __syncthreads();
+    if (s_dead) return;                         // an earlier exchange timed out: the communicator is dead, the host reports LVB_ERR_COMM
     const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(ctrl) + 1u;
     const int phase = (int)(epoch & 1u);
     double* my_data = reinterpret_cast<double*>(mine + XB_FLAGS + XB_CTRL + (size_t)phase * XB_DATA);
@@ -98,12 +102,15 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2PArgs a, double* _
         const unsigned int* f = reinterpret_cast<const unsigned int*>(mine) + slot + threadIdx.x;
         unsigned long long t0, t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        while (ld_acquire_sys(f) != epoch) {                         // a lost peer must not hang the GPU: give up after 20 s
+        while (ld_acquire_sys(f) != epoch) {
+            // a lost or mismatched peer must neither hang the GPU nor kill the process: after the timeout the kernel records which
+            // peer stayed silent and returns; every later exchange returns at once and the host turns the flag into LVB_ERR_COMM
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 20000000000ull) __trap();
+            if (t1 - t0 > a.timeout_ns) { atomicCAS(ctrl + 2, 0u, 1u + (unsigned int)threadIdx.x); s_dead = 1; break; }
         }
     }
     __syncthreads();
+    if (s_dead) return;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
         double s = 0.0;
         for (int r = 0; r < a.world; ++r) s += __ldcv(reinterpret_cast<const double*>(a.peer[r] + XB_FLAGS + XB_CTRL + (size_t)phase * XB_DATA) + i);
@@ -124,7 +131,8 @@ static int p2p_setup(lvb_ctx* ctx) {
     cudaIpcMemHandle_t mine; memset(&mine, 0, sizeof(mine));
     if (ok) {
         if (cudaMalloc((void**)&ctx->xbuf, XB_TOTAL) != cudaSuccess) { ok = 0; ctx->xbuf = nullptr; cudaGetLastError(); }
-        else if (cudaMemset(ctx->xbuf, 0, XB_TOTAL) != cudaSuccess || cudaIpcGetMemHandle(&mine, ctx->xbuf) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+        // zeroed on the context's stream, which is synchronised below before any peer can learn the handle
+        else if (cudaMemsetAsync(ctx->xbuf, 0, XB_TOTAL, ctx->stream) != cudaSuccess || cudaIpcGetMemHandle(&mine, ctx->xbuf) != cudaSuccess) { ok = 0; cudaGetLastError(); }
     }
     unsigned char* d_all = nullptr;
     const size_t hb = sizeof(cudaIpcMemHandle_t);
@@ -165,7 +173,7 @@ int comm_allreduce_sum_f64(lvb_ctx* ctx, double* buf, size_t count) {
     if (ctx->p2p_ok && count * sizeof(double) <= (size_t)XB_DATA) {
         P2PArgs a;
         for (int r = 0; r < 8; ++r) a.peer[r] = ctx->xpeer[r];
-        a.rank = ctx->rank; a.world = ctx->world;
+        a.rank = ctx->rank; a.world = ctx->world; a.timeout_ns = ctx->p2p_timeout_ns;
         const int blocks = (int)std::min<size_t>(XB_BLOCKS, (count + 255) / 256);
         p2p_allreduce_kernel<<<std::max(1, blocks), 256, 0, ctx->stream>>>(a, buf, (int)count);
         ctx->launches++;
@@ -175,6 +183,33 @@ int comm_allreduce_sum_f64(lvb_ctx* ctx, double* buf, size_t count) {
     }
     const int rc = g_nccl.all_reduce(buf, buf, count, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->comm, ctx->stream);
     if (rc != 0) return nccl_fail(rc, "ncclAllReduce");
+    return LVB_OK;
+}
+
+// Turns the sticky error word of the in-kernel exchange into LVB_ERR_COMM.  Called where the host looks at device state anyway.
+int comm_check(lvb_ctx* ctx) {
+    if (ctx->world <= 1 || !ctx->p2p_ok || !ctx->xbuf) return LVB_OK;
+    unsigned int word = 0;
+    LVB_CUDA(cudaMemcpyAsync(&word, ctx->xbuf + XB_FLAGS + 8, sizeof(word), cudaMemcpyDeviceToHost, ctx->stream));
+    LVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (word) {
+        set_error("peer-memory all-reduce on rank %d timed out after %.1f s waiting for rank %u: the ranks issued different collective sequences "
+                  "or a peer is gone; this communicator is unusable", ctx->rank, ctx->p2p_timeout_ns * 1e-9, word - 1u);
+        return LVB_ERR_COMM;
+    }
+    return LVB_OK;
+}
+
+// max over the ranks of a host double (seconds), so that wall-clock decisions are the same on every rank (collective)
+int comm_max_seconds(lvb_ctx* ctx, double* seconds) {
+    if (ctx->world <= 1) return LVB_OK;
+    if (!ctx->scratch_i32) LVB_CUDA(cudaMalloc((void**)&ctx->scratch_i32, 64));
+    int us = (int)std::min(2.0e9, std::max(0.0, *seconds * 1e6));
+    LVB_CUDA(cudaMemcpyAsync(ctx->scratch_i32, &us, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    LVB_TRY(comm_allreduce_max_i32(ctx, ctx->scratch_i32, 1));
+    LVB_CUDA(cudaMemcpyAsync(&us, ctx->scratch_i32, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *seconds = us * 1e-6;
     return LVB_OK;
 }
 
@@ -241,6 +276,8 @@ int lvb_ctx_create(int device, void* cuda_stream, lvb_ctx** out) {
     c->use_graph = !(no_graph && no_graph[0] == '1');
     const char* ev = getenv("LVB_EVAL_VARIANT");
     if (ev) c->eval_variant = atoi(ev);
+    const char* pt = getenv("LVB_P2P_TIMEOUT_MS");
+    if (pt && atof(pt) > 0) c->p2p_timeout_ns = (unsigned long long)(atof(pt) * 1e6);
     const char* ce = getenv("LVB_CHECK_EVERY");
     if (ce && atoi(ce) > 0) c->check_every = atoi(ce);
     *out = c;
@@ -251,6 +288,7 @@ void lvb_ctx_destroy(lvb_ctx* ctx) {
     if (!ctx) return;
     for (int r = 0; r < 8; ++r) if (ctx->xpeer[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->xpeer[r]);
     if (ctx->xbuf) cudaFree(ctx->xbuf);
+    if (ctx->scratch_i32) cudaFree(ctx->scratch_i32);
     if (ctx->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(ctx->comm);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);

@@ -571,8 +571,13 @@ int lvb_icp_scan_to_map(lvb_icp* h, int mode, const void* scan, int n, int strid
         LVB_TRY(icheck("icp iteration"));
         LVB_CUDA(cudaMemcpyAsync(&hs, h->st.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
         LVB_CUDA(cudaStreamSynchronize(s));
+        LVB_TRY(comm_check(ctx));
         if (hs.lm.done) break;
-        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= opt.max_solver_time_in_seconds) break;
+        if (opt.max_solver_time_in_seconds < 1e8) {      // collective decision when the queries are sharded (see lvb_ba_solve)
+            double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            LVB_TRY(comm_max_seconds(ctx, &el));
+            if (el >= opt.max_solver_time_in_seconds) break;
+        }
     }
     const int fr[2][3] = {{1, 2, 5}, {0, 3, 4}};
     for (int k = 0; k < 3; ++k) rpyxyz[fr[mode][k]] = hs.x[k];

@@ -39,6 +39,8 @@ struct lvb_ctx {
     unsigned char* xbuf = nullptr;
     unsigned char* xpeer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool p2p_ok = false;
+    unsigned long long p2p_timeout_ns = 20000000000ull;   // env LVB_P2P_TIMEOUT_MS; a silent peer becomes LVB_ERR_COMM, not a hang
+    int* scratch_i32 = nullptr;                           // device word for small host-driven collectives (comm_max_seconds)
 };
 
 namespace lvb {
@@ -47,6 +49,8 @@ int comm_allreduce_sum_f64(lvb_ctx* ctx, double* buf, size_t count);   // no-op 
 bool comm_graph_safe(const lvb_ctx* ctx, size_t max_count);          // every all-reduce of <= max_count doubles is a capturable kernel
 int comm_allreduce_min_i32(lvb_ctx* ctx, int* buf, size_t count);      // device buffer, no-op when world == 1
 int comm_allreduce_max_i32(lvb_ctx* ctx, int* buf, size_t count);
+int comm_check(lvb_ctx* ctx);                                          // LVB_ERR_COMM when an in-kernel exchange timed out
+int comm_max_seconds(lvb_ctx* ctx, double* seconds);                   // collective: max over the ranks (no-op when world == 1)
 
 // Minimal owning device buffer on the stream-ordered allocator: a problem object allocates ~40 arrays, and
 // cudaMalloc (a device-wide synchronising call, ~0.1 ms each) would dominate the end-to-end time of a solve that
@@ -139,6 +143,8 @@ __device__ inline void lm_control_post(LmState& s) {
     const double model_cost_change = 0.5 * (s.mcc_a - s.mcc_b);
     if (s.solve_fail || !(model_cost_change > 0.0) || !isfinite(model_cost_change)) {
         if (++s.invalid >= s.max_invalid) { s.done = 1; s.termination = 2; return; }
+        // LevenbergMarquardtStrategy::StepIsInvalid() is `StepRejected(0.0)` in Ceres 1.x / 2.x (levenberg_marquardt_strategy.cc;
+        // the `radius *= 0.5` rule belongs to DoglegStrategy::StepRejected): same shrink as a rejected step  [upstream]
         s.radius = s.radius / s.decrease_factor; s.decrease_factor *= 2.0;
         return;
     }

@@ -46,6 +46,14 @@ def main():
     e0 = synth.relative_rpyxyz(sc["map_pose"], sc["frame_pose"])
     lo, hi = rank * len(sc["scan"]) // world, (rank + 1) * len(sc["scan"]) // world
     e, si = fa.scan_to_map(sc["mode"], sc["scan"][lo:hi], sc["frame_pose"], sc["map_pose"], e0, sc["weight"], -1.0, sc["huber_a"], sc["thr"])
+    # wall-clock cap on a sharded solve (Backend::Optimize always sets one, backend.cpp:208): the stop decision is collective,
+    # so a tiny budget must end the solve early on every rank together instead of leaving a peer inside a collective
+    pc = backend.Problem.from_dict(ctx, synth.shard_ba_problem(d, rank, world))
+    scap = pc.solve(max_num_iterations=40, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0, max_solver_time_in_seconds=2e-3)
+    caps = torch.tensor([scap.num_iterations], device="cuda")
+    gathered = [torch.zeros_like(caps) for _ in range(world)]
+    dist.all_gather(gathered, caps)
+    cap_iters = [int(g.item()) for g in gathered]
     ok = True
     if rank == 0:
         from oracle import binding
@@ -69,10 +77,23 @@ def main():
             "rho": np.max(np.abs(rho.cpu().numpy() - po.inv_depths())) < 1e-6,
             "icp_blocks": si.num_residual_blocks == sio.num_residual_blocks,
             "icp_pose": np.max(np.abs(e - eo)) < 1e-7,
+            "capped_same_iterations_everywhere": len(set(cap_iters)) == 1 and 1 <= cap_iters[0] < 40,
         }
         ok = all(checks.values())
         print("MULTIGPU", "OK" if ok else "FAIL", checks, "cost", s.final_cost, so.final_cost)
     dist.barrier()
+    # last, because it kills the communicator: a collective only rank 0 issues must surface as LVB_ERR_COMM with a message on
+    # rank 0 (bounded wait), not as a trap / SIGABRT
+    if os.environ.get("LVB_P2P_TIMEOUT_MS") and rank == 0 and os.environ.get("LVB_NO_P2P") != "1":
+        try:
+            backend.Problem.from_dict(ctx, synth.shard_ba_problem(d, rank, world)).solve(max_num_iterations=3)
+            print("MISMATCH not detected"); ok = False
+        except Exception as exc:
+            good = "timed out" in str(exc) or "NCCL" in str(exc)
+            print("MISMATCH", "reported" if good else "unexpected", str(exc)[:200]); ok = ok and good
+        os._exit(0 if ok else 1)            # NCCL cannot be shut down cleanly after a deliberate mismatch
+    if os.environ.get("LVB_P2P_TIMEOUT_MS"):
+        os._exit(0)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

@@ -231,7 +231,8 @@ def test_reference_backend_drives_the_cuda_path(mode, tmp_path):
         assert np.max(np.abs(so - sg)) < 1e-4
     else:
         # gauge-free problem: compare what is observable
-        assert g["after.rel_t"] < 0.05 * g["before.rel_t"] and g["after.rel_r"] < 0.05 * g["before.rel_r"]
+        # same bounds as the CPU twins above: FullBA alone reaches 2 %, the whole Initializer chain 7 % of the initial translation error
+        assert g["after.rel_t"] < (0.05 if mode == 2 else 0.12) * g["before.rel_t"] and g["after.rel_r"] < 0.05 * g["before.rel_r"]
         # (the indefinite-prior whitening makes these problems stiff -- entries ~1e9 -- and they have a gauge: the two LM runs are
         # compared on what they achieve, not digit by digit)
         assert abs(g["after.rel_t"] - o["after.rel_t"]) < 0.05 * o["after.rel_t"] + 1e-5 and abs(g["after.rel_r"] - o["after.rel_r"]) < 0.05 * o["after.rel_r"] + 1e-6
