@@ -258,6 +258,12 @@ LVB_API int lvb_lidar_extract_features(lvb_ctx* ctx, const lvb_lidar_config* cfg
 /* ---- profiling hooks (used by tools/kernel_timing*.py; not part of the drop-in surface) */
 /* enable != 0: record a CUDA event after every kernel of the BA pass (disables the graph); 0: print the per-kernel times */
 LVB_API int lvb_debug_timing(int enable);
+/* as lvb_debug_timing(0), but writes "kernel_name microseconds" lines (launch order) into out instead of printing them */
+LVB_API int lvb_debug_timing_report(char* out, int cap);
+/* the reduced-system solver alone (parity test of the multifrontal tree, ba_tree.cuh): S x = b for an SPD band matrix stored as
+ * n rows of band + 1 entries (row i = columns i - band .. i), true half bandwidth <= band - 31; use_tree 0 forces the single-CTA
+ * envelope kernel; *levels_out = tree levels used (0: single CTA) */
+LVB_API int lvb_debug_band_solve(lvb_ctx* ctx, int n, int band, const double* S_band, const double* b, double* x, int use_tree, int* levels_out);
 /* SM clock counters of ba_cholesky_kernel summed over calls: {diag, panel, trailing, backward, total, calls, -, -} */
 LVB_API int lvb_debug_cholesky_clocks(long long out[8], int reset);
 

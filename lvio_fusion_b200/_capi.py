@@ -119,6 +119,8 @@ _LVB_ONLY = {
     "ba_set_schur_mode": (C.c_int, [VP, C.c_int]),
     "debug_timing": (C.c_int, [C.c_int]),
     "debug_cholesky_clocks": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
+    "debug_timing_report": (C.c_int, [C.c_char_p, C.c_int]),
+    "debug_band_solve": (C.c_int, [VP, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, c_int_p]),
 }
 
 EXPORTED_SYMBOLS = ["lvb_" + k for k in list(_SIGS) + list(_LVB_ONLY)]

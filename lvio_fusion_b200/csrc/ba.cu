@@ -18,6 +18,7 @@
 #include <math.h>
 #include <algorithm>
 #include <chrono>
+#include <functional>
 #include <map>
 #include <string.h>
 #include <cuda_bf16.h>
@@ -1017,6 +1018,8 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
     if (tid == 0) { tA = clock64(); g_chol_dbg[0] += t_diag; g_chol_dbg[1] += t_panel; g_chol_dbg[2] += t_trail; g_chol_dbg[3] += tA - t0; g_chol_dbg[4] += tA - t_begin; g_chol_dbg[5] += 1; }
 }
 
+#include "ba_tree.cuh"
+
 // ------------------------------------------------------------------ back-substitution + candidate point
 __global__ void __launch_bounds__(TPB) ba_update_kernel(BaDev d) {
     __shared__ double s_red[TPB / 32];
@@ -1159,6 +1162,10 @@ struct lvb_ba {
     int dimc = 0, n_pose_free = 0, n_vec3_free = 0, n_rho_free = 0;
     std::vector<int> canon;             // internal camera-system offset -> canonical (poses first, then vec3) offset
     DevBuf<int> chol_rmax, chol_cmin;   // envelope of S per 32-column block step
+    // multifrontal tree over the banded system (ba_tree.cuh); tree_levels == 0: single-CTA envelope Cholesky
+    DevBuf<Front> fronts; DevBuf<double> front_pool;
+    std::vector<int> level_first, level_count;
+    int tree_levels = 0; size_t tree_factor_smem = 0, tree_back_smem = 0;
     // device
     DevBuf<double> poses, vec3, rho, c_poses, c_vec3, c_rho;
     DevBuf<int> pose_off, vec3_off, rho_slot, lm_start, lm_fac;
@@ -1198,6 +1205,8 @@ static int init_tables() {
     LVB_CUDA(cudaMemcpyToSymbol(c_tri_a, a, sizeof(a)));
     LVB_CUDA(cudaMemcpyToSymbol(c_tri_b, b, sizeof(b)));
     LVB_CUDA(cudaFuncSetAttribute(ba_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    LVB_CUDA(cudaFuncSetAttribute(ba_front_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    LVB_CUDA(cudaFuncSetAttribute(ba_front_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (TPB * 31 + MAX_STAGE_POSES * 7 + 2) * 8));
     LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (TPB * 31 + MAX_STAGE_POSES * 7 + 2) * 8));
     LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel<0, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (MAX_STAGE_POSES * 7 + 2) * 8));
@@ -1217,12 +1226,56 @@ static void mark(struct lvb_ba* ba, const char* name);
 #define LAUNCH(ba, kernel, grid, block, smem, ...)                                        \
     do { if ((grid) > 0) { kernel<<<(grid), (block), (smem), (ba)->ctx->stream>>>(__VA_ARGS__); (ba)->ctx->launches++; mark(ba, #kernel); } } while (0)
 
-static std::vector<std::pair<const char*, cudaEvent_t>> g_marks;
-static bool g_timing = false;
-static void mark(lvb_ba* ba, const char* name) {
-    if (!g_timing) return;
-    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ba->ctx->stream); g_marks.push_back({name, e});
+// Separator tree of the banded reduced system (see ba_tree.cuh): complete binary tree with 2^D leaves, separators of width
+// w = band.  Leaves keep >= 2w unknowns so that a separator is coupled to nothing beyond its two neighbouring subtrees.
+static int build_front_tree(int n, int band, int max_leaves, std::vector<Front>& out, std::vector<int>& level_first, std::vector<int>& level_count,
+                            size_t& pool_doubles, int& max_panel_rows, int& max_nb) {
+    out.clear(); level_first.clear(); level_count.clear(); pool_doubles = 0; max_panel_rows = 0; max_nb = 0;
+    const int w = band;
+    int D = 0;
+    while ((1 << (D + 1)) <= max_leaves) {
+        const long long P = 1ll << (D + 1);
+        const long long leaf = ((long long)n - (P - 1) * w) / P;
+        if (leaf < 2ll * w || leaf < 64) break;
+        ++D;
+    }
+    if (D == 0) return 0;
+    struct Node { int o0, m, bL0, wL, bR0, wR, c0, c1, h; };
+    std::vector<Node> nodes;
+    std::function<int(int, int, int, int, int, int, int)> rec = [&](int a, int b, int depth, int bL0, int wL, int bR0, int wR) -> int {
+        if (depth == D) { nodes.push_back({a, b - a, bL0, wL, bR0, wR, -1, -1, 0}); return (int)nodes.size() - 1; }
+        const int s0 = a + (b - a - w) / 2;
+        const int c0 = rec(a, s0, depth + 1, bL0, wL, s0, w);
+        const int c1 = rec(s0 + w, b, depth + 1, s0, w, bR0, wR);
+        nodes.push_back({s0, w, bL0, wL, bR0, wR, c0, c1, D - depth});
+        return (int)nodes.size() - 1;
+    };
+    rec(0, n, 0, 0, 0, 0, 0);
+    std::vector<int> ids(nodes.size()), new_id(nodes.size());
+    for (size_t i = 0; i < ids.size(); ++i) ids[i] = (int)i;
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return nodes[a].h != nodes[b].h ? nodes[a].h < nodes[b].h : nodes[a].o0 < nodes[b].o0; });
+    for (size_t i = 0; i < ids.size(); ++i) new_id[ids[i]] = (int)i;
+    level_first.assign(D + 1, 0); level_count.assign(D + 1, 0);
+    for (size_t i = 0; i < ids.size(); ++i) {
+        const Node& nd = nodes[ids[i]];
+        Front F;
+        F.o0 = nd.o0; F.m = nd.m; F.wL = nd.wL; F.wR = nd.wR; F.bL0 = nd.bL0; F.bR0 = nd.bR0;
+        F.actR = nd.h == 0 ? std::max(0, nd.m - band) : 0;
+        F.child0 = nd.c0 < 0 ? -1 : new_id[nd.c0]; F.child1 = nd.c1 < 0 ? -1 : new_id[nd.c1];
+        F.nb = nd.wL + nd.wR; F.ld = (nd.m + F.nb + 1) & ~1;
+        F.bd = (long long)pool_doubles;
+        pool_doubles += ((size_t)(F.nb + 1) * F.ld + 1) & ~(size_t)1;
+        if (level_count[nd.h] == 0) level_first[nd.h] = (int)i;
+        level_count[nd.h]++;
+        max_nb = std::max(max_nb, F.nb);
+        max_panel_rows = std::max(max_panel_rows, std::min(nd.m, band) + F.nb + 1);
+        out.push_back(F);
+    }
+    return D + 1;
 }
+
+static void mark(lvb_ba* ba, const char* name) { lvb::timing_mark(ba->ctx->stream, name); }
+#define g_timing lvb::g_timing
 
 static int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
@@ -1527,10 +1580,25 @@ int lvb_ba_finalize(lvb_ba* ba) {
     else              { ba->srow = band; ba->soff = band; ba->nS = (size_t)ba->dimc * (size_t)(band + 1); }
     ba->band = band; ba->panel_rows = panel_rows;
     ba->chol_smem = (size_t)(32 * 33 + 32 + 128 + std::max((panel_rows + 2) * 34, (CHOL_T / 32) * 32)) * 8;      // panel, later the backward partial sums
-    if (ba->solvable && (ba->chol_smem > 227 * 1024 - 256 || ba->nS > ((size_t)3 << 30))) {
+    // banded systems: split the chain by a separator tree when the band leaves room for at least two leaves (ba_tree.cuh)
+    ba->tree_levels = 0;
+    std::vector<Front> h_fronts;
+    size_t pool_doubles = 0;
+    {
+        static const bool no_tree = getenv("LVB_NO_TREE") && getenv("LVB_NO_TREE")[0] == '1';
+        int rows = 0, mnb = 0, max_leaves = 1;
+        while (max_leaves * 2 <= std::max(2, ctx->sm_count)) max_leaves *= 2;
+        if (ba->solvable && !dense_layout && !no_tree) {
+            const int lv = build_front_tree(ba->dimc, band, max_leaves, h_fronts, ba->level_first, ba->level_count, pool_doubles, rows, mnb);
+            const size_t fs = (size_t)(32 * 33 + 32 + 128 + (rows + 2) * 34) * 8, bs_ = (size_t)(((mnb + 1) & ~1) + (CHOL_T / 32) * 32) * 8;
+            if (lv > 0 && fs <= 227 * 1024 - 256 && pool_doubles < ((size_t)1 << 31)) { ba->tree_levels = lv; ba->tree_factor_smem = fs; ba->tree_back_smem = bs_; }
+        }
+    }
+    if (ba->solvable && ba->tree_levels == 0 && (ba->chol_smem > 227 * 1024 - 256 || ba->nS > ((size_t)3 << 30))) {
         ba->solvable = false;
         ba->unsolvable_why = "the envelope of the reduced camera system is too wide for the direct solver of this build";
     }
+    if (ba->solvable && ba->nS > ((size_t)3 << 30)) { ba->solvable = false; ba->unsolvable_why = "the banded reduced camera system exceeds 24 GB"; }
     if (!ba->solvable) ba->nS = 1;
     if (sw_group.empty()) { sw_group.push_back(0); sw_lm.assign(32, -1); }
     if (grp_ns.empty()) { grp_ns.push_back(0); grp_off.assign(MAX_TRACK, -1); }
@@ -1554,6 +1622,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
     LVB_TRY(ba->grp_off.upload(grp_off.data(), grp_off.size(), s));
     LVB_TRY(ba->chol_rmax.upload(chol_rmax.data(), chol_rmax.size(), s));
     LVB_TRY(ba->chol_cmin.upload(chol_cmin.data(), chol_cmin.size(), s));
+    if (ba->tree_levels > 0) { LVB_TRY(ba->fronts.upload(h_fronts.data(), h_fronts.size(), s)); LVB_TRY(ba->front_pool.ensure(pool_doubles)); }
     // tensor-core Schur operands: compact pose dimensions (<= 128) and the zero-initialised split-bf16 U^T tiles
     ba->tc_ok = ba->solvable && dense_layout && 6 * npf <= 128 && npf > 0 && ctx->world == 1;
     {
@@ -1788,10 +1857,29 @@ static int launch_linearize_and_reduce(lvb_ba* ba, bool standalone) {
     return check_launch("linearize");
 }
 
+// rhs <- S^-1 rhs (+ the LM pre-check): multifrontal tree over the banded system, or the single-CTA envelope Cholesky
+static int launch_reduced_solve(lvb_ba* ba) {
+    BaDev& d = ba->dev;
+    lvb_ctx* ctx = ba->ctx;
+    if (ba->tree_levels > 0) {
+        // multifrontal tree: leaves (all SMs) -> ... -> root, then the back-substitution root -> leaves; 2 (levels + 1) launches
+        const Front* fr = ba->fronts.p;
+        LAUNCH(ba, lm_control_pre_kernel, 1, 1, 0, d.st);
+        ba_front_init_kernel<<<dim3(16, ba->level_count[0]), 256, 0, ctx->stream>>>(fr, ba->level_count[0], d.S, d.rhs, ba->front_pool.p, d.srow, d.soff, ba->band, d.st);
+        ctx->launches++; mark(ba, "ba_front_init_kernel");
+        for (int l = 0; l < ba->tree_levels; ++l)
+            LAUNCH(ba, ba_front_factor_kernel, ba->level_count[l], CHOL_T, ba->tree_factor_smem, fr, ba->level_first[l], d.S, d.rhs, ba->front_pool.p, d.srow, d.soff, ba->band, ba->chol_invd.p, d.st);
+        for (int l = ba->tree_levels - 1; l >= 0; --l)
+            LAUNCH(ba, ba_front_backward_kernel, ba->level_count[l], CHOL_T, ba->tree_back_smem, fr, ba->level_first[l], d.S, d.rhs, ba->front_pool.p, d.srow, d.soff, ba->band, ba->chol_invd.p, d.st);
+    } else
+    LAUNCH(ba, ba_cholesky_kernel, 1, CHOL_T, ba->chol_smem, d.S, d.rhs, d.dimc, d.srow, d.soff, ba->chol_invd.p, d.st, 1, ba->chol_rmax.p, ba->chol_cmin.p);
+    return LVB_OK;
+}
+
 static int launch_step(lvb_ba* ba) {
     BaDev& d = ba->dev;
     lvb_ctx* ctx = ba->ctx;
-    LAUNCH(ba, ba_cholesky_kernel, 1, CHOL_T, ba->chol_smem, d.S, d.rhs, d.dimc, d.srow, d.soff, ba->chol_invd.p, d.st, 1, ba->chol_rmax.p, ba->chol_cmin.p);
+    LVB_TRY(launch_reduced_solve(ba));
     LAUNCH(ba, ba_update_kernel, nblk((size_t)d.n_poses + d.n_vec3 + d.n_rho, TPB), TPB, 0, d);
     const bool fork = use_side_branch(ba);
     if (fork) { LVB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream)); LVB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0)); }
@@ -1875,6 +1963,7 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
     cudaStream_t s = ba->ctx->stream;
     LmState h;
     memset(&h, 0, sizeof(h));
+    mark(ba, "begin");
     LVB_TRY(launch_clear(ba));
     // The pass is a fixed sequence of launches whose kernels all read their control flags from the device state,
     // so it is captured once into a CUDA graph and replayed; the host looks at the state only every
@@ -1941,20 +2030,61 @@ int lvb_ba_set_schur_mode(lvb_ba* ba, int mode) {
     return LVB_OK;
 }
 
-LVB_API int lvb_debug_timing(int enable) {
-    if (!enable && g_timing) {
-        cudaDeviceSynchronize();
-        for (size_t i = 1; i < g_marks.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, g_marks[i - 1].second, g_marks[i].second); printf("%-40s %8.2f us\n", g_marks[i].first, ms * 1e3); }
-        for (auto& m : g_marks) cudaEventDestroy(m.second);
-        g_marks.clear();
-    }
-    g_timing = enable != 0;
-    return LVB_OK;
-}
-
 LVB_API int lvb_debug_cholesky_clocks(long long out[8], int reset) {
     LVB_CUDA(cudaMemcpyFromSymbol(out, g_chol_dbg, 8 * sizeof(long long)));
     if (reset) { long long z[8] = {0}; LVB_CUDA(cudaMemcpyToSymbol(g_chol_dbg, z, sizeof(z))); }
+    return LVB_OK;
+}
+
+// Direct access to the reduced-system solver for its own parity test (tests/test_gpu_band_solver.py): solves S x = b for a
+// symmetric positive definite band matrix given as n rows of (band + 1) entries (row i: columns i - band .. i; the true half
+// bandwidth must be <= band - 31, the block-granular slack the envelope kernel needs).  use_tree = 0 forces the single-CTA kernel.
+LVB_API int lvb_debug_band_solve(lvb_ctx* ctx, int n, int band, const double* S_band, const double* b, double* x, int use_tree, int* levels_out) {
+    if (!ctx || n <= 0 || band < 31 || !S_band || !b || !x) { set_error("bad arguments"); return LVB_ERR_INVALID; }
+    LVB_CUDA(cudaSetDevice(ctx->device)); lvb::g_alloc_stream = ctx->stream;
+    LVB_TRY(init_tables());
+    lvb_ba ba;
+    ba.ctx = ctx;
+    cudaStream_t s = ctx->stream;
+    ba.dimc = n; ba.band = band; ba.srow = band; ba.soff = band; ba.nS = (size_t)n * (band + 1);
+    LVB_TRY(ba.arena.ensure(ba.nS + n));
+    LVB_CUDA(cudaMemcpyAsync(ba.arena.p, S_band, ba.nS * sizeof(double), cudaMemcpyHostToDevice, s));
+    LVB_CUDA(cudaMemcpyAsync(ba.arena.p + ba.nS, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    LVB_TRY(ba.chol_invd.ensure(n + 32));
+    LVB_TRY(ba.st.ensure(1));
+    lvb_solve_options opt; lvb_default_options(&opt);
+    LmState h; lm_init(h, opt);
+    const double one = 1.0; memcpy(&h.grad_max_bits, &one, sizeof(double));        // not converged: the pre-check lets the solve run
+    LVB_CUDA(cudaMemcpyAsync(ba.st.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    const int nstep = (n + 31) / 32;
+    std::vector<int> rmax(nstep + 2, 0), cmin(nstep + 2, 0);
+    int panel_rows = 2;
+    for (int st = 0; st < nstep; ++st) {
+        const int kb = st * 32, bs = std::min(32, n - kb);
+        rmax[st] = std::min(n - 1, kb + band); cmin[st] = std::max(0, kb + bs - 1 - band);
+        panel_rows = std::max(panel_rows, rmax[st] - (kb + bs) + 2);
+    }
+    LVB_TRY(ba.chol_rmax.upload(rmax.data(), rmax.size(), s)); LVB_TRY(ba.chol_cmin.upload(cmin.data(), cmin.size(), s));
+    ba.chol_smem = (size_t)(32 * 33 + 32 + 128 + std::max((panel_rows + 2) * 34, (CHOL_T / 32) * 32)) * 8;
+    std::vector<Front> fr; size_t pool = 0; int rows = 0, mnb = 0, max_leaves = 1;
+    while (max_leaves * 2 <= std::max(2, ctx->sm_count)) max_leaves *= 2;
+    ba.tree_levels = 0;
+    if (use_tree) {
+        const int lv = build_front_tree(n, band, max_leaves, fr, ba.level_first, ba.level_count, pool, rows, mnb);
+        ba.tree_factor_smem = (size_t)(32 * 33 + 32 + 128 + (rows + 2) * 34) * 8; ba.tree_back_smem = (size_t)(((mnb + 1) & ~1) + (CHOL_T / 32) * 32) * 8;
+        if (lv > 0 && ba.tree_factor_smem <= 227 * 1024 - 256) { ba.tree_levels = lv; LVB_TRY(ba.fronts.upload(fr.data(), fr.size(), s)); LVB_TRY(ba.front_pool.ensure(pool)); }
+    }
+    if (levels_out) *levels_out = ba.tree_levels;
+    if (ba.tree_levels == 0 && ba.chol_smem > 227 * 1024 - 256) { set_error("band too wide for the single-CTA kernel"); return LVB_ERR_UNSUPPORTED; }
+    BaDev& d = ba.dev;
+    memset(&d, 0, sizeof(d));
+    d.dimc = n; d.srow = ba.srow; d.soff = ba.soff; d.nS = ba.nS; d.S = ba.arena.p; d.rhs = ba.arena.p + ba.nS; d.st = ba.st.p;
+    LVB_TRY(launch_reduced_solve(&ba));
+    LVB_TRY(check_launch("band solve"));
+    LVB_CUDA(cudaMemcpyAsync(x, d.rhs, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    LVB_CUDA(cudaMemcpyAsync(&h, ba.st.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    LVB_CUDA(cudaStreamSynchronize(s));
+    if (h.solve_fail) { set_error("band solve: non-positive pivot"); return LVB_ERR_NUMERIC; }
     return LVB_OK;
 }
 

@@ -1,0 +1,298 @@
+// ba_tree.cuh -- multifrontal (nested-dissection) Cholesky of the banded reduced camera system: many SMs instead of one.
+//
+// What it replaces: SuiteSparse's supernodal Cholesky behind SPARSE_SCHUR (/root/reference/src/lvio_fusion/src/backend.cpp:207).
+// The reduced system of a trajectory is block-banded (keyframe-interleaved ordering, half bandwidth B): a single CTA walking the
+// band is a chain of dimc dependent pivots (42 ms at 75 000 unknowns).  Any w >= B consecutive unknowns separate the chain, so
+// the unknowns are split by a complete binary tree of separators:
+//
+//      [ leaf 0 | s | leaf 1 | S | leaf 2 | s | leaf 3 ]          s: level-1 separators, S: root
+//
+// Every tree node owns a *front*: its own unknowns (leaf: a banded segment, internal node: a dense separator block) followed by
+// the <= 2 ancestor separators that bound its subtree (the border) and the right-hand side as one more row.  A front is
+// eliminated by ONE CTA with a partial Cholesky over its own columns -- the blocked right-looking kernel of ba_cholesky_kernel
+// with the border rows riding along in every panel -- which leaves  L_own,  W = L_own^-1 A_own,border  (in the border rows),
+// y = L_own^-1 b_own  and the update  -W^T W  of the border x border block.  All fronts of a level run concurrently (grid = number
+// of fronts), a parent extend-adds its two children's updates in its prologue; log2(P) + 1 launches factor the whole system and
+// the same number of launches, root first, back-substitute.  Own x own blocks are factored in place in the banded storage of S
+// (a separator of width w = B fits inside the band), border rows live in a pool.
+#pragma once
+
+struct Front {
+    int o0, m;              // own unknowns [o0, o0 + m)
+    int wL, wR;             // widths of the bounding ancestor separators (0 at the ends of the trajectory)
+    int bL0, bR0;           // their first unknowns
+    int actR;               // own column from which the right-border rows can be non-zero (leaves: m - band; internal: 0)
+    int child0, child1;     // front ids, -1 for leaves
+    int ld, nb;             // border array: (nb + 1) rows (borders, then the rhs row) x ld (= m own columns + nb border columns)
+    long long bd;           // offset of the border array in the pool (doubles)
+};
+
+#define SG(i_, j_) S[(size_t)(i_) * (size_t)srow + (size_t)(j_) + (size_t)soff]
+
+// Leaves: zero the border arrays and gather the couplings with the bounding separators out of the band (the left one
+// transposed: in the front the separator comes after the segment) and the right-hand side.  Grid-wide, HBM-bound.
+__global__ void __launch_bounds__(256) ba_front_init_kernel(const Front* __restrict__ fr, int n_leaves, const double* __restrict__ S, const double* __restrict__ rhs,
+                                                             double* __restrict__ pool, long long srow, long long soff, int band, const LmState* st) {
+    if (st->done) return;
+    for (int f = blockIdx.y; f < n_leaves; f += gridDim.y) {
+        const Front F = fr[f];
+        double* Bd = pool + F.bd;
+        const size_t total = (size_t)(F.nb + 1) * F.ld;
+        for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+            const int q = (int)(e / F.ld), c = (int)(e - (size_t)q * F.ld);
+            double v = 0.0;
+            if (c < F.m) {
+                if (q < F.wL) { const int gi = F.o0 + c, gj = F.bL0 + q; if (gi - gj <= band) v = SG(gi, gj); }
+                else if (q < F.nb) { const int gi = F.bR0 + (q - F.wL), gj = F.o0 + c; if (gi - gj <= band) v = SG(gi, gj); }
+                else v = rhs[F.o0 + c];
+            }
+            Bd[e] = v;
+        }
+    }
+}
+
+// One CTA per front of a level.  Shared memory: D (32 x 33), invd (32), Lc (2 x 64), P (panel rows x 34).
+__global__ void __launch_bounds__(CHOL_T) ba_front_factor_kernel(const Front* __restrict__ fr, int first, double* __restrict__ S, const double* __restrict__ rhs,
+                                                                  double* __restrict__ pool, long long srow, long long soff, int band,
+                                                                  double* __restrict__ invd_g, LmState* st) {
+    if (st->done) return;
+    extern __shared__ __align__(16) double sm[];
+    double* D = sm;                    // 32 x 33   diagonal block of L
+    double* invd = sm + 32 * 33;       // 32        reciprocals of diag(L) of the current block
+    double* Lc = invd + 32;            // 2 x 64    column of the diagonal block being factored (double buffered broadcast)
+    double* P = Lc + 128;              // rows x 34 panel
+    __shared__ int fail;
+    const Front F = fr[first + blockIdx.x];
+    const int n = F.m, nb = F.nb, ld = F.ld;
+    double* Bd = pool + F.bd;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    if (tid == 0) fail = 0;
+    if (F.child0 >= 0) {
+        // ---- internal front: own part of the rhs, zero elsewhere, then extend-add the two children's update matrices
+        const int total = (nb + 1) * ld;
+        for (int e = tid; e < total; e += nt) { const int q = e / ld, c = e - q * ld; Bd[e] = (q == nb && c < n) ? rhs[F.o0 + c] : 0.0; }
+        __syncthreads();
+        for (int ch = 0; ch < 2; ++ch) {
+            const Front C = fr[ch ? F.child1 : F.child0];
+            const double* Bc = pool + C.bd;
+            // child border id t -> this front: left child: [0, wL_c) = my left border, the rest = my own unknowns;
+            //                                    right child: [0, wL_c) = my own unknowns, the rest = my right border
+            const int cn = C.nb;
+            for (int e = tid; e < (cn + 1) * cn; e += nt) {
+                const int r = e / cn, c = e - r * cn;
+                if (c > r) continue;
+                const double u = Bc[(size_t)r * C.ld + C.m + c];
+                if (u == 0.0) continue;
+                bool c_own; int c_idx;
+                if (ch == 0) { c_own = c >= C.wL; c_idx = c_own ? c - C.wL : c; } else { c_own = c < C.wL; c_idx = c_own ? c : F.wL + (c - C.wL); }
+                if (r == cn) { Bd[(size_t)nb * ld + (c_own ? c_idx : n + c_idx)] += u; continue; }
+                bool r_own; int r_idx;
+                if (ch == 0) { r_own = r >= C.wL; r_idx = r_own ? r - C.wL : r; } else { r_own = r < C.wL; r_idx = r_own ? r : F.wL + (r - C.wL); }
+                if (r_own && c_own) SG(F.o0 + r_idx, F.o0 + c_idx) += u;              // r_idx >= c_idx: the maps are monotone
+                else if (r_own) Bd[(size_t)c_idx * ld + r_idx] += u;                   // A(own, left border): stored transposed
+                else if (c_own) Bd[(size_t)r_idx * ld + c_idx] += u;                   // A(right border, own)
+                else Bd[(size_t)r_idx * ld + n + c_idx] += u;                          // border x border
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // Software-pipelined over the 32-column block steps with look-ahead (see ba_cholesky_kernel): while warps 1.. finish the
+    // trailing update of step kb, warp 0 updates the next diagonal block first (tile 0) and factors it.
+    for (int kb = -32; kb < n; kb += 32) {
+        const int bs = min(32, n - kb);
+        if (kb >= 0) {
+            // ---- panel rows: own rows below the block inside the band | active border rows | rhs row
+            const int r1 = kb + bs;
+            const int nr1 = max(0, min(n - 1, kb + band) - r1 + 1);
+            const int nbp = F.wL + ((r1 > F.actR) ? F.wR : 0);
+            const int m = nr1 + nbp + 1;
+            // row_base(p)[c] = entry of panel row p in own column c (c >= n: border column c - n); col_of(p) = its own column index
+#define ROW_BASE(p_) (((p_) < nr1) ? (&SG(F.o0 + r1 + (p_), F.o0)) : (Bd + (size_t)((((p_) - nr1) < nbp) ? ((p_) - nr1) : nb) * ld))
+#define COL_OF(p_) (((p_) < nr1) ? (r1 + (p_)) : (n + ((((p_) - nr1) < nbp) ? ((p_) - nr1) : nb)))
+            for (int rr = tid; rr < m; rr += nt) {
+                double* src = ROW_BASE(rr) + kb;
+                double a[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] = (j < bs) ? src[j] : 0.0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    a[j] *= invd[j];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) if (k > j) a[k] -= a[j] * D[k * 33 + j];
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { P[rr * 34 + j] = a[j]; if (j < bs) src[j] = a[j]; }
+            }
+            __syncthreads();
+            // ---- trailing update A22 -= P P^T on the lower triangle: one warp per 32 x 32 tile, 4 x 8 register micro-tiles
+            const int ntile = (m + 31) >> 5;
+            const int total = ntile * (ntile + 1) / 2;
+            for (int t = (warp == 0) ? 0 : warp; t < total; t += (warp == 0) ? total : (nw - 1)) {
+                int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+                while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+                while (ti * (ti + 1) / 2 > t) --ti;
+                const int tj = t - ti * (ti + 1) / 2;
+                const int ry = lane >> 2, cx = lane & 3;
+                const int r0 = ti * 32 + ry, c0 = tj * 32 + cx;
+                double acc[4][8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+                const double2* rp[4]; const double2* cp[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rp[i] = reinterpret_cast<const double2*>(P + (size_t)min(r0 + 8 * i, m - 1) * 34);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cp[j] = reinterpret_cast<const double2*>(P + (size_t)min(c0 + 4 * j, m - 1) * 34);
+#pragma unroll 2
+                for (int k = 0; k < 16; ++k) {
+                    double2 rv[4], cv[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) rv[i] = rp[i][k];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) cv[j] = cp[j][k];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { acc[i][j] += rv[i].x * cv[j].x; acc[i][j] += rv[i].y * cv[j].y; }
+                }
+                int colx[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const int jp = min(c0 + 4 * j, m - 1); colx[j] = COL_OF(jp); }
+                double cur[4][8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ip = min(r0 + 8 * i, m - 1);
+                    const double* src = ROW_BASE(ip);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const int jp = c0 + 4 * j; cur[i][j] = (r0 + 8 * i < m && jp < m - 1 && jp <= ip) ? src[colx[j]] : 0.0; }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ip = r0 + 8 * i;
+                    if (ip >= m) continue;
+                    double* dst = ROW_BASE(ip);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const int jp = c0 + 4 * j; if (jp < m - 1 && jp <= ip) dst[colx[j]] = cur[i][j] - acc[i][j]; }
+                }
+            }
+#undef ROW_BASE
+#undef COL_OF
+        }
+        const int kn = kb + 32, bn = min(32, n - kn);
+        // ---- diagonal block kn: warp 0 holds one row per lane in registers and factors it with shuffles (4 groups of 8 columns)
+        if (kn < n) {
+            __syncwarp();
+            if (warp == 0) {
+                double a[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] = (lane < bn && j <= lane) ? SG(F.o0 + kn + lane, F.o0 + kn + j) : ((j == lane) ? 1.0 : 0.0);
+                int bad = 0;
+                double d0 = __shfl_sync(0xffffffffu, a[0], 0);
+                if (!(d0 > 0.0)) { bad = 1; d0 = 1.0; }
+                double inv = rsqrt(d0);
+#pragma unroll 1
+                for (int c0 = 0; c0 < 32; c0 += 8) {
+                    const int rel = lane - c0;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int j = c0 + jj;
+                        if (rel >= jj) a[jj] *= inv;
+                        if (rel == jj) { invd[j] = inv; invd_g[F.o0 + kn + j] = inv; }
+                        const double lj = (rel >= jj) ? a[jj] : 0.0;
+                        D[lane * 33 + j] = lj;
+                        if (lane < bn && rel >= jj && j < bn) SG(F.o0 + kn + lane, F.o0 + kn + j) = lj;
+                        double* buf = Lc + (jj & 1) * 64;
+                        buf[lane] = a[jj];
+                        double inv_next = 1.0;
+                        if (j + 1 < 32) {
+                            double dn = __shfl_sync(0xffffffffu, a[jj + 1] - a[jj] * a[jj], j + 1);
+                            if (!(dn > 0.0)) { bad = 1; dn = 1.0; }
+                            inv_next = rsqrt(dn);
+                        }
+                        __syncwarp();
+                        const double2* bp = reinterpret_cast<const double2*>(buf + c0);
+#pragma unroll
+                        for (int p = 0; p < 16; ++p) {
+                            if (2 * p + 1 > jj) {
+                                const double2 v = bp[p];
+                                if (2 * p > jj && rel >= 2 * p) a[2 * p] -= a[jj] * v.x;
+                                if (rel >= 2 * p + 1) a[2 * p + 1] -= a[jj] * v.y;
+                            }
+                        }
+                        inv = inv_next;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 24; ++r) a[r] = a[r + 8];
+#pragma unroll
+                    for (int r = 24; r < 32; ++r) a[r] = 0.0;
+                }
+                if (bad && lane == 0) fail = 1;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && fail) st->solve_fail = 1;
+}
+
+// Back-substitution of one level (root level first): x_own = L_own^-T (y - W x_border), x in place in `x` (the rhs vector).
+// Shared memory: xb (nb) + part (warps x 32).
+__global__ void __launch_bounds__(CHOL_T) ba_front_backward_kernel(const Front* __restrict__ fr, int first, const double* __restrict__ S, double* __restrict__ x,
+                                                                    const double* __restrict__ pool, long long srow, long long soff, int band,
+                                                                    const double* __restrict__ invd_g, const LmState* st) {
+    if (st->done) return;
+    extern __shared__ __align__(16) double sm[];
+    const Front F = fr[first + blockIdx.x];
+    const int n = F.m, nb = F.nb, ld = F.ld;
+    const double* Bd = pool + F.bd;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    double* xb = sm;
+    double* part = sm + ((nb + 1) & ~1);
+    for (int q = tid; q < nb; q += nt) xb[q] = x[q < F.wL ? F.bL0 + q : F.bR0 + (q - F.wL)];
+    __syncthreads();
+    const int last = ((n - 1) / 32) * 32;
+    for (int kb = last; kb >= 0; kb -= 32) {
+        const int bs = min(32, n - kb);
+        const int rend = min(n - 1, kb + band);
+        const int nbq = (kb + bs > F.actR) ? nb : F.wL;          // right-border rows are zero left of actR
+        double col[32];
+        double t = 0.0, my_inv = 1.0;
+        if (warp == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) col[i] = (i < bs && lane < bs && i >= lane) ? SG(F.o0 + kb + i, F.o0 + kb + lane) : 0.0;
+            if (lane < bs) { t = Bd[(size_t)nb * ld + kb + lane]; my_inv = invd_g[F.o0 + kb + lane]; }
+        }
+        double acc = 0.0;
+        if (lane < bs) {
+            for (int r0 = kb + bs + warp; r0 <= rend; r0 += 16 * nw) {
+                double lv[16], xv[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) { const int r = r0 + u * nw; const bool ok = r <= rend; lv[u] = ok ? SG(F.o0 + r, F.o0 + kb + lane) : 0.0; xv[u] = ok ? x[F.o0 + r] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) acc += lv[u] * xv[u];
+            }
+            for (int q0 = warp; q0 < nbq; q0 += 16 * nw) {
+                double lv[16], xv[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) { const int q = q0 + u * nw; const bool ok = q < nbq; lv[u] = ok ? Bd[(size_t)q * ld + kb + lane] : 0.0; xv[u] = ok ? xb[q] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) acc += lv[u] * xv[u];
+            }
+        }
+        part[warp * 32 + lane] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            for (int w = 0; w < nw; ++w) t -= part[w * 32 + lane];
+#pragma unroll
+            for (int j = 31; j >= 0; --j) {
+                const double xj = __shfl_sync(0xffffffffu, t * my_inv, j);
+                if (lane == j) t = xj;
+                else if (lane < j) t -= col[j] * xj;
+            }
+            if (lane < bs) x[F.o0 + kb + lane] = t;
+        }
+        __syncthreads();
+    }
+}
+#undef SG

@@ -26,6 +26,13 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return LVB_ERR_CUDA;
 }
 
+bool g_timing = false;
+static std::vector<std::pair<const char*, cudaEvent_t>> g_marks;
+void timing_mark(cudaStream_t s, const char* name) {
+    if (!g_timing) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); g_marks.push_back({name, e});
+}
+
 // ---- NCCL through dlopen ---------------------------------------------------------------
 struct NcclId { char internal[128]; };
 typedef int (*fn_get_unique_id)(NcclId*);
@@ -179,10 +186,12 @@ int comm_allreduce_sum_f64(lvb_ctx* ctx, double* buf, size_t count) {
         ctx->launches++;
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("p2p all-reduce launch failed: %s", cudaGetErrorString(e)); return LVB_ERR_CUDA; }
+        timing_mark(ctx->stream, "p2p_allreduce_kernel");
         return LVB_OK;
     }
     const int rc = g_nccl.all_reduce(buf, buf, count, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->comm, ctx->stream);
     if (rc != 0) return nccl_fail(rc, "ncclAllReduce");
+    timing_mark(ctx->stream, "ncclAllReduce");
     return LVB_OK;
 }
 
@@ -302,6 +311,35 @@ long long lvb_launch_count(lvb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int lvb_ctx_synchronize(lvb_ctx* ctx) {
     if (!ctx) return LVB_ERR_INVALID;
     LVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LVB_OK;
+}
+
+int lvb_debug_timing(int enable) {
+    if (!enable && g_timing) {
+        cudaDeviceSynchronize();
+        for (size_t i = 1; i < g_marks.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, g_marks[i - 1].second, g_marks[i].second); printf("%-40s %8.2f us\n", g_marks[i].first, ms * 1e3); }
+        for (auto& m : g_marks) cudaEventDestroy(m.second);
+        g_marks.clear();
+    }
+    g_timing = enable != 0;
+    return LVB_OK;
+}
+
+// Same as lvb_debug_timing(0), but the per-kernel times ("name microseconds" per line, in launch order) go into `out`
+// (bench.py sums them by kernel: CUDA events on the launching stream around every kernel of the pass).
+int lvb_debug_timing_report(char* out, int cap) {
+    if (!out || cap <= 0) { set_error("bad buffer"); return LVB_ERR_INVALID; }
+    cudaDeviceSynchronize();
+    int pos = 0; out[0] = 0;
+    for (size_t i = 1; i < g_marks.size(); ++i) {
+        float ms = 0; cudaEventElapsedTime(&ms, g_marks[i - 1].second, g_marks[i].second);
+        const int w = snprintf(out + pos, (size_t)(cap - pos), "%s %.3f\n", g_marks[i].first, ms * 1e3);
+        if (w < 0 || w >= cap - pos) break;
+        pos += w;
+    }
+    for (auto& m : g_marks) cudaEventDestroy(m.second);
+    g_marks.clear();
+    g_timing = false;
     return LVB_OK;
 }
 

@@ -369,7 +369,7 @@ struct lvb_icp {
 };
 
 #define ILAUNCH(h, kernel, grid, block, ...)                                              \
-    do { if ((grid) > 0) { kernel<<<(grid), (block), 0, (h)->ctx->stream>>>(__VA_ARGS__); (h)->ctx->launches++; } } while (0)
+    do { if ((grid) > 0) { kernel<<<(grid), (block), 0, (h)->ctx->stream>>>(__VA_ARGS__); (h)->ctx->launches++; lvb::timing_mark((h)->ctx->stream, #kernel); } } while (0)
 
 static inline int inblk(size_t n, int per) { return (int)((n + per - 1) / per); }
 static int icheck(const char* what) {
@@ -551,6 +551,7 @@ int lvb_icp_scan_to_map(lvb_icp* h, int mode, const void* scan, int n, int strid
     lvb_solve_options opt;
     if (options) opt = *options; else lvb_default_options(&opt);
     IcpDev d;
+    lvb::timing_mark(h->ctx->stream, "begin");
     LVB_TRY(upload_scan(h, scan, n, stride, frame_pose, h->cell_size * h->cell_size, dist_thr, d));
     if ((double)h->cell_size * h->cell_size * (1.0 + 1e-6) < dist_thr) {
         set_error("dist_thr %.6g exceeds the map's cell_size^2 %.6g", dist_thr, (double)h->cell_size * h->cell_size); return LVB_ERR_INVALID; }

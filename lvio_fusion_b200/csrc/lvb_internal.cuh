@@ -49,6 +49,9 @@ int comm_allreduce_sum_f64(lvb_ctx* ctx, double* buf, size_t count);   // no-op 
 bool comm_graph_safe(const lvb_ctx* ctx, size_t max_count);          // every all-reduce of <= max_count doubles is a capturable kernel
 int comm_allreduce_min_i32(lvb_ctx* ctx, int* buf, size_t count);      // device buffer, no-op when world == 1
 int comm_allreduce_max_i32(lvb_ctx* ctx, int* buf, size_t count);
+// per-kernel timing (lvb_debug_timing): a CUDA event on the launching stream after every kernel, named; off by default
+extern bool g_timing;
+void timing_mark(cudaStream_t s, const char* name);
 int comm_check(lvb_ctx* ctx);                                          // LVB_ERR_COMM when an in-kernel exchange timed out
 int comm_max_seconds(lvb_ctx* ctx, double* seconds);                   // collective: max over the ranks (no-op when world == 1)
 

@@ -82,18 +82,20 @@ def main():
         ok = all(checks.values())
         print("MULTIGPU", "OK" if ok else "FAIL", checks, "cost", s.final_cost, so.final_cost)
     dist.barrier()
-    # last, because it kills the communicator: a collective only rank 0 issues must surface as LVB_ERR_COMM with a message on
-    # rank 0 (bounded wait), not as a trap / SIGABRT
-    if os.environ.get("LVB_P2P_TIMEOUT_MS") and rank == 0 and os.environ.get("LVB_NO_P2P") != "1":
-        try:
-            backend.Problem.from_dict(ctx, synth.shard_ba_problem(d, rank, world)).solve(max_num_iterations=3)
-            print("MISMATCH not detected"); ok = False
-        except Exception as exc:
-            good = "timed out" in str(exc) or "NCCL" in str(exc)
-            print("MISMATCH", "reported" if good else "unexpected", str(exc)[:200]); ok = ok and good
-        os._exit(0 if ok else 1)            # NCCL cannot be shut down cleanly after a deliberate mismatch
-    if os.environ.get("LVB_P2P_TIMEOUT_MS"):
-        os._exit(0)
+    # last, because it kills the communicator: a solve only rank 0 starts (its in-kernel all-reduce never hears from the peer) must
+    # surface as LVB_ERR_COMM with a message after the bounded wait, not as a trap / SIGABRT or a hang
+    if os.environ.get("LVB_P2P_TIMEOUT_MS") and os.environ.get("LVB_NO_P2P") != "1":
+        pm = backend.Problem.from_dict(ctx, synth.shard_ba_problem(d, rank, world))       # collective, every rank
+        dist.barrier()
+        if rank == 0:
+            try:
+                pm.solve(max_num_iterations=3)
+                print("MISMATCH not detected"); ok = False
+            except Exception as exc:
+                good = "timed out" in str(exc)
+                print("MISMATCH", "reported" if good else "unexpected", str(exc)[:240]); ok = ok and good
+        sys.stdout.flush()
+        os._exit(0 if ok else 1)            # the communicator cannot be shut down cleanly after a deliberate mismatch
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

@@ -1,0 +1,65 @@
+"""The reduced-system solver on its own (SuiteSparse's role behind SPARSE_SCHUR, backend.cpp:207): random SPD band systems through
+the multifrontal separator tree (ba_tree.cuh) and through the single-CTA envelope kernel, against numpy's dense solve."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from lvio_fusion_b200 import _capi
+
+pytestmark = pytest.mark.gpu
+
+
+def _band_spd(n, true_band, rng):
+    a = np.zeros((n, n))
+    for i in range(n):
+        lo = max(0, i - true_band)
+        a[i, lo:i + 1] = rng.normal(size=i + 1 - lo)
+    s = a @ a.T
+    s[np.abs(np.subtract.outer(np.arange(n), np.arange(n))) > true_band] = 0.0
+    return s + 1e-3 * np.diag(np.diag(s)) + 1e-6 * np.eye(n)
+
+
+def _pack(s, band):
+    n = len(s)
+    out = np.zeros((n, band + 1))
+    for i in range(n):
+        lo = max(0, i - band)
+        out[i, band - (i - lo):] = s[i, lo:i + 1]
+    return out
+
+
+@pytest.mark.parametrize("n,true_band,expect_tree", [(150, 40, False), (700, 45, True), (1200, 59, True), (2500, 33, True), (4000, 75, True), (9000, 50, True)])
+def test_tree_and_single_cta_solve_match_numpy(lvb_ctx, n, true_band, expect_tree):
+    rng = np.random.default_rng(n)
+    s = _band_spd(n, true_band, rng)
+    b = rng.normal(size=n)
+    want = np.linalg.solve(s, b)
+    band = true_band + 31
+    packed = np.ascontiguousarray(_pack(s, band))
+    api = lvb_ctx.api
+    for use_tree in (1, 0):
+        x = np.zeros(n)
+        lv = C.c_int(-1)
+        api.check(api.debug_band_solve(lvb_ctx.h, n, band, packed.ctypes.data_as(_capi.c_double_p), b.ctypes.data_as(_capi.c_double_p),
+                                       x.ctypes.data_as(_capi.c_double_p), use_tree, C.byref(lv)), "debug_band_solve")
+        if use_tree:
+            assert (lv.value > 0) == expect_tree, lv.value
+        else:
+            assert lv.value == 0
+        err = np.max(np.abs(x - want)) / np.max(np.abs(want))
+        resid = np.max(np.abs(s @ x - b)) / np.max(np.abs(b))
+        assert err < 1e-8 and resid < 1e-9, (use_tree, lv.value, err, resid)
+
+
+def test_indefinite_system_is_reported(lvb_ctx):
+    n, true_band = 900, 40
+    rng = np.random.default_rng(5)
+    s = _band_spd(n, true_band, rng)
+    s[600, 600] = -1.0
+    band = true_band + 31
+    packed = np.ascontiguousarray(_pack(s, band)); b = np.ones(n); x = np.zeros(n)
+    api = lvb_ctx.api
+    rc = api.debug_band_solve(lvb_ctx.h, n, band, packed.ctypes.data_as(_capi.c_double_p), b.ctypes.data_as(_capi.c_double_p),
+                              x.ctypes.data_as(_capi.c_double_p), 1, None)
+    assert rc != 0 and b"pivot" in api.last_error()
