@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_front_factor_kernel(const Front* __
                     for (int jj = 0; jj < 8; ++jj) {
                         const int j = c0 + jj;
                         if (rel >= jj) a[jj] *= inv;
-                        if (rel == jj) { invd[j] = inv; invd_g[F.o0 + kn + j] = inv; }
+                        if (rel == jj) { invd[j] = inv; if (j < bn) invd_g[F.o0 + kn + j] = inv; }   // (beyond bn: the next front's unknowns)
                         const double lj = (rel >= jj) ? a[jj] : 0.0;
                         D[lane * 33 + j] = lj;
                         if (lane < bn && rel >= jj && j < bn) SG(F.o0 + kn + lane, F.o0 + kn + j) = lj;
