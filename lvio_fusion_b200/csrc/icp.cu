@@ -61,7 +61,9 @@ struct IcpDev {
     IcpState* st;
     int rank, world;
     const int* order;            // query visiting order (spatially sorted) or nullptr
-    int knn_variant;             // 0: x-run search (knn3_query_runs), 1: per-voxel Chebyshev rings (env LVB_KNN_VARIANT, A/B)
+    int knn_variant;             // 0: shared-memory tiles per coarse block (icp_tile_kernel), 1: per-query voxel rings only (env LVB_KNN_VARIANT)
+    const int* q_start;          // per coarse block (4 x 4 x 4 voxels): first position in `order` (counting sort), or nullptr
+    int cgx, cgy, cgz;
 };
 
 __device__ __forceinline__ float3 load_xyz(const unsigned char* base, int i, int stride) {
@@ -187,58 +189,6 @@ __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
     return b;
 }
 
-// Same result, far fewer probes: voxel keys are x-major, so the voxels [x0, x1] of one (y, z) row are ONE contiguous run of the
-// sorted map -- two cell_start loads and a linear scan instead of a probe (two dependent loads + box test) per voxel.
-//   phase 1: the 3 x 3 x 3 cube around the query's voxel as 9 runs -> an upper bound D on the third-best distance;
-//   phase 2: every (dy, dz) row whose slab distance is within D, scanned over the x extent D still allows (the part phase 1
-//            covered is skipped so no point is seen twice); D tightens while the rows are walked.
-// Every point with d2 <= the final third-best distance is visited (bounds are relaxed by 1 % + 1e-6 against float rounding, as
-// in scan_voxel), and best_insert orders by (d2, index), so the outcome does not depend on the visiting order: bit-identical.
-__device__ __forceinline__ void scan_run(const IcpDev& d, const Grid& g, float3 q, int x0, int x1, int iy, int iz, Best3& b) {
-    x0 = max(x0, 0); x1 = min(x1, g.gx - 1);
-    if (x0 > x1) return;
-    const int c = g.gx * (iy + g.gy * iz);
-    const int s = d.cell_start[c + x0], e = d.cell_start[c + x1 + 1];
-    for (int j = s; j < e; ++j) {
-        const float4 m = __ldg(&d.map[j]);
-        const float dx = __fsub_rn(m.x, q.x), dy = __fsub_rn(m.y, q.y), dz = __fsub_rn(m.z, q.z);
-        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        best_insert(b, d2, __float_as_int(m.w), j);
-    }
-}
-__device__ __forceinline__ float slab_dist(float v, float lo, float cell) { return fmaxf(fmaxf(lo - v, v - (lo + cell)), 0.0f); }
-
-__device__ __forceinline__ Best3 knn3_query_runs(const IcpDev& d, float3 q) {
-    Best3 b;
-    b.d[0] = b.d[1] = b.d[2] = INFINITY; b.i[0] = b.i[1] = b.i[2] = 0x7fffffff; b.p[0] = b.p[1] = b.p[2] = -1;
-    const Grid& g = d.g;
-    const int cx = cell_coord(q.x, g.minx, g.inv_cell), cy = cell_coord(q.y, g.miny, g.inv_cell), cz = cell_coord(q.z, g.minz, g.inv_cell);
-    for (int dz = -1; dz <= 1; ++dz) {
-        const int iz = cz + dz; if (iz < 0 || iz >= g.gz) continue;
-        for (int dy = -1; dy <= 1; ++dy) { const int iy = cy + dy; if (iy < 0 || iy >= g.gy) continue; scan_run(d, g, q, cx - 1, cx + 1, iy, iz, b); }
-    }
-    const int R = g.ring;
-    for (int dz = -R; dz <= R; ++dz) {
-        const int iz = cz + dz; if (iz < 0 || iz >= g.gz) continue;
-        const float ez = slab_dist(q.z, g.minz + iz * g.cell, g.cell), ez2 = ez * ez;
-        if (ez2 * 0.99f - 1e-6f > fminf(b.d[2], d.max_d2)) continue;
-        for (int dy = -R; dy <= R; ++dy) {
-            const int iy = cy + dy; if (iy < 0 || iy >= g.gy) continue;
-            const float ey = slab_dist(q.y, g.miny + iy * g.cell, g.cell);
-            const float row2 = (ey * ey + ez2) * 0.99f - 1e-6f;
-            const float D = fminf(b.d[2], d.max_d2);
-            if (row2 > D) continue;
-            // voxel cx + k (k > 0) lies at least (k - 1) * cell away in x: needed while (k - 1) * cell <= sqrt(D - row2)
-            const int X = min(R, (int)(sqrtf(D - row2) * 1.01f * g.inv_cell) + 1);
-            if (dz >= -1 && dz <= 1 && dy >= -1 && dy <= 1) {
-                if (X >= 2) { scan_run(d, g, q, cx - X, cx - 2, iy, iz, b); scan_run(d, g, q, cx + 2, cx + X, iy, iz, b); }
-            } else scan_run(d, g, q, cx - X, cx + X, iy, iz, b);
-        }
-    }
-    for (int j = 0; j < 3; ++j) if (!(b.d[j] <= d.max_d2)) { b.d[j] = INFINITY; b.i[j] = -1; b.p[j] = -1; }
-    return b;
-}
-
 // Coarse spatial key of a query (blocks of 4x4x4 voxels) so that the lanes of a warp walk the same voxel lists and
 // their 16-byte map loads hit the same L1 lines instead of 32 different L2 sectors.
 __global__ void icp_query_key_kernel(IcpDev d, int cgx, int cgy, int cgz, int* __restrict__ key, int* __restrict__ counts) {
@@ -265,7 +215,7 @@ __global__ void __launch_bounds__(ITPB) icp_knn_kernel(IcpDev d, int* __restrict
     if (t >= d.K) return;
     const int i = d.order ? d.order[t] : t;
     const float3 q = transform_f32(d.tf, load_xyz(d.scan, i, d.stride));
-    const Best3 b = d.knn_variant ? knn3_query(d, q) : knn3_query_runs(d, q);
+    const Best3 b = knn3_query(d, q);
     for (int j = 0; j < 3; ++j) { idx_out[3 * i + j] = b.i[j]; d2_out[3 * i + j] = b.d[j]; }
 }
 
@@ -275,7 +225,7 @@ __global__ void __launch_bounds__(ITPB) icp_associate_kernel(IcpDev d) {
     if (t >= d.K) return;
     const int i = d.order ? d.order[t] : t;
     const float3 q = transform_f32(d.tf, load_xyz(d.scan, i, d.stride));
-    const Best3 b = d.knn_variant ? knn3_query(d, q) : knn3_query_runs(d, q);
+    const Best3 b = knn3_query(d, q);
     int ok = 1;
     for (int j = 0; j < 3; ++j) if (!(b.i[j] >= 0 && b.i[j] < d.P && (double)b.d[j] < d.thr)) ok = 0;
     d.accepted[i] = (unsigned char)ok;
@@ -284,6 +234,87 @@ __global__ void __launch_bounds__(ITPB) icp_associate_kernel(IcpDev d) {
     const V3 n = plane_normal(v3(a.x, a.y, a.z), v3(bb.x, bb.y, bb.z), v3(c.x, c.y, c.z));
     d.pa[i] = a.x; d.pa[d.K + i] = a.y; d.pa[2 * d.K + i] = a.z;
     d.nrm[i] = n.x; d.nrm[d.K + i] = n.y; d.nrm[2 * (size_t)d.K + i] = n.z;
+}
+
+// K8, tiled: the queries are already sorted by coarse block (4 x 4 x 4 voxels = one search radius cubed).  Every neighbour within the
+// radius of a query of block B lies in B's 3 x 3 x 3 block neighbourhood = 12 x 12 voxel rows, and a voxel row is ONE contiguous run
+// of the x-major sorted map: the CTA gathers those <= 144 runs into shared memory with coalesced 16-byte loads (the map is read
+// from L2 / HBM once per block instead of once per query and voxel) and every query of the block then scans the staged points
+// with broadcast shared-memory reads.  Same float32 no-FMA distance, same (d2, index) order => bit-identical to the ring search,
+// which remains the path for blocks whose neighbourhood exceeds the staging area and for small scans.
+enum { TILE_T = 128, TILE_CAP = 7168, TILE_ROWS = 144 };      // 7168 x 16 B = 112 KB of candidates
+template <int ASSOC>
+__global__ void __launch_bounds__(TILE_T) icp_tile_kernel(IcpDev d, int* __restrict__ idx_out, float* __restrict__ d2_out) {
+    extern __shared__ __align__(16) float4 s_pts[];
+    __shared__ int s_off[TILE_ROWS + 1], s_src[TILE_ROWS], s_warp[TILE_T / 32 + 1];
+    const Grid& g = d.g;
+    const int nc = d.cgx * d.cgy * d.cgz;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = blockIdx.x; c < nc; c += gridDim.x) {
+        const int q0 = d.q_start[c], q1 = d.q_start[c + 1];
+        if (q0 == q1) continue;
+        const int bx = c % d.cgx, by = (c / d.cgx) % d.cgy, bz = c / (d.cgx * d.cgy);
+        const int x0 = max(0, 4 * bx - 4), x1 = min(g.gx - 1, 4 * bx + 7);
+        // run lengths of the 144 voxel rows (two passes of 128 threads), exclusive scan -> s_off
+        int total = 0;
+        for (int base = 0; base < TILE_ROWS; base += TILE_T) {
+            const int t = base + tid;
+            int len = 0, src = 0;
+            if (t < TILE_ROWS) {
+                const int iy = 4 * by - 4 + t % 12, iz = 4 * bz - 4 + t / 12;
+                if (iy >= 0 && iy < g.gy && iz >= 0 && iz < g.gz) {
+                    const int rb = g.gx * (iy + g.gy * iz);
+                    src = d.cell_start[rb + x0]; len = d.cell_start[rb + x1 + 1] - src;
+                }
+            }
+            int inc = len;
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            if (lane == 31) s_warp[warp] = inc;
+            __syncthreads();
+            int wbase = 0;
+            for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+            int all = 0;
+            for (int w = 0; w < TILE_T / 32; ++w) all += s_warp[w];
+            if (t < TILE_ROWS) { s_off[t] = total + wbase + inc - len; s_src[t] = src; }
+            total += all;
+            __syncthreads();
+        }
+        if (tid == 0) s_off[TILE_ROWS] = total;
+        const bool staged = total <= TILE_CAP;
+        __syncthreads();
+        if (staged) {
+            for (int r = warp; r < TILE_ROWS; r += TILE_T / 32) {
+                const int o = s_off[r], len = s_off[r + 1] - o, src = s_src[r];
+                for (int j = lane; j < len; j += 32) s_pts[o + j] = __ldg(&d.map[src + j]);
+            }
+            __syncthreads();
+        }
+        for (int qq = q0 + tid; qq < q1; qq += TILE_T) {
+            const int i = d.order[qq];
+            const float3 q = transform_f32(d.tf, load_xyz(d.scan, i, d.stride));
+            Best3 b;
+            if (staged) {
+                b.d[0] = b.d[1] = b.d[2] = INFINITY; b.i[0] = b.i[1] = b.i[2] = 0x7fffffff; b.p[0] = b.p[1] = b.p[2] = -1;
+                for (int j = 0; j < total; ++j) {
+                    const float4 m = s_pts[j];
+                    const float dx = __fsub_rn(m.x, q.x), dy = __fsub_rn(m.y, q.y), dz = __fsub_rn(m.z, q.z);
+                    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    if (d2 <= d.max_d2) best_insert(b, d2, __float_as_int(m.w), j);
+                }
+                for (int j = 0; j < 3; ++j) if (!(b.d[j] <= d.max_d2)) { b.d[j] = INFINITY; b.i[j] = -1; b.p[j] = -1; }
+            } else b = knn3_query(d, q);
+            if (!ASSOC) { for (int j = 0; j < 3; ++j) { idx_out[3 * i + j] = b.i[j]; d2_out[3 * i + j] = b.d[j]; } continue; }
+            int ok = 1;
+            for (int j = 0; j < 3; ++j) if (!(b.i[j] >= 0 && b.i[j] < d.P && (double)b.d[j] < d.thr)) ok = 0;
+            d.accepted[i] = (unsigned char)ok;
+            if (!ok) continue;
+            const float4 a = staged ? s_pts[b.p[0]] : d.map[b.p[0]], bb = staged ? s_pts[b.p[1]] : d.map[b.p[1]], cc = staged ? s_pts[b.p[2]] : d.map[b.p[2]];
+            const V3 n = plane_normal(v3(a.x, a.y, a.z), v3(bb.x, bb.y, bb.z), v3(cc.x, cc.y, cc.z));
+            d.pa[i] = a.x; d.pa[d.K + i] = a.y; d.pa[2 * d.K + i] = a.z;
+            d.nrm[i] = n.x; d.nrm[d.K + i] = n.y; d.nrm[2 * (size_t)d.K + i] = n.z;
+        }
+        __syncthreads();
+    }
 }
 
 __device__ __forceinline__ void icp_substitute(const IcpState& s, const double* x, double* e) {
@@ -467,7 +498,7 @@ static int upload_scan(lvb_icp* h, const void* scan, int n, int stride, const do
     d.accepted = h->accepted.p; d.pa = h->pa.p; d.nrm = h->nrm.p; d.st = h->st.p;
     d.rank = h->ctx->rank; d.world = h->ctx->world;
     { static const int kv = getenv("LVB_KNN_VARIANT") ? atoi(getenv("LVB_KNN_VARIANT")) : 0; d.knn_variant = kv; }
-    d.order = nullptr;
+    d.order = nullptr; d.q_start = nullptr; d.cgx = d.cgy = d.cgz = 0;
     if (n >= 4096) {       // spatial visiting order: counting sort of the queries by coarse voxel block
         const Grid& g = h->grid;
         const int cgx = (g.gx + 3) >> 2, cgy = (g.gy + 3) >> 2, cgz = (g.gz + 3) >> 2;
@@ -482,7 +513,28 @@ static int upload_scan(lvb_icp* h, const void* scan, int n, int stride, const do
         ILAUNCH(h, scan_add_kernel, nb, 1024, h->q_start.p, nc, h->q_sums.p, h->q_start.p + nc, h->q_total.p);
         ILAUNCH(h, icp_query_scatter_kernel, (n + 255) / 256, 256, n, h->q_key.p, h->q_start.p, h->q_fill.p, h->q_order.p);
         d.order = h->q_order.p;
+        d.q_start = h->q_start.p; d.cgx = cgx; d.cgy = cgy; d.cgz = cgz;
     }
+    return LVB_OK;
+}
+
+static bool use_tiles(const IcpDev& d) { return d.knn_variant == 0 && d.q_start != nullptr; }
+static int tile_attr() {
+    static bool done = false;
+    if (!done) {
+        LVB_CUDA(cudaFuncSetAttribute(icp_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TILE_CAP * sizeof(float4))));
+        LVB_CUDA(cudaFuncSetAttribute(icp_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TILE_CAP * sizeof(float4))));
+        done = true;
+    }
+    return LVB_OK;
+}
+static int tile_grid(lvb_icp* h, const IcpDev& d) { return std::max(1, std::min(d.cgx * d.cgy * d.cgz, 8 * h->ctx->sm_count)); }
+static int launch_associate(lvb_icp* h, const IcpDev& d, int n) {
+    if (use_tiles(d)) {
+        LVB_TRY(tile_attr());
+        icp_tile_kernel<1><<<tile_grid(h, d), TILE_T, TILE_CAP * sizeof(float4), h->ctx->stream>>>(d, nullptr, nullptr);
+        h->ctx->launches++; lvb::timing_mark(h->ctx->stream, "icp_tile_kernel<1>");
+    } else ILAUNCH(h, icp_associate_kernel, inblk(n, ITPB), ITPB, d);
     return LVB_OK;
 }
 
@@ -664,7 +716,8 @@ int lvb_icp_knn3(lvb_icp* h, const void* scan, int n, int stride, const double f
     LVB_TRY(upload_scan(h, scan, n, stride, frame_pose, max_d2, 0.0, d));
     if (n == 0) return LVB_OK;
     LVB_TRY(h->knn_idx.ensure((size_t)n * 3)); LVB_TRY(h->knn_d2.ensure((size_t)n * 3));
-    ILAUNCH(h, icp_knn_kernel, inblk(n, ITPB), ITPB, d, h->knn_idx.p, h->knn_d2.p);
+    if (use_tiles(d)) { LVB_TRY(tile_attr()); icp_tile_kernel<0><<<tile_grid(h, d), TILE_T, TILE_CAP * sizeof(float4), h->ctx->stream>>>(d, h->knn_idx.p, h->knn_d2.p); h->ctx->launches++; lvb::timing_mark(h->ctx->stream, "icp_tile_kernel<0>"); }
+    else ILAUNCH(h, icp_knn_kernel, inblk(n, ITPB), ITPB, d, h->knn_idx.p, h->knn_d2.p);
     LVB_TRY(icheck("knn3"));
     LVB_TRY(h->knn_idx.download(idx, (size_t)n * 3, h->ctx->stream));
     LVB_TRY(h->knn_d2.download(d2, (size_t)n * 3, h->ctx->stream));
@@ -698,7 +751,7 @@ int lvb_icp_eval(lvb_icp* h, int mode, const void* scan, int n, int stride, cons
     if (n == 0) return LVB_OK;
     LVB_TRY(init_state(h, mode, map_pose, rpyxyz, weight, -1.0, 0.0, nullptr));
     LVB_TRY(h->eval_r.ensure(n)); LVB_TRY(h->eval_J.ensure((size_t)n * 3));
-    ILAUNCH(h, icp_associate_kernel, inblk(n, ITPB), ITPB, d);
+    LVB_TRY(launch_associate(h, d, n));
     ILAUNCH(h, icp_eval_kernel, inblk(n, ITPB), ITPB, d, h->eval_r.p, h->eval_J.p);
     LVB_TRY(icheck("icp_eval"));
     cudaStream_t s = h->ctx->stream;
@@ -725,7 +778,7 @@ int lvb_icp_scan_to_map(lvb_icp* h, int mode, const void* scan, int n, int strid
     LVB_TRY(init_state(h, mode, map_pose, rpyxyz, weight, prior_weight, huber_a, &opt));
     cudaStream_t s = h->ctx->stream;
     lvb_ctx* ctx = h->ctx;
-    ILAUNCH(h, icp_associate_kernel, inblk(n, ITPB), ITPB, d);
+    LVB_TRY(launch_associate(h, d, n));
     const int lin_blocks = std::max(1, std::min(inblk(n, ITPB), 4 * ctx->sm_count));
     IcpState hs;
     memset(&hs, 0, sizeof(hs));

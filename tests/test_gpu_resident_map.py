@@ -57,7 +57,7 @@ def test_resident_map_equals_per_call_path(lvb_ctx, kind, ground):
     args = (sc["mode"], sc["scan"], sc["frame_pose"], sc["map_pose"], e0, sc["weight"], -1.0, sc["huber_a"], sc["thr"])
     ea, sa = fa.scan_to_map(*args)
     eb, sb = fb.scan_to_map(*args)
-    assert sa.num_residual_blocks == sb.num_residual_blocks and np.array_equal(ea, eb)
+    assert sa.num_residual_blocks == sb.num_residual_blocks and np.max(np.abs(ea - eb)) < 1e-11        # (the 3 x 3 sums are reduced with atomics)
     # sliding the window: the scan just registered becomes a keyframe cloud without a second upload; the oldest one leaves
     fb.map_append(103, None, sc["frame_pose"])
     fb.map_evict(100)
