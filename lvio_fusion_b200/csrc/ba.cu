@@ -25,6 +25,7 @@
 #include "lvb_internal.cuh"
 #include "lvb_math.cuh"
 #include "lvb_imu_warp.cuh"
+#include "lvb_chol.cuh"
 
 using namespace lvb;
 
@@ -575,15 +576,6 @@ __device__ __forceinline__ void atomic_max_nonneg(unsigned long long* p, double 
 }
 
 
-// S <- lower(Hpp), rhs <- -gc, gcr <- gc, diagH <- diag(Hpp), scalars <- 0
-__global__ void ba_build_S_kernel(BaDev d) {
-    if (d.st->done) return;
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    if (gid < 16) d.scal[gid] = 0.0;
-    for (size_t i = gid; i < d.nS; i += stride) d.S[i] = d.Hpp[i];          // only the lower triangle / band is ever written
-    for (size_t r = gid; r < (size_t)d.dimc; r += stride) { d.diagH[r] = d.Hpp[SIDX(d, r, r)]; d.rhs[r] = -d.gc[r]; d.gcr[r] = d.gc[r]; }
-}
-
 // K5: eliminate the inverse depths.  One warp per 32 landmarks that share their set of pose offsets
 // (finalize() groups and pads them).  Lane l writes u_l = sqrt(1/h_l) [w_l | g_l] (its couplings merged by
 // pose slot) as a row of a shared-memory tile; the warp then forms the lower triangle of U^T U and subtracts
@@ -802,6 +794,39 @@ __device__ __forceinline__ void prepare_camera_block(const BaDev& d, int i) {
     }
 }
 
+// S <- lower(Hpp), rhs <- -gc, gcr <- gc, diagH <- diag(Hpp), scalars <- 0.
+// FUSE_DAMP (single GPU): the camera blocks' Jacobi scale, LM damping and gradient max-norm (prepare_camera_block) ride along: the
+// bulk copy skips the diagonal and the thread that owns a block fills that block's rows (diagonal of S, rhs, gcr, diagH) and damps
+// them itself, so there is no ordering hazard -- the Schur kernel's `S -= ...` atomics that follow commute with the damping.
+// Sharded problems damp after the all-reduce instead (the diagonal must be the global one) and keep ba_prepare_camera_kernel.
+template <int FUSE_DAMP>
+__global__ void ba_build_S_kernel(BaDev d) {
+    if (d.st->done) return;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    if (gid < 16) d.scal[gid] = 0.0;
+    const size_t dstep = (size_t)d.srow + 1;                                   // distance between consecutive diagonal entries
+    for (size_t i = gid; i < d.nS; i += stride) {
+        if (FUSE_DAMP && i >= (size_t)d.soff && (i - (size_t)d.soff) % dstep == 0) continue;
+        d.S[i] = d.Hpp[i];          // only the lower triangle / band is ever written
+    }
+    if (!FUSE_DAMP) {
+        for (size_t r = gid; r < (size_t)d.dimc; r += stride) { d.diagH[r] = d.Hpp[SIDX(d, r, r)]; d.rhs[r] = -d.gc[r]; d.gcr[r] = d.gc[r]; }
+    } else {
+        for (size_t i = gid; i < (size_t)(d.n_poses + d.n_vec3); i += stride) {
+            const bool is_pose = i < (size_t)d.n_poses;
+            const int off = is_pose ? d.pose_off[i] : d.vec3_off[i - d.n_poses];
+            if (off < 0) continue;
+            const int w = is_pose ? 6 : 3;
+            for (int k = 0; k < w; ++k) {
+                const int r = off + k;
+                const double h = d.Hpp[SIDX(d, r, r)];
+                d.diagH[r] = h; d.rhs[r] = -d.gc[r]; d.gcr[r] = d.gc[r]; d.S[SIDX(d, r, r)] = h;
+            }
+            prepare_camera_block(d, (int)i);
+        }
+    }
+}
+
 __global__ void ba_prepare_camera_kernel(BaDev d) {
     if (d.st->done) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -821,10 +846,9 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
     if (run_control_pre) { if (threadIdx.x == 0) lm_control_pre(*st); __syncthreads(); }
     if (st->done) return;
     extern __shared__ __align__(16) double sm[];
-    double* D = sm;                    // 32 x 33   diagonal block of L
-    double* invd = sm + 32 * 33;       // 32        reciprocals of diag(L) of the current block (all of them: invd_g)
-    double* Lc = invd + 32;            // 2 x 64    column of the diagonal block being factored (double buffered broadcast)
-    double* P = Lc + 128;              // rows x 34 panel (16 B aligned rows for broadcast double2 loads)
+    double* Dt = sm;                   // 32 x 34   diagonal block of L, column-major: Dt[j * 34 + k] = L[k][j] (lvb_chol.cuh)
+    double* invd = sm + 32 * 34;       // 32        reciprocals of diag(L) of the current block
+    double* P = invd + 32;             // rows x 34 panel (16 B aligned rows for broadcast double2 loads)
     __shared__ int fail;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     if (tid == 0) fail = 0;
@@ -847,12 +871,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
                 double a[32];
     #pragma unroll
                 for (int j = 0; j < 32; ++j) a[j] = (j < bs) ? src[j] : 0.0;
-    #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    a[j] *= invd[j];
-    #pragma unroll
-                    for (int k = 0; k < 32; ++k) if (k > j) a[k] -= a[j] * D[k * 33 + j];
-                }
+                chol_panel_row(a, Dt, invd);
     #pragma unroll
                 for (int j = 0; j < 32; ++j) { P[rr * 34 + j] = a[j]; if (j < bs) src[j] = a[j]; }
             }
@@ -918,55 +937,14 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
             __syncwarp();
             if (warp == 0) {
                 const long long t_d0 = clock64();
-                // Registers hold row `lane` of the block.  The 32 columns are processed in 4 groups of 8: inside a group the
-                // code is unrolled (register indices are compile-time), between groups the row is shifted left by 8, so the
-                // loop body exists once (the fully unrolled form is ~4000 instructions and starves the instruction cache).
-                // Column j goes through shared memory: the other columns read L[k][j] as broadcast LDS.128 (two columns per
-                // load) instead of two shuffles per column.
+                // one row per lane in registers; lvb_chol.cuh::chol_diag32 (4 groups of 8 columns, deferred rank-8 updates)
                 double a[32];
     #pragma unroll
                 for (int j = 0; j < 32; ++j) a[j] = (lane < bn && j <= lane) ? SA(kn + lane, kn + j) : ((j == lane) ? 1.0 : 0.0);
-                int bad = 0;
-                double d0 = __shfl_sync(0xffffffffu, a[0], 0);
-                if (!(d0 > 0.0)) { bad = 1; d0 = 1.0; }
-                double inv = rsqrt(d0);
-    #pragma unroll 1
-                for (int c0 = 0; c0 < 32; c0 += 8) {
-                    const int rel = lane - c0;                    // register index of this lane's diagonal entry
-    #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const int j = c0 + jj;
-                        if (rel >= jj) a[jj] *= inv;                  // l_ij (lane j: sqrt(d_jj))
-                        if (rel == jj) { invd[j] = inv; invd_g[kn + j] = inv; }
-                        const double lj = (rel >= jj) ? a[jj] : 0.0;
-                        D[lane * 33 + j] = lj;
-                        if (lane < bn && rel >= jj && j < bn) SA(kn + lane, kn + j) = lj;
-                        double* buf = Lc + (jj & 1) * 64;
-                        buf[lane] = a[jj];
-                        // next pivot first: lane j+1 owns everything its diagonal entry needs, its rsqrt overlaps the update
-                        double inv_next = 1.0;
-                        if (j + 1 < 32) {
-                            double dn = __shfl_sync(0xffffffffu, a[jj + 1] - a[jj] * a[jj], j + 1);
-                            if (!(dn > 0.0)) { bad = 1; dn = 1.0; }
-                            inv_next = rsqrt(dn);
-                        }
-                        __syncwarp();
-                        const double2* bp = reinterpret_cast<const double2*>(buf + c0);
-    #pragma unroll
-                        for (int p = 0; p < 16; ++p) {                // register pair (2p, 2p+1) = columns c0 + 2p, c0 + 2p + 1
-                            if (2 * p + 1 > jj) {
-                                const double2 v = bp[p];             // entries beyond column 31 are never used (rel < their index)
-                                if (2 * p > jj && rel >= 2 * p) a[2 * p] -= a[jj] * v.x;
-                                if (rel >= 2 * p + 1) a[2 * p + 1] -= a[jj] * v.y;
-                            }
-                        }
-                        inv = inv_next;
-                    }
-    #pragma unroll
-                    for (int r = 0; r < 24; ++r) a[r] = a[r + 8];
-    #pragma unroll
-                    for (int r = 24; r < 32; ++r) a[r] = 0.0;
-                }
+                const int bad = chol_diag32(a, lane, bn, Dt, invd, [&](int j, double lj, double inv) {
+                    if (inv != 0.0) invd_g[kn + j] = inv;                      // (n + 32 entries: the tail of the last block is scratch)
+                    if (lane < bn && lane >= j && j < bn) SA(kn + lane, kn + j) = lj;
+                });
                 t_diag += clock64() - t_d0;
                 if (bad && lane == 0) fail = 1;
             }
@@ -1843,7 +1821,9 @@ static int launch_linearize_and_reduce(lvb_ba* ba, bool standalone) {
         LAUNCH_ON(ba, ctx->side, ba_linearize_other_kernel<0>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
         LVB_CUDA(cudaEventRecord(ctx->ev_join, ctx->side)); LVB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     } else LAUNCH(ba, ba_linearize_other_kernel<0>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
-    LAUNCH(ba, ba_build_S_kernel, std::min(1024, nblk(nH, 256)), 256, 0, d);
+    const bool fuse_damp = ctx->world == 1;
+    if (fuse_damp) LAUNCH(ba, ba_build_S_kernel<1>, std::min(1024, nblk(nH, 256)), 256, 0, d);
+    else LAUNCH(ba, ba_build_S_kernel<0>, std::min(1024, nblk(nH, 256)), 256, 0, d);
     LAUNCH(ba, ba_schur_kernel, nblk(d.n_schur_warps, TPB / 32), TPB, ba->schur_smem, d, std::max(1, ba->schur_cols_max));
     if (d.tc_mode) LAUNCH(ba, ba_schur_tc_kernel, ba->n_tc_chunks / TC_CHUNKS, 128, (size_t)TC_CHUNKS * TC_CHUNK_BYTES, d, ba->n_tc_chunks);
     if (ctx->world > 1) {
@@ -1852,7 +1832,7 @@ static int launch_linearize_and_reduce(lvb_ba* ba, bool standalone) {
         LAUNCH(ba, ba_unpack_scalars_kernel, 1, 1, 0, d);
     }
     // (fusing this into the Cholesky prologue was measured: it perturbs that kernel's register allocation and is slower)
-    LAUNCH(ba, ba_prepare_camera_kernel, nblk(d.n_poses + d.n_vec3, 128), 128, 0, d);
+    if (!fuse_damp) LAUNCH(ba, ba_prepare_camera_kernel, nblk(d.n_poses + d.n_vec3, 128), 128, 0, d);
     if (standalone) LAUNCH(ba, lm_control_pre_kernel, 1, 1, 0, d.st);
     return check_launch("linearize");
 }

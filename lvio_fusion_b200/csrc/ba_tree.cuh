@@ -57,10 +57,9 @@ __global__ void __launch_bounds__(CHOL_T) ba_front_factor_kernel(const Front* __
                                                                   double* __restrict__ invd_g, LmState* st) {
     if (st->done) return;
     extern __shared__ __align__(16) double sm[];
-    double* D = sm;                    // 32 x 33   diagonal block of L
-    double* invd = sm + 32 * 33;       // 32        reciprocals of diag(L) of the current block
-    double* Lc = invd + 32;            // 2 x 64    column of the diagonal block being factored (double buffered broadcast)
-    double* P = Lc + 128;              // rows x 34 panel
+    double* Dt = sm;                   // 32 x 34   diagonal block of L, column-major: Dt[j * 34 + k] = L[k][j] (lvb_chol.cuh)
+    double* invd = sm + 32 * 34;       // 32        reciprocals of diag(L) of the current block
+    double* P = invd + 32;             // rows x 34 panel (16 B aligned rows for broadcast double2 loads)
     __shared__ int fail;
     const Front F = fr[first + blockIdx.x];
     const int n = F.m, nb = F.nb, ld = F.ld;
@@ -115,12 +114,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_front_factor_kernel(const Front* __
                 double a[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) a[j] = (j < bs) ? src[j] : 0.0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    a[j] *= invd[j];
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) if (k > j) a[k] -= a[j] * D[k * 33 + j];
-                }
+                chol_panel_row(a, Dt, invd);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { P[rr * 34 + j] = a[j]; if (j < bs) src[j] = a[j]; }
             }
@@ -188,46 +182,10 @@ __global__ void __launch_bounds__(CHOL_T) ba_front_factor_kernel(const Front* __
                 double a[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) a[j] = (lane < bn && j <= lane) ? SG(F.o0 + kn + lane, F.o0 + kn + j) : ((j == lane) ? 1.0 : 0.0);
-                int bad = 0;
-                double d0 = __shfl_sync(0xffffffffu, a[0], 0);
-                if (!(d0 > 0.0)) { bad = 1; d0 = 1.0; }
-                double inv = rsqrt(d0);
-#pragma unroll 1
-                for (int c0 = 0; c0 < 32; c0 += 8) {
-                    const int rel = lane - c0;
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const int j = c0 + jj;
-                        if (rel >= jj) a[jj] *= inv;
-                        if (rel == jj) { invd[j] = inv; if (j < bn) invd_g[F.o0 + kn + j] = inv; }   // (beyond bn: the next front's unknowns)
-                        const double lj = (rel >= jj) ? a[jj] : 0.0;
-                        D[lane * 33 + j] = lj;
-                        if (lane < bn && rel >= jj && j < bn) SG(F.o0 + kn + lane, F.o0 + kn + j) = lj;
-                        double* buf = Lc + (jj & 1) * 64;
-                        buf[lane] = a[jj];
-                        double inv_next = 1.0;
-                        if (j + 1 < 32) {
-                            double dn = __shfl_sync(0xffffffffu, a[jj + 1] - a[jj] * a[jj], j + 1);
-                            if (!(dn > 0.0)) { bad = 1; dn = 1.0; }
-                            inv_next = rsqrt(dn);
-                        }
-                        __syncwarp();
-                        const double2* bp = reinterpret_cast<const double2*>(buf + c0);
-#pragma unroll
-                        for (int p = 0; p < 16; ++p) {
-                            if (2 * p + 1 > jj) {
-                                const double2 v = bp[p];
-                                if (2 * p > jj && rel >= 2 * p) a[2 * p] -= a[jj] * v.x;
-                                if (rel >= 2 * p + 1) a[2 * p + 1] -= a[jj] * v.y;
-                            }
-                        }
-                        inv = inv_next;
-                    }
-#pragma unroll
-                    for (int r = 0; r < 24; ++r) a[r] = a[r + 8];
-#pragma unroll
-                    for (int r = 24; r < 32; ++r) a[r] = 0.0;
-                }
+                const int bad = chol_diag32(a, lane, bn, Dt, invd, [&](int j, double lj, double inv) {
+                    if (inv != 0.0 && j < bn) invd_g[F.o0 + kn + j] = inv;     // (beyond bn: the next front's unknowns)
+                    if (lane < bn && lane >= j && j < bn) SG(F.o0 + kn + lane, F.o0 + kn + j) = lj;
+                });
                 if (bad && lane == 0) fail = 1;
             }
         }
