@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--skip-roofline", action="store_true")
     ap.add_argument("--skip-global", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--blocks", type=int, default=0, help="repetitions of the timed region (0: enough for >= 50 solves); profiler runs use 1")
     args = ap.parse_args()
     if args.quick:
         args.skip_icp = args.skip_roofline = args.skip_global = args.skip_cpu = True
@@ -265,7 +266,7 @@ def main():
             its = run_solves(prob, d, lvb, steps, PER)
             launches = c.launch_count() - l0
             # the K-step timed region, repeated so that >= 50 solves stand behind the number; the median block is reported
-            blocks = max(5, -(-50 * PER // max(1, steps)))
+            blocks = args.blocks if args.blocks > 0 else max(5, -(-50 * PER // max(1, steps)))
             times, its = timed_blocks(lambda: run_solves(prob, d, lvb, steps, PER), blocks)
             ms = float(np.median(times))
             res = {"rows": rows, "iters": its, "ms": ms, "launches": int(launches), "blocks": blocks,

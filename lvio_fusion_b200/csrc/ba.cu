@@ -7,7 +7,7 @@
 //   factor constants   SoA planes per kind: plane k of kind K at fc[K] + k*n[K]  (coalesced reads)
 //   factor indices     SoA int32 planes fi[K] + k*n[K]
 //   IMU constants      AoS per factor, 287 doubles: 17 scalars, five 3x3 sub-blocks, U (15x15)
-//   accumulators       Hpp (dimc x dimc, lower), gc, Hll, gl, per-TwoFrame-factor W rows (12 planes)
+//   accumulators       Hpp (dimc x dimc, lower), gc, Hll, gl, per-TwoFrame-factor W rows (one 96 B record per factor)
 //   reduction arena    [ S | rhs | gc | diag(Hpp) | 16 scalars ]  -- the one buffer all-reduced per iteration
 //
 // Kernels (K-numbers of SURVEY.md section 2):
@@ -326,7 +326,7 @@ __device__ __forceinline__ void warp_syrk_flush(const BaDev& d, const double* A 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(TPB) ba_linearize_kernel(BaDev d, BlockRanges R) {
+__device__ __forceinline__ void linearize_visual_body(const BaDev& d, const BlockRanges& R, const int b) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ double s_red[TPB / 32];
@@ -336,7 +336,6 @@ __global__ void __launch_bounds__(TPB) ba_linearize_kernel(BaDev d, BlockRanges 
     const double* Psrc = MODE == 0 ? d.poses : d.c_poses;
     const double* Rho = MODE == 0 ? d.rho : d.c_rho;
     double* cost_target = MODE == 0 ? &d.st->cost_acc : &d.st->cand_cost_acc;
-    const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double cost = 0.0;
     const size_t pose_bytes = d.stage_poses ? (((size_t)d.n_poses * 56 + 16 + 15) & ~(size_t)15) : 0;
@@ -368,10 +367,16 @@ __global__ void __launch_bounds__(TPB) ba_linearize_kernel(BaDev d, BlockRanges 
                     if (h != 0.0) atomicAdd(&d.Hll[il], h);
                     if (g != 0.0) atomicAdd(&d.gl[il], g);
                 }
+                // coupling rows W = J_rho^T [J_1 | J_2], one 96-byte record per factor (the Schur and back-substitution kernels gather
+                // them per landmark: a record is 3 sectors, the former 12 planes were 12)
+                double wv[12];
                 for (int k = 0; k < 6; ++k) {
-                    w[(size_t)k * n + f] = (lfree && off1 >= 0) ? o.Jrho[0] * o.J1[k] + o.Jrho[1] * o.J1[6 + k] : 0.0;
-                    w[(size_t)(6 + k) * n + f] = (lfree && off2 >= 0) ? o.Jrho[0] * o.J2[k] + o.Jrho[1] * o.J2[6 + k] : 0.0;
+                    wv[k] = (lfree && off1 >= 0) ? o.Jrho[0] * o.J1[k] + o.Jrho[1] * o.J1[6 + k] : 0.0;
+                    wv[6 + k] = (lfree && off2 >= 0) ? o.Jrho[0] * o.J2[k] + o.Jrho[1] * o.J2[6 + k] : 0.0;
                 }
+                double2* wr = reinterpret_cast<double2*>(w + (size_t)f * 12);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) wr[k] = make_double2(wv[2 * k], wv[2 * k + 1]);
             }
         }
         if (MODE == 0) {
@@ -453,9 +458,12 @@ __global__ void __launch_bounds__(TPB) ba_linearize_kernel(BaDev d, BlockRanges 
     block_add(cost, cost_target, s_red);
 }
 
-// IMU (one warp per factor) and the two prior kinds: rare, register-hungry blocks kept out of the visual kernel
 template <int MODE>
-__global__ void __launch_bounds__(TPB) ba_linearize_other_kernel(BaDev d, BlockRanges R) {
+__global__ void __launch_bounds__(TPB) ba_linearize_kernel(BaDev d, BlockRanges R) { linearize_visual_body<MODE>(d, R, blockIdx.x); }
+
+// IMU (one warp per factor) and the two prior kinds: rare, register-hungry blocks kept out of the visual kernel at map scale
+template <int MODE>
+__device__ __forceinline__ void linearize_other_body(const BaDev& d, const BlockRanges& R, const int b /* absolute block index >= R.b[3] */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double s_red[TPB / 32];
     const LmState* st = d.st;
@@ -464,7 +472,6 @@ __global__ void __launch_bounds__(TPB) ba_linearize_other_kernel(BaDev d, BlockR
     const double* Psrc = MODE == 0 ? d.poses : d.c_poses;
     const double* V = MODE == 0 ? d.vec3 : d.c_vec3;
     double* cost_target = MODE == 0 ? &d.st->cost_acc : &d.st->cand_cost_acc;
-    const int b = blockIdx.x + R.b[3];
     double cost = 0.0;
     if (b < R.b[4]) {   // ---- IMU: one warp per factor
         double* s_raw = reinterpret_cast<double*>(smem_raw);     // 4 x 480
@@ -556,6 +563,19 @@ __global__ void __launch_bounds__(TPB) ba_linearize_other_kernel(BaDev d, BlockR
     block_add(cost, cost_target, s_red);
 }
 
+template <int MODE>
+__global__ void __launch_bounds__(TPB) ba_linearize_other_kernel(BaDev d, BlockRanges R) { linearize_other_body<MODE>(d, R, blockIdx.x + R.b[3]); }
+
+// Window-sized problems: ONE launch for all factor kinds.  The IMU blocks are a long single-warp dependency chain (~20 us) and the
+// visual blocks a short wide one; in one grid -- IMU and priors first so they start at once -- they overlap instead of running
+// back to back, and a launch is saved.  (At map scale the visual kernel's occupancy matters and the kernels stay separate.)
+template <int MODE>
+__global__ void __launch_bounds__(TPB) ba_linearize_all_kernel(BaDev d, BlockRanges R) {
+    const int n_other = R.b[6] - R.b[3];
+    if ((int)blockIdx.x < n_other) linearize_other_body<MODE>(d, R, (int)blockIdx.x + R.b[3]);
+    else linearize_visual_body<MODE>(d, R, (int)blockIdx.x - n_other);
+}
+
 // ------------------------------------------------------------------ per-iteration system assembly
 __global__ void ba_zero_kernel(BaDev d) {
     const LmState* st = d.st;
@@ -611,7 +631,7 @@ __global__ void __launch_bounds__(TPB) ba_schur_kernel(BaDev d, int cols_max) {
                 for (int side = 0; side < 2; ++side) {
                     const int sl = d.tf_slot[(size_t)side * n + f];
                     if (sl < 0) continue;
-                    for (int k = 0; k < 6; ++k) row[6 * sl + k] += d.tf_w[(size_t)(6 * side + k) * n + f];
+                    for (int k = 0; k < 6; ++k) row[6 * sl + k] += d.tf_w[(size_t)f * 12 + 6 * side + k];
                 }
             }
             const double sh = sqrt(1.0 / hl);
@@ -1040,7 +1060,7 @@ __global__ void __launch_bounds__(TPB) ba_update_kernel(BaDev d) {
                 for (int side = 0; side < 2; ++side) {
                     const int off = d.pose_off[ix[(size_t)(1 + side) * n + f]];
                     if (off < 0) continue;
-                    for (int k = 0; k < 6; ++k) s += d.tf_w[(size_t)(6 * side + k) * n + f] * dc[off + k];
+                    for (int k = 0; k < 6; ++k) s += d.tf_w[(size_t)f * 12 + 6 * side + k] * dc[off + k];
                 }
             }
             const double lam = d.lam_l[l];
@@ -1191,6 +1211,8 @@ static int init_tables() {
     LVB_CUDA(cudaFuncSetAttribute(ba_eval_two_frame_kernel<0, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (MAX_STAGE_POSES * 7 + 2) * 8));
     LVB_CUDA(cudaFuncSetAttribute(ba_linearize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     LVB_CUDA(cudaFuncSetAttribute(ba_linearize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    LVB_CUDA(cudaFuncSetAttribute(ba_linearize_all_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    LVB_CUDA(cudaFuncSetAttribute(ba_linearize_all_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     LVB_CUDA(cudaFuncSetAttribute(ba_schur_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_CHUNKS * TC_CHUNK_BYTES));
     LVB_CUDA(cudaFuncSetAttribute(ba_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (TPB / 32) * 32 * (6 * MAX_TRACK + 1) * 8));
     g_tables_ready = true;
@@ -1799,6 +1821,11 @@ int lvb_ba_eval_device(lvb_ba* ba, int kind) {
     return launch_eval(ba, kind, ba->eval_r.p, ba->eval_J.p);
 }
 
+static bool merged_linearize(lvb_ba* ba) {
+    static const bool off = getenv("LVB_NO_MERGED_LINEARIZE") && getenv("LVB_NO_MERGED_LINEARIZE")[0] == '1';
+    return !off && ba->srow == ba->dimc && ba->soff == 0 && ba->ranges.b[3] > 0 && ba->ranges.b[6] > ba->ranges.b[3];      // dense layout = window-sized
+}
+
 static bool use_side_branch(lvb_ba* ba) {
     // not inside a captured graph: replaying a graph with parallel branches was measured to be erratic (0.19 - 0.9 ms per
     // pass on the same build), a linear graph is stable
@@ -1813,14 +1840,19 @@ static int launch_linearize_and_reduce(lvb_ba* ba, bool standalone) {
     BaDev& d = ba->dev;
     lvb_ctx* ctx = ba->ctx;
     const size_t nH = d.nS;
-    // the visual and the IMU / prior linearisations are independent (both only add into the accumulators): two branches
-    const bool fork = use_side_branch(ba);
+    // the visual and the IMU / prior linearisations are independent (both only add into the accumulators): one grid for both at
+    // window size, two kernels (parallel branches when launched directly) at map scale
+    const bool one_grid = merged_linearize(ba);
+    const bool fork = !one_grid && use_side_branch(ba);
+    if (one_grid) LAUNCH(ba, ba_linearize_all_kernel<0>, ba->ranges.b[6], TPB, std::max(ba->lin_smem, ba->imu_smem), d, ba->ranges);
+    else {
     if (fork) { LVB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream)); LVB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0)); }
     LAUNCH(ba, ba_linearize_kernel<0>, ba->ranges.b[3], TPB, ba->lin_smem, d, ba->ranges);
     if (fork) {
         LAUNCH_ON(ba, ctx->side, ba_linearize_other_kernel<0>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
         LVB_CUDA(cudaEventRecord(ctx->ev_join, ctx->side)); LVB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     } else LAUNCH(ba, ba_linearize_other_kernel<0>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
+    }
     const bool fuse_damp = ctx->world == 1;
     if (fuse_damp) LAUNCH(ba, ba_build_S_kernel<1>, std::min(1024, nblk(nH, 256)), 256, 0, d);
     else LAUNCH(ba, ba_build_S_kernel<0>, std::min(1024, nblk(nH, 256)), 256, 0, d);
@@ -1861,13 +1893,17 @@ static int launch_step(lvb_ba* ba) {
     lvb_ctx* ctx = ba->ctx;
     LVB_TRY(launch_reduced_solve(ba));
     LAUNCH(ba, ba_update_kernel, nblk((size_t)d.n_poses + d.n_vec3 + d.n_rho, TPB), TPB, 0, d);
-    const bool fork = use_side_branch(ba);
+    const bool one_grid = merged_linearize(ba);
+    const bool fork = !one_grid && use_side_branch(ba);
+    if (one_grid) LAUNCH(ba, ba_linearize_all_kernel<1>, ba->ranges.b[6], TPB, std::max(ba->lin_smem, ba->imu_smem), d, ba->ranges);
+    else {
     if (fork) { LVB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream)); LVB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0)); }
     LAUNCH(ba, ba_linearize_kernel<1>, ba->ranges.b[3], TPB, ba->lin_smem, d, ba->ranges);
     if (fork) {
         LAUNCH_ON(ba, ctx->side, ba_linearize_other_kernel<1>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
         LVB_CUDA(cudaEventRecord(ctx->ev_join, ctx->side)); LVB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     } else LAUNCH(ba, ba_linearize_other_kernel<1>, ba->ranges.b[6] - ba->ranges.b[3], TPB, ba->imu_smem, d, ba->ranges);
+    }
     if (ctx->world > 1) LVB_TRY(comm_allreduce_sum_f64(ctx, &d.st->cand_cost_acc, 5));
     const bool wide = d.nS > ((size_t)1 << 20) || (size_t)d.n_poses * 7 + (size_t)d.n_vec3 * 3 + d.n_rho > ((size_t)1 << 17);
     LAUNCH(ba, ba_post_kernel, 1, wide ? 32 : 1024, 0, d, wide ? 1 : 0);

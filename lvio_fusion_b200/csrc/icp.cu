@@ -61,10 +61,6 @@ struct IcpDev {
     IcpState* st;
     int rank, world;
     const int* order;            // query visiting order (spatially sorted) or nullptr
-    int knn_variant;             // 0: shared-memory tiles per coarse block (icp_tile_kernel), 1: per-query voxel rings only (env LVB_KNN_VARIANT)
-    const int* q_start;          // per coarse block (4 x 4 x 4 voxels): first position in `order` (counting sort), or nullptr
-    int cgx, cgy, cgz;
-    int tile_cap;                // points the shared-memory staging area holds
 };
 
 __device__ __forceinline__ float3 load_xyz(const unsigned char* base, int i, int stride) {
@@ -192,6 +188,11 @@ __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
 
 // Coarse spatial key of a query (blocks of 4x4x4 voxels) so that the lanes of a warp walk the same voxel lists and
 // their 16-byte map loads hit the same L1 lines instead of 32 different L2 sectors.
+// Measured alternatives that lost against this per-query ring walk (round 2, 120 k queries vs 1 M points, 0.50 ms): scanning
+// x-major voxel ROWS as contiguous runs (fewer probes, but no per-voxel culling: 0.78 ms); staging a coarse block's 3 x 3 x 3
+// neighbourhood in shared memory per CTA and searching there (ring search on the staged copy 1.4 - 1.8 ms, brute force 4.4 ms):
+// a block holds ~25 queries that look at ~50 points each, while its neighbourhood is ~3 000 points -- the staging reads 60x more
+// map than the queries need.
 __global__ void icp_query_key_kernel(IcpDev d, int cgx, int cgy, int cgz, int* __restrict__ key, int* __restrict__ counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.K) return;
@@ -235,134 +236,6 @@ __global__ void __launch_bounds__(ITPB) icp_associate_kernel(IcpDev d) {
     const V3 n = plane_normal(v3(a.x, a.y, a.z), v3(bb.x, bb.y, bb.z), v3(c.x, c.y, c.z));
     d.pa[i] = a.x; d.pa[d.K + i] = a.y; d.pa[2 * d.K + i] = a.z;
     d.nrm[i] = n.x; d.nrm[d.K + i] = n.y; d.nrm[2 * (size_t)d.K + i] = n.z;
-}
-
-// The ring search of knn3_query on a staged tile: voxel (ix, iy, iz) -> tile-local offsets in shared memory, points in shared memory.
-struct Tile { const float4* pts; const int* vox; int x0, y0, z0, nx; };
-__device__ __forceinline__ void scan_voxel_tile(const IcpDev& d, const Grid& g, const Tile& t, float3 q, int ix, int iy, int iz, Best3& b) {
-    const int lx = ix - t.x0, ly = iy - t.y0, lz = iz - t.z0;
-    if (lx < 0 || lx >= t.nx || ly < 0 || ly >= 12 || lz < 0 || lz >= 12) return;     // beyond the tile = beyond the radius (or the grid)
-    const int* v = t.vox + (lz * 12 + ly) * 13 + lx;
-    const int s = v[0], e = v[1];
-    if (s == e) return;
-    const float bx0 = g.minx + ix * g.cell, by0 = g.miny + iy * g.cell, bz0 = g.minz + iz * g.cell;
-    const float ex = fmaxf(fmaxf(bx0 - q.x, q.x - (bx0 + g.cell)), 0.0f);
-    const float ey = fmaxf(fmaxf(by0 - q.y, q.y - (by0 + g.cell)), 0.0f);
-    const float ez = fmaxf(fmaxf(bz0 - q.z, q.z - (bz0 + g.cell)), 0.0f);
-    const float bd = (ex * ex + ey * ey + ez * ez) * 0.99f - 1e-6f;
-    if (bd > b.d[2] || bd > d.max_d2) return;
-    for (int j = s; j < e; ++j) {
-        const float4 m = t.pts[j];
-        const float dx = __fsub_rn(m.x, q.x), dy = __fsub_rn(m.y, q.y), dz = __fsub_rn(m.z, q.z);
-        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        best_insert(b, d2, __float_as_int(m.w), j);
-    }
-}
-__device__ __forceinline__ Best3 knn3_query_tile(const IcpDev& d, const Tile& t, float3 q) {
-    Best3 b;
-    b.d[0] = b.d[1] = b.d[2] = INFINITY; b.i[0] = b.i[1] = b.i[2] = 0x7fffffff; b.p[0] = b.p[1] = b.p[2] = -1;
-    const Grid& g = d.g;
-    const int cx = cell_coord(q.x, g.minx, g.inv_cell), cy = cell_coord(q.y, g.miny, g.inv_cell), cz = cell_coord(q.z, g.minz, g.inv_cell);
-    scan_voxel_tile(d, g, t, q, cx, cy, cz, b);
-    for (int r = 1; r <= g.ring; ++r) {
-        const float lb = (r - 1) * g.cell;
-        const float lb2 = lb * lb * 0.99f;
-        if (b.d[2] < lb2 || lb2 > d.max_d2) break;
-        for (int dz = -r; dz <= r; ++dz) {
-            const bool zface = (dz == -r || dz == r);
-            for (int dy = -r; dy <= r; ++dy) {
-                const bool yface = (dy == -r || dy == r);
-                if (zface || yface) { for (int dx = -r; dx <= r; ++dx) scan_voxel_tile(d, g, t, q, cx + dx, cy + dy, cz + dz, b); }
-                else { scan_voxel_tile(d, g, t, q, cx - r, cy + dy, cz + dz, b); scan_voxel_tile(d, g, t, q, cx + r, cy + dy, cz + dz, b); }
-            }
-        }
-    }
-    for (int j = 0; j < 3; ++j) if (!(b.d[j] <= d.max_d2)) { b.d[j] = INFINITY; b.i[j] = -1; b.p[j] = -1; }
-    return b;
-}
-
-// K8, tiled: the queries are already sorted by coarse block (4 x 4 x 4 voxels = one search radius cubed).  Every neighbour within the
-// radius of a query of block B lies in B's 3 x 3 x 3 block neighbourhood = 12 x 12 voxel rows, and a voxel row is ONE contiguous run
-// of the x-major sorted map: the CTA gathers those <= 144 runs into shared memory with coalesced 16-byte loads (the map is read
-// from L2 / HBM once per block instead of once per query and voxel) together with the tile-local voxel offsets, and every query of
-// the block runs the same Chebyshev-ring search as knn3_query on the staged copy: the ~100 dependent probes per query hit shared
-// memory instead of L2.  Same float32 no-FMA distance, same (d2, index) order => bit-identical; the global-memory ring search
-// remains the path for blocks whose neighbourhood exceeds the staging area and for small scans.  (Scanning the whole staged
-// neighbourhood by brute force was measured 8x slower than the ring search: ~3 000 candidates per query at this density.)
-enum { TILE_T = 128, TILE_CAP_MAX = 12288, TILE_ROWS = 144 };   // staging area: d.tile_cap points (16 B each), env LVB_TILE_CAP
-template <int ASSOC>
-__global__ void __launch_bounds__(TILE_T) icp_tile_kernel(IcpDev d, int* __restrict__ idx_out, float* __restrict__ d2_out) {
-    extern __shared__ __align__(16) float4 s_pts[];
-    __shared__ int s_off[TILE_ROWS + 1], s_src[TILE_ROWS], s_warp[TILE_T / 32 + 1], s_vox[TILE_ROWS * 13];
-    const Grid& g = d.g;
-    const int nc = d.cgx * d.cgy * d.cgz;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int c = blockIdx.x; c < nc; c += gridDim.x) {
-        const int q0 = d.q_start[c], q1 = d.q_start[c + 1];
-        if (q0 == q1) continue;
-        const int bx = c % d.cgx, by = (c / d.cgx) % d.cgy, bz = c / (d.cgx * d.cgy);
-        const int x0 = max(0, 4 * bx - 4), x1 = min(g.gx - 1, 4 * bx + 7);
-        // run lengths of the 144 voxel rows (two passes of 128 threads), exclusive scan -> s_off
-        int total = 0;
-        for (int base = 0; base < TILE_ROWS; base += TILE_T) {
-            const int t = base + tid;
-            int len = 0, src = 0;
-            if (t < TILE_ROWS) {
-                const int iy = 4 * by - 4 + t % 12, iz = 4 * bz - 4 + t / 12;
-                if (iy >= 0 && iy < g.gy && iz >= 0 && iz < g.gz) {
-                    const int rb = g.gx * (iy + g.gy * iz);
-                    src = d.cell_start[rb + x0]; len = d.cell_start[rb + x1 + 1] - src;
-                }
-            }
-            int inc = len;
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-            if (lane == 31) s_warp[warp] = inc;
-            __syncthreads();
-            int wbase = 0;
-            for (int w = 0; w < warp; ++w) wbase += s_warp[w];
-            int all = 0;
-            for (int w = 0; w < TILE_T / 32; ++w) all += s_warp[w];
-            if (t < TILE_ROWS) { s_off[t] = total + wbase + inc - len; s_src[t] = src; }
-            total += all;
-            __syncthreads();
-        }
-        if (tid == 0) s_off[TILE_ROWS] = total;
-        const bool staged = total <= d.tile_cap;
-        __syncthreads();
-        if (staged) {
-            for (int r = warp; r < TILE_ROWS; r += TILE_T / 32) {
-                const int o = s_off[r], len = s_off[r + 1] - o, src = s_src[r];
-                for (int j = lane; j < len; j += 32) s_pts[o + j] = __ldg(&d.map[src + j]);
-            }
-            for (int e = tid; e < TILE_ROWS * 13; e += TILE_T) {       // tile-local first point of every voxel (+ one past the row's last)
-                const int r = e / 13, x = e - r * 13;
-                const int iy = 4 * by - 4 + r % 12, iz = 4 * bz - 4 + r / 12;
-                int v = s_off[r];
-                if (iy >= 0 && iy < g.gy && iz >= 0 && iz < g.gz) v += d.cell_start[g.gx * (iy + g.gy * iz) + min(x0 + x, x1 + 1)] - s_src[r];
-                s_vox[e] = v;
-            }
-            __syncthreads();
-        }
-        Tile tile; tile.pts = s_pts; tile.vox = s_vox; tile.x0 = x0; tile.y0 = 4 * by - 4; tile.z0 = 4 * bz - 4; tile.nx = x1 - x0 + 1;
-        for (int qq = q0 + tid; qq < q1; qq += TILE_T) {
-            const int i = d.order[qq];
-            const float3 q = transform_f32(d.tf, load_xyz(d.scan, i, d.stride));
-            Best3 b;
-            if (staged) {
-                b = knn3_query_tile(d, tile, q);
-            } else b = knn3_query(d, q);
-            if (!ASSOC) { for (int j = 0; j < 3; ++j) { idx_out[3 * i + j] = b.i[j]; d2_out[3 * i + j] = b.d[j]; } continue; }
-            int ok = 1;
-            for (int j = 0; j < 3; ++j) if (!(b.i[j] >= 0 && b.i[j] < d.P && (double)b.d[j] < d.thr)) ok = 0;
-            d.accepted[i] = (unsigned char)ok;
-            if (!ok) continue;
-            const float4 a = staged ? s_pts[b.p[0]] : d.map[b.p[0]], bb = staged ? s_pts[b.p[1]] : d.map[b.p[1]], cc = staged ? s_pts[b.p[2]] : d.map[b.p[2]];
-            const V3 n = plane_normal(v3(a.x, a.y, a.z), v3(bb.x, bb.y, bb.z), v3(cc.x, cc.y, cc.z));
-            d.pa[i] = a.x; d.pa[d.K + i] = a.y; d.pa[2 * d.K + i] = a.z;
-            d.nrm[i] = n.x; d.nrm[d.K + i] = n.y; d.nrm[2 * (size_t)d.K + i] = n.z;
-        }
-        __syncthreads();
-    }
 }
 
 __device__ __forceinline__ void icp_substitute(const IcpState& s, const double* x, double* e) {
@@ -545,9 +418,7 @@ static int upload_scan(lvb_icp* h, const void* scan, int n, int stride, const do
     d.max_d2 = max_d2; d.thr = thr;
     d.accepted = h->accepted.p; d.pa = h->pa.p; d.nrm = h->nrm.p; d.st = h->st.p;
     d.rank = h->ctx->rank; d.world = h->ctx->world;
-    { static const int kv = getenv("LVB_KNN_VARIANT") ? atoi(getenv("LVB_KNN_VARIANT")) : 0; d.knn_variant = kv; }
-    { static const int tc = getenv("LVB_TILE_CAP") ? std::max(256, std::min((int)TILE_CAP_MAX, atoi(getenv("LVB_TILE_CAP")))) : 6144; d.tile_cap = tc; }
-    d.order = nullptr; d.q_start = nullptr; d.cgx = d.cgy = d.cgz = 0;
+    d.order = nullptr;
     if (n >= 4096) {       // spatial visiting order: counting sort of the queries by coarse voxel block
         const Grid& g = h->grid;
         const int cgx = (g.gx + 3) >> 2, cgy = (g.gy + 3) >> 2, cgz = (g.gz + 3) >> 2;
@@ -562,28 +433,7 @@ static int upload_scan(lvb_icp* h, const void* scan, int n, int stride, const do
         ILAUNCH(h, scan_add_kernel, nb, 1024, h->q_start.p, nc, h->q_sums.p, h->q_start.p + nc, h->q_total.p);
         ILAUNCH(h, icp_query_scatter_kernel, (n + 255) / 256, 256, n, h->q_key.p, h->q_start.p, h->q_fill.p, h->q_order.p);
         d.order = h->q_order.p;
-        d.q_start = h->q_start.p; d.cgx = cgx; d.cgy = cgy; d.cgz = cgz;
     }
-    return LVB_OK;
-}
-
-static bool use_tiles(const IcpDev& d) { return d.knn_variant == 0 && d.q_start != nullptr; }
-static int tile_attr() {
-    static bool done = false;
-    if (!done) {
-        LVB_CUDA(cudaFuncSetAttribute(icp_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TILE_CAP_MAX * sizeof(float4))));
-        LVB_CUDA(cudaFuncSetAttribute(icp_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TILE_CAP_MAX * sizeof(float4))));
-        done = true;
-    }
-    return LVB_OK;
-}
-static int tile_grid(lvb_icp* h, const IcpDev& d) { return std::max(1, std::min(d.cgx * d.cgy * d.cgz, 16 * h->ctx->sm_count)); }
-static int launch_associate(lvb_icp* h, const IcpDev& d, int n) {
-    if (use_tiles(d)) {
-        LVB_TRY(tile_attr());
-        icp_tile_kernel<1><<<tile_grid(h, d), TILE_T, (size_t)d.tile_cap * sizeof(float4), h->ctx->stream>>>(d, nullptr, nullptr);
-        h->ctx->launches++; lvb::timing_mark(h->ctx->stream, "icp_tile_kernel<1>");
-    } else ILAUNCH(h, icp_associate_kernel, inblk(n, ITPB), ITPB, d);
     return LVB_OK;
 }
 
@@ -765,8 +615,7 @@ int lvb_icp_knn3(lvb_icp* h, const void* scan, int n, int stride, const double f
     LVB_TRY(upload_scan(h, scan, n, stride, frame_pose, max_d2, 0.0, d));
     if (n == 0) return LVB_OK;
     LVB_TRY(h->knn_idx.ensure((size_t)n * 3)); LVB_TRY(h->knn_d2.ensure((size_t)n * 3));
-    if (use_tiles(d)) { LVB_TRY(tile_attr()); icp_tile_kernel<0><<<tile_grid(h, d), TILE_T, (size_t)d.tile_cap * sizeof(float4), h->ctx->stream>>>(d, h->knn_idx.p, h->knn_d2.p); h->ctx->launches++; lvb::timing_mark(h->ctx->stream, "icp_tile_kernel<0>"); }
-    else ILAUNCH(h, icp_knn_kernel, inblk(n, ITPB), ITPB, d, h->knn_idx.p, h->knn_d2.p);
+    ILAUNCH(h, icp_knn_kernel, inblk(n, ITPB), ITPB, d, h->knn_idx.p, h->knn_d2.p);
     LVB_TRY(icheck("knn3"));
     LVB_TRY(h->knn_idx.download(idx, (size_t)n * 3, h->ctx->stream));
     LVB_TRY(h->knn_d2.download(d2, (size_t)n * 3, h->ctx->stream));
@@ -800,7 +649,7 @@ int lvb_icp_eval(lvb_icp* h, int mode, const void* scan, int n, int stride, cons
     if (n == 0) return LVB_OK;
     LVB_TRY(init_state(h, mode, map_pose, rpyxyz, weight, -1.0, 0.0, nullptr));
     LVB_TRY(h->eval_r.ensure(n)); LVB_TRY(h->eval_J.ensure((size_t)n * 3));
-    LVB_TRY(launch_associate(h, d, n));
+    ILAUNCH(h, icp_associate_kernel, inblk(n, ITPB), ITPB, d);
     ILAUNCH(h, icp_eval_kernel, inblk(n, ITPB), ITPB, d, h->eval_r.p, h->eval_J.p);
     LVB_TRY(icheck("icp_eval"));
     cudaStream_t s = h->ctx->stream;
@@ -827,7 +676,7 @@ int lvb_icp_scan_to_map(lvb_icp* h, int mode, const void* scan, int n, int strid
     LVB_TRY(init_state(h, mode, map_pose, rpyxyz, weight, prior_weight, huber_a, &opt));
     cudaStream_t s = h->ctx->stream;
     lvb_ctx* ctx = h->ctx;
-    LVB_TRY(launch_associate(h, d, n));
+    ILAUNCH(h, icp_associate_kernel, inblk(n, ITPB), ITPB, d);
     const int lin_blocks = std::max(1, std::min(inblk(n, ITPB), 4 * ctx->sm_count));
     IcpState hs;
     memset(&hs, 0, sizeof(hs));
