@@ -319,6 +319,26 @@ def main():
         line["kernels"] = {"window10_us_per_iteration": {k: round(v, 2) for k, v in sorted(split.items(), key=lambda kv: -kv[1])},
                            "compute_us": round(sum(split.values()) - comm, 2), "allreduce_us": round(comm, 2),
                            "note": "direct launches with an event after each kernel (the timed legs replay a CUDA graph); includes launch gaps"}
+        # the only dense contraction of the path on the tensor cores (north_star: tcgen05 for the Schur reduce): same window, schur_mode = 1
+        if world == 1:
+            def run_tc(iters):
+                n = 0
+                while n < iters:
+                    p10.update_params(d10["poses"], d10["vec3"], d10["rho"])
+                    o = bench_options(lvb, PER); o.schur_mode = 1
+                    n += max(1, p10.solve(o).num_iterations)
+                return n
+            run_tc(3 * PER)
+            t_tc, it_tc = timed_blocks(lambda: run_tc(args.steps), 5)
+            s_fp = p10.solve(bench_options(lvb, PER)); p10.update_params(d10["poses"], d10["vec3"], d10["rho"])
+            o = bench_options(lvb, PER); o.schur_mode = 1
+            s_tc = p10.solve(o)
+            tc_split = kernel_split(lvb, lambda: run_tc(PER), PER)
+            line["schur_tc"] = {"ms_per_step": float(np.median(t_tc)) / it_tc, "fp64_ms_per_step": w10["ms"] / w10["iters"],
+                                "final_cost_rel_diff": abs(s_tc.final_cost - s_fp.final_cost) / s_fp.final_cost,
+                                "us_per_iteration": {k: round(v, 2) for k, v in tc_split.items() if "schur" in k},
+                                "note": "ba_schur_tc_kernel: tcgen05.mma kind::f16 on split-bf16 operands (hi/mid/lo), FP32 accumulation in TMEM, FP64 epilogue; "
+                                        "opt-in (schur_mode = 1): the contraction is ~0.2 GFLOP per iteration, so packing + the FP64 scatter cost what the tensor pipe saves"}
         p10.close()
 
         # ---------------- north_star's target shape: 20 keyframes, 8000 landmarks, 19 IMU factors (N = 1)

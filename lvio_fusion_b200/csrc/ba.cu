@@ -1190,6 +1190,14 @@ struct lvb_ba {
     size_t pose_smem = 0, imu_smem = 0;
 };
 
+// the pass graph is either the problem's own or the context's cached one (borrowed while ctx->graph_owner == ba)
+static void drop_graph(lvb_ba* ba) {
+    if (!ba->pass_graph) return;
+    if (ba->pass_graph == ba->ctx->graph_cache) { if (ba->ctx->graph_owner == ba) ba->ctx->graph_owner = nullptr; }
+    else cudaGraphExecDestroy(ba->pass_graph);
+    ba->pass_graph = nullptr;
+}
+
 static const int kConstStride[6] = {5, 6, 5, IMU_RAW, 8, 9};
 static const int kIdxStride[6] = {3, 1, 1, 8, 2, 1};
 static const int kResDim[6] = {2, 2, 2, 15, 6, 6};
@@ -1294,7 +1302,7 @@ int lvb_ba_create(lvb_ctx* ctx, lvb_ba** out) {
     *out = b;
     return LVB_OK;
 }
-void lvb_ba_destroy(lvb_ba* ba) { if (ba) { cudaSetDevice(ba->ctx->device); if (ba->pass_graph) cudaGraphExecDestroy(ba->pass_graph); delete ba; } }
+void lvb_ba_destroy(lvb_ba* ba) { if (ba) { cudaSetDevice(ba->ctx->device); drop_graph(ba); delete ba; } }
 
 int lvb_ba_set_cameras(lvb_ba* ba, const double cam[22]) { memcpy(ba->cam, cam, sizeof(ba->cam)); ba->have_cam = true; ba->finalized = false; return LVB_OK; }
 
@@ -1321,7 +1329,7 @@ int lvb_ba_add_factors(lvb_ba* ba, int kind, int n, const double* consts, const 
 int lvb_ba_set_loss(lvb_ba* ba, int kind, double a) {
     if (kind < 0 || kind >= 6) { set_error("bad kind"); return LVB_ERR_INVALID; }
     ba->huber[kind] = a;
-    if (ba->finalized) { ba->dev.huber[kind] = a; if (ba->pass_graph) { cudaGraphExecDestroy(ba->pass_graph); ba->pass_graph = nullptr; } }
+    if (ba->finalized) { ba->dev.huber[kind] = a; drop_graph(ba); }
     return LVB_OK;
 }
 
@@ -1715,7 +1723,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
     R.b[6] = R.b[5] + nblk(ba->nd[5], TPB);
     const size_t smem_imu = (size_t)(4 * 480 * 2 + 4 * 32) * 8 + 4 * 32 * 4;
     const size_t smem_pose = d.stage_poses ? ((size_t)np * 56 + 16) : 0;
-    if (ba->pass_graph) { cudaGraphExecDestroy(ba->pass_graph); ba->pass_graph = nullptr; }
+    drop_graph(ba);
     ba->pose_smem = smem_pose; ba->imu_smem = smem_imu;
     ba->lin_smem = ((smem_pose + 15) & ~(size_t)15) + (size_t)(TPB / 32) * SYRK_ROWS * SYRK_LD * 8;
     ba->schur_smem = (size_t)(TPB / 32) * 32 * (size_t)std::max(1, cols_max) * 8;
@@ -1932,7 +1940,7 @@ static int upload_state(lvb_ba* ba, const lvb_solve_options* o, double radius_ov
 static void apply_schur_mode(lvb_ba* ba, int mode) {
     const int m = (mode == 1 && ba->tc_ok) ? 1 : 0;
     ba->dev.tc_mode = m;
-    if (ba->pass_graph && ba->graph_mode != m) { cudaGraphExecDestroy(ba->pass_graph); ba->pass_graph = nullptr; }
+    if (ba->pass_graph && ba->graph_mode != m) drop_graph(ba);
     ba->graph_mode = m;
 }
 
@@ -1999,7 +2007,12 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
             chunk = pass == 0 ? 1 : std::max(1, std::min(chunk, (int)((opt.max_solver_time_in_seconds - el) / (el / pass))));
         }
         // instantiating a graph costs a few hundred microseconds: only worth it for a long solve or a reused problem
-        const bool use_graph = graph_ok && (ba->pass_graph || (pass >= 8 && opt.max_num_iterations - pass >= 16) || ba->solves_done >= 1);
+        // a borrowed graph only stays valid while this problem is the one the context's cached exec was last updated for
+        if (ba->pass_graph && ba->pass_graph == ba->ctx->graph_cache && ba->ctx->graph_owner != ba) ba->pass_graph = nullptr;
+        // instantiating a graph costs a few hundred microseconds: worth it for a long solve or a reused problem; re-targeting the
+        // context's cached exec to a fresh problem (cudaGraphExecUpdate) costs a few tens: worth it from a handful of iterations on
+        const bool cache_ok = ba->ctx->use_graph_cache && opt.max_num_iterations >= 3 && ba->solves_done == 0;
+        const bool use_graph = graph_ok && (ba->pass_graph || (pass >= 8 && opt.max_num_iterations - pass >= 16) || ba->solves_done >= 1 || cache_ok);
         if (use_graph && !ba->pass_graph) {
             cudaGraph_t g = nullptr;
             const long long before = ba->ctx->launches;
@@ -2011,9 +2024,21 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
             cudaError_t ce = cudaStreamEndCapture(s, &g);
             if (rc != LVB_OK) { if (g) cudaGraphDestroy(g); return rc; }
             LVB_CUDA(ce);
-            ce = cudaGraphInstantiate(&ba->pass_graph, g, 0);
+            lvb_ctx* cx = ba->ctx;
+            const bool own = ba->solves_done >= 1 || !cx->use_graph_cache;      // a reused problem keeps a graph of its own
+            if (!own && cx->graph_cache) {
+                cudaGraphExecUpdateResultInfo info;
+                if (cudaGraphExecUpdate(cx->graph_cache, g, &info) == cudaSuccess) { ba->pass_graph = cx->graph_cache; cx->graph_owner = ba; }
+                else { cudaGetLastError(); cudaGraphExecDestroy(cx->graph_cache); cx->graph_cache = nullptr; cx->graph_owner = nullptr; }
+            }
+            if (!ba->pass_graph) {
+                cudaGraphExec_t ex = nullptr;
+                ce = cudaGraphInstantiate(&ex, g, 0);
+                if (ce != cudaSuccess) { cudaGraphDestroy(g); LVB_CUDA(ce); }
+                ba->pass_graph = ex;
+                if (!own) { cx->graph_cache = ex; cx->graph_owner = ba; }
+            }
             cudaGraphDestroy(g);
-            LVB_CUDA(ce);
             ba->pass_launches = (int)(ba->ctx->launches - before);
             ba->ctx->launches = before;                     // capture is not execution
         }

@@ -285,6 +285,8 @@ int lvb_ctx_create(int device, void* cuda_stream, lvb_ctx** out) {
     c->use_graph = !(no_graph && no_graph[0] == '1');
     const char* ev = getenv("LVB_EVAL_VARIANT");
     if (ev) c->eval_variant = atoi(ev);
+    const char* ngc = getenv("LVB_NO_GRAPH_CACHE");
+    c->use_graph_cache = !(ngc && ngc[0] == '1');
     const char* pt = getenv("LVB_P2P_TIMEOUT_MS");
     if (pt && atof(pt) > 0) c->p2p_timeout_ns = (unsigned long long)(atof(pt) * 1e6);
     const char* ce = getenv("LVB_CHECK_EVERY");
@@ -298,6 +300,7 @@ void lvb_ctx_destroy(lvb_ctx* ctx) {
     for (int r = 0; r < 8; ++r) if (ctx->xpeer[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->xpeer[r]);
     if (ctx->xbuf) cudaFree(ctx->xbuf);
     if (ctx->scratch_i32) cudaFree(ctx->scratch_i32);
+    if (ctx->graph_cache) cudaGraphExecDestroy(ctx->graph_cache);
     if (ctx->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(ctx->comm);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);

@@ -41,6 +41,12 @@ struct lvb_ctx {
     bool p2p_ok = false;
     unsigned long long p2p_timeout_ns = 20000000000ull;   // env LVB_P2P_TIMEOUT_MS; a silent peer becomes LVB_ERR_COMM, not a hang
     int* scratch_i32 = nullptr;                           // device word for small host-driven collectives (comm_max_seconds)
+    // One instantiated LM-pass graph per context, re-targeted to each new problem with cudaGraphExecUpdate (a fresh capture costs a
+    // few tens of microseconds, an instantiation a few hundred): the reference builds a new problem per keyframe (Backend::Optimize),
+    // so without this the first -- usually only -- solve of a problem could never replay a graph.
+    cudaGraphExec_t graph_cache = nullptr;
+    const void* graph_owner = nullptr;                    // the lvb_ba whose parameters the cached graph currently holds
+    bool use_graph_cache = true;                          // env LVB_NO_GRAPH_CACHE=1 disables
 };
 
 namespace lvb {
