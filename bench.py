@@ -441,6 +441,34 @@ def main():
                            "e2e": {"value": ICP_K / (icp_e2e_ms * 1e-3), "unit": "points/s", "ms_per_scan": icp_e2e_ms,
                                    "note": "map upload + voxel build + scan upload + association + 4 LM iterations"},
                            "workload": "configs[2]: %d-point scan vs %d-point map, surf gate, Huber 0.1" % (ICP_K, ICP_P)}
+            if world == 1:
+                # the same keyframe through the device-resident map: the three keyframe clouds of the map frame are
+                # already in HBM (Mapping::ToWorld put them there when their keyframes were registered); per keyframe: BuildMapFrame
+                # (merge + voxel hash on the device), scan upload + scan-to-map, ToWorld of the new keyframe, eviction of the oldest
+                fr = backend.FeatureAssociation(ctx)
+                ident = np.array([0, 0, 0, 1, 0, 0, 0.0])
+                thirds = np.array_split(np.arange(ICP_P), 3)
+                for k, idx in enumerate(thirds):
+                    fr.map_append(k, np.ascontiguousarray(sc["map"][idx]), ident)
+
+                def keyframe():
+                    fr.map_build([0, 1, 2], sc["cell_size"])
+                    fr.scan_to_map(*argsicp)
+                    fr.map_append(3, None, sc["frame_pose"])
+                    fr.map_evict(3)
+                for _ in range(3):
+                    keyframe()
+                walls = []
+                for _ in range(5):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    keyframe()
+                    torch.cuda.synchronize()
+                    walls.append((time.perf_counter() - t0) * 1e3)
+                line["icp"]["e2e_resident_map"] = {"value": ICP_K / (float(np.median(walls)) * 1e-3), "unit": "points/s", "ms_per_keyframe": float(np.median(walls)),
+                                                   "note": "lvb_icp_map_build (3 resident keyframe clouds -> 1M-point map frame, on the device) + scan upload + "
+                                                           "association + 4 LM iterations + lvb_icp_map_append of the registered scan + evict; host wall clock"}
+                fr.close()
             isplit = kernel_split(lvb, lambda: fa.scan_to_map(*argsicp), 1)
             line["kernels"]["icp_us_per_scan"] = {k: round(v, 1) for k, v in sorted(isplit.items(), key=lambda kv: -kv[1])}
             us = isplit.get("icp_associate_kernel")

@@ -1171,6 +1171,7 @@ struct lvb_ba {
     int n_schur_warps = 0, schur_cols_max = 0;
     size_t schur_smem = 0, lin_smem = 0;
     cudaGraphExec_t pass_graph = nullptr;
+    bool graph_borrowed = false;        // pass_graph is the context's cached exec (never destroyed from here)
     int pass_launches = 0;
     bool capturing = false;
     bool imu_checked = true;
@@ -1193,9 +1194,9 @@ struct lvb_ba {
 // the pass graph is either the problem's own or the context's cached one (borrowed while ctx->graph_owner == ba)
 static void drop_graph(lvb_ba* ba) {
     if (!ba->pass_graph) return;
-    if (ba->pass_graph == ba->ctx->graph_cache) { if (ba->ctx->graph_owner == ba) ba->ctx->graph_owner = nullptr; }
+    if (ba->graph_borrowed) { if (ba->ctx->graph_owner == ba) ba->ctx->graph_owner = nullptr; }
     else cudaGraphExecDestroy(ba->pass_graph);
-    ba->pass_graph = nullptr;
+    ba->pass_graph = nullptr; ba->graph_borrowed = false;
 }
 
 static const int kConstStride[6] = {5, 6, 5, IMU_RAW, 8, 9};
@@ -2008,7 +2009,7 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
         }
         // instantiating a graph costs a few hundred microseconds: only worth it for a long solve or a reused problem
         // a borrowed graph only stays valid while this problem is the one the context's cached exec was last updated for
-        if (ba->pass_graph && ba->pass_graph == ba->ctx->graph_cache && ba->ctx->graph_owner != ba) ba->pass_graph = nullptr;
+        if (ba->graph_borrowed && (ba->ctx->graph_owner != ba || ba->ctx->graph_cache != ba->pass_graph)) { ba->pass_graph = nullptr; ba->graph_borrowed = false; }
         // instantiating a graph costs a few hundred microseconds: worth it for a long solve or a reused problem; re-targeting the
         // context's cached exec to a fresh problem (cudaGraphExecUpdate) costs a few tens: worth it from a handful of iterations on
         const bool cache_ok = ba->ctx->use_graph_cache && opt.max_num_iterations >= 3 && ba->solves_done == 0;
@@ -2028,14 +2029,14 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
             const bool own = ba->solves_done >= 1 || !cx->use_graph_cache;      // a reused problem keeps a graph of its own
             if (!own && cx->graph_cache) {
                 cudaGraphExecUpdateResultInfo info;
-                if (cudaGraphExecUpdate(cx->graph_cache, g, &info) == cudaSuccess) { ba->pass_graph = cx->graph_cache; cx->graph_owner = ba; }
+                if (cudaGraphExecUpdate(cx->graph_cache, g, &info) == cudaSuccess) { ba->pass_graph = cx->graph_cache; ba->graph_borrowed = true; cx->graph_owner = ba; }
                 else { cudaGetLastError(); cudaGraphExecDestroy(cx->graph_cache); cx->graph_cache = nullptr; cx->graph_owner = nullptr; }
             }
             if (!ba->pass_graph) {
                 cudaGraphExec_t ex = nullptr;
                 ce = cudaGraphInstantiate(&ex, g, 0);
                 if (ce != cudaSuccess) { cudaGraphDestroy(g); LVB_CUDA(ce); }
-                ba->pass_graph = ex;
+                ba->pass_graph = ex; ba->graph_borrowed = !own;
                 if (!own) { cx->graph_cache = ex; cx->graph_owner = ba; }
             }
             cudaGraphDestroy(g);
