@@ -885,6 +885,10 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
             // ---- panel: rows below the block + the rhs row (last):  x L^T = a, right-looking, no divisions
             // only rows inside the envelope of this block column take part (S is block-banded by construction)
             m = env_rmax[kb >> 5] - (kb + bs) + 1 + 1;
+            // the diagonal block factored during the previous step's look-ahead goes to its place in S (the backward pass reads it
+            // there) with all threads, row by row; Dt stays valid until warp 0 starts the next block after this panel phase
+            for (int e = tid; e < 32 * 32; e += nt) { const int k = e >> 5, j = e & 31; if (j <= k && k < bs) SA(kb + k, kb + j) = Dt[j * 34 + k]; }
+            if (tid < bs) invd_g[kb + tid] = invd[tid];
             for (int rr = tid; rr < m; rr += nt) {
                 const bool is_rhs = (rr == m - 1);
                 double* src = is_rhs ? (rhs + kb) : &SA(kb + bs + rr, kb);
@@ -961,10 +965,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
                 double a[32];
     #pragma unroll
                 for (int j = 0; j < 32; ++j) a[j] = (lane < bn && j <= lane) ? SA(kn + lane, kn + j) : ((j == lane) ? 1.0 : 0.0);
-                const int bad = chol_diag32(a, lane, bn, Dt, invd, [&](int j, double lj, double inv) {
-                    if (inv != 0.0) invd_g[kn + j] = inv;                      // (n + 32 entries: the tail of the last block is scratch)
-                    if (lane < bn && lane >= j && j < bn) SA(kn + lane, kn + j) = lj;
-                });
+                const int bad = chol_diag32(a, lane, Dt, invd);
                 t_diag += clock64() - t_d0;
                 if (bad && lane == 0) fail = 1;
             }

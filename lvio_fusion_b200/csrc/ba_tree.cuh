@@ -109,6 +109,9 @@ __global__ void __launch_bounds__(CHOL_T) ba_front_factor_kernel(const Front* __
             // row_base(p)[c] = entry of panel row p in own column c (c >= n: border column c - n); col_of(p) = its own column index
 #define ROW_BASE(p_) (((p_) < nr1) ? (&SG(F.o0 + r1 + (p_), F.o0)) : (Bd + (size_t)((((p_) - nr1) < nbp) ? ((p_) - nr1) : nb) * ld))
 #define COL_OF(p_) (((p_) < nr1) ? (r1 + (p_)) : (n + ((((p_) - nr1) < nbp) ? ((p_) - nr1) : nb)))
+            // the diagonal block factored during the previous step's look-ahead goes to its place in S (all threads, row by row)
+            for (int e = tid; e < 32 * 32; e += nt) { const int k = e >> 5, j = e & 31; if (j <= k && k < bs) SG(F.o0 + kb + k, F.o0 + kb + j) = Dt[j * 34 + k]; }
+            if (tid < bs) invd_g[F.o0 + kb + tid] = invd[tid];
             for (int rr = tid; rr < m; rr += nt) {
                 double* src = ROW_BASE(rr) + kb;
                 double a[32];
@@ -182,10 +185,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_front_factor_kernel(const Front* __
                 double a[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) a[j] = (lane < bn && j <= lane) ? SG(F.o0 + kn + lane, F.o0 + kn + j) : ((j == lane) ? 1.0 : 0.0);
-                const int bad = chol_diag32(a, lane, bn, Dt, invd, [&](int j, double lj, double inv) {
-                    if (inv != 0.0 && j < bn) invd_g[F.o0 + kn + j] = inv;     // (beyond bn: the next front's unknowns)
-                    if (lane < bn && lane >= j && j < bn) SG(F.o0 + kn + lane, F.o0 + kn + j) = lj;
-                });
+                const int bad = chol_diag32(a, lane, Dt, invd);
                 if (bad && lane == 0) fail = 1;
             }
         }

@@ -7,10 +7,11 @@
 // One warp, lane = row of the block, a[r] = entry (lane, c0 + r) of the block (lower triangle valid), bn = rows/columns in use.
 // The 32 columns go in 4 groups of 8.  Inside a group a finished column is applied at once only to the group's own columns (<= 7
 // FMAs per lane, operands broadcast from Dt with <= 4 LDS.128); the columns right of the group receive the group's rank-8 update
-// in one sweep afterwards -- independent FMAs at full issue rate instead of sitting in the pivot chain.  Per column the chain is
-// mul -> FMA -> shuffle -> rsqrt.  `store(j, l_lane_j, inv_or_0)` lets the caller put L (and the reciprocal pivot) where it lives.
-template <class Store>
-__device__ __forceinline__ int chol_diag32(double (&a)[32], const int lane, const int bn, double* __restrict__ Dt, double* __restrict__ invd, Store store) {
+// in one sweep afterwards.  Per column the chain is mul -> FMA -> shuffle -> rsqrt, and a single warp issues it at ~0.25 IPC, so
+// the instruction count per column is what matters: entries above the diagonal are don't-care and are updated without per-lane
+// predicates (garbage stays garbage, nothing valid ever reads it), and nothing is stored to global memory here -- the caller
+// copies the finished block (Dt, invd) to its place with all threads at the start of the next panel phase.
+__device__ __forceinline__ int chol_diag32(double (&a)[32], const int lane, double* __restrict__ Dt, double* __restrict__ invd) {
     int bad = 0;
     double d0 = __shfl_sync(0xffffffffu, a[0], 0);
     if (!(d0 > 0.0)) { bad = 1; d0 = 1.0; }
@@ -21,11 +22,9 @@ __device__ __forceinline__ int chol_diag32(double (&a)[32], const int lane, cons
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
             const int j = c0 + jj;
-            if (rel >= jj) a[jj] *= inv;              // l_ij (lane j: sqrt(d_jj))
-            const double lj = (rel >= jj) ? a[jj] : 0.0;
-            Dt[j * 34 + lane] = lj;
+            a[jj] *= inv;                             // l_ij for lanes >= j (lane j: sqrt(d_jj)); don't-care above the diagonal
+            Dt[j * 34 + lane] = a[jj];
             if (rel == jj) invd[j] = inv;
-            store(j, lj, rel == jj ? inv : 0.0);
             // next pivot inside the group: lane j + 1 owns everything its diagonal entry still needs
             double inv_next = 1.0;
             if (jj < 7) {
@@ -39,8 +38,8 @@ __device__ __forceinline__ int chol_diag32(double (&a)[32], const int lane, cons
             for (int p = 0; p < 4; ++p) {
                 if (2 * p + 1 > jj) {
                     const double2 v = bp[p];
-                    if (2 * p > jj && rel >= 2 * p) a[2 * p] -= a[jj] * v.x;
-                    if (rel >= 2 * p + 1) a[2 * p + 1] -= a[jj] * v.y;
+                    if (2 * p > jj) a[2 * p] -= a[jj] * v.x;
+                    a[2 * p + 1] -= a[jj] * v.y;
                 }
             }
             inv = inv_next;
