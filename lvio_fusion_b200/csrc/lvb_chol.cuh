@@ -4,18 +4,33 @@
 // Shared-memory operand: Dt[j * 34 + k] = L[k][j] (the block's factor, column-major with a 16-byte aligned stride), invd[j] = 1 / L[j][j].
 #pragma once
 
-// One warp, lane = row of the block, a[r] = entry (lane, c0 + r) of the block (lower triangle valid), bn = rows/columns in use.
-// The 32 columns go in 4 groups of 8.  Inside a group a finished column is applied at once only to the group's own columns (<= 7
-// FMAs per lane, operands broadcast from Dt with <= 4 LDS.128); the columns right of the group receive the group's rank-8 update
-// in one sweep afterwards.  Per column the chain is mul -> FMA -> shuffle -> rsqrt, and a single warp issues it at ~0.25 IPC, so
-// the instruction count per column is what matters: entries above the diagonal are don't-care and are updated without per-lane
-// predicates (garbage stays garbage, nothing valid ever reads it), and nothing is stored to global memory here -- the caller
-// copies the finished block (Dt, invd) to its place with all threads at the start of the next panel phase.
+// 1 / sqrt(x) for a positive normal x without the library routine's special-case branch: a single warp is an in-order machine, and
+// that branch (plus the call behind it) fences the scheduler, so nothing independent could be interleaved into the pivot chain's
+// latency.  MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-20) + two coupled Newton (Goldschmidt) steps: 2^-40, then below 2^-52.
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    h = fma(h, r, h);
+    return h + h;
+}
+
+// One warp, lane = row of the block, a[r] = entry (lane, c0 + r) of the block (lower triangle valid).
+// The 32 columns go in 4 groups of 8.  Inside a group a finished column is applied at once only to the group's own columns: its
+// entries L[c0 + r][j] come from the owning lanes by shuffle (no shared-memory round trip, no warp barrier in the chain); the
+// columns right of the group receive the group's rank-8 update in one sweep afterwards, operands broadcast from Dt as LDS.128.
+// Per column the dependent chain is mul -> shuffle -> FMA -> shuffle -> rsqrt (~110 cycles); everything else is independent work
+// the scheduler can place into its shadow because the loop body is branch-free.  Entries above the diagonal are don't-care and are
+// updated without per-lane predicates (garbage stays garbage, nothing valid ever reads it), and nothing is stored to global memory
+// here -- the caller copies the finished block (Dt, invd) to its place with all threads at the start of the next panel phase.
 __device__ __forceinline__ int chol_diag32(double (&a)[32], const int lane, double* __restrict__ Dt, double* __restrict__ invd) {
     int bad = 0;
     double d0 = __shfl_sync(0xffffffffu, a[0], 0);
     if (!(d0 > 0.0)) { bad = 1; d0 = 1.0; }
-    double inv = rsqrt(d0);
+    double inv = rsqrt_pos(d0);
 #pragma unroll 1
     for (int c0 = 0; c0 < 32; c0 += 8) {
         const int rel = lane - c0;                    // register index of this lane's diagonal entry
@@ -25,26 +40,19 @@ __device__ __forceinline__ int chol_diag32(double (&a)[32], const int lane, doub
             a[jj] *= inv;                             // l_ij for lanes >= j (lane j: sqrt(d_jj)); don't-care above the diagonal
             Dt[j * 34 + lane] = a[jj];
             if (rel == jj) invd[j] = inv;
-            // next pivot inside the group: lane j + 1 owns everything its diagonal entry still needs
-            double inv_next = 1.0;
-            if (jj < 7) {
-                double dn = __shfl_sync(0xffffffffu, a[jj + 1] - a[jj] * a[jj], j + 1);
-                if (!(dn > 0.0)) { bad = 1; dn = 1.0; }
-                inv_next = rsqrt(dn);
-            }
-            __syncwarp();
-            const double2* bp = reinterpret_cast<const double2*>(Dt + j * 34 + c0);      // L[c0 + r][j], r = 0..7
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                if (2 * p + 1 > jj) {
-                    const double2 v = bp[p];
-                    if (2 * p > jj) a[2 * p] -= a[jj] * v.x;
-                    a[2 * p + 1] -= a[jj] * v.y;
+            for (int r = jj + 1; r < 8; ++r) {        // r = jj + 1 first: it completes the next pivot
+                const double v = __shfl_sync(0xffffffffu, a[jj], c0 + r);
+                a[r] -= a[jj] * v;
+                if (r == jj + 1) {
+                    double dn = __shfl_sync(0xffffffffu, a[jj + 1], j + 1);
+                    if (!(dn > 0.0)) { bad = 1; dn = 1.0; }
+                    inv = rsqrt_pos(dn);
                 }
             }
-            inv = inv_next;
         }
         if (c0 < 24) {
+            __syncwarp();                             // the group's columns are in Dt
             // rank-8 update of the columns right of the group: a[r] -= sum_k L[lane][c0 + k] * L[c0 + r][c0 + k].  Register 8 (the next
             // pivot's column) first, so that its shuffle + rsqrt overlap the rest of the sweep.
 #pragma unroll
@@ -54,7 +62,7 @@ __device__ __forceinline__ int chol_diag32(double (&a)[32], const int lane, doub
             }
             double dn = __shfl_sync(0xffffffffu, a[8], c0 + 8);
             if (!(dn > 0.0)) { bad = 1; dn = 1.0; }
-            inv = rsqrt(dn);
+            inv = rsqrt_pos(dn);
 #pragma unroll
             for (int r = 10; r < 32; r += 2) {
                 if (c0 + r < 32) {                    // warp-uniform
@@ -71,6 +79,7 @@ __device__ __forceinline__ int chol_diag32(double (&a)[32], const int lane, doub
 #pragma unroll
         for (int r = 24; r < 32; ++r) a[r] = 0.0;
     }
+    __syncwarp();
     return bad;
 }
 
