@@ -473,57 +473,89 @@ __device__ __forceinline__ void linearize_other_body(const BaDev& d, const Block
     const double* V = MODE == 0 ? d.vec3 : d.c_vec3;
     double* cost_target = MODE == 0 ? &d.st->cost_acc : &d.st->cand_cost_acc;
     double cost = 0.0;
-    if (b < R.b[4]) {   // ---- IMU: one warp per factor
-        double* s_raw = reinterpret_cast<double*>(smem_raw);     // 4 x 480
-        double* s_Jw = s_raw + 4 * 480;                          // 4 x 480
-        double* s_r = s_Jw + 4 * 480;                            // 4 x 32
-        int* s_gidx = reinterpret_cast<int*>(s_r + 4 * 32);      // 4 x 32
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int f = (b - R.b[3]) * 4 + warp;
+    if (b < R.b[4]) {   // ---- IMU: one CTA (4 warps) per factor
+        // The eight Jacobian blocks and the residual are nine different scalar programs: as nine lanes of one warp they ran one
+        // after the other (divergence), which made this factor kind a ~15 us single-warp chain.  Here they are spread over the four
+        // warps (lane 0 each, heavy blocks on different warps), the constants and U come from shared memory, and the whitening and
+        // the J^T J accumulation use all 128 threads.
+        double* s_raw = reinterpret_cast<double*>(smem_raw);     // 480: raw ambient Jacobian 15 x 32, later the tangent Jacobian 15 x 30
+        double* s_Jw = s_raw + 480;                              // 480: whitened ambient Jacobian
+        double* s_r = s_Jw + 480;                                // 32 : raw residual 0..14, whitened 16..30
+        double* s_c = s_r + 32;                                  // 288: the factor's constants (17 scalars, five 3x3 blocks, U, init flag)
+        int* s_gidx = reinterpret_cast<int*>(s_c + IMU_STRIDE);  // 32
+        const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+        const int f = b - R.b[3];
         const int n = d.n[3];
-        if (f < n) {
-            double* raw = s_raw + warp * 480; double* Jw = s_Jw + warp * 480; double* rr = s_r + warp * 32; int* gidx = s_gidx + warp * 32;
-            imu_warp_eval(d, f, Psrc, V, raw, Jw, rr, MODE == 0);
-            double s = (lane < 15) ? rr[16 + lane] * rr[16 + lane] : 0.0;
-            s = warp_sum(s);
-            double rho_v, sr;
-            huber(d.huber[3], s, &rho_v, &sr);
-            if (lane == 0) cost = 0.5 * rho_v;
-            if (MODE == 0) {
-                const int* ix = d.fi[3];
-                // tangent Jacobian Jt[15][30] into `raw` (cols: pose_i 6 | v ba bg 9 | pose_j 6 | v ba bg 9)
-                if (lane < 15) {
-                    const double* a = Jw + 32 * lane;
-                    double* t = raw + 30 * lane;
-                    double t6[6];
-                    ambient_row_to_tangent(Psrc + 7 * ix[f], a, t6);
-                    for (int k = 0; k < 6; ++k) t[k] = t6[k] * sr;
-                    for (int k = 0; k < 9; ++k) t[6 + k] = a[7 + k] * sr;
-                    ambient_row_to_tangent(Psrc + 7 * ix[4 * n + f], a + 16, t6);
-                    for (int k = 0; k < 6; ++k) t[15 + k] = t6[k] * sr;
-                    for (int k = 0; k < 9; ++k) t[21 + k] = a[23 + k] * sr;
-                    rr[16 + lane] *= sr;
-                }
-                if (lane < 30) {
-                    int blk, loc;
-                    if (lane < 6) { blk = 0; loc = lane; } else if (lane < 15) { blk = 1 + (lane - 6) / 3; loc = (lane - 6) % 3; }
-                    else if (lane < 21) { blk = 4; loc = lane - 15; } else { blk = 5 + (lane - 21) / 3; loc = (lane - 21) % 3; }
-                    const int id = ix[(size_t)blk * n + f];
-                    const int off = id < 0 ? -1 : ((blk == 0 || blk == 4) ? d.pose_off[id] : d.vec3_off[id]);
-                    gidx[lane] = off < 0 ? -1 : off + loc;
-                }
-                __syncwarp();
-                if (lane < 30 && gidx[lane] >= 0) {
-                    double g = 0; for (int i = 0; i < 15; ++i) g += raw[30 * i + lane] * rr[16 + i];
-                    atomicAdd(&d.gc[gidx[lane]], g);
-                }
-                for (int e = lane; e < 465; e += 32) {
-                    const int a = c_tri_a[e], bb = c_tri_b[e];
-                    const int ga = gidx[a], gb = gidx[bb];
-                    if (ga < 0 || gb < 0) continue;
-                    double h = 0; for (int i = 0; i < 15; ++i) h += raw[30 * i + a] * raw[30 * i + bb];
-                    if (ga >= gb) atomicAdd(&d.Hpp[SIDX(d, ga, gb)], h); else atomicAdd(&d.Hpp[SIDX(d, gb, ga)], h);
-                }
+        const int* ix = d.fi[3];
+        {
+            const double* c = d.fc[3] + (size_t)f * IMU_STRIDE;
+            for (int e = tid; e < IMU_STRIDE; e += TPB) s_c[e] = c[e];
+            for (int e = tid; e < 480; e += TPB) s_raw[e] = 0.0;
+        }
+        __syncthreads();
+        if (lane == 0) {
+            const ImuConst k = load_imu_const(s_c);
+            const double* Ti = Psrc + 7 * ix[f]; const double* Vi = V + 3 * ix[n + f]; const double* Bai = V + 3 * ix[2 * n + f]; const double* Bgi = V + 3 * ix[3 * n + f];
+            const double zero3[3] = {0.0, 0.0, 0.0};         // ImuInitError: Baj = Bgj = 0 (imu_error.hpp:141-142), idx = -1
+            const int i6 = ix[6 * n + f], i7 = ix[7 * n + f];
+            const double* Tj = Psrc + 7 * ix[4 * n + f]; const double* Vj = V + 3 * ix[5 * n + f]; const double* Baj = i6 < 0 ? zero3 : V + 3 * i6; const double* Bgj = i7 < 0 ? zero3 : V + 3 * i7;
+            // tasks 0..7 = Jacobian blocks (pose_i v_i ba_i bg_i pose_j v_j ba_j bg_j), 8 = residual; heavy ones: 0, 3, 4, 8
+            const int tasks[4][3] = {{0, -1, -1}, {3, 1, 5}, {4, 2, 6}, {8, 7, -1}};
+            for (int t = 0; t < 3; ++t) {
+                const int task = tasks[warp][t];
+                if (task < 0) continue;
+                if (task == 8) imu_raw_residual(k, Ti, Vi, Bai, Bgi, Tj, Vj, Baj, Bgj, s_r);
+                else if (MODE == 0 && !(task >= 6 && s_c[287] != 0.0)) imu_raw_jacobian_block(k, task, Ti, Vi, Bgi, Tj, Vj, s_raw);
+            }
+        }
+        __syncthreads();
+        const double* U = s_c + 62;
+        if (tid < 15) { double sacc = 0; for (int k = 0; k < 15; ++k) sacc += U[15 * tid + k] * s_r[k]; s_r[16 + tid] = sacc; }
+        if (MODE == 0) for (int e = tid; e < 480; e += TPB) {
+            const int i = e >> 5, j = e & 31;
+            double sacc = 0; for (int k = i; k < 15; ++k) sacc += U[15 * i + k] * s_raw[32 * k + j];     // U is upper triangular
+            s_Jw[e] = sacc;
+        }
+        __syncthreads();
+        double s = 0.0;
+        for (int i = 0; i < 15; ++i) s += s_r[16 + i] * s_r[16 + i];
+        double rho_v, sr;
+        huber(d.huber[3], s, &rho_v, &sr);
+        if (tid == 0) cost = 0.5 * rho_v;
+        if (MODE == 0) {
+            // tangent Jacobian Jt[15][30] into s_raw (cols: pose_i 6 | v ba bg 9 | pose_j 6 | v ba bg 9)
+            __syncthreads();                                      // every thread has read the whitened residual
+            if (tid < 15) {
+                const double* a = s_Jw + 32 * tid;
+                double* t = s_raw + 30 * tid;
+                double t6[6];
+                ambient_row_to_tangent(Psrc + 7 * ix[f], a, t6);
+                for (int k = 0; k < 6; ++k) t[k] = t6[k] * sr;
+                for (int k = 0; k < 9; ++k) t[6 + k] = a[7 + k] * sr;
+                ambient_row_to_tangent(Psrc + 7 * ix[4 * n + f], a + 16, t6);
+                for (int k = 0; k < 6; ++k) t[15 + k] = t6[k] * sr;
+                for (int k = 0; k < 9; ++k) t[21 + k] = a[23 + k] * sr;
+                s_r[16 + tid] *= sr;
+            } else if (tid >= 32 && tid < 62) {
+                const int l = tid - 32;
+                int blk, loc;
+                if (l < 6) { blk = 0; loc = l; } else if (l < 15) { blk = 1 + (l - 6) / 3; loc = (l - 6) % 3; }
+                else if (l < 21) { blk = 4; loc = l - 15; } else { blk = 5 + (l - 21) / 3; loc = (l - 21) % 3; }
+                const int id = ix[(size_t)blk * n + f];
+                const int off = id < 0 ? -1 : ((blk == 0 || blk == 4) ? d.pose_off[id] : d.vec3_off[id]);
+                s_gidx[l] = off < 0 ? -1 : off + loc;
+            }
+            __syncthreads();
+            if (tid < 30 && s_gidx[tid] >= 0) {
+                double g = 0; for (int i = 0; i < 15; ++i) g += s_raw[30 * i + tid] * s_r[16 + i];
+                atomicAdd(&d.gc[s_gidx[tid]], g);
+            }
+            for (int e = tid; e < 465; e += TPB) {
+                const int a = c_tri_a[e], bb = c_tri_b[e];
+                const int ga = s_gidx[a], gb = s_gidx[bb];
+                if (ga < 0 || gb < 0) continue;
+                double h = 0; for (int i = 0; i < 15; ++i) h += s_raw[30 * i + a] * s_raw[30 * i + bb];
+                if (ga >= gb) atomicAdd(&d.Hpp[SIDX(d, ga, gb)], h); else atomicAdd(&d.Hpp[SIDX(d, gb, ga)], h);
             }
         }
     } else {   // ---- PoseGraphError / PoseError priors: one thread per block
@@ -1720,10 +1752,10 @@ int lvb_ba_finalize(lvb_ba* ba) {
     R.b[1] = R.b[0] + nblk(ba->nd[0], TPB);
     R.b[2] = R.b[1] + nblk(ba->nd[1], TPB);
     R.b[3] = R.b[2] + nblk(ba->nd[2], TPB);
-    R.b[4] = R.b[3] + nblk(ba->nd[3], 4);
+    R.b[4] = R.b[3] + ba->nd[3];                    // one CTA per IMU factor
     R.b[5] = R.b[4] + nblk(ba->nd[4], TPB);
     R.b[6] = R.b[5] + nblk(ba->nd[5], TPB);
-    const size_t smem_imu = (size_t)(4 * 480 * 2 + 4 * 32) * 8 + 4 * 32 * 4;
+    const size_t smem_imu = (size_t)(480 * 2 + 32 + IMU_STRIDE) * 8 + 32 * 4;
     const size_t smem_pose = d.stage_poses ? ((size_t)np * 56 + 16) : 0;
     drop_graph(ba);
     ba->pose_smem = smem_pose; ba->imu_smem = smem_imu;
