@@ -63,6 +63,7 @@ struct BaDev {
     LmState* st;
     int rank0, rank, world;
     int stage_poses;
+    int imu_cta;                        // 1: one CTA per IMU factor (window-sized problems: latency), 0: one warp per factor (map scale)
     Cams cams;
 };
 
@@ -473,7 +474,7 @@ __device__ __forceinline__ void linearize_other_body(const BaDev& d, const Block
     const double* V = MODE == 0 ? d.vec3 : d.c_vec3;
     double* cost_target = MODE == 0 ? &d.st->cost_acc : &d.st->cand_cost_acc;
     double cost = 0.0;
-    if (b < R.b[4]) {   // ---- IMU: one CTA (4 warps) per factor
+    if (b < R.b[4] && d.imu_cta) {   // ---- IMU, window size: one CTA (4 warps) per factor
         // The eight Jacobian blocks and the residual are nine different scalar programs: as nine lanes of one warp they ran one
         // after the other (divergence), which made this factor kind a ~15 us single-warp chain.  Here they are spread over the four
         // warps (lane 0 each, heavy blocks on different warps), the constants and U come from shared memory, and the whitening and
@@ -556,6 +557,59 @@ __device__ __forceinline__ void linearize_other_body(const BaDev& d, const Block
                 if (ga < 0 || gb < 0) continue;
                 double h = 0; for (int i = 0; i < 15; ++i) h += s_raw[30 * i + a] * s_raw[30 * i + bb];
                 if (ga >= gb) atomicAdd(&d.Hpp[SIDX(d, ga, gb)], h); else atomicAdd(&d.Hpp[SIDX(d, gb, ga)], h);
+            }
+        }
+    } else if (b < R.b[4]) {   // ---- IMU, map scale: one warp per factor, four factors per CTA (throughput: thousands of factors)
+        double* s_raw = reinterpret_cast<double*>(smem_raw);     // 4 x 480
+        double* s_Jw = s_raw + 4 * 480;                          // 4 x 480
+        double* s_r = s_Jw + 4 * 480;                            // 4 x 32
+        int* s_gidx = reinterpret_cast<int*>(s_r + 4 * 32);      // 4 x 32
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int f = (b - R.b[3]) * 4 + warp;
+        const int n = d.n[3];
+        if (f < n) {
+            double* raw = s_raw + warp * 480; double* Jw = s_Jw + warp * 480; double* rr = s_r + warp * 32; int* gidx = s_gidx + warp * 32;
+            imu_warp_eval(d, f, Psrc, V, raw, Jw, rr, MODE == 0);
+            double s = (lane < 15) ? rr[16 + lane] * rr[16 + lane] : 0.0;
+            s = warp_sum(s);
+            double rho_v, sr;
+            huber(d.huber[3], s, &rho_v, &sr);
+            if (lane == 0) cost = 0.5 * rho_v;
+            if (MODE == 0) {
+                const int* ix = d.fi[3];
+                // tangent Jacobian Jt[15][30] into `raw` (cols: pose_i 6 | v ba bg 9 | pose_j 6 | v ba bg 9)
+                if (lane < 15) {
+                    const double* a = Jw + 32 * lane;
+                    double* t = raw + 30 * lane;
+                    double t6[6];
+                    ambient_row_to_tangent(Psrc + 7 * ix[f], a, t6);
+                    for (int k = 0; k < 6; ++k) t[k] = t6[k] * sr;
+                    for (int k = 0; k < 9; ++k) t[6 + k] = a[7 + k] * sr;
+                    ambient_row_to_tangent(Psrc + 7 * ix[4 * n + f], a + 16, t6);
+                    for (int k = 0; k < 6; ++k) t[15 + k] = t6[k] * sr;
+                    for (int k = 0; k < 9; ++k) t[21 + k] = a[23 + k] * sr;
+                    rr[16 + lane] *= sr;
+                }
+                if (lane < 30) {
+                    int blk, loc;
+                    if (lane < 6) { blk = 0; loc = lane; } else if (lane < 15) { blk = 1 + (lane - 6) / 3; loc = (lane - 6) % 3; }
+                    else if (lane < 21) { blk = 4; loc = lane - 15; } else { blk = 5 + (lane - 21) / 3; loc = (lane - 21) % 3; }
+                    const int id = ix[(size_t)blk * n + f];
+                    const int off = id < 0 ? -1 : ((blk == 0 || blk == 4) ? d.pose_off[id] : d.vec3_off[id]);
+                    gidx[lane] = off < 0 ? -1 : off + loc;
+                }
+                __syncwarp();
+                if (lane < 30 && gidx[lane] >= 0) {
+                    double g = 0; for (int i = 0; i < 15; ++i) g += raw[30 * i + lane] * rr[16 + i];
+                    atomicAdd(&d.gc[gidx[lane]], g);
+                }
+                for (int e = lane; e < 465; e += 32) {
+                    const int a = c_tri_a[e], bb = c_tri_b[e];
+                    const int ga = gidx[a], gb = gidx[bb];
+                    if (ga < 0 || gb < 0) continue;
+                    double h = 0; for (int i = 0; i < 15; ++i) h += raw[30 * i + a] * raw[30 * i + bb];
+                    if (ga >= gb) atomicAdd(&d.Hpp[SIDX(d, ga, gb)], h); else atomicAdd(&d.Hpp[SIDX(d, gb, ga)], h);
+                }
             }
         }
     } else {   // ---- PoseGraphError / PoseError priors: one thread per block
@@ -657,13 +711,28 @@ __global__ void __launch_bounds__(TPB) ba_schur_kernel(BaDev d, int cols_max) {
         const double hl = h + lam;
         if (hl > 0.0 && ns > 0) {
             const int n = d.n[0];
-            for (int e = d.lm_start[l]; e < d.lm_start[l + 1]; ++e) {
-                const int f = d.lm_fac[e];
-                if (f < 0) continue;
-                for (int side = 0; side < 2; ++side) {
-                    const int sl = d.tf_slot[(size_t)side * n + f];
-                    if (sl < 0) continue;
-                    for (int k = 0; k < 6; ++k) row[6 * sl + k] += d.tf_w[(size_t)f * 12 + 6 * side + k];
+            // gather the landmark's coupling records four factors at a time: all index loads of a batch are issued before the first
+            // use (factor id -> slots -> 96-byte record is a chain of three dependent round trips; one factor at a time made this
+            // kernel L2-latency bound, 35 long-scoreboard stall cycles per issue at map scale)
+            const int e1 = d.lm_start[l + 1];
+            for (int eb = d.lm_start[l]; eb < e1; eb += 4) {
+                int f[4], s0[4], s1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) f[u] = (eb + u < e1) ? d.lm_fac[eb + u] : -1;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int fc = max(f[u], 0); s0[u] = d.tf_slot[fc]; s1[u] = d.tf_slot[(size_t)n + fc]; }      // unconditional (clamped) loads: no branches between them
+                double2 w[4][6];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double2* src = reinterpret_cast<const double2*>(d.tf_w + (size_t)max(f[u], 0) * 12);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) w[u][k] = src[k];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (f[u] < 0) continue;
+                    if (s0[u] >= 0) { double* t = row + 6 * s0[u]; t[0] += w[u][0].x; t[1] += w[u][0].y; t[2] += w[u][1].x; t[3] += w[u][1].y; t[4] += w[u][2].x; t[5] += w[u][2].y; }
+                    if (s1[u] >= 0) { double* t = row + 6 * s1[u]; t[0] += w[u][3].x; t[1] += w[u][3].y; t[2] += w[u][4].x; t[3] += w[u][4].y; t[4] += w[u][5].x; t[5] += w[u][5].y; }
                 }
             }
             const double sh = sqrt(1.0 / hl);
@@ -1087,13 +1156,26 @@ __global__ void __launch_bounds__(TPB) ba_update_kernel(BaDev d) {
             const int n = d.n[0];
             const int* ix = d.fi[0];
             double s = d.gl[l];
-            for (int e = e0; e < e1; ++e) {
-                const int f = d.lm_fac[e];
-                if (f < 0) continue;
-                for (int side = 0; side < 2; ++side) {
-                    const int off = d.pose_off[ix[(size_t)(1 + side) * n + f]];
-                    if (off < 0) continue;
-                    for (int k = 0; k < 6; ++k) s += d.tf_w[(size_t)f * 12 + 6 * side + k] * dc[off + k];
+            for (int eb = e0; eb < e1; eb += 4) {      // four factors at a time, loads before uses (see ba_schur_kernel)
+                int f[4], o0[4], o1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) f[u] = (eb + u < e1) ? d.lm_fac[eb + u] : -1;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int fc = max(f[u], 0); o0[u] = ix[(size_t)n + fc]; o1[u] = ix[(size_t)2 * n + fc]; }      // unconditional (clamped) loads
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { o0[u] = d.pose_off[o0[u]]; o1[u] = d.pose_off[o1[u]]; }
+                double2 w[4][6];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double2* src = reinterpret_cast<const double2*>(d.tf_w + (size_t)max(f[u], 0) * 12);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) w[u][k] = src[k];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (f[u] < 0) continue;
+                    if (o0[u] >= 0) { const double* t = dc + o0[u]; s += w[u][0].x * t[0] + w[u][0].y * t[1] + w[u][1].x * t[2] + w[u][1].y * t[3] + w[u][2].x * t[4] + w[u][2].y * t[5]; }
+                    if (o1[u] >= 0) { const double* t = dc + o1[u]; s += w[u][3].x * t[0] + w[u][3].y * t[1] + w[u][4].x * t[2] + w[u][4].y * t[3] + w[u][5].x * t[4] + w[u][5].y * t[5]; }
                 }
             }
             const double lam = d.lam_l[l];
@@ -1304,6 +1386,7 @@ static int build_front_tree(int n, int band, int max_leaves, std::vector<Front>&
         F.o0 = nd.o0; F.m = nd.m; F.wL = nd.wL; F.wR = nd.wR; F.bL0 = nd.bL0; F.bR0 = nd.bR0;
         F.actR = nd.h == 0 ? std::max(0, nd.m - band) : 0;
         F.child0 = nd.c0 < 0 ? -1 : new_id[nd.c0]; F.child1 = nd.c1 < 0 ? -1 : new_id[nd.c1];
+        F.parent = -1; F.side = 0;
         F.nb = nd.wL + nd.wR; F.ld = (nd.m + F.nb + 1) & ~1;
         F.bd = (long long)pool_doubles;
         pool_doubles += ((size_t)(F.nb + 1) * F.ld + 1) & ~(size_t)1;
@@ -1312,6 +1395,10 @@ static int build_front_tree(int n, int band, int max_leaves, std::vector<Front>&
         max_nb = std::max(max_nb, F.nb);
         max_panel_rows = std::max(max_panel_rows, std::min(nd.m, band) + F.nb + 1);
         out.push_back(F);
+    }
+    for (size_t i = 0; i < out.size(); ++i) {
+        if (out[i].child0 >= 0) { out[out[i].child0].parent = (int)i; out[out[i].child0].side = 0; }
+        if (out[i].child1 >= 0) { out[out[i].child1].parent = (int)i; out[out[i].child1].side = 1; }
     }
     return D + 1;
 }
@@ -1752,10 +1839,11 @@ int lvb_ba_finalize(lvb_ba* ba) {
     R.b[1] = R.b[0] + nblk(ba->nd[0], TPB);
     R.b[2] = R.b[1] + nblk(ba->nd[1], TPB);
     R.b[3] = R.b[2] + nblk(ba->nd[2], TPB);
-    R.b[4] = R.b[3] + ba->nd[3];                    // one CTA per IMU factor
+    d.imu_cta = dense_layout ? 1 : 0;
+    R.b[4] = R.b[3] + (d.imu_cta ? ba->nd[3] : nblk(ba->nd[3], 4));
     R.b[5] = R.b[4] + nblk(ba->nd[4], TPB);
     R.b[6] = R.b[5] + nblk(ba->nd[5], TPB);
-    const size_t smem_imu = (size_t)(480 * 2 + 32 + IMU_STRIDE) * 8 + 32 * 4;
+    const size_t smem_imu = d.imu_cta ? (size_t)(480 * 2 + 32 + IMU_STRIDE) * 8 + 32 * 4 : (size_t)(4 * 480 * 2 + 4 * 32) * 8 + 4 * 32 * 4;
     const size_t smem_pose = d.stage_poses ? ((size_t)np * 56 + 16) : 0;
     drop_graph(ba);
     ba->pose_smem = smem_pose; ba->imu_smem = smem_imu;
@@ -1919,7 +2007,8 @@ static int launch_reduced_solve(lvb_ba* ba) {
         // multifrontal tree: leaves (all SMs) -> ... -> root, then the back-substitution root -> leaves; 2 (levels + 1) launches
         const Front* fr = ba->fronts.p;
         LAUNCH(ba, lm_control_pre_kernel, 1, 1, 0, d.st);
-        ba_front_init_kernel<<<dim3(16, ba->level_count[0]), 256, 0, ctx->stream>>>(fr, ba->level_count[0], d.S, d.rhs, ba->front_pool.p, d.srow, d.soff, ba->band, d.st);
+        const int n_fronts = ba->level_first[ba->tree_levels - 1] + ba->level_count[ba->tree_levels - 1];
+        ba_front_init_kernel<<<dim3(16, n_fronts), 256, 0, ctx->stream>>>(fr, n_fronts, d.S, d.rhs, ba->front_pool.p, d.srow, d.soff, ba->band, d.st);
         ctx->launches++; mark(ba, "ba_front_init_kernel");
         for (int l = 0; l < ba->tree_levels; ++l)
             LAUNCH(ba, ba_front_factor_kernel, ba->level_count[l], CHOL_T, ba->tree_factor_smem, fr, ba->level_first[l], d.S, d.rhs, ba->front_pool.p, d.srow, d.soff, ba->band, ba->chol_invd.p, d.st);

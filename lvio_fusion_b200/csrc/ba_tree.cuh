@@ -12,7 +12,7 @@
 // eliminated by ONE CTA with a partial Cholesky over its own columns -- the blocked right-looking kernel of ba_cholesky_kernel
 // with the border rows riding along in every panel -- which leaves  L_own,  W = L_own^-1 A_own,border  (in the border rows),
 // y = L_own^-1 b_own  and the update  -W^T W  of the border x border block.  All fronts of a level run concurrently (grid = number
-// of fronts), a parent extend-adds its two children's updates in its prologue; log2(P) + 1 launches factor the whole system and
+// of fronts), a child adds its update into its parent's front when it is done (extend-add); log2(P) + 1 launches factor the system and
 // the same number of launches, root first, back-substitute.  Own x own blocks are factored in place in the banded storage of S
 // (a separator of width w = B fits inside the band), border rows live in a pool.
 #pragma once
@@ -23,28 +23,34 @@ struct Front {
     int bL0, bR0;           // their first unknowns
     int actR;               // own column from which the right-border rows can be non-zero (leaves: m - band; internal: 0)
     int child0, child1;     // front ids, -1 for leaves
+    int parent, side;       // parent front id (-1: root) and which child this is (0: left, 1: right)
     int ld, nb;             // border array: (nb + 1) rows (borders, then the rhs row) x ld (= m own columns + nb border columns)
     long long bd;           // offset of the border array in the pool (doubles)
 };
 
 #define SG(i_, j_) S[(size_t)(i_) * (size_t)srow + (size_t)(j_) + (size_t)soff]
 
-// Leaves: zero the border arrays and gather the couplings with the bounding separators out of the band (the left one
-// transposed: in the front the separator comes after the segment) and the right-hand side.  Grid-wide, HBM-bound.
-__global__ void __launch_bounds__(256) ba_front_init_kernel(const Front* __restrict__ fr, int n_leaves, const double* __restrict__ S, const double* __restrict__ rhs,
+// Every front's border array before the factorisation starts.  Leaves: zeros, the couplings with the bounding separators
+// gathered out of the band (the left one transposed: in the front the separator comes after the segment) and the right-hand
+// side.  Internal fronts: zeros and their own part of the right-hand side -- their children add the rest (extend-add at the end of
+// ba_front_factor_kernel).  Grid-wide, HBM-bound.
+__global__ void __launch_bounds__(256) ba_front_init_kernel(const Front* __restrict__ fr, int n_fronts, const double* __restrict__ S, const double* __restrict__ rhs,
                                                              double* __restrict__ pool, long long srow, long long soff, int band, const LmState* st) {
     if (st->done) return;
-    for (int f = blockIdx.y; f < n_leaves; f += gridDim.y) {
+    for (int f = blockIdx.y; f < n_fronts; f += gridDim.y) {
         const Front F = fr[f];
         double* Bd = pool + F.bd;
         const size_t total = (size_t)(F.nb + 1) * F.ld;
+        const bool leaf = F.child0 < 0;
         for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
             const int q = (int)(e / F.ld), c = (int)(e - (size_t)q * F.ld);
             double v = 0.0;
             if (c < F.m) {
-                if (q < F.wL) { const int gi = F.o0 + c, gj = F.bL0 + q; if (gi - gj <= band) v = SG(gi, gj); }
-                else if (q < F.nb) { const int gi = F.bR0 + (q - F.wL), gj = F.o0 + c; if (gi - gj <= band) v = SG(gi, gj); }
-                else v = rhs[F.o0 + c];
+                if (q == F.nb) v = rhs[F.o0 + c];
+                else if (leaf) {
+                    if (q < F.wL) { const int gi = F.o0 + c, gj = F.bL0 + q; if (gi - gj <= band) v = SG(gi, gj); }
+                    else { const int gi = F.bR0 + (q - F.wL), gj = F.o0 + c; if (gi - gj <= band) v = SG(gi, gj); }
+                }
             }
             Bd[e] = v;
         }
@@ -66,35 +72,6 @@ __global__ void __launch_bounds__(CHOL_T) ba_front_factor_kernel(const Front* __
     double* Bd = pool + F.bd;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     if (tid == 0) fail = 0;
-    if (F.child0 >= 0) {
-        // ---- internal front: own part of the rhs, zero elsewhere, then extend-add the two children's update matrices
-        const int total = (nb + 1) * ld;
-        for (int e = tid; e < total; e += nt) { const int q = e / ld, c = e - q * ld; Bd[e] = (q == nb && c < n) ? rhs[F.o0 + c] : 0.0; }
-        __syncthreads();
-        for (int ch = 0; ch < 2; ++ch) {
-            const Front C = fr[ch ? F.child1 : F.child0];
-            const double* Bc = pool + C.bd;
-            // child border id t -> this front: left child: [0, wL_c) = my left border, the rest = my own unknowns;
-            //                                    right child: [0, wL_c) = my own unknowns, the rest = my right border
-            const int cn = C.nb;
-            for (int e = tid; e < (cn + 1) * cn; e += nt) {
-                const int r = e / cn, c = e - r * cn;
-                if (c > r) continue;
-                const double u = Bc[(size_t)r * C.ld + C.m + c];
-                if (u == 0.0) continue;
-                bool c_own; int c_idx;
-                if (ch == 0) { c_own = c >= C.wL; c_idx = c_own ? c - C.wL : c; } else { c_own = c < C.wL; c_idx = c_own ? c : F.wL + (c - C.wL); }
-                if (r == cn) { Bd[(size_t)nb * ld + (c_own ? c_idx : n + c_idx)] += u; continue; }
-                bool r_own; int r_idx;
-                if (ch == 0) { r_own = r >= C.wL; r_idx = r_own ? r - C.wL : r; } else { r_own = r < C.wL; r_idx = r_own ? r : F.wL + (r - C.wL); }
-                if (r_own && c_own) SG(F.o0 + r_idx, F.o0 + c_idx) += u;              // r_idx >= c_idx: the maps are monotone
-                else if (r_own) Bd[(size_t)c_idx * ld + r_idx] += u;                   // A(own, left border): stored transposed
-                else if (c_own) Bd[(size_t)r_idx * ld + c_idx] += u;                   // A(right border, own)
-                else Bd[(size_t)r_idx * ld + n + c_idx] += u;                          // border x border
-            }
-            __syncthreads();
-        }
-    }
     __syncthreads();
     // Software-pipelined over the 32-column block steps with look-ahead (see ba_cholesky_kernel): while warps 1.. finish the
     // trailing update of step kb, warp 0 updates the next diagonal block first (tile 0) and factors it.
@@ -192,6 +169,38 @@ __global__ void __launch_bounds__(CHOL_T) ba_front_factor_kernel(const Front* __
         __syncthreads();
     }
     if (tid == 0 && fail) st->solve_fail = 1;
+    // ---- extend-add: this front's update matrix (border x border block + the rhs row's border part) goes into its parent's front.
+    // Done here, by the child, with fire-and-forget reductions: as a prologue of the parent it was a chain of dependent
+    // load -> read-modify-write round trips on a single CTA (150 of the 180 us of every internal level).  The sibling adds into the
+    // same own x own block and rhs entries of the parent concurrently, hence the atomics; the parent's array was initialised by
+    // ba_front_init_kernel, and the parent level's launch comes after this one in stream order.
+    if (F.parent >= 0) {
+        const Front Pf = fr[F.parent];
+        double* Bp = pool + Pf.bd;
+        const int pn = Pf.m, pld = Pf.ld, pnb = Pf.nb;
+        // my border id t -> parent front: left child: [0, wL) = parent's left border, the rest = parent's own unknowns;
+        //                                right child: [0, wL) = parent's own unknowns, the rest = parent's right border
+        const int total = (nb + 1) * nb;
+        for (int e0 = tid; e0 < total; e0 += 4 * nt) {
+            double u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const int e = e0 + k * nt; const int r = e / nb, c = e - r * nb; u[k] = (e < total && c <= r) ? Bd[(size_t)r * ld + n + c] : 0.0; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (u[k] == 0.0) continue;
+                const int e = e0 + k * nt; const int r = e / nb, c = e - r * nb;
+                bool c_own; int c_idx;
+                if (F.side == 0) { c_own = c >= F.wL; c_idx = c_own ? c - F.wL : c; } else { c_own = c < F.wL; c_idx = c_own ? c : Pf.wL + (c - F.wL); }
+                if (r == nb) { atomicAdd(&Bp[(size_t)pnb * pld + (c_own ? c_idx : pn + c_idx)], u[k]); continue; }
+                bool r_own; int r_idx;
+                if (F.side == 0) { r_own = r >= F.wL; r_idx = r_own ? r - F.wL : r; } else { r_own = r < F.wL; r_idx = r_own ? r : Pf.wL + (r - F.wL); }
+                if (r_own && c_own) atomicAdd(&SG(Pf.o0 + r_idx, Pf.o0 + c_idx), u[k]);          // r_idx >= c_idx: the maps are monotone
+                else if (r_own) atomicAdd(&Bp[(size_t)c_idx * pld + r_idx], u[k]);                 // A(own, left border): stored transposed
+                else if (c_own) atomicAdd(&Bp[(size_t)r_idx * pld + c_idx], u[k]);                 // A(right border, own)
+                else atomicAdd(&Bp[(size_t)r_idx * pld + pn + c_idx], u[k]);                       // border x border
+            }
+        }
+    }
 }
 
 // Back-substitution of one level (root level first): x_own = L_own^-T (y - W x_border), x in place in `x` (the rhs vector).
