@@ -699,6 +699,7 @@ __global__ void __launch_bounds__(TPB) ba_schur_kernel(BaDev d, int cols_max) {
     double* row = U + (size_t)lane * ncol;
     for (int k = 0; k < ncol; ++k) row[k] = 0.0;
     const int l = d.sw_lm[(size_t)w * 32 + lane];
+    unsigned long long gmax_bits = 0ull;          // |gradient| of this lane's inverse depth as ordered bits (NaN -> +inf)
     if (l >= 0) {
         // Jacobi scale (first pass), LM damping and gradient max-norm of this inverse depth
         LmState* st = d.st;
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(TPB) ba_schur_kernel(BaDev d, int cols_max) {
         const double sc = d.scale_l[l], sc2 = sc * sc;
         const double lam = fmin(fmax(sc2 * h, st->min_diag), st->max_diag) / (st->radius * sc2);
         d.lam_l[l] = lam;
-        if (st->need_linearize && d.lm_start[l + 1] > d.lm_start[l]) atomic_max_nonneg(&st->grad_max_bits, d.gl[l]);
+        if (st->need_linearize && d.lm_start[l + 1] > d.lm_start[l]) { const double gv = d.gl[l]; gmax_bits = (gv == gv) ? (unsigned long long)__double_as_longlong(fabs(gv)) : 0x7ff0000000000000ull; }
         const double hl = h + lam;
         if (hl > 0.0 && ns > 0) {
             const int n = d.n[0];
@@ -741,6 +742,9 @@ __global__ void __launch_bounds__(TPB) ba_schur_kernel(BaDev d, int cols_max) {
         }
     }
     __syncwarp();
+    // one atomicMax per warp, not per landmark: at map scale 500 000 atomics on the one address serialised in L2 (most of the kernel)
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, gmax_bits, o); gmax_bits = v > gmax_bits ? v : gmax_bits; }
+    if (lane == 0 && gmax_bits) atomicMax(&d.st->grad_max_bits, gmax_bits);
     const int* offs = d.grp_off + (size_t)g * MAX_TRACK;
     if (d.tc_mode) {
         // tensor-core mode: this warp only (a) adds its rhs column  sum_l u_l g_l / h_l  in FP64 and (b) writes its 32
@@ -888,11 +892,12 @@ __global__ void ba_unpack_scalars_kernel(BaDev d) {
 }
 
 // camera blocks: Jacobi scale, damping added to diag(S), gradient max-norm ||x - Plus(x,-g)||_inf
-__device__ __forceinline__ void prepare_camera_block(const BaDev& d, int i) {
+// returns the block's gradient max-norm as ordered bits (0: nothing to report); the caller reduces over the warp and issues ONE atomicMax
+__device__ __forceinline__ unsigned long long prepare_camera_block(const BaDev& d, int i) {
     LmState* st = d.st;
     const bool is_pose = i < d.n_poses;
     const int off = is_pose ? d.pose_off[i] : d.vec3_off[i - d.n_poses];
-    if (off < 0) return;
+    if (off < 0) return 0ull;
     const int w = is_pose ? 6 : 3;
     for (int k = 0; k < w; ++k) {
         const double h = d.diagH[off + k];
@@ -911,8 +916,13 @@ __device__ __forceinline__ void prepare_camera_block(const BaDev& d, int i) {
             pose_plus(x, ng, out);
             for (int k = 0; k < 7; ++k) { const double df = fabs(x[k] - out[k]); gm = (df == df) ? fmax(gm, df) : INFINITY; }
         } else for (int k = 0; k < 3; ++k) { const double df = fabs(d.gcr[off + k]); gm = (df == df) ? fmax(gm, df) : INFINITY; }
-        atomic_max_nonneg(&st->grad_max_bits, gm);
+        return (gm == gm) ? (unsigned long long)__double_as_longlong(fabs(gm)) : 0x7ff0000000000000ull;
     }
+    return 0ull;
+}
+__device__ __forceinline__ void warp_max_to_state(LmState* st, unsigned long long bits) {
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, bits, o); bits = v > bits ? v : bits; }
+    if ((threadIdx.x & 31) == 0 && bits) atomicMax(&st->grad_max_bits, bits);
 }
 
 // S <- lower(Hpp), rhs <- -gc, gcr <- gc, diagH <- diag(Hpp), scalars <- 0.
@@ -933,6 +943,7 @@ __global__ void ba_build_S_kernel(BaDev d) {
     if (!FUSE_DAMP) {
         for (size_t r = gid; r < (size_t)d.dimc; r += stride) { d.diagH[r] = d.Hpp[SIDX(d, r, r)]; d.rhs[r] = -d.gc[r]; d.gcr[r] = d.gc[r]; }
     } else {
+        unsigned long long gbits = 0ull;
         for (size_t i = gid; i < (size_t)(d.n_poses + d.n_vec3); i += stride) {
             const bool is_pose = i < (size_t)d.n_poses;
             const int off = is_pose ? d.pose_off[i] : d.vec3_off[i - d.n_poses];
@@ -943,15 +954,16 @@ __global__ void ba_build_S_kernel(BaDev d) {
                 const double h = d.Hpp[SIDX(d, r, r)];
                 d.diagH[r] = h; d.rhs[r] = -d.gc[r]; d.gcr[r] = d.gc[r]; d.S[SIDX(d, r, r)] = h;
             }
-            prepare_camera_block(d, (int)i);
+            gbits = max(gbits, prepare_camera_block(d, (int)i));
         }
+        warp_max_to_state(d.st, gbits);
     }
 }
 
 __global__ void ba_prepare_camera_kernel(BaDev d) {
     if (d.st->done) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < d.n_poses + d.n_vec3) prepare_camera_block(d, i);
+    warp_max_to_state(d.st, (i < d.n_poses + d.n_vec3) ? prepare_camera_block(d, i) : 0ull);
 }
 
 __global__ void lm_control_pre_kernel(LmState* st) { lm_control_pre(*st); }
@@ -1776,19 +1788,23 @@ int lvb_ba_finalize(lvb_ba* ba) {
             const int n = ba->nd[k];
             const std::vector<int>& ord = ba->order[k];
             const int is = kIdxStride[k];
-            iplanes.assign((size_t)std::max(1, n) * is, 0);
+            iplanes.resize((size_t)std::max(1, n) * is);
+            if (n == 0) std::fill(iplanes.begin(), iplanes.end(), 0);
             const int32_t* hi = ba->h_fi[k].data();
-            for (int j = 0; j < is; ++j) { int* dst = iplanes.data() + (size_t)j * n; for (int i = 0; i < n; ++i) { const int f = ord[i] >= 0 ? ord[i] : -1 - ord[i]; dst[i] = hi[(size_t)f * is + j]; } }
+            // record-major walk: one contiguous source record per block, `is` / `cs` output streams (the plane-major walk re-read the
+            // strided source once per plane)
+            for (int i = 0; i < n; ++i) { const int f = ord[i] >= 0 ? ord[i] : -1 - ord[i]; const int32_t* src = hi + (size_t)f * is; for (int j = 0; j < is; ++j) iplanes[(size_t)j * n + i] = src[j]; }
             LVB_TRY(ba->fi[k].upload(iplanes.data(), iplanes.size(), s));
             if (k == 3) continue;
             const int cs = kConstStride[k];
-            planes.assign((size_t)std::max(1, n) * cs, 0.0);
+            planes.resize((size_t)std::max(1, n) * cs);
+            if (n == 0) std::fill(planes.begin(), planes.end(), 0.0);
             const int wcol = (k == 0) ? 4 : (k == 1 ? 5 : -1);     // weight column, zeroed on padding
             const double* hc = ba->h_fc[k].data();
-            for (int j = 0; j < cs; ++j) {
-                double* dst = planes.data() + (size_t)j * n;
-                if (j == wcol) for (int i = 0; i < n; ++i) dst[i] = ord[i] < 0 ? 0.0 : hc[(size_t)ord[i] * cs + j];
-                else for (int i = 0; i < n; ++i) { const int f = ord[i] >= 0 ? ord[i] : -1 - ord[i]; dst[i] = hc[(size_t)f * cs + j]; }
+            for (int i = 0; i < n; ++i) {
+                const bool pad = ord[i] < 0;
+                const double* src = hc + (size_t)(pad ? -1 - ord[i] : ord[i]) * cs;
+                for (int j = 0; j < cs; ++j) planes[(size_t)j * n + i] = (pad && j == wcol) ? 0.0 : src[j];
             }
             LVB_TRY(ba->fc[k].upload(planes.data(), planes.size(), s));
         }
