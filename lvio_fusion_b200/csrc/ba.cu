@@ -1363,11 +1363,13 @@ static void mark(struct lvb_ba* ba, const char* name);
     do { if ((grid) > 0) { kernel<<<(grid), (block), (smem), (ba)->ctx->stream>>>(__VA_ARGS__); (ba)->ctx->launches++; mark(ba, #kernel); } } while (0)
 
 // Separator tree of the banded reduced system (see ba_tree.cuh): complete binary tree with 2^D leaves, separators of width
-// w = band.  Leaves keep >= 2w unknowns so that a separator is coupled to nothing beyond its two neighbouring subtrees.
-static int build_front_tree(int n, int band, int max_leaves, std::vector<Front>& out, std::vector<int>& level_first, std::vector<int>& level_count,
+// w = true half bandwidth.  Leaves keep >= 2w unknowns so that a separator is coupled to nothing beyond its two neighbouring subtrees.
+static int build_front_tree(int n, int band, int sep, int max_leaves, std::vector<Front>& out, std::vector<int>& level_first, std::vector<int>& level_count,
                             size_t& pool_doubles, int& max_panel_rows, int& max_nb) {
     out.clear(); level_first.clear(); level_count.clear(); pool_doubles = 0; max_panel_rows = 0; max_nb = 0;
-    const int w = band;
+    // separator width: the TRUE half bandwidth is enough to separate (the storage band carries up to 31 columns of block-step slack);
+    // a front's cost grows with the cube of it
+    const int w = std::max(1, std::min(sep, band));
     int D = 0;
     while ((1 << (D + 1)) <= max_leaves) {
         const long long P = 1ll << (D + 1);
@@ -1668,7 +1670,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
     PROF("schur groups");
     // ---- envelope of S: first structurally non-zero column per row, from every coupling the assembly can create
     std::vector<int> chol_rmax(ba->dimc / 32 + 2, 0), chol_cmin(ba->dimc / 32 + 2, 0);
-    int band = 0, panel_rows = 2;
+    int band = 0, panel_rows = 2, true_band = 0;
     if (ba->solvable) {
         std::vector<int> first(ba->dimc);
         std::vector<int> fb(blks.size());
@@ -1696,7 +1698,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
             LVB_CUDA(cudaMemcpyAsync(fb.data(), tmp.p, fb.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
             LVB_CUDA(cudaStreamSynchronize(s));
         }
-        for (int r = 0; r < ba->dimc; ++r) first[r] = fb[blk_of_off[r]];
+        for (int r = 0; r < ba->dimc; ++r) { first[r] = fb[blk_of_off[r]]; true_band = std::max(true_band, r - first[r]); }
         // rmax per 32-column step by a backward sweep: rows whose first column lies left of the end of the step
         {
             const int nstep = (ba->dimc + 31) / 32;
@@ -1730,7 +1732,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
         int rows = 0, mnb = 0, max_leaves = 1;
         while (max_leaves * 2 <= std::max(2, ctx->sm_count)) max_leaves *= 2;
         if (ba->solvable && !dense_layout && !no_tree) {
-            const int lv = build_front_tree(ba->dimc, band, max_leaves, h_fronts, ba->level_first, ba->level_count, pool_doubles, rows, mnb);
+            const int lv = build_front_tree(ba->dimc, band, true_band, max_leaves, h_fronts, ba->level_first, ba->level_count, pool_doubles, rows, mnb);
             const size_t fs = (size_t)(32 * 33 + 32 + 128 + (rows + 2) * 34) * 8, bs_ = (size_t)(((mnb + 1) & ~1) + (CHOL_T / 32) * 32) * 8;
             if (lv > 0 && fs <= 227 * 1024 - 256 && pool_doubles < ((size_t)1 << 31)) { ba->tree_levels = lv; ba->tree_factor_smem = fs; ba->tree_back_smem = bs_; }
         }
@@ -2250,7 +2252,7 @@ LVB_API int lvb_debug_band_solve(lvb_ctx* ctx, int n, int band, const double* S_
     while (max_leaves * 2 <= std::max(2, ctx->sm_count)) max_leaves *= 2;
     ba.tree_levels = 0;
     if (use_tree) {
-        const int lv = build_front_tree(n, band, max_leaves, fr, ba.level_first, ba.level_count, pool, rows, mnb);
+        const int lv = build_front_tree(n, band, band - 31, max_leaves, fr, ba.level_first, ba.level_count, pool, rows, mnb);
         ba.tree_factor_smem = (size_t)(32 * 33 + 32 + 128 + (rows + 2) * 34) * 8; ba.tree_back_smem = (size_t)(((mnb + 1) & ~1) + (CHOL_T / 32) * 32) * 8;
         if (lv > 0 && ba.tree_factor_smem <= 227 * 1024 - 256) { ba.tree_levels = lv; LVB_TRY(ba.fronts.upload(fr.data(), fr.size(), s)); LVB_TRY(ba.front_pool.ensure(pool)); }
     }
