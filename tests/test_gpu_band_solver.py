@@ -29,7 +29,8 @@ def _pack(s, band):
     return out
 
 
-@pytest.mark.parametrize("n,true_band,expect_tree", [(150, 40, False), (700, 45, True), (1200, 59, True), (2500, 33, True), (4000, 75, True), (9000, 50, True)])
+@pytest.mark.parametrize("n,true_band,expect_tree", [(150, 40, False), (700, 45, True), (1200, 59, True), (2500, 33, True), (4000, 75, True), (9000, 50, True),
+                                                     (900, 23, True), (1500, 10, True), (600, 31, True), (2000, 5, True)])
 def test_tree_and_single_cta_solve_match_numpy(lvb_ctx, n, true_band, expect_tree):
     rng = np.random.default_rng(n)
     s = _band_spd(n, true_band, rng)
