@@ -64,7 +64,35 @@ public:
                    resolution_ * resolution_ * 25, frame->weights.lidar_surf, new ceres::HuberLoss(0.1), handles_of_thread()[this].surf);
     }
 
+    // ---- device-resident map.  Mapping::ToWorld (mapping.cpp:205-220) -> AppendKeyframe: the keyframe's two
+    // robot-frame feature clouds go to the device once and stay there in the world frame; Mapping::BuildMapFrame (:114-137) ->
+    // BuildMapFrame: merge of the given keyframes in order, SegmentGround on the merged ground cloud, voxel hash -- all on the
+    // device.  After a BuildMapFrame the two ScanToMapWith* members register against that resident map frame and no longer upload
+    // map_frame's clouds; UsePerCallMap() goes back to the per-call behaviour (Relocator::RelocateByPoints hands over its own map).
+    template <class Cloud>
+    bool AppendKeyframe(long long key, const Cloud& ground_robot, const Cloud& surf_robot, const double* pose7) {
+        Handles& h = handles_of_thread()[this];
+        if (!ensure_handles(h)) return false;
+        const int stride = (int)sizeof(assoc_detail::cloud_data(ground_robot, 0)[0]);
+        lvb_icp_map_evict(h.ground, key); lvb_icp_map_evict(h.surf, key);            // re-registering a keyframe (ToWorld(start)) replaces its clouds
+        return lvb_icp_map_append(h.ground, key, assoc_detail::cloud_data(ground_robot, 0), (int)ground_robot.size(), stride, pose7) == LVB_OK &&
+               lvb_icp_map_append(h.surf, key, assoc_detail::cloud_data(surf_robot, 0), (int)surf_robot.size(), stride, pose7) == LVB_OK;
+    }
+    bool EvictKeyframe(long long key) {
+        Handles& h = handles_of_thread()[this];
+        return ensure_handles(h) && lvb_icp_map_evict(h.ground, key) == LVB_OK && lvb_icp_map_evict(h.surf, key) == LVB_OK;
+    }
+    bool BuildMapFrame(const long long* keys, int n_keys, double ground_ransac_threshold) {
+        Handles& h = handles_of_thread()[this];
+        if (!ensure_handles(h)) return false;
+        h.resident = lvb_icp_map_build(h.ground, keys, n_keys, cell_of(resolution_ * resolution_ * 100), ground_ransac_threshold, nullptr) == LVB_OK &&
+                     lvb_icp_map_build(h.surf, keys, n_keys, cell_of(resolution_ * resolution_ * 25), -1.0, nullptr) == LVB_OK;
+        return h.resident;
+    }
+    void UsePerCallMap() { handles_of_thread()[this].resident = false; }
+
 private:
+    static float cell_of(double thr) { return std::nextafter((float)std::sqrt(thr), 1e30f) * 1.0001f; }
     template <class FramePtr, class Cloud, class Problem>
     bool add(int mode, FramePtr frame, FramePtr map_frame, const Cloud& scan, const Cloud& map, double* para, Problem& problem, bool relocate,
              double thr, double weight, ceres::LossFunction* loss, lvb_icp*& icp) {
@@ -72,8 +100,8 @@ private:
         if (!rt.ensure()) { delete loss; return false; }
         if (!icp && lvb_icp_create(rt.ctx, &icp) != LVB_OK) { delete loss; return false; }
         const int stride = (int)sizeof(assoc_detail::cloud_data(scan, 0)[0]);
-        const float cell = std::nextafter((float)std::sqrt(thr), 1e30f) * 1.0001f;
-        if (lvb_icp_set_map(icp, assoc_detail::cloud_data(map, 0), (int)map.size(), stride, cell) != LVB_OK) { delete loss; return false; }
+        if (!handles_of_thread()[this].resident &&
+            lvb_icp_set_map(icp, assoc_detail::cloud_data(map, 0), (int)map.size(), stride, cell_of(thr)) != LVB_OK) { delete loss; return false; }
         if (mode == 0) { problem.AddParameterBlock(para + 1, 1); problem.AddParameterBlock(para + 2, 1); problem.AddParameterBlock(para + 5, 1); }
         else { problem.AddParameterBlock(para + 0, 1); problem.AddParameterBlock(para + 3, 1); problem.AddParameterBlock(para + 4, 1); }
         double* x0 = mode == 0 ? para + 1 : para + 0; double* x1 = mode == 0 ? para + 2 : para + 3; double* x2 = mode == 0 ? para + 5 : para + 4;
@@ -92,7 +120,12 @@ private:
     // lvb_icp handles (voxel hash + scratch on one context's stream) are single-threaded and the context is per host thread
     // (ceres_shim.h): Mapping::Optimize and Relocator::RelocateByPoints reach the same object from two threads without a lock
     // (mapping.cpp:155-177, relocator.cpp:188-206), so every thread gets its own pair.
-    struct Handles { lvb_icp* ground = nullptr; lvb_icp* surf = nullptr; };
+    struct Handles { lvb_icp* ground = nullptr; lvb_icp* surf = nullptr; bool resident = false; };
+    static bool ensure_handles(Handles& h) {
+        lvb::Runtime& rt = lvb::Runtime::get();
+        if (!rt.ensure()) return false;
+        return (h.ground || lvb_icp_create(rt.ctx, &h.ground) == LVB_OK) && (h.surf || lvb_icp_create(rt.ctx, &h.surf) == LVB_OK);
+    }
     static std::unordered_map<const void*, Handles>& handles_of_thread() { static thread_local std::unordered_map<const void*, Handles> m; return m; }
     double resolution_;
 };

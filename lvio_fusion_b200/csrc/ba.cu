@@ -31,7 +31,7 @@ using namespace lvb;
 
 namespace {
 
-enum { TPB = 128, IMU_STRIDE = 17 + 45 + 225 + 1, IMU_RAW = 469, MAX_DIMC = 736, MAX_STAGE_POSES = 512, MAX_TRACK = 16, CHOL_T = 256, SYRK_ROWS = 64, SYRK_LD = 14, SYRK_CS = 66 };
+enum { TPB = 128, IMU_STRIDE = 17 + 45 + 225 + 1, IMU_RAW = 469, MAX_DIMC = 736, MAX_STAGE_POSES = 512, MAX_TRACK = 16, CHOL_T = 256, SYRK_ROWS = 64, SYRK_LD = 14 };
 
 __device__ long long g_chol_dbg[8];     // accumulated SM clocks per Cholesky phase (diag, panel, trailing, backward, total)
 __device__ unsigned char c_tri_a[465];   // lower-triangle enumeration e -> (a, b), a >= b; global (not __constant__):
@@ -307,19 +307,15 @@ __global__ void ba_eval_prior_kernel(BaDev d, int kind, double* __restrict__ r_o
 // Warp-level SYRK: the 32 blocks of a warp share their pose key (finalize() sorts and pads), so the warp
 // writes its Jacobian rows [2 x ncol per lane] to shared memory, each lane then owns a few entries of the
 // lower triangle of A^T A (A = [J_1 | J_2 | r] or [J | r]) and issues ONE red.global per entry instead of 32.
-__device__ __forceinline__ void warp_syrk_flush(const BaDev& d, const double* A /*column-major: A[col * SYRK_CS + row], 64 rows*/, int ncol, int off1, int off2) {
+__device__ __forceinline__ void warp_syrk_flush(const BaDev& d, const double* A /*64 x SYRK_LD*/, int ncol, int off1, int off2) {
     const int lane = threadIdx.x & 31;
     const int nent = ncol * (ncol + 1) / 2;
     for (int e = lane; e < nent; e += 32) {
         const int a = c_tri_a[e], b = c_tri_b[e];                 // a >= b, both < ncol <= 13
         if (a == ncol - 1 && b == ncol - 1) continue;             // r.r : the cost goes through block_add
-        // dot product of two columns: contiguous in shared memory, two rows per LDS.128 (the row-major tile needed two LDS.64 per FMA)
-        const double2* ca = reinterpret_cast<const double2*>(A + a * SYRK_CS);
-        const double2* cb = reinterpret_cast<const double2*>(A + b * SYRK_CS);
-        double v = 0.0, v2 = 0.0;
+        double v = 0.0;
 #pragma unroll 8
-        for (int r = 0; r < SYRK_ROWS / 2; ++r) { const double2 x = ca[r], y = cb[r]; v += x.x * y.x; v2 += x.y * y.y; }
-        v += v2;
+        for (int r = 0; r < SYRK_ROWS; ++r) v += A[r * SYRK_LD + a] * A[r * SYRK_LD + b];
         if (v == 0.0) continue;
         const int gb = (ncol == 13) ? (b < 6 ? (off1 < 0 ? -1 : off1 + b) : (off2 < 0 ? -1 : off2 + b - 6)) : (off1 < 0 ? -1 : off1 + b);
         if (gb < 0) continue;
@@ -344,7 +340,7 @@ __device__ __forceinline__ void linearize_visual_body(const BaDev& d, const Bloc
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double cost = 0.0;
     const size_t pose_bytes = d.stage_poses ? (((size_t)d.n_poses * 56 + 16 + 15) & ~(size_t)15) : 0;
-    double* A = reinterpret_cast<double*>(smem_raw + pose_bytes) + (size_t)warp * SYRK_LD * SYRK_CS;      // per warp: 14 columns x 66
+    double* A = reinterpret_cast<double*>(smem_raw + pose_bytes) + (size_t)warp * SYRK_ROWS * SYRK_LD;
     const double* P = stage_poses(d, Psrc, reinterpret_cast<double*>(smem_raw), &bar);
     if (b < R.b[1]) {            // ---- a1 TwoFrameReprojectionError
         const int n = d.n[0];
@@ -393,11 +389,11 @@ __device__ __forceinline__ void linearize_visual_body(const BaDev& d, const Bloc
                 const int k1 = __shfl_sync(0xffffffffu, i1, leader), k2 = __shfl_sync(0xffffffffu, i2, leader);
                 const int o1 = __shfl_sync(0xffffffffu, off1, leader), o2 = __shfl_sync(0xffffffffu, off2, leader);
                 const bool mine = valid && i1 == k1 && i2 == k2;
-                double2* rows = reinterpret_cast<double2*>(A + 2 * lane);              // this lane's two rows (2 lane, 2 lane + 1) of column k: rows[k * SYRK_CS / 2]
+                double* row0 = A + (2 * lane) * SYRK_LD; double* row1 = row0 + SYRK_LD;
                 if (mine) {
-                    for (int k = 0; k < 6; ++k) { rows[k * (SYRK_CS / 2)] = make_double2(o.J1[k], o.J1[6 + k]); rows[(6 + k) * (SYRK_CS / 2)] = make_double2(o.J2[k], o.J2[6 + k]); }
-                    rows[12 * (SYRK_CS / 2)] = make_double2(o.r[0], o.r[1]);
-                } else for (int k = 0; k < 13; ++k) rows[k * (SYRK_CS / 2)] = make_double2(0.0, 0.0);
+                    for (int k = 0; k < 6; ++k) { row0[k] = o.J1[k]; row1[k] = o.J1[6 + k]; row0[6 + k] = o.J2[k]; row1[6 + k] = o.J2[6 + k]; }
+                    row0[12] = o.r[0]; row1[12] = o.r[1];
+                } else for (int k = 0; k < 13; ++k) { row0[k] = 0.0; row1[k] = 0.0; }
                 __syncwarp();
                 warp_syrk_flush(d, A, 13, o1, o2);
                 __syncwarp();
@@ -430,11 +426,11 @@ __device__ __forceinline__ void linearize_visual_body(const BaDev& d, const Bloc
                 const int leader = __ffs(todo) - 1;
                 const int k1 = __shfl_sync(0xffffffffu, ip, leader), o1 = __shfl_sync(0xffffffffu, off, leader);
                 const bool mine = valid && ip == k1;
-                double2* rows = reinterpret_cast<double2*>(A + 2 * lane);
+                double* row0 = A + (2 * lane) * SYRK_LD; double* row1 = row0 + SYRK_LD;
                 if (mine) {
-                    for (int k = 0; k < 6; ++k) rows[k * (SYRK_CS / 2)] = make_double2(o.J[k], o.J[6 + k]);
-                    rows[6 * (SYRK_CS / 2)] = make_double2(o.r[0], o.r[1]);
-                } else for (int k = 0; k < 7; ++k) rows[k * (SYRK_CS / 2)] = make_double2(0.0, 0.0);
+                    for (int k = 0; k < 6; ++k) { row0[k] = o.J[k]; row1[k] = o.J[6 + k]; }
+                    row0[6] = o.r[0]; row1[6] = o.r[1];
+                } else for (int k = 0; k < 7; ++k) { row0[k] = 0.0; row1[k] = 0.0; }
                 __syncwarp();
                 warp_syrk_flush(d, A, 7, o1, -1);
                 __syncwarp();
@@ -1873,7 +1869,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
     const size_t smem_pose = d.stage_poses ? ((size_t)np * 56 + 16) : 0;
     drop_graph(ba);
     ba->pose_smem = smem_pose; ba->imu_smem = smem_imu;
-    ba->lin_smem = ((smem_pose + 15) & ~(size_t)15) + (size_t)(TPB / 32) * SYRK_LD * SYRK_CS * 8;
+    ba->lin_smem = ((smem_pose + 15) & ~(size_t)15) + (size_t)(TPB / 32) * SYRK_ROWS * SYRK_LD * 8;
     ba->schur_smem = (size_t)(TPB / 32) * 32 * (size_t)std::max(1, cols_max) * 8;
     PROF("tail");
 #undef PROF

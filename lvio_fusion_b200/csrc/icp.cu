@@ -186,8 +186,8 @@ __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
     return b;
 }
 
-// The same search by a group of QG = 4 adjacent lanes per query: the dz slabs of every Chebyshev ring are dealt round-robin to the
-// lanes of the group, every lane keeps its own best three, and after each ring the group merges them with two butterfly steps
+// The same search by a group of QG = 4 adjacent lanes per query: the (dz, dy) voxel rows of every Chebyshev ring are dealt round-robin
+// to the lanes of the group, every lane keeps its own best three, and after each ring the group merges them with two butterfly steps
 // (every lane then holds the best three of the union, so the ring-exit test is the sequential one).  A query's ~100 dependent
 // voxel probes become four independent chains: the kernel is L2-latency bound, not throughput bound.  best_insert orders by
 // (d2, index), so the merged result is the sequential result bit for bit; pruning inside a ring only uses the lane's own bound
@@ -213,13 +213,11 @@ __device__ __forceinline__ Best3 knn3_query_group(const IcpDev& d, float3 q, int
         const float lb = (r - 1) * gr.cell;
         const float lb2 = lb * lb * 0.99f;
         if (b.d[2] < lb2 || lb2 > d.max_d2) break;            // group-uniform: every lane holds the merged best three
-        for (int dz = -r + g; dz <= r; dz += QG) {
-            const bool zface = (dz == -r || dz == r);
-            for (int dy = -r; dy <= r; ++dy) {
-                const bool yface = (dy == -r || dy == r);
-                if (zface || yface) { for (int dx = -r; dx <= r; ++dx) scan_voxel(d, gr, q, cx + dx, cy + dy, cz + dz, b); }
-                else { scan_voxel(d, gr, q, cx - r, cy + dy, cz + dz, b); scan_voxel(d, gr, q, cx + r, cy + dy, cz + dz, b); }
-            }
+        const int side = 2 * r + 1;
+        for (int row = g; row < side * side; row += QG) {      // the shell's (dz, dy) rows dealt round-robin: face rows hold 2r+1 voxels, the others 2
+            const int dz = row / side - r, dy = row - (row / side) * side - r;
+            if (dz == -r || dz == r || dy == -r || dy == r) { for (int dx = -r; dx <= r; ++dx) scan_voxel(d, gr, q, cx + dx, cy + dy, cz + dz, b); }
+            else { scan_voxel(d, gr, q, cx - r, cy + dy, cz + dz, b); scan_voxel(d, gr, q, cx + r, cy + dy, cz + dz, b); }
         }
         best_merge(b, 1); best_merge(b, 2);
     }

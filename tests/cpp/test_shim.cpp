@@ -98,7 +98,7 @@ struct LidarFeature { Cloud points_ground, points_surf; };
 struct Weights { double visual = 71.8856, lidar_ground = 1, lidar_surf = 0.01; };
 struct LFrame { SE3d pose; std::shared_ptr<LidarFeature> feature_lidar; Weights weights; std::vector<int> features_left; };
 
-static int run_icp(const char* in, const char* out) {
+static int run_icp(const char* in, const char* out, bool resident = false) {
     FILE* f = fopen(in, "rb"); if (!f) { perror(in); return 2; }
     std::vector<int32_t> h = ri(f, 4);            // n_scan n_map mode n_features_left
     std::vector<double> fp = rd(f, 7), mp = rd(f, 7), e = rd(f, 6);
@@ -114,6 +114,23 @@ static int run_icp(const char* in, const char* out) {
     for (int i = 0; i < h[1]; ++i) mc.pts.push_back(PointXYZI{map[4 * i], map[4 * i + 1], map[4 * i + 2], 1.f, 0.f, 0.f, 0.f, 0.f});
     frame->features_left.resize(h[3]);
     lvio_fusion::FeatureAssociation association(0.2);
+#ifndef LVB_NO_RESIDENT_MAP
+    if (resident) {
+        // the map frame comes from three keyframe clouds already on the device (Mapping::ToWorld put them there),
+        // merged and hashed there (Mapping::BuildMapFrame); map_frame's own clouds are emptied to show they are no longer uploaded
+        const double ident[7] = {0, 0, 0, 1, 0, 0, 0};
+        const size_t third = (mc.pts.size() + 2) / 3;
+        long long keys[3] = {7, 8, 9};
+        for (int k = 0; k < 3; ++k) {
+            Cloud part; part.pts.assign(mc.pts.begin() + std::min(mc.pts.size(), k * third), mc.pts.begin() + std::min(mc.pts.size(), (k + 1) * third));
+            if (!association.AppendKeyframe(keys[k], part, part, ident)) { fprintf(stderr, "append failed: %s\n", lvb_last_error()); return 3; }
+        }
+        if (!association.BuildMapFrame(keys, 3, -1.0)) { fprintf(stderr, "build failed: %s\n", lvb_last_error()); return 3; }
+        mc.pts.clear();
+    }
+#else
+    (void)resident;
+#endif
     double rpyxyz[6]; for (int k = 0; k < 6; ++k) rpyxyz[k] = e[k];
     ceres::Problem problem;
     const bool ok = h[2] == 0 ? association.ScanToMapWithGround(frame, map_frame, rpyxyz, problem) : association.ScanToMapWithSegmented(frame, map_frame, rpyxyz, problem);
@@ -146,6 +163,6 @@ static int run_ba_threads(const char* in, const char* out, int n) {
 
 int main(int argc, char** argv) {
     if (argc == 5 && std::string(argv[1]) == "ba_threads") return run_ba_threads(argv[2], argv[3], std::atoi(argv[4]));
-    if (argc != 4) { fprintf(stderr, "usage: test_shim ba|icp in.bin out.bin | ba_threads in.bin out.bin n\n"); return 1; }
-    return argv[1][0] == 'b' ? run_ba(argv[2], argv[3]) : run_icp(argv[2], argv[3]);
+    if (argc != 4) { fprintf(stderr, "usage: test_shim ba|icp|icp_resident in.bin out.bin | ba_threads in.bin out.bin n\n"); return 1; }
+    return argv[1][0] == 'b' ? run_ba(argv[2], argv[3]) : run_icp(argv[2], argv[3], std::string(argv[1]) == "icp_resident");
 }

@@ -27,6 +27,7 @@ def build_shim_binary_on_oracle():
     syms = subprocess.run(["nm", "-D", os.path.join(odir, "liboracle.so")], capture_output=True, text=True, check=True).stdout.split("\n")
     defs = ["-Dlvb_%s=orc_%s" % (t.split()[2][4:], t.split()[2][4:]) for t in syms if len(t.split()) == 3 and t.split()[1] == "T" and t.split()[2].startswith("orc_")]
     out = BIN + "_orc"
+    defs.append("-DLVB_NO_RESIDENT_MAP")          # the oracle mirrors the per-call entry points only
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread"] + defs + ["-I" + os.path.join(ROOT, "include"), "-o", out, src, "-L" + odir, "-loracle", "-Wl,-rpath," + odir])
     return out
 

@@ -49,3 +49,7 @@ def test_mapping_shaped_scan_to_map_through_the_shim(tmp_path, orc_ctx, kind):
     assert int(out[8]) == so.num_residual_blocks
     assert abs(out[7] - so.final_cost) < 1e-7 * max(so.final_cost, 1e-30)
     assert np.max(np.abs(out[:6] - eo)) < 1e-7
+    # the same registration against a device-resident map frame (AppendKeyframe x3 + BuildMapFrame)
+    subprocess.check_call([exe, "icp_resident", str(tmp_path / "in.bin"), str(tmp_path / "out_r.bin")])
+    out_r = np.fromfile(tmp_path / "out_r.bin", dtype=np.float64)
+    assert int(out_r[8]) == int(out[8]) and np.max(np.abs(out_r[:6] - out[:6])) < 1e-10
