@@ -200,7 +200,9 @@ __device__ __forceinline__ void best_merge(Best3& b, int step) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) { od[j] = __shfl_xor_sync(mask, b.d[j], step); oi[j] = __shfl_xor_sync(mask, b.i[j], step); op[j] = __shfl_xor_sync(mask, b.p[j], step); }
 #pragma unroll
-    for (int j = 0; j < 3; ++j) if (op[j] >= 0) best_insert(b, od[j], oi[j], op[j]);
+    // after the first merge every lane of the group holds the same best three, so most of what the partner sends is already here:
+    // a point is identified by its original index
+    for (int j = 0; j < 3; ++j) if (op[j] >= 0 && oi[j] != b.i[0] && oi[j] != b.i[1] && oi[j] != b.i[2]) best_insert(b, od[j], oi[j], op[j]);
 }
 __device__ __forceinline__ Best3 knn3_query_group(const IcpDev& d, float3 q, int g) {
     Best3 b;
