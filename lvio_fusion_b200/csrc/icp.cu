@@ -186,54 +186,14 @@ __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
     return b;
 }
 
-// The same search by a group of QG = 4 adjacent lanes per query: the (dz, dy) voxel rows of every Chebyshev ring are dealt round-robin
-// to the lanes of the group, every lane keeps its own best three, and after each ring the group merges them with two butterfly steps
-// (every lane then holds the best three of the union, so the ring-exit test is the sequential one).  A query's ~100 dependent
-// voxel probes become four independent chains: the kernel is L2-latency bound, not throughput bound.  best_insert orders by
-// (d2, index), so the merged result is the sequential result bit for bit; pruning inside a ring only uses the lane's own bound
-// (looser, never wrong).
-enum { QG = 4 };
-__device__ __forceinline__ void best_merge(Best3& b, int step) {
-    // only the group's own four lanes take part: groups of one warp leave the ring loop at different radii
-    const unsigned mask = 0xFu << ((threadIdx.x & 31) & ~(QG - 1));
-    float od[3]; int oi[3], op[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { od[j] = __shfl_xor_sync(mask, b.d[j], step); oi[j] = __shfl_xor_sync(mask, b.i[j], step); op[j] = __shfl_xor_sync(mask, b.p[j], step); }
-#pragma unroll
-    // after the first merge every lane of the group holds the same best three, so most of what the partner sends is already here:
-    // a point is identified by its original index
-    for (int j = 0; j < 3; ++j) if (op[j] >= 0 && oi[j] != b.i[0] && oi[j] != b.i[1] && oi[j] != b.i[2]) best_insert(b, od[j], oi[j], op[j]);
-}
-__device__ __forceinline__ Best3 knn3_query_group(const IcpDev& d, float3 q, int g) {
-    Best3 b;
-    b.d[0] = b.d[1] = b.d[2] = INFINITY; b.i[0] = b.i[1] = b.i[2] = 0x7fffffff; b.p[0] = b.p[1] = b.p[2] = -1;
-    const Grid& gr = d.g;
-    const int cx = cell_coord(q.x, gr.minx, gr.inv_cell), cy = cell_coord(q.y, gr.miny, gr.inv_cell), cz = cell_coord(q.z, gr.minz, gr.inv_cell);
-    if (g == 0) scan_voxel(d, gr, q, cx, cy, cz, b);
-    best_merge(b, 1); best_merge(b, 2);
-    for (int r = 1; r <= gr.ring; ++r) {
-        const float lb = (r - 1) * gr.cell;
-        const float lb2 = lb * lb * 0.99f;
-        if (b.d[2] < lb2 || lb2 > d.max_d2) break;            // group-uniform: every lane holds the merged best three
-        const int side = 2 * r + 1;
-        for (int row = g; row < side * side; row += QG) {      // the shell's (dz, dy) rows dealt round-robin: face rows hold 2r+1 voxels, the others 2
-            const int dz = row / side - r, dy = row - (row / side) * side - r;
-            if (dz == -r || dz == r || dy == -r || dy == r) { for (int dx = -r; dx <= r; ++dx) scan_voxel(d, gr, q, cx + dx, cy + dy, cz + dz, b); }
-            else { scan_voxel(d, gr, q, cx - r, cy + dy, cz + dz, b); scan_voxel(d, gr, q, cx + r, cy + dy, cz + dz, b); }
-        }
-        best_merge(b, 1); best_merge(b, 2);
-    }
-    for (int j = 0; j < 3; ++j) if (!(b.d[j] <= d.max_d2)) { b.d[j] = INFINITY; b.i[j] = -1; b.p[j] = -1; }
-    return b;
-}
-
 // Coarse spatial key of a query (blocks of 4x4x4 voxels) so that the lanes of a warp walk the same voxel lists and
 // their 16-byte map loads hit the same L1 lines instead of 32 different L2 sectors.
 // Measured alternatives that lost against this per-query ring walk (round 2, 120 k queries vs 1 M points, 0.50 ms): scanning
 // x-major voxel ROWS as contiguous runs (fewer probes, but no per-voxel culling: 0.78 ms); staging a coarse block's 3 x 3 x 3
 // neighbourhood in shared memory per CTA and searching there (ring search on the staged copy 1.4 - 1.8 ms, brute force 4.4 ms):
 // a block holds ~25 queries that look at ~50 points each, while its neighbourhood is ~3 000 points -- the staging reads 60x more
-// map than the queries need.
+// map than the queries need; four lanes per query (a ring's voxel rows dealt round-robin, butterfly merge of the best three after
+// every ring): 0.57 ms -- the lanes prune with their own looser bounds and scan more voxels than the chain they shorten.
 __global__ void icp_query_key_kernel(IcpDev d, int cgx, int cgy, int cgz, int* __restrict__ key, int* __restrict__ counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.K) return;
@@ -254,23 +214,21 @@ __global__ void icp_query_scatter_kernel(int n, const int* __restrict__ key, con
 }
 
 __global__ void __launch_bounds__(ITPB) icp_knn_kernel(IcpDev d, int* __restrict__ idx_out, float* __restrict__ d2_out) {
-    const int t = (blockIdx.x * ITPB + threadIdx.x) / QG, g = threadIdx.x & (QG - 1);
-    const int tc = min(t, d.K - 1);                              // whole groups stay in the shuffles; surplus groups redo the last query
-    const int i = d.order ? d.order[tc] : tc;
+    const int t = blockIdx.x * ITPB + threadIdx.x;
+    if (t >= d.K) return;
+    const int i = d.order ? d.order[t] : t;
     const float3 q = transform_f32(d.tf, load_xyz(d.scan, i, d.stride));
-    const Best3 b = knn3_query_group(d, q, g);
-    if (t >= d.K || g != 0) return;
+    const Best3 b = knn3_query(d, q);
     for (int j = 0; j < 3; ++j) { idx_out[3 * i + j] = b.i[j]; d2_out[3 * i + j] = b.d[j]; }
 }
 
 // K8: transform + 3-NN + gate (association.cpp:296-300) + plane constants (lidar_error.hpp:13-18)
 __global__ void __launch_bounds__(ITPB) icp_associate_kernel(IcpDev d) {
-    const int t = (blockIdx.x * ITPB + threadIdx.x) / QG, g = threadIdx.x & (QG - 1);
-    const int tc = min(t, d.K - 1);
-    const int i = d.order ? d.order[tc] : tc;
+    const int t = blockIdx.x * ITPB + threadIdx.x;
+    if (t >= d.K) return;
+    const int i = d.order ? d.order[t] : t;
     const float3 q = transform_f32(d.tf, load_xyz(d.scan, i, d.stride));
-    const Best3 b = knn3_query_group(d, q, g);
-    if (t >= d.K || g != 0) return;
+    const Best3 b = knn3_query(d, q);
     int ok = 1;
     for (int j = 0; j < 3; ++j) if (!(b.i[j] >= 0 && b.i[j] < d.P && (double)b.d[j] < d.thr)) ok = 0;
     d.accepted[i] = (unsigned char)ok;
@@ -658,7 +616,7 @@ int lvb_icp_knn3(lvb_icp* h, const void* scan, int n, int stride, const double f
     LVB_TRY(upload_scan(h, scan, n, stride, frame_pose, max_d2, 0.0, d));
     if (n == 0) return LVB_OK;
     LVB_TRY(h->knn_idx.ensure((size_t)n * 3)); LVB_TRY(h->knn_d2.ensure((size_t)n * 3));
-    ILAUNCH(h, icp_knn_kernel, inblk((size_t)n * QG, ITPB), ITPB, d, h->knn_idx.p, h->knn_d2.p);
+    ILAUNCH(h, icp_knn_kernel, inblk(n, ITPB), ITPB, d, h->knn_idx.p, h->knn_d2.p);
     LVB_TRY(icheck("knn3"));
     LVB_TRY(h->knn_idx.download(idx, (size_t)n * 3, h->ctx->stream));
     LVB_TRY(h->knn_d2.download(d2, (size_t)n * 3, h->ctx->stream));
@@ -692,7 +650,7 @@ int lvb_icp_eval(lvb_icp* h, int mode, const void* scan, int n, int stride, cons
     if (n == 0) return LVB_OK;
     LVB_TRY(init_state(h, mode, map_pose, rpyxyz, weight, -1.0, 0.0, nullptr));
     LVB_TRY(h->eval_r.ensure(n)); LVB_TRY(h->eval_J.ensure((size_t)n * 3));
-    ILAUNCH(h, icp_associate_kernel, inblk((size_t)n * QG, ITPB), ITPB, d);
+    ILAUNCH(h, icp_associate_kernel, inblk(n, ITPB), ITPB, d);
     ILAUNCH(h, icp_eval_kernel, inblk(n, ITPB), ITPB, d, h->eval_r.p, h->eval_J.p);
     LVB_TRY(icheck("icp_eval"));
     cudaStream_t s = h->ctx->stream;
@@ -719,7 +677,7 @@ int lvb_icp_scan_to_map(lvb_icp* h, int mode, const void* scan, int n, int strid
     LVB_TRY(init_state(h, mode, map_pose, rpyxyz, weight, prior_weight, huber_a, &opt));
     cudaStream_t s = h->ctx->stream;
     lvb_ctx* ctx = h->ctx;
-    ILAUNCH(h, icp_associate_kernel, inblk((size_t)n * QG, ITPB), ITPB, d);
+    ILAUNCH(h, icp_associate_kernel, inblk(n, ITPB), ITPB, d);
     const int lin_blocks = std::max(1, std::min(inblk(n, ITPB), 4 * ctx->sm_count));
     IcpState hs;
     memset(&hs, 0, sizeof(hs));
