@@ -26,6 +26,7 @@
 #include "lvb_math.cuh"
 #include "lvb_imu_warp.cuh"
 #include "lvb_chol.cuh"
+#include "lvb_p2p.cuh"
 
 using namespace lvb;
 
@@ -964,6 +965,41 @@ __global__ void ba_prepare_camera_kernel(BaDev d) {
     if (d.st->done) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     warp_max_to_state(d.st, (i < d.n_poses + d.n_vec3) ? prepare_camera_block(d, i) : 0ull);
+}
+
+// Sharded problems, window size: the exchange of the reduced system and everything that only exists because of it, in ONE kernel
+// over NVLink peer memory -- the scalars ride in the arena (packed on the fly while the contribution is copied into the exchange
+// buffer), the sum over the ranks is formed with loads from the peers' buffers, and the CTA that finishes last unpacks the scalars
+// and applies the camera damping, which needs the global diagonal.  (Four launches before: pack, all-reduce, unpack, damping.)
+__global__ void __launch_bounds__(256) ba_allreduce_fused_kernel(P2PArgs a, BaDev d, int count) {
+    LmState* st = d.st;
+    const bool active = !st->done;                      // identical on every rank; the exchange itself always runs
+    double* buf = d.S;
+    const int i_scal = (int)(d.scal - d.S);
+    const int need_lin = st->need_linearize;
+    const double my_cost = st->cost_acc;
+    const double my_gmax = __longlong_as_double((long long)st->grad_max_bits);
+    bool last; unsigned int epoch;
+    const bool alive = p2p_allreduce_body(a, buf, count, [&](int i) -> double {
+        if (active && i == i_scal) return need_lin ? my_cost : 0.0;
+        if (active && i == i_scal + 1 + d.rank) return my_gmax;
+        return __ldcg(buf + i);
+    }, &last, &epoch);
+    if (!alive || !last) return;
+    if (active) {
+        if (threadIdx.x == 0) {
+            if (need_lin) st->cost_acc = __ldcg(d.scal);
+            double m = 0.0;
+            for (int r = 0; r < d.world; ++r) m = fmax(m, __ldcg(d.scal + 1 + r));
+            st->grad_max_bits = (unsigned long long)__double_as_longlong(m);
+        }
+        __syncthreads();
+        unsigned long long gbits = 0ull;
+        for (int i = threadIdx.x; i < d.n_poses + d.n_vec3; i += blockDim.x) gbits = max(gbits, prepare_camera_block(d, i));
+        warp_max_to_state(st, gbits);
+        __syncthreads();
+    }
+    p2p_finish_epoch(a, epoch);
 }
 
 __global__ void lm_control_pre_kernel(LmState* st) { lm_control_pre(*st); }
@@ -2010,13 +2046,18 @@ static int launch_linearize_and_reduce(lvb_ba* ba, bool standalone) {
     else LAUNCH(ba, ba_build_S_kernel<0>, std::min(1024, nblk(nH, 256)), 256, 0, d);
     LAUNCH(ba, ba_schur_kernel, nblk(d.n_schur_warps, TPB / 32), TPB, ba->schur_smem, d, std::max(1, ba->schur_cols_max));
     if (d.tc_mode) LAUNCH(ba, ba_schur_tc_kernel, ba->n_tc_chunks / TC_CHUNKS, 128, (size_t)TC_CHUNKS * TC_CHUNK_BYTES, d, ba->n_tc_chunks);
-    if (ctx->world > 1) {
+    const size_t n_arena = nH + 3 * (size_t)d.dimc + 16;
+    P2PArgs pa;
+    const bool fused_comm = ctx->world > 1 && comm_p2p_args(ctx, n_arena, &pa) && (size_t)(d.n_poses + d.n_vec3) <= 4096;
+    if (fused_comm) {
+        LAUNCH(ba, ba_allreduce_fused_kernel, (int)std::max<size_t>(1, std::min<size_t>(XB_BLOCKS, (n_arena + 255) / 256)), 256, 0, pa, d, (int)n_arena);
+    } else if (ctx->world > 1) {
         LAUNCH(ba, ba_pack_scalars_kernel, 1, 1, 0, d);
-        LVB_TRY(comm_allreduce_sum_f64(ctx, d.S, nH + 3 * (size_t)d.dimc + 16));
+        LVB_TRY(comm_allreduce_sum_f64(ctx, d.S, n_arena));
         LAUNCH(ba, ba_unpack_scalars_kernel, 1, 1, 0, d);
     }
     // (fusing this into the Cholesky prologue was measured: it perturbs that kernel's register allocation and is slower)
-    if (!fuse_damp) LAUNCH(ba, ba_prepare_camera_kernel, nblk(d.n_poses + d.n_vec3, 128), 128, 0, d);
+    if (!fuse_damp && !fused_comm) LAUNCH(ba, ba_prepare_camera_kernel, nblk(d.n_poses + d.n_vec3, 128), 128, 0, d);
     if (standalone) LAUNCH(ba, lm_control_pre_kernel, 1, 1, 0, d.st);
     return check_launch("linearize");
 }
