@@ -221,7 +221,9 @@ __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
 // neighbourhood in shared memory per CTA and searching there (ring search on the staged copy 1.4 - 1.8 ms, brute force 4.4 ms):
 // a block holds ~25 queries that look at ~50 points each, while its neighbourhood is ~3 000 points -- the staging reads 60x more
 // map than the queries need; four lanes per query (a ring's voxel rows dealt round-robin, butterfly merge of the best three after
-// every ring): 0.57 ms -- the lanes prune with their own looser bounds and scan more voxels than the chain they shorten.
+// every ring): 0.57 ms -- the lanes prune with their own looser bounds and scan more voxels than the chain they shorten; runs only for
+// the face rows of the outer rings (r >= 2): 0.57 ms.  The kernel takes ~0.47 - 0.50 ms whether a rank holds 120 k, 60 k or 30 k of
+// the queries (round-2 runs at 1 / 2 / 4 GPUs): its duration is set by its slowest warps, not by the query count.
 __global__ void icp_query_key_kernel(IcpDev d, int cgx, int cgy, int cgz, int* __restrict__ key, int* __restrict__ counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.K) return;
