@@ -162,31 +162,6 @@ __device__ __forceinline__ void scan_voxel(const IcpDev& d, const Grid& g, float
     }
 }
 
-// The voxels [x0, x1] of one (iy, iz) row are ONE contiguous run of the x-major sorted map: two cell_start loads and a linear scan.
-// Used for the face rows of the outer rings (r >= 2), which a query only reaches where the map is sparse: there the kernel's
-// duration is its slowest thread (a query without neighbours probes all 729 voxels of the radius, two dependent loads each), and a
-// run replaces 2r + 1 probes by one.  Rings 0 and 1 keep the per-voxel probes, whose box test prunes dense voxels.
-__device__ __forceinline__ void scan_run(const IcpDev& d, const Grid& g, float3 q, int x0, int x1, int iy, int iz, Best3& b) {
-    if (iy < 0 || iz < 0 || iy >= g.gy || iz >= g.gz) return;
-    x0 = max(x0, 0); x1 = min(x1, g.gx - 1);
-    if (x0 > x1) return;
-    const int c = g.gx * (iy + g.gy * iz);
-    const int s = d.cell_start[c + x0], e = d.cell_start[c + x1 + 1];
-    if (s == e) return;
-    const float bx0 = g.minx + x0 * g.cell, bx1 = g.minx + (x1 + 1) * g.cell, by0 = g.miny + iy * g.cell, bz0 = g.minz + iz * g.cell;
-    const float ex = fmaxf(fmaxf(bx0 - q.x, q.x - bx1), 0.0f);
-    const float ey = fmaxf(fmaxf(by0 - q.y, q.y - (by0 + g.cell)), 0.0f);
-    const float ez = fmaxf(fmaxf(bz0 - q.z, q.z - (bz0 + g.cell)), 0.0f);
-    const float bd = (ex * ex + ey * ey + ez * ez) * 0.99f - 1e-6f;     // conservative distance to the run's box
-    if (bd > b.d[2] || bd > d.max_d2) return;
-    for (int j = s; j < e; ++j) {
-        const float4 m = __ldg(&d.map[j]);
-        const float dx = __fsub_rn(m.x, q.x), dy = __fsub_rn(m.y, q.y), dz = __fsub_rn(m.z, q.z);
-        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        best_insert(b, d2, __float_as_int(m.w), j);
-    }
-}
-
 __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
     Best3 b;
     b.d[0] = b.d[1] = b.d[2] = INFINITY; b.i[0] = b.i[1] = b.i[2] = 0x7fffffff; b.p[0] = b.p[1] = b.p[2] = -1;
@@ -202,10 +177,7 @@ __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
             const bool zface = (dz == -r || dz == r);
             for (int dy = -r; dy <= r; ++dy) {
                 const bool yface = (dy == -r || dy == r);
-                if (zface || yface) {
-                    if (r >= 2) scan_run(d, g, q, cx - r, cx + r, cy + dy, cz + dz, b);
-                    else for (int dx = -r; dx <= r; ++dx) scan_voxel(d, g, q, cx + dx, cy + dy, cz + dz, b);
-                }
+                if (zface || yface) { for (int dx = -r; dx <= r; ++dx) scan_voxel(d, g, q, cx + dx, cy + dy, cz + dz, b); }
                 else { scan_voxel(d, g, q, cx - r, cy + dy, cz + dz, b); scan_voxel(d, g, q, cx + r, cy + dy, cz + dz, b); }
             }
         }
