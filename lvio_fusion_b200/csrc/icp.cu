@@ -61,6 +61,8 @@ struct IcpDev {
     IcpState* st;
     int rank, world;
     const int* order;            // query visiting order (spatially sorted) or nullptr
+    const int* coarse;           // occupancy of the 4 x 4 x 4-voxel blocks of the map grid (1: holds points)
+    int cbx, cby, cbz;           // its dimensions
 };
 
 __device__ __forceinline__ float3 load_xyz(const unsigned char* base, int i, int stride) {
@@ -84,7 +86,7 @@ __global__ void icp_bbox_kernel(const unsigned char* pts, int n, int stride, int
 __device__ __forceinline__ int cell_coord(float v, float mn, float inv_cell) { return (int)floorf((v - mn) * inv_cell); }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-__global__ void icp_count_kernel(const unsigned char* pts, int n, int stride, Grid g, int* cell_of, int* counts) {
+__global__ void icp_count_kernel(const unsigned char* pts, int n, int stride, Grid g, int* cell_of, int* counts, int* coarse, int cbx, int cby) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float3 p = load_xyz(pts, i, stride);
@@ -94,6 +96,7 @@ __global__ void icp_count_kernel(const unsigned char* pts, int n, int stride, Gr
     const int c = ix + g.gx * (iy + g.gy * iz);
     cell_of[i] = c;
     atomicAdd(&counts[c], 1);
+    coarse[(ix >> 2) + cbx * ((iy >> 2) + cby * (iz >> 2))] = 1;       // benign race: every writer stores 1
 }
 
 __global__ void icp_scatter_kernel(const unsigned char* pts, int n, int stride, const int* cell_of, const int* cell_start, int* fill, float4* sorted) {
@@ -143,7 +146,12 @@ __device__ __forceinline__ void best_insert(Best3& b, float d, int i, int p) {
 // exact 3-NN of q among map points with d2 <= max_d2 (max_d2 <= radius^2).  Voxels are visited in Chebyshev
 // rings around the query's voxel; a ring r >= 1 cannot hold a point closer than (r-1)*cell, so the search stops
 // as soon as the third-best distance is strictly below that bound (strict: ties are broken by index).
-__device__ __forceinline__ void scan_voxel(const IcpDev& d, const Grid& g, float3 q, int ix, int iy, int iz, Best3& b) {
+struct Occ { unsigned mask; int bx, by, bz; };        // occupancy bits of the 3 x 3 x 3 coarse blocks around the query's block (bx, by, bz)
+__device__ __forceinline__ void scan_voxel(const IcpDev& d, const Grid& g, float3 q, int ix, int iy, int iz, Best3& b, const Occ& occ) {
+    // an empty coarse block holds no points: skip without touching memory.  A query without neighbours otherwise walks all 729 voxels
+    // of the radius at two dependent L2 round trips each (~0.5 ms for ONE thread), and the kernel lasts as long as its slowest thread.
+    const int bit = ((iz >> 2) - occ.bz + 1) * 9 + ((iy >> 2) - occ.by + 1) * 3 + ((ix >> 2) - occ.bx + 1);
+    if (!((occ.mask >> bit) & 1u)) return;
     if (ix < 0 || iy < 0 || iz < 0 || ix >= g.gx || iy >= g.gy || iz >= g.gz) return;
     const int c = ix + g.gx * (iy + g.gy * iz);
     const int s = d.cell_start[c], e = d.cell_start[c + 1];
@@ -167,7 +175,14 @@ __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
     b.d[0] = b.d[1] = b.d[2] = INFINITY; b.i[0] = b.i[1] = b.i[2] = 0x7fffffff; b.p[0] = b.p[1] = b.p[2] = -1;
     const Grid& g = d.g;
     const int cx = cell_coord(q.x, g.minx, g.inv_cell), cy = cell_coord(q.y, g.miny, g.inv_cell), cz = cell_coord(q.z, g.minz, g.inv_cell);
-    scan_voxel(d, g, q, cx, cy, cz, b);
+    Occ occ; occ.mask = 0u; occ.bx = cx >> 2; occ.by = cy >> 2; occ.bz = cz >> 2;       // (ring <= 4 voxels: every probed voxel lies in these 27 blocks)
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {                  // 27 independent loads, one round trip
+        const int x = occ.bx + k % 3 - 1, y = occ.by + (k / 3) % 3 - 1, z = occ.bz + k / 9 - 1;
+        const bool in = x >= 0 && y >= 0 && z >= 0 && x < d.cbx && y < d.cby && z < d.cbz;
+        if (in && __ldg(&d.coarse[x + d.cbx * (y + d.cby * z)])) occ.mask |= 1u << k;
+    }
+    scan_voxel(d, g, q, cx, cy, cz, b, occ);
     for (int r = 1; r <= g.ring; ++r) {
         const float lb = (r - 1) * g.cell;
         const float lb2 = lb * lb * 0.99f;
@@ -177,8 +192,8 @@ __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
             const bool zface = (dz == -r || dz == r);
             for (int dy = -r; dy <= r; ++dy) {
                 const bool yface = (dy == -r || dy == r);
-                if (zface || yface) { for (int dx = -r; dx <= r; ++dx) scan_voxel(d, g, q, cx + dx, cy + dy, cz + dz, b); }
-                else { scan_voxel(d, g, q, cx - r, cy + dy, cz + dz, b); scan_voxel(d, g, q, cx + r, cy + dy, cz + dz, b); }
+                if (zface || yface) { for (int dx = -r; dx <= r; ++dx) scan_voxel(d, g, q, cx + dx, cy + dy, cz + dz, b, occ); }
+                else { scan_voxel(d, g, q, cx - r, cy + dy, cz + dz, b, occ); scan_voxel(d, g, q, cx + r, cy + dy, cz + dz, b, occ); }
             }
         }
     }
@@ -380,7 +395,8 @@ struct lvb_icp {
     Grid grid;
     DevBuf<unsigned char> map_raw, scan_raw, accepted;
     DevBuf<float4> map_sorted;
-    DevBuf<int> cell_of, counts, cell_start, fill, block_sums, bbox, total;
+    DevBuf<int> cell_of, counts, cell_start, fill, block_sums, bbox, total, coarse;
+    int cbx = 0, cby = 0, cbz = 0;
     DevBuf<float> pa;
     DevBuf<double> nrm, eval_r, eval_J;
     DevBuf<int> knn_idx;
@@ -416,6 +432,7 @@ static int upload_scan(lvb_icp* h, const void* scan, int n, int stride, const do
     LVB_TRY(h->nrm.ensure((size_t)std::max(1, n) * 3));
     LVB_TRY(h->st.ensure(1));
     d.map = h->map_sorted.p; d.cell_start = h->cell_start.p; d.g = h->grid; d.P = h->P;
+    d.coarse = h->coarse.p; d.cbx = h->cbx; d.cby = h->cby; d.cbz = h->cbz;
     d.scan = h->scan_raw.p; d.K = n; d.stride = stride;
     for (int i = 0; i < 7; ++i) d.tf[i] = (float)frame_pose[i];
     d.max_d2 = max_d2; d.thr = thr;
@@ -490,7 +507,10 @@ static int build_hash(lvb_icp* h, const unsigned char* d_points, int n, int stri
     LVB_TRY(h->block_sums.ensure(nb)); LVB_TRY(h->total.ensure(1));
     LVB_CUDA(cudaMemsetAsync(h->counts.p, 0, (size_t)ncell * sizeof(int), s));
     LVB_CUDA(cudaMemsetAsync(h->fill.p, 0, (size_t)ncell * sizeof(int), s));
-    ILAUNCH(h, icp_count_kernel, inblk(n, 256), 256, d_points, n, stride, g, h->cell_of.p, h->counts.p);
+    h->cbx = (g.gx + 3) >> 2; h->cby = (g.gy + 3) >> 2; h->cbz = (g.gz + 3) >> 2;
+    LVB_TRY(h->coarse.ensure((size_t)h->cbx * h->cby * h->cbz));
+    LVB_CUDA(cudaMemsetAsync(h->coarse.p, 0, (size_t)h->cbx * h->cby * h->cbz * sizeof(int), s));
+    ILAUNCH(h, icp_count_kernel, inblk(n, 256), 256, d_points, n, stride, g, h->cell_of.p, h->counts.p, h->coarse.p, h->cbx, h->cby);
     ILAUNCH(h, scan_block_kernel, nb, 1024, h->counts.p, h->cell_start.p, ncell, h->block_sums.p);
     ILAUNCH(h, scan_sums_kernel, 1, 1024, h->block_sums.p, nb, h->total.p);
     ILAUNCH(h, scan_add_kernel, nb, 1024, h->cell_start.p, ncell, h->block_sums.p, h->cell_start.p + ncell, h->total.p);
