@@ -170,42 +170,6 @@ __device__ __forceinline__ void scan_voxel(const IcpDev& d, const Grid& g, float
     }
 }
 
-// A face row of a ring: the voxels cx - r .. cx + r of one (iy, iz).  Their cell_start entries are consecutive ints: all of them are
-// loaded first (one round trip for the row instead of one per voxel -- the probes of a query that finds fewer than three neighbours
-// are a chain of 729 dependent round trips otherwise, and the kernel lasts as long as its slowest thread), then the occupied
-// voxels are scanned exactly as scan_voxel does (same box test, same order).
-__device__ __forceinline__ void scan_row(const IcpDev& d, const Grid& g, float3 q, int cx, int r, int iy, int iz, Best3& b, const Occ& occ) {
-    if (iy < 0 || iz < 0 || iy >= g.gy || iz >= g.gz) return;
-    const int rowbit = ((iz >> 2) - occ.bz + 1) * 9 + ((iy >> 2) - occ.by + 1) * 3;
-    if (!((occ.mask >> rowbit) & 7u)) return;                     // none of the three coarse blocks of this row holds a point
-    const int x0 = max(cx - r, 0), x1 = min(cx + r, g.gx - 1);
-    if (x0 > x1) return;
-    const int* cs = d.cell_start + (size_t)g.gx * (iy + g.gy * iz) + x0;
-    int st[10];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) st[k] = (k <= x1 - x0 + 1) ? __ldg(cs + k) : 0;
-    const float by0 = g.miny + iy * g.cell, bz0 = g.minz + iz * g.cell;
-    const float ey = fmaxf(fmaxf(by0 - q.y, q.y - (by0 + g.cell)), 0.0f);
-    const float ez = fmaxf(fmaxf(bz0 - q.z, q.z - (bz0 + g.cell)), 0.0f);
-    const float eyz = ey * ey + ez * ez;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        if (k > x1 - x0) break;
-        const int s0 = st[k], e0 = st[k + 1];
-        if (s0 == e0) continue;
-        const float bx0 = g.minx + (x0 + k) * g.cell;
-        const float ex = fmaxf(fmaxf(bx0 - q.x, q.x - (bx0 + g.cell)), 0.0f);
-        const float bd = (ex * ex + eyz) * 0.99f - 1e-6f;
-        if (bd > b.d[2] || bd > d.max_d2) continue;
-        for (int j = s0; j < e0; ++j) {
-            const float4 m = __ldg(&d.map[j]);
-            const float dx = __fsub_rn(m.x, q.x), dy = __fsub_rn(m.y, q.y), dz = __fsub_rn(m.z, q.z);
-            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            best_insert(b, d2, __float_as_int(m.w), j);
-        }
-    }
-}
-
 __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
     Best3 b;
     b.d[0] = b.d[1] = b.d[2] = INFINITY; b.i[0] = b.i[1] = b.i[2] = 0x7fffffff; b.p[0] = b.p[1] = b.p[2] = -1;
@@ -228,7 +192,7 @@ __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
             const bool zface = (dz == -r || dz == r);
             for (int dy = -r; dy <= r; ++dy) {
                 const bool yface = (dy == -r || dy == r);
-                if (zface || yface) scan_row(d, g, q, cx, r, cy + dy, cz + dz, b, occ);
+                if (zface || yface) { for (int dx = -r; dx <= r; ++dx) scan_voxel(d, g, q, cx + dx, cy + dy, cz + dz, b, occ); }
                 else { scan_voxel(d, g, q, cx - r, cy + dy, cz + dz, b, occ); scan_voxel(d, g, q, cx + r, cy + dy, cz + dz, b, occ); }
             }
         }
