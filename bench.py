@@ -136,13 +136,18 @@ def cpu_icp(orc, octx, T):
             "sample": "all %d queries vs the %d-point map: kd-tree build + exact 3-NN + gate + 4 LM iterations, %d threads" % (ICP_K, ICP_P, T)}
 
 
+def workload_text(rows):
+    return ("configs[1]: KITTI-shaped stereo+IMU 10-keyframe window, %d landmarks per GPU (sharded by landmark, one in-kernel all-reduce of the "
+            "reduced system over NVLink peer memory per iteration), %d residual rows total; step = one LM iteration" % (N_LM, rows))
+
+
 def reference_arm(args):
     """CPU arm: the oracle restatement of the reference's Ceres+PCL path on the host cores."""
     from oracle import binding
     orc = binding.load()
     T = cpu_threads()
     octx = backend.Context(orc)
-    d = synth.make_ba_problem(N_KF, N_LM, with_imu=True, seed=synth.SEED)
+    d = synth.make_ba_problem(N_KF, N_LM * max(1, args.gpus), with_imu=True, seed=synth.SEED)     # the same (weak-scaled) window the GPU arm shards
     rows = synth.count_rows(d)
     p = backend.Problem.from_dict(octx, d)
     run_solves(p, d, orc, max(1, args.warmup), PER, T)
@@ -155,7 +160,7 @@ def reference_arm(args):
         "impl": "reference", "metric": "ba_residual_jacobian_rows_per_s", "value": val, "unit": "rows/s", "n_gpus": args.gpus,
         "steps": it, "warmup": args.warmup, "ms_per_step": 1e3 * dt / it, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: KITTI-shaped stereo+IMU 10-keyframe window, %d landmarks, %d residual rows; step = one LM iteration" % (N_LM, rows)},
+        "config": {"workload": workload_text(rows), "blocks": synth.count_blocks(d), "iters_per_solve": PER},
         "cpu_baseline": {"value": val, "unit": "rows/s", "cores": T, "kind": "port",
                          "sample": "%d LM iterations of the full configs[1] window (oracle restatement of Ceres SPARSE_SCHUR, %d threads); the reference itself cannot be built here" % (it, T)},
         "window20": {"value": w20, "unit": "rows/s", "cores": T, "sample": "%d LM iterations of the 20-keyframe / %d-landmark window" % (it20, W20_LM)},
@@ -304,7 +309,7 @@ def main():
         line = {
             "metric": "ba_residual_jacobian_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": w10["iters"], "warmup": args.warmup,
             "ms_per_step": w10["ms"] / w10["iters"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: KITTI-shaped stereo+IMU 10-keyframe window, %d landmarks per GPU (sharded by landmark, one in-kernel all-reduce of the reduced system over NVLink peer memory per iteration), %d residual rows total; step = one LM iteration" % (N_LM, w10["rows"]),
+            "config": {"workload": workload_text(w10["rows"]),
                        "blocks": synth.count_blocks(w10["full"]), "iters_per_solve": PER,
                        "timing": "median of %d repetitions of the %d-step timed region (min %.4f / max %.4f ms per step)" % (w10["blocks"], w10["iters"], w10["ms_min"] / w10["iters"], w10["ms_max"] / w10["iters"]),
                        "l2": "BA working set (~3 MB) is L2-resident by design; the roofline legs stream 394 MB / 97 MB per launch (> 126 MB L2 together with their outputs)"},

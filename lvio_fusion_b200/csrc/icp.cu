@@ -211,14 +211,14 @@ __device__ __forceinline__ Best3 knn3_query(const IcpDev& d, float3 q) {
 // every ring): 0.57 ms -- the lanes prune with their own looser bounds and scan more voxels than the chain they shorten; runs only for
 // the face rows of the outer rings (r >= 2): 0.57 ms.  The kernel takes ~0.47 - 0.50 ms whether a rank holds 120 k, 60 k or 30 k of
 // the queries (round-2 runs at 1 / 2 / 4 GPUs): its duration is set by its slowest warps, not by the query count.
-__global__ void icp_query_key_kernel(IcpDev d, int cgx, int cgy, int cgz, int* __restrict__ key, int* __restrict__ counts) {
+__global__ void icp_query_key_kernel(IcpDev d, int shift, int cgx, int cgy, int cgz, int* __restrict__ key, int* __restrict__ counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.K) return;
     const float3 q = transform_f32(d.tf, load_xyz(d.scan, i, d.stride));
     const Grid& g = d.g;
-    const int ix = clampi(cell_coord(q.x, g.minx, g.inv_cell), 0, g.gx - 1) >> 2;
-    const int iy = clampi(cell_coord(q.y, g.miny, g.inv_cell), 0, g.gy - 1) >> 2;
-    const int iz = clampi(cell_coord(q.z, g.minz, g.inv_cell), 0, g.gz - 1) >> 2;
+    const int ix = clampi(cell_coord(q.x, g.minx, g.inv_cell), 0, g.gx - 1) >> shift;
+    const int iy = clampi(cell_coord(q.y, g.miny, g.inv_cell), 0, g.gy - 1) >> shift;
+    const int iz = clampi(cell_coord(q.z, g.minz, g.inv_cell), 0, g.gz - 1) >> shift;
     const int c = ix + cgx * (iy + cgy * iz);
     key[i] = c;
     atomicAdd(&counts[c], 1);
@@ -441,13 +441,21 @@ static int upload_scan(lvb_icp* h, const void* scan, int n, int stride, const do
     d.order = nullptr;
     if (n >= 4096) {       // spatial visiting order: counting sort of the queries by coarse voxel block
         const Grid& g = h->grid;
-        const int cgx = (g.gx + 3) >> 2, cgy = (g.gy + 3) >> 2, cgz = (g.gz + 3) >> 2;
+        // key granularity: blocks of 2 x 2 x 2 voxels (measured on configs[2], association kernel: 4 x 4 x 4 blocks 0.51 ms, 2 x 2 x 2
+        // 0.44 ms, single voxels 0.50 ms plus a slower sort) -- coarser only when the grid would need more than 8 M counters;
+        // env LVB_ICP_SORT_SHIFT forces one (A/B)
+        static const int forced = getenv("LVB_ICP_SORT_SHIFT") ? atoi(getenv("LVB_ICP_SORT_SHIFT")) : -1;
+        int shift = 1;
+        while (forced < 0 && (double)((g.gx >> shift) + 1) * ((g.gy >> shift) + 1) * ((g.gz >> shift) + 1) > 8.0e6) ++shift;
+        if (forced >= 0) shift = forced;
+        const int rnd = (1 << shift) - 1;
+        const int cgx = (g.gx + rnd) >> shift, cgy = (g.gy + rnd) >> shift, cgz = (g.gz + rnd) >> shift;
         const int nc = cgx * cgy * cgz, nb = (nc + 1023) / 1024;
         LVB_TRY(h->q_key.ensure(n)); LVB_TRY(h->q_order.ensure(n)); LVB_TRY(h->q_counts.ensure(nc)); LVB_TRY(h->q_fill.ensure(nc));
         LVB_TRY(h->q_start.ensure((size_t)nc + 1)); LVB_TRY(h->q_sums.ensure(nb)); LVB_TRY(h->q_total.ensure(1));
         LVB_CUDA(cudaMemsetAsync(h->q_counts.p, 0, (size_t)nc * sizeof(int), s));
         LVB_CUDA(cudaMemsetAsync(h->q_fill.p, 0, (size_t)nc * sizeof(int), s));
-        ILAUNCH(h, icp_query_key_kernel, (n + 255) / 256, 256, d, cgx, cgy, cgz, h->q_key.p, h->q_counts.p);
+        ILAUNCH(h, icp_query_key_kernel, (n + 255) / 256, 256, d, shift, cgx, cgy, cgz, h->q_key.p, h->q_counts.p);
         ILAUNCH(h, scan_block_kernel, nb, 1024, h->q_counts.p, h->q_start.p, nc, h->q_sums.p);
         ILAUNCH(h, scan_sums_kernel, 1, 1024, h->q_sums.p, nb, h->q_total.p);
         ILAUNCH(h, scan_add_kernel, nb, 1024, h->q_start.p, nc, h->q_sums.p, h->q_start.p + nc, h->q_total.p);
