@@ -45,6 +45,8 @@ EVAL_KF, EVAL_LM = 5000, 500000      # configs[4] scale
 # dram__bytes_read.sum + dram__bytes_write.sum of one ba_eval_two_frame_kernel launch at that scale, from the `ncu --set full`
 # capture summarised in profiles/eval_r1_v3_summary.txt (75.19 MB + 293.14 MB): a constant from that capture, not measured in-run
 EVAL_DRAM_BYTES_PER_LAUNCH = 368.33e6
+# the same for ba_linearize_kernel<0> at that scale: profiles/global_r2_final_summary.txt (143.74 MB read + 115.21 MB written)
+FUSED_DRAM_BYTES_PER_LAUNCH = 258.95e6
 BYTES_TWO_FRAME = 308                # 40 const + 12 idx + 16 r + 240 J
 BYTES_FUSED = {0: 52, 1: 52, 2: 44}  # SURVEY 8(d) fused mode: TwoFrame, PoseOnly, TwoCamera
 BYTES_KNN_QUERY = 40                 # query 16 + idx 12 + d2 12, plus 16 B per map point amortised over the queries
@@ -413,7 +415,8 @@ def main():
                 alg = sum(n * BYTES_FUSED[k] for k, n in zip((0, 1, 2), nblk))
                 if us:
                     line["roofline_fused"] = {"bound": "hbm", "achieved": alg / (us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (us * 1e-6) / 1e9 / peak,
-                                              "traffic": None, "kernel": "ba_linearize_kernel<0>", "blocks": nblk, "bytes_per_block": [BYTES_FUSED[k] for k in (0, 1, 2)],
+                                              "traffic": FUSED_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/global_r2_final_summary.txt (ncu --set full), not measured in-run",
+                                              "kernel": "ba_linearize_kernel<0>", "blocks": nblk, "bytes_per_block": [BYTES_FUSED[k] for k in (0, 1, 2)],
                                               "us_per_launch": us, "peak_source": peak_src, "total_blocks": g_blocks,
                                               "note": "algorithmic bytes are SURVEY 8(d)'s fused-mode figures; the kernel also writes the per-factor coupling rows the Schur step reads"}
             gp.close()
@@ -482,7 +485,8 @@ def main():
                 line["icp"]["knn_only"] = {"value": ICP_K / (us * 1e-6), "unit": "points/s", "us": us,
                                            "note": "icp_associate_kernel alone: float32 transform + exact 3-NN + gate + plane normal"}
                 line["icp"]["roofline"] = {"bound": "hbm", "achieved": alg / (us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (us * 1e-6) / 1e9 / peak,
-                                           "traffic": None, "kernel": "icp_associate_kernel", "bytes_per_query": BYTES_KNN_QUERY + 16.0 * ICP_P / ICP_K,
+                                           "traffic": 17.53e6, "traffic_source": "profiles/icp_r2_final_summary.txt (ncu --set full), not measured in-run",
+                                           "kernel": "icp_associate_kernel", "bytes_per_query": BYTES_KNN_QUERY + 16.0 * ICP_P / ICP_K,
                                            "us_per_launch": us, "peak_source": peak_src,
                                            "note": "algorithmic minimum of SURVEY 8(d) (40 B/query + the map read once); the voxel ring scan is L2-latency work on top"}
 
