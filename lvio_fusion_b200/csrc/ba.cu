@@ -1008,37 +1008,117 @@ __global__ void lm_control_pre_kernel(LmState* st) { lm_control_pre(*st); }
 // Right-looking blocked (32) factorisation of the lower triangle of S (n x n, row-major, in L2/HBM) with
 // the right-hand side carried along as an extra row (so the forward substitution is free), then a
 // blocked backward substitution.  Result: rhs <- S^-1 rhs.
+//
+// Schedule of one 32-column step k (look-ahead of depth one, the serial part on its own warp):
+//   warp 0     : panel solve of the 32 "head" rows (= the rows of diagonal block k + 1), one row per lane;  update of diagonal block
+//                k + 1 by these rows as one 32 x 32 register-tiled product, handed to the row-per-lane layout of the factorisation
+//                through shared memory (no trip through global memory);  factorisation of block k + 1 into the OTHER (Dt, invd) buffer
+//   warps 1..7 : the INVERSE of block k of L to the block's place in S (for the backward pass);  panel solve of the remaining rows +
+//                the rhs row;  named barrier (warp 0 only arrives, once its head rows are in shared memory);  trailing update of
+//                everything but diagonal block k + 1
+// so the pivot chain of block k + 1 overlaps the panel and the trailing update of step k instead of following them.
 #define SA(i_, j_) S[(size_t)(i_) * (size_t)srow + (size_t)(j_) + (size_t)soff]
+enum { CHOL_DT = 32 * 34 + 32, CHOL_HDR = 2 * CHOL_DT };        // doubles: (Dt, invd) twice, then the panel
 __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict__ S, double* __restrict__ rhs, int n, long long srow, long long soff,
                                                                   double* __restrict__ invd_g, LmState* st, int run_control_pre,
                                                                   const int* __restrict__ env_rmax, const int* __restrict__ env_cmin) {
     if (run_control_pre) { if (threadIdx.x == 0) lm_control_pre(*st); __syncthreads(); }
     if (st->done) return;
     extern __shared__ __align__(16) double sm[];
-    double* Dt = sm;                   // 32 x 34   diagonal block of L, column-major: Dt[j * 34 + k] = L[k][j] (lvb_chol.cuh)
-    double* invd = sm + 32 * 34;       // 32        reciprocals of diag(L) of the current block
-    double* P = invd + 32;             // rows x 34 panel (16 B aligned rows for broadcast double2 loads)
+    double* P = sm + CHOL_HDR;         // rows x 34 panel (16 B aligned rows for broadcast double2 loads)
     __shared__ int fail;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     if (tid == 0) fail = 0;
     long long t_diag = 0, t_panel = 0, t_trail = 0, t0 = clock64(), tA;
     const long long t_begin = t0;
+    // ---- diagonal block 0: warp 0, one row per lane in registers (lvb_chol.cuh)
+    if (warp == 0) {
+        const int b0 = min(32, n);
+        double a[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = (lane < b0 && j <= lane) ? SA(lane, j) : ((j == lane) ? 1.0 : 0.0);
+        const int bad = chol_diag32_pair(a, lane, sm, sm + 32 * 34);
+        if (bad && lane == 0) fail = 1;
+    }
     __syncthreads();
-    // Software-pipelined over the 32-column block steps with look-ahead: while warps 1.. finish the trailing update
-    // of step kb, warp 0 updates the next diagonal block first (tile 0) and factors it, so the serial shuffle
-    // chain of the diagonal factorisation overlaps the FP64-throughput part.  Iteration kb = -32 only factors block 0.
-    for (int kb = -32; kb < n; kb += 32) {
-        const int bs = min(32, n - kb);
-        int m = 0;
-        if (kb >= 0) {
-            // ---- panel: rows below the block + the rhs row (last):  x L^T = a, right-looking, no divisions
-            // only rows inside the envelope of this block column take part (S is block-banded by construction)
-            m = env_rmax[kb >> 5] - (kb + bs) + 1 + 1;
-            // the diagonal block factored during the previous step's look-ahead goes to its place in S (the backward pass reads it
-            // there) with all threads, row by row; Dt stays valid until warp 0 starts the next block after this panel phase
-            for (int e = tid; e < 32 * 32; e += nt) { const int k = e >> 5, j = e & 31; if (j <= k && k < bs) SA(kb + k, kb + j) = Dt[j * 34 + k]; }
-            if (tid < bs) invd_g[kb + tid] = invd[tid];
-            for (int rr = tid; rr < m; rr += nt) {
+    tA = clock64(); t_diag += tA - t0; t0 = tA;
+    for (int kb = 0; kb < n; kb += 32) {
+        const int bs = min(32, n - kb), kn = kb + 32;
+        const int hb = max(0, min(32, n - kn));                    // rows of the next diagonal block ("head" rows of the panel)
+        double* Dt = sm + ((kb >> 5) & 1) * CHOL_DT;               // block kb of L, column-major: Dt[j * 34 + k] = L[k][j]
+        double* invd = Dt + 32 * 34;
+        double* Dn = sm + (((kb >> 5) & 1) ^ 1) * CHOL_DT;
+        // panel rows: the rows below the block inside the envelope of this block column (S is block-banded by construction) + the rhs row (last)
+        const int m = env_rmax[kb >> 5] - (kb + bs) + 1 + 1;
+        const int mh = min(hb, m - 1);                             // head rows inside the envelope
+        if (warp == 0 && hb > 0) {
+            double x[32], a[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = (lane < mh && j < bs) ? SA(kn + lane, kb + j) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = (lane < hb && j <= lane) ? SA(kn + lane, kn + j) : ((j == lane) ? 1.0 : 0.0);
+            chol_panel_row(x, Dt, invd);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (lane < mh) { P[lane * 34 + j] = x[j]; if (j < bs) SA(kn + lane, kb + j) = x[j]; }
+            __syncwarp();
+            asm volatile("bar.arrive 1, %0;" :: "r"(nt) : "memory");
+            tA = clock64(); t_panel += tA - t0; t0 = tA;
+            // diagonal block kn -= (head rows)(head rows)^T: computed as a 32 x 32 tile in the 4 x 8 register micro-tile layout of the
+            // trailing update (12 LDS.128 per 64 DFMA; the row-per-lane layout would need one LDS.128 per 2 DFMA and is bound by the
+            // shared-memory return path), then passed through the free diagonal-block buffer to the row-per-lane layout of the
+            // factorisation.  Head rows outside the envelope are structurally zero and have no panel row.
+            if (mh > 0) {
+                const int ry = lane >> 2, cx = lane & 3;
+                double acc[4][8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+                const double2* rp[4]; const double2* cp[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rp[i] = reinterpret_cast<const double2*>(P + (size_t)min(ry + 8 * i, mh - 1) * 34);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cp[j] = reinterpret_cast<const double2*>(P + (size_t)min(cx + 4 * j, mh - 1) * 34);
+#pragma unroll 2
+                for (int k = 0; k < 16; ++k) {
+                    double2 rv[4], cv[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) rv[i] = rp[i][k];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) cv[j] = cp[j][k];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { acc[i][j] += rv[i].x * cv[j].x; acc[i][j] += rv[i].y * cv[j].y; }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) Dn[(ry + 8 * i) * 34 + cx + 4 * j] = (ry + 8 * i < mh && cx + 4 * j < mh) ? acc[i][j] : 0.0;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] -= Dn[lane * 34 + j];
+                __syncwarp();
+            }
+            const int bad = chol_diag32_pair(a, lane, Dn, Dn + 32 * 34);
+            if (bad && lane == 0) fail = 1;
+            tA = clock64(); t_diag += tA - t0; t0 = tA;
+        } else {
+            const int wid = hb > 0 ? warp - 1 : warp, nwk = hb > 0 ? nw - 1 : nw;       // the warps doing this part
+            const int t2 = wid * 32 + lane, nt2 = nwk * 32;
+            // the INVERSE of block kb of L goes to the block's place in S: the backward pass then applies a diagonal block as 32 independent
+            // FMAs per lane instead of a 32-step substitution chain.  Column c of L^-1 is the panel solve of the unit row e_c; one warp
+            // (the last one, which has the fewest panel rows) does it while the others are in the panel.
+            if (wid == nwk - 1) {
+                double e[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) e[j] = (j == lane) ? 1.0 : 0.0;
+                chol_panel_row(e, Dt, invd);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j >= lane && j < bs) SA(kb + j, kb + lane) = e[j];
+            }
+            // ---- panel, the rows warp 0 does not take:  x L^T = a, right-looking, no divisions
+            for (int rr = mh + t2; rr < m; rr += nt2) {
                 const bool is_rhs = (rr == m - 1);
                 double* src = is_rhs ? (rhs + kb) : &SA(kb + bs + rr, kb);
                 double a[32];
@@ -1048,18 +1128,20 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
     #pragma unroll
                 for (int j = 0; j < 32; ++j) { P[rr * 34 + j] = a[j]; if (j < bs) src[j] = a[j]; }
             }
-            __syncthreads();
-            tA = clock64(); t_panel += tA - t0; t0 = tA;
+            asm volatile("bar.sync 1, %0;" :: "r"(nt) : "memory");
             // ---- trailing update A22 -= P P^T on the lower triangle.  One warp per 32x32 tile, each lane a 4x8
             // register micro-tile (rows ry+8i, columns cx+4j: consecutive lanes touch consecutive panel rows, so the
-            // LDS.128 operand loads are bank-conflict free and every loaded value feeds 4 or 8 DFMAs).
+            // LDS.128 operand loads are bank-conflict free and every loaded value feeds 4 or 8 DFMAs).  The head rows of
+            // tile (0, 0) -- diagonal block kn -- are warp 0's.
             const int ntile = (m + 31) >> 5;
-            const int total = ntile * (ntile + 1) / 2;
-            for (int t = (warp == 0) ? 0 : warp; t < total; t += (warp == 0) ? total : (nw - 1)) {
+            const int total = (m > 1) ? ntile * (ntile + 1) / 2 : 0;
+            for (int t = wid; t < total; t += nwk) {
+                if (t == 0 && mh >= min(32, m)) continue;
                 int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
                 while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
                 while (ti * (ti + 1) / 2 > t) --ti;
                 const int tj = t - ti * (ti + 1) / 2;
+                const int row_lo = (t == 0) ? mh : 0;
                 const int ry = lane >> 2, cx = lane & 3;
                 const int r0 = ti * 32 + ry, c0 = tj * 32 + cx;
                 double acc[4][8];
@@ -1092,51 +1174,36 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
                     const int ip = min(r0 + 8 * i, m - 1);
                     const double* src = (ip == m - 1) ? (rhs + kb + bs) : &SA(kb + bs + ip, kb + bs);
     #pragma unroll
-                    for (int j = 0; j < 8; ++j) { const int jp = c0 + 4 * j; cur[i][j] = (r0 + 8 * i < m && jp < m - 1 && jp <= ip) ? src[jp] : 0.0; }
+                    for (int j = 0; j < 8; ++j) { const int jp = c0 + 4 * j; cur[i][j] = (r0 + 8 * i < m && r0 + 8 * i >= row_lo && jp < m - 1 && jp <= ip) ? src[jp] : 0.0; }
                 }
     #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int ip = r0 + 8 * i;
-                    if (ip >= m) continue;
+                    if (ip >= m || ip < row_lo) continue;
                     double* dst = (ip == m - 1) ? (rhs + kb + bs) : &SA(kb + bs + ip, kb + bs);
     #pragma unroll
                     for (int j = 0; j < 8; ++j) { const int jp = c0 + 4 * j; if (jp < m - 1 && jp <= ip) dst[jp] = cur[i][j] - acc[i][j]; }
                 }
             }
         }
-        const int kn = kb + 32, bn = min(32, n - kn);
-        // ---- diagonal block kn: warp 0 holds one row per lane in registers and factors it with shuffles
-        if (kn < n) {
-            __syncwarp();
-            if (warp == 0) {
-                const long long t_d0 = clock64();
-                // one row per lane in registers; lvb_chol.cuh::chol_diag32 (4 groups of 8 columns, deferred rank-8 updates)
-                double a[32];
-    #pragma unroll
-                for (int j = 0; j < 32; ++j) a[j] = (lane < bn && j <= lane) ? SA(kn + lane, kn + j) : ((j == lane) ? 1.0 : 0.0);
-                const int bad = chol_diag32(a, lane, Dt, invd);
-                t_diag += clock64() - t_d0;
-                if (bad && lane == 0) fail = 1;
-            }
-        }
         __syncthreads();
         tA = clock64(); t_trail += tA - t0; t0 = tA;
     }
     // ---- backward substitution  L^T x = y  (y is in rhs), left-looking per 32-column block:
-    //   x_k = D_k^-T (y_k - sum_{r below} L[r][k-block]^T x_r)
+    //   x_k = D_k^-T (y_k - sum_{r below} L[r][k-block]^T x_r),  D_k^-1 stored in place of D_k by the factorisation
     // the sum is a GEMV over the envelope rows spread over all warps (independent coalesced loads, one L2 round trip per
-    // batch), then warp 0 solves the 32 unknowns of the block with shuffles.  x overwrites rhs.
+    // batch), then warp 0 applies the inverse diagonal block: 32 independent FMAs per lane, no substitution chain.  x overwrites rhs.
     const int last = ((n - 1) / 32) * 32;
     double* part = P;                                 // nw x 32 partial sums
     for (int kb = last; kb >= 0; kb -= 32) {
         const int bs = min(32, n - kb);
         const int rend = env_rmax[kb >> 5];
-        double col[32];                               // warp 0: column `lane` of the diagonal block, col[i] = L[kb+i][kb+lane], i >= lane
-        double t = 0.0, my_inv = 1.0;
+        double col[32];                               // warp 0: column `lane` of the inverse diagonal block, col[i] = Linv[kb+i][kb+lane], i >= lane
+        double t = 0.0;
         if (warp == 0) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) col[i] = (i < bs && lane < bs && i >= lane) ? SA(kb + i, kb + lane) : 0.0;
-            if (lane < bs) { t = rhs[kb + lane]; my_inv = invd_g[kb + lane]; }
+            if (lane < bs) t = rhs[kb + lane];
         }
         double acc = 0.0;
         if (lane < bs) {
@@ -1152,12 +1219,16 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
         __syncthreads();
         if (warp == 0) {
             for (int w = 0; w < nw; ++w) t -= part[w * 32 + lane];
+            // x = D^-T t with the stored inverse: x_lane = sum_{j >= lane} Linv[j][lane] t_j
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
 #pragma unroll
-            for (int j = 31; j >= 0; --j) {
-                const double xj = __shfl_sync(0xffffffffu, t * my_inv, j);     // lane j's t is final here
-                if (lane == j) t = xj;
-                else if (lane < j) t -= col[j] * xj;
+            for (int j = 0; j < 32; j += 4) {
+                y0 = fma(col[j], __shfl_sync(0xffffffffu, t, j), y0);
+                y1 = fma(col[j + 1], __shfl_sync(0xffffffffu, t, j + 1), y1);
+                y2 = fma(col[j + 2], __shfl_sync(0xffffffffu, t, j + 2), y2);
+                y3 = fma(col[j + 3], __shfl_sync(0xffffffffu, t, j + 3), y3);
             }
+            t = (y0 + y1) + (y2 + y3);
             if (lane < bs) rhs[kb + lane] = t;
         }
         __syncthreads();
@@ -1762,7 +1833,7 @@ int lvb_ba_finalize(lvb_ba* ba) {
     if (dense_layout) { ba->srow = ba->dimc; ba->soff = 0; ba->nS = (size_t)ba->dimc * ba->dimc; }
     else              { ba->srow = band; ba->soff = band; ba->nS = (size_t)ba->dimc * (size_t)(band + 1); }
     ba->band = band; ba->panel_rows = panel_rows;
-    ba->chol_smem = (size_t)(32 * 33 + 32 + 128 + std::max((panel_rows + 2) * 34, (CHOL_T / 32) * 32)) * 8;      // panel, later the backward partial sums
+    ba->chol_smem = (size_t)(CHOL_HDR + std::max(panel_rows + 2, 34) * 34) * 8;      // two diagonal-block buffers + the panel (>= 34 rows; later the backward partial sums)
     // banded systems: split the chain by a separator tree when the band leaves room for at least two leaves (ba_tree.cuh)
     ba->tree_levels = 0;
     std::vector<Front> h_fronts;
@@ -2292,7 +2363,7 @@ LVB_API int lvb_debug_band_solve(lvb_ctx* ctx, int n, int band, const double* S_
         panel_rows = std::max(panel_rows, rmax[st] - (kb + bs) + 2);
     }
     LVB_TRY(ba.chol_rmax.upload(rmax.data(), rmax.size(), s)); LVB_TRY(ba.chol_cmin.upload(cmin.data(), cmin.size(), s));
-    ba.chol_smem = (size_t)(32 * 33 + 32 + 128 + std::max((panel_rows + 2) * 34, (CHOL_T / 32) * 32)) * 8;
+    ba.chol_smem = (size_t)(CHOL_HDR + std::max(panel_rows + 2, 34) * 34) * 8;
     std::vector<Front> fr; size_t pool = 0; int rows = 0, mnb = 0, max_leaves = 1;
     while (max_leaves * 2 <= std::max(2, ctx->sm_count)) max_leaves *= 2;
     ba.tree_levels = 0;

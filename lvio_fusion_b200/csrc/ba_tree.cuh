@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_front_factor_kernel(const Front* __
                 double a[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) a[j] = (lane < bn && j <= lane) ? SG(F.o0 + kn + lane, F.o0 + kn + j) : ((j == lane) ? 1.0 : 0.0);
-                const int bad = chol_diag32(a, lane, Dt, invd);
+                const int bad = chol_diag32_pair(a, lane, Dt, invd);
                 if (bad && lane == 0) fail = 1;
             }
         }

@@ -83,6 +83,71 @@ __device__ __forceinline__ int chol_diag32(double (&a)[32], const int lane, doub
     return bad;
 }
 
+// 1 / sqrt(x), seed + ONE third-order step  y (1 + e/2 + 3 e^2/8),  e = 1 - x y^2: the seed is good to ~2^-20 (tools/lat_probe.cu prints
+// the measured worst case), the truncation term 5/16 e^3 is then below 2^-58, and the dependent chain is MUFU + 4 FP64 operations
+// instead of MUFU + 6.
+__device__ __forceinline__ double rsqrt_pos3(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(e, 0.375, 0.5), ye = y * e;
+    return fma(ye, p, y);
+}
+
+// Same contract as chol_diag32, two columns per pivot step.  The 2 x 2 pivot block [[p, q], [q, c]] is factored in closed form:
+// L11 = sqrt(p), L21 = q / L11, L22 = sqrt(det / p) with det = p c - q^2, so the two reciprocal square roots 1 / sqrt(p) and 1 / sqrt(det)
+// are independent and run side by side -- one MUFU + refinement latency per TWO columns -- and the broadcast / update round trip
+// (shuffle -> FMA -> shuffle) is also paid once per pair.
+__device__ __forceinline__ int chol_diag32_pair(double (&a)[32], const int lane, double* __restrict__ Dt, double* __restrict__ invd) {
+    int bad = 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 32; c0 += 8) {
+#pragma unroll
+        for (int jj = 0; jj < 8; jj += 2) {
+            const int j = c0 + jj;
+            double p = __shfl_sync(0xffffffffu, a[jj], j);
+            const double q = __shfl_sync(0xffffffffu, a[jj], j + 1);
+            const double c = __shfl_sync(0xffffffffu, a[jj + 1], j + 1);
+            double det = fma(p, c, -q * q);
+            if (!(p > 0.0) || !(det > 0.0)) { bad = 1; p = 1.0; det = 1.0; }
+            const double i1 = rsqrt_pos3(p), id = rsqrt_pos3(det);
+            const double l11 = p * i1, l21 = q * i1;
+            const double i2 = id * l11;
+            const double l1 = a[jj] * i1;
+            const double l2 = fma(-l1, l21, a[jj + 1]) * i2;
+            a[jj] = l1; a[jj + 1] = l2;
+            Dt[j * 34 + lane] = l1; Dt[(j + 1) * 34 + lane] = l2;
+            if (lane == j) { invd[j] = i1; invd[j + 1] = i2; }
+#pragma unroll
+            for (int r = jj + 2; r < 8; ++r) {
+                const double v1 = __shfl_sync(0xffffffffu, l1, c0 + r), v2 = __shfl_sync(0xffffffffu, l2, c0 + r);
+                a[r] = fma(-l2, v2, fma(-l1, v1, a[r]));
+            }
+        }
+        if (c0 < 24) {
+            __syncwarp();                             // the group's columns are in Dt
+            // rank-8 update of the columns right of the group; registers 8 and 9 (the next pivot pair) first
+#pragma unroll
+            for (int r = 8; r < 32; r += 2) {
+                if (c0 + r < 32) {                    // warp-uniform
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const double2 v = *reinterpret_cast<const double2*>(Dt + (c0 + k) * 34 + c0 + r);
+                        a[r] -= a[k] * v.x; a[r + 1] -= a[k] * v.y;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 24; ++r) a[r] = a[r + 8];
+#pragma unroll
+        for (int r = 24; r < 32; ++r) a[r] = 0.0;
+    }
+    __syncwarp();
+    return bad;
+}
+
 // One panel row: x L^T = a for the 32 columns of the block (right-looking, no divisions), operands broadcast from Dt as LDS.128.
 __device__ __forceinline__ void chol_panel_row(double (&a)[32], const double* __restrict__ Dt, const double* __restrict__ invd) {
 #pragma unroll
