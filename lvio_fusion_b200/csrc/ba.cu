@@ -1384,6 +1384,7 @@ struct lvb_ba {
     double cam[22];
     bool have_cam = false;
     std::vector<double> h_poses, h_vec3, h_rho;
+    std::vector<double> r_params; bool host_fresh = false;      // parameter blocks as last read back (one round trip serves the three getters)
     std::vector<uint8_t> h_pose_const, h_vec3_const, h_rho_const;
     std::vector<double> h_fc[6];
     std::vector<int32_t> h_fi[6];
@@ -1399,6 +1400,7 @@ struct lvb_ba {
     std::vector<int> level_first, level_count;
     int tree_levels = 0; size_t tree_factor_smem = 0, tree_back_smem = 0;
     // device
+    DevBuf<unsigned char> upload_arena;      // one allocation for everything finalize uploads (the buffers below are views into it)
     DevBuf<double> poses, vec3, rho, c_poses, c_vec3, c_rho;
     DevBuf<int> pose_off, vec3_off, rho_slot, lm_start, lm_fac;
     DevBuf<int> tf_slot, sw_group, sw_lm, grp_ns, grp_off;
@@ -1534,6 +1536,104 @@ static int check_launch(const char* what) {
     return LVB_OK;
 }
 
+// AoS -> SoA of one factor kind in device order: record i of the output is caller record ord[i] (or a padding copy of record
+// -1 - ord[i] with its weight column zeroed).  Compile-time strides for the visual kinds: the generic loop spends its time on the
+// loop control of a 5-iteration inner loop.
+template <int CS> static void gather_planes(double* __restrict__ out, const double* __restrict__ hc, const int* __restrict__ ord, int n, int wcol) {
+    for (int i = 0; i < n; ++i) {
+        if (i + 16 < n) { const int g = ord[i + 16] >= 0 ? ord[i + 16] : -1 - ord[i + 16]; __builtin_prefetch(hc + (size_t)g * CS); __builtin_prefetch(hc + (size_t)g * CS + CS - 1); }
+        const bool pad = ord[i] < 0;
+        const double* src = hc + (size_t)(pad ? -1 - ord[i] : ord[i]) * CS;
+#pragma GCC unroll 8
+        for (int j = 0; j < CS; ++j) out[(size_t)j * n + i] = src[j];
+        if (pad && wcol >= 0) out[(size_t)wcol * n + i] = 0.0;
+    }
+}
+template <int IS> static void gather_index_planes(int* __restrict__ out, const int32_t* __restrict__ hi, const int* __restrict__ ord, int n) {
+    for (int i = 0; i < n; ++i) {
+        if (i + 16 < n) { const int g = ord[i + 16] >= 0 ? ord[i + 16] : -1 - ord[i + 16]; __builtin_prefetch(hi + (size_t)g * IS); }
+        const int32_t* src = hi + (size_t)(ord[i] >= 0 ? ord[i] : -1 - ord[i]) * IS;
+#pragma GCC unroll 8
+        for (int j = 0; j < IS; ++j) out[(size_t)j * n + i] = src[j];
+    }
+}
+
+// Assembles the arrays a problem uploads in the context's pinned staging area; commit() sends them to the device with ONE copy into
+// ONE allocation and points the DevBufs at their pieces (finalize used to issue ~40 pageable cudaMemcpyAsync calls: 0.29 of its
+// 0.53 ms at window size).  A reserve() hands out staging memory to be filled in place (the AoS -> SoA transposition writes its
+// planes there directly); the pointer is good until the next reserve / put.  Map-scale problems (more than STAGE_MAX bytes of
+// factors) keep the per-array uploads: pinning hundreds of megabytes costs more than it saves.
+struct Stager {
+    enum : size_t { STAGE_MAX = (size_t)24 << 20 };
+    lvb_ctx* ctx; cudaStream_t s; bool staged; size_t used = 0;
+    struct Item { void* buf; size_t off, count; void (*bind)(void*, unsigned char*, size_t, size_t); };
+    std::vector<Item> items;
+    std::vector<unsigned char> scratch;               // direct mode: the memory reserve() hands out
+    void* pending_buf = nullptr; size_t pending_count = 0; int (*pending_up)(void*, const void*, size_t, cudaStream_t) = nullptr;
+    template <class T> static void bind_fn(void* b, unsigned char* base, size_t off, size_t count) { static_cast<DevBuf<T>*>(b)->set_view(reinterpret_cast<T*>(base + off), count); }
+    template <class T> static int up_fn(void* b, const void* src, size_t count, cudaStream_t st) { return static_cast<DevBuf<T>*>(b)->upload(static_cast<const T*>(src), count, st); }
+    Stager(lvb_ctx* c, size_t estimate) : ctx(c), s(c->stream), staged(estimate <= STAGE_MAX) {
+        static const bool off = getenv("LVB_NO_STAGING") && getenv("LVB_NO_STAGING")[0] == '1';      // A/B switch
+        if (off) staged = false;
+    }
+    int begin() {
+        if (!staged) return LVB_OK;
+        if (!ctx->stage_ev) LVB_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming));
+        if (ctx->stage_busy) { LVB_CUDA(cudaEventSynchronize(ctx->stage_ev)); ctx->stage_busy = false; }      // the previous problem's copy has read it
+        return LVB_OK;
+    }
+    int grow(size_t need) {
+        if (need <= ctx->stage_cap) return LVB_OK;
+        size_t cap = std::max<size_t>(std::max<size_t>(2 * ctx->stage_cap, need), (size_t)4 << 20);
+        unsigned char* q = nullptr;
+        LVB_CUDA(cudaHostAlloc((void**)&q, cap, cudaHostAllocDefault));
+        if (used) memcpy(q, ctx->stage_h, used);
+        if (ctx->stage_h) cudaFreeHost(ctx->stage_h);
+        ctx->stage_h = q; ctx->stage_cap = cap;
+        return LVB_OK;
+    }
+    // memory for `count` elements of dst, to be filled by the caller before the next reserve / put; finish() after filling
+    template <class T> int reserve(DevBuf<T>& dst, size_t count, T** out) {
+        const size_t c = std::max<size_t>(count, 1), bytes = c * sizeof(T);
+        if (staged) {
+            const size_t off = (used + 255) & ~(size_t)255;
+            LVB_TRY(grow(off + bytes + 256));
+            if (off > used) memset(ctx->stage_h + used, 0, off - used);
+            items.push_back({&dst, off, c, &bind_fn<T>});
+            used = off + bytes;
+            *out = reinterpret_cast<T*>(ctx->stage_h + off);
+        } else {
+            scratch.resize(bytes);
+            pending_buf = &dst; pending_count = count; pending_up = &up_fn<T>;
+            *out = reinterpret_cast<T*>(scratch.data());
+        }
+        return LVB_OK;
+    }
+    int finish() {
+        if (staged || !pending_buf) return LVB_OK;
+        void* b = pending_buf; pending_buf = nullptr;
+        return pending_up(b, scratch.data(), pending_count, s);      // pageable source: the call returns once it has been staged by the driver
+    }
+    template <class T> int put(DevBuf<T>& dst, const T* src, size_t count) {
+        if (!staged) return dst.upload(src, count, s);
+        T* q = nullptr;
+        LVB_TRY(reserve(dst, count, &q));
+        if (count) memcpy(q, src, count * sizeof(T));
+        return LVB_OK;
+    }
+    int commit(DevBuf<unsigned char>& arena) {
+        if (!staged) return LVB_OK;
+        // a fresh allocation every time: the views of an earlier finalize may still be referenced by work in flight on the stream
+        arena.release();
+        LVB_TRY(arena.ensure(std::max<size_t>(used, 256)));
+        LVB_CUDA(cudaMemcpyAsync(arena.p, ctx->stage_h, used, cudaMemcpyHostToDevice, s));
+        LVB_CUDA(cudaEventRecord(ctx->stage_ev, s));
+        ctx->stage_busy = true;
+        for (const Item& it : items) it.bind(it.buf, arena.p, it.off, it.count);
+        return LVB_OK;
+    }
+};
+
 extern "C" {
 
 int lvb_ba_create(lvb_ctx* ctx, lvb_ba** out) {
@@ -1581,18 +1681,28 @@ int lvb_ba_finalize(lvb_ba* ba) {
     auto prof_t = std::chrono::steady_clock::now();
 #define PROF(name) do { if (prof_on) { const auto t_ = std::chrono::steady_clock::now(); fprintf(stderr, "[finalize] %-28s %8.1f us\n", name, std::chrono::duration<double, std::micro>(t_ - prof_t).count()); prof_t = t_; } } while (0)
     lvb_ctx* ctx = ba->ctx;
+    ba->host_fresh = false;
     LVB_CUDA(cudaSetDevice(ctx->device)); lvb::g_alloc_stream = ctx->stream;
     cudaStream_t s = ctx->stream;
+    size_t stage_estimate = (ba->h_poses.size() + ba->h_vec3.size() + ba->h_rho.size()) * 24;
+    for (int k = 0; k < 6; ++k) stage_estimate += ba->h_fc[k].size() * 8 + ba->h_fi[k].size() * 12;
+    Stager stg(ctx, stage_estimate);
+    LVB_TRY(stg.begin());
     if (!ba->have_cam) { set_error("cameras not set"); return LVB_ERR_STATE; }
     const int np = (int)ba->h_poses.size() / 7, nv = (int)ba->h_vec3.size() / 3, nr = (int)ba->h_rho.size();
-    // validate indices
-    for (int k = 0; k < 6; ++k) for (int f = 0; f < ba->n[k]; ++f) for (int j = 0; j < kIdxStride[k]; ++j) {
-        const int v = ba->h_fi[k][(size_t)f * kIdxStride[k] + j];
-        int lim = np;
-        if ((k == 0 && j == 0) || k == 2) lim = nr;
-        if (k == 3 && j != 0 && j != 4) lim = nv;
-        if (k == 3 && (j == 6 || j == 7) && v == -1 && ba->h_fc[3][(size_t)f * IMU_RAW + 467] >= 0.0) continue;     // ImuInitError has no j-side bias blocks
-        if (v < 0 || v >= lim) { set_error("factor kind %d block %d: index %d out of range [0,%d)", k, f, v, lim); return LVB_ERR_INVALID; }
+    // validate indices (the TwoFrame list is the long one: a branch-free pass; the other kinds through the general rule)
+    {
+        const int32_t* ix = ba->h_fi[0].data();
+        int bad = 0;
+        for (int f = 0; f < ba->n[0]; ++f, ix += 3) bad |= ((unsigned)ix[0] >= (unsigned)nr) | ((unsigned)ix[1] >= (unsigned)np) | ((unsigned)ix[2] >= (unsigned)np);
+        for (int k = bad ? 0 : 1; k < 6; ++k) for (int f = 0; f < ba->n[k]; ++f) for (int j = 0; j < kIdxStride[k]; ++j) {
+            const int v = ba->h_fi[k][(size_t)f * kIdxStride[k] + j];
+            int lim = np;
+            if ((k == 0 && j == 0) || k == 2) lim = nr;
+            if (k == 3 && j != 0 && j != 4) lim = nv;
+            if (k == 3 && (j == 6 || j == 7) && v == -1 && ba->h_fc[3][(size_t)f * IMU_RAW + 467] >= 0.0) continue;     // ImuInitError has no j-side bias blocks
+            if (v < 0 || v >= lim) { set_error("factor kind %d block %d: index %d out of range [0,%d)", k, f, v, lim); return LVB_ERR_INVALID; }
+        }
     }
     PROF("validate");
     // slots / offsets.  Unknowns of the reduced camera system are ordered keyframe by keyframe
@@ -1685,14 +1795,28 @@ int lvb_ba_finalize(lvb_ba* ba) {
     }
     PROF("factor sort + pad");
     const int n_tf = ba->nd[0];
-    auto tf_src = [&](int i) { const int o = ba->order[0][i]; return o >= 0 ? o : -1 - o; };
-    // landmark CSR over device positions: TwoFrame i -> i, TwoCamera f -> -(f+1); padding is skipped
+    // landmark CSR over device positions: TwoFrame i -> i, TwoCamera f -> -(f+1); padding is skipped.  The count runs over the caller's
+    // order (sequential); the fill has to follow the device order, so its gather is prefetched, and it also notes the two free-pose
+    // offsets of every entry (lm_off) so that the grouping below never goes back to the factor records.
     std::vector<int> lm_start(nr + 1, 0);
-    for (int i = 0; i < n_tf; ++i) if (ba->order[0][i] >= 0) lm_start[ba->h_fi[0][3 * (size_t)ba->order[0][i]] + 1]++;
+    {
+        const int32_t* ix = ba->h_fi[0].data();
+        for (int f = 0; f < ba->n[0]; ++f) lm_start[ix[3 * (size_t)f] + 1]++;
+    }
     for (int f = 0; f < ba->n[2]; ++f) lm_start[ba->h_fi[2][f] + 1]++;
     for (int i = 0; i < nr; ++i) lm_start[i + 1] += lm_start[i];
-    std::vector<int> lm_fac(std::max(1, lm_start[nr])), fill(lm_start.begin(), lm_start.end() - 1);
-    for (int i = 0; i < n_tf; ++i) if (ba->order[0][i] >= 0) lm_fac[fill[ba->h_fi[0][3 * (size_t)ba->order[0][i]]]++] = i;
+    std::vector<int> lm_fac(std::max(1, lm_start[nr])), lm_off(2 * (size_t)std::max(1, lm_start[nr]), -1), fill(lm_start.begin(), lm_start.end() - 1);
+    {
+        const int32_t* hi = ba->h_fi[0].data();
+        const int* ord = ba->order[0].data();
+        for (int i = 0; i < n_tf; ++i) {
+            if (i + 16 < n_tf && ord[i + 16] >= 0) __builtin_prefetch(hi + 3 * (size_t)ord[i + 16]);
+            if (ord[i] < 0) continue;
+            const int32_t* ix = hi + 3 * (size_t)ord[i];
+            const int pos = fill[ix[0]]++;
+            lm_fac[pos] = i; lm_off[2 * (size_t)pos] = pose_off[ix[1]]; lm_off[2 * (size_t)pos + 1] = pose_off[ix[2]];
+        }
+    }
     for (int f = 0; f < ba->n[2]; ++f) lm_fac[fill[ba->h_fi[2][f]]++] = -(f + 1);
 
     PROF("landmark CSR");
@@ -1710,10 +1834,9 @@ int lvb_ba_finalize(lvb_ba* ba) {
             if (rho_slot[l] < 0) continue;
             int sig[MAX_TRACK + 1], ns = 0;
             for (int e = lm_start[l]; e < lm_start[l + 1]; ++e) {
-                const int i = lm_fac[e]; if (i < 0) continue;
-                const int f = tf_src(i);
+                if (lm_fac[e] < 0) continue;
                 for (int side = 1; side <= 2; ++side) {
-                    const int off = pose_off[ba->h_fi[0][3 * (size_t)f + side]];
+                    const int off = lm_off[2 * (size_t)e + side - 1];
                     if (off < 0) continue;
                     int p = 0; while (p < ns && sig[p] < off) ++p;
                     if (p < ns && sig[p] == off) continue;
@@ -1757,9 +1880,8 @@ int lvb_ba_finalize(lvb_ba* ba) {
             members[g].push_back(l);
             for (int e = lm_start[l]; e < lm_start[l + 1]; ++e) {
                 const int i = lm_fac[e]; if (i < 0) continue;
-                const int f = tf_src(i);
                 for (int side = 1; side <= 2; ++side) {
-                    const int off = pose_off[ba->h_fi[0][3 * (size_t)f + side]];
+                    const int off = lm_off[2 * (size_t)e + side - 1];
                     if (off < 0) continue;
                     int p = 0; while (sig[p] != off) ++p;
                     tf_slot[(size_t)(side - 1) * n_tf + i] = p;
@@ -1858,71 +1980,75 @@ int lvb_ba_finalize(lvb_ba* ba) {
     if (grp_ns.empty()) { grp_ns.push_back(0); grp_off.assign(MAX_TRACK, -1); }
 
     PROF("envelope");
-    LVB_TRY(ba->poses.upload(ba->h_poses.data(), ba->h_poses.size(), s));
-    LVB_TRY(ba->vec3.upload(ba->h_vec3.data(), ba->h_vec3.size(), s));
-    LVB_TRY(ba->rho.upload(ba->h_rho.data(), ba->h_rho.size(), s));
-    LVB_TRY(ba->c_poses.upload(ba->h_poses.data(), ba->h_poses.size(), s));
-    LVB_TRY(ba->c_vec3.upload(ba->h_vec3.data(), ba->h_vec3.size(), s));
-    LVB_TRY(ba->c_rho.upload(ba->h_rho.data(), ba->h_rho.size(), s));
-    LVB_TRY(ba->pose_off.upload(pose_off.data(), np, s));
-    LVB_TRY(ba->vec3_off.upload(vec3_off.data(), nv, s));
-    LVB_TRY(ba->rho_slot.upload(rho_slot.data(), nr, s));
-    LVB_TRY(ba->lm_start.upload(lm_start.data(), nr + 1, s));
-    LVB_TRY(ba->lm_fac.upload(lm_fac.data(), lm_fac.size(), s));
-    LVB_TRY(ba->tf_slot.upload(tf_slot.data(), tf_slot.size(), s));
-    LVB_TRY(ba->sw_group.upload(sw_group.data(), sw_group.size(), s));
-    LVB_TRY(ba->sw_lm.upload(sw_lm.data(), sw_lm.size(), s));
-    LVB_TRY(ba->grp_ns.upload(grp_ns.data(), grp_ns.size(), s));
-    LVB_TRY(ba->grp_off.upload(grp_off.data(), grp_off.size(), s));
-    LVB_TRY(ba->chol_rmax.upload(chol_rmax.data(), chol_rmax.size(), s));
-    LVB_TRY(ba->chol_cmin.upload(chol_cmin.data(), chol_cmin.size(), s));
-    if (ba->tree_levels > 0) { LVB_TRY(ba->fronts.upload(h_fronts.data(), h_fronts.size(), s)); LVB_TRY(ba->front_pool.ensure(pool_doubles)); }
+    LVB_TRY(stg.put(ba->poses, ba->h_poses.data(), ba->h_poses.size()));
+    LVB_TRY(stg.put(ba->vec3, ba->h_vec3.data(), ba->h_vec3.size()));
+    LVB_TRY(stg.put(ba->rho, ba->h_rho.data(), ba->h_rho.size()));
+    LVB_TRY(stg.put(ba->c_poses, ba->h_poses.data(), ba->h_poses.size()));
+    LVB_TRY(stg.put(ba->c_vec3, ba->h_vec3.data(), ba->h_vec3.size()));
+    LVB_TRY(stg.put(ba->c_rho, ba->h_rho.data(), ba->h_rho.size()));
+    LVB_TRY(stg.put(ba->pose_off, pose_off.data(), np));
+    LVB_TRY(stg.put(ba->vec3_off, vec3_off.data(), nv));
+    LVB_TRY(stg.put(ba->rho_slot, rho_slot.data(), nr));
+    LVB_TRY(stg.put(ba->lm_start, lm_start.data(), nr + 1));
+    LVB_TRY(stg.put(ba->lm_fac, lm_fac.data(), lm_fac.size()));
+    LVB_TRY(stg.put(ba->tf_slot, tf_slot.data(), tf_slot.size()));
+    LVB_TRY(stg.put(ba->sw_group, sw_group.data(), sw_group.size()));
+    LVB_TRY(stg.put(ba->sw_lm, sw_lm.data(), sw_lm.size()));
+    LVB_TRY(stg.put(ba->grp_ns, grp_ns.data(), grp_ns.size()));
+    LVB_TRY(stg.put(ba->grp_off, grp_off.data(), grp_off.size()));
+    LVB_TRY(stg.put(ba->chol_rmax, chol_rmax.data(), chol_rmax.size()));
+    LVB_TRY(stg.put(ba->chol_cmin, chol_cmin.data(), chol_cmin.size()));
+    if (ba->tree_levels > 0) { LVB_TRY(stg.put(ba->fronts, h_fronts.data(), h_fronts.size())); LVB_TRY(ba->front_pool.ensure(pool_doubles)); }
     // tensor-core Schur operands: compact pose dimensions (<= 128) and the zero-initialised split-bf16 U^T tiles
     ba->tc_ok = ba->solvable && dense_layout && 6 * npf <= 128 && npf > 0 && ctx->world == 1;
     {
         std::vector<int> cdim(std::max(1, ba->dimc), -1), coff(128, -1);
         int c = 0;
         for (size_t b = 0; b < blks.size(); ++b) if (blks[b].type == 0 && c + 6 <= 128) { for (int k = 0; k < 6; ++k) { cdim[blk_start[b] + k] = c + k; coff[c + k] = blk_start[b] + k; } c += 6; }
-        LVB_TRY(ba->tc_cdim.upload(cdim.data(), cdim.size(), s));
-        LVB_TRY(ba->tc_off.upload(coff.data(), coff.size(), s));
+        LVB_TRY(stg.put(ba->tc_cdim, cdim.data(), cdim.size()));
+        LVB_TRY(stg.put(ba->tc_off, coff.data(), coff.size()));
         ba->n_tc_chunks = ba->tc_ok ? ((2 * ba->n_schur_warps + TC_CHUNKS - 1) / TC_CHUNKS) * TC_CHUNKS : 0;
         LVB_TRY(ba->tc_u.ensure((size_t)std::max(1, ba->n_tc_chunks) * 3 * 2048));
         LVB_CUDA(cudaMemsetAsync(ba->tc_u.p, 0, (size_t)std::max(1, ba->n_tc_chunks) * 3 * 2048 * sizeof(unsigned short), s));
     }
 
     PROF("uploads (params, structure)");
-    // factor planes in device order (AoS -> SoA transpose on the host; IMU stays AoS and is packed on the device).
-    // cudaMemcpyAsync from pageable memory returns once the source has been staged, so the host vectors can go out of
-    // scope without a stream synchronisation; the IMU kernel is launched last because a pageable copy waits for the
-    // work queued before it.
+    // factor planes in device order (AoS -> SoA transpose on the host, written straight into the staging area; IMU stays AoS and
+    // is packed on the device).  The one copy to the device is issued when the last array is in place; the IMU kernel follows it.
     {
-        std::vector<double> planes; std::vector<int> iplanes;
         for (int k = 0; k < 6; ++k) {
             const int n = ba->nd[k];
             const std::vector<int>& ord = ba->order[k];
             const int is = kIdxStride[k];
-            iplanes.resize((size_t)std::max(1, n) * is);
-            if (n == 0) std::fill(iplanes.begin(), iplanes.end(), 0);
+            int* iplanes = nullptr;
+            LVB_TRY(stg.reserve(ba->fi[k], (size_t)std::max(1, n) * is, &iplanes));
+            if (n == 0) std::fill(iplanes, iplanes + is, 0);
             const int32_t* hi = ba->h_fi[k].data();
             // record-major walk: one contiguous source record per block, `is` / `cs` output streams (the plane-major walk re-read the
-            // strided source once per plane)
-            for (int i = 0; i < n; ++i) { const int f = ord[i] >= 0 ? ord[i] : -1 - ord[i]; const int32_t* src = hi + (size_t)f * is; for (int j = 0; j < is; ++j) iplanes[(size_t)j * n + i] = src[j]; }
-            LVB_TRY(ba->fi[k].upload(iplanes.data(), iplanes.size(), s));
+            // strided source once per plane); the device order is a permutation of the caller's, so the gather prefetches its records
+            if (is == 3) gather_index_planes<3>(iplanes, hi, ord.data(), n);
+            else if (is == 1) gather_index_planes<1>(iplanes, hi, ord.data(), n);
+            else for (int i = 0; i < n; ++i) { const int f = ord[i] >= 0 ? ord[i] : -1 - ord[i]; const int32_t* src = hi + (size_t)f * is; for (int j = 0; j < is; ++j) iplanes[(size_t)j * n + i] = src[j]; }
+            LVB_TRY(stg.finish());
             if (k == 3) continue;
             const int cs = kConstStride[k];
-            planes.resize((size_t)std::max(1, n) * cs);
-            if (n == 0) std::fill(planes.begin(), planes.end(), 0.0);
+            double* planes = nullptr;
+            LVB_TRY(stg.reserve(ba->fc[k], (size_t)std::max(1, n) * cs, &planes));
+            if (n == 0) std::fill(planes, planes + cs, 0.0);
             const int wcol = (k == 0) ? 4 : (k == 1 ? 5 : -1);     // weight column, zeroed on padding
             const double* hc = ba->h_fc[k].data();
-            for (int i = 0; i < n; ++i) {
+            if (cs == 5) gather_planes<5>(planes, hc, ord.data(), n, wcol);
+            else if (cs == 6) gather_planes<6>(planes, hc, ord.data(), n, wcol);
+            else for (int i = 0; i < n; ++i) {
                 const bool pad = ord[i] < 0;
                 const double* src = hc + (size_t)(pad ? -1 - ord[i] : ord[i]) * cs;
                 for (int j = 0; j < cs; ++j) planes[(size_t)j * n + i] = (pad && j == wcol) ? 0.0 : src[j];
             }
-            LVB_TRY(ba->fc[k].upload(planes.data(), planes.size(), s));
+            LVB_TRY(stg.finish());
         }
         const int n = ba->nd[3];
-        LVB_TRY(ba->imu_raw.upload(ba->h_fc[3].data(), ba->h_fc[3].size(), s));
+        LVB_TRY(stg.put(ba->imu_raw, ba->h_fc[3].data(), ba->h_fc[3].size()));
+        LVB_TRY(stg.commit(ba->upload_arena));      // everything uploaded so far: one copy
         LVB_TRY(ba->fc[3].ensure((size_t)std::max(1, n) * IMU_STRIDE));
         LVB_TRY(ba->imu_status.ensure(std::max(1, n)));
         if (n) {
@@ -1995,6 +2121,7 @@ int lvb_ba_dims(lvb_ba* ba, int* dimc, int* nrf, int* rows) {
 int lvb_ba_update_params(lvb_ba* ba, const double* P, const double* V, const double* R) {
     if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
     cudaStream_t s = ba->ctx->stream;
+    ba->host_fresh = false;
     LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
     if (P) { ba->h_poses.assign(P, P + ba->h_poses.size()); LVB_TRY(ba->poses.upload(P, ba->h_poses.size(), s)); }
     if (V) { ba->h_vec3.assign(V, V + ba->h_vec3.size()); LVB_TRY(ba->vec3.upload(V, ba->h_vec3.size(), s)); }
@@ -2189,8 +2316,8 @@ static int upload_state(lvb_ba* ba, const lvb_solve_options* o, double radius_ov
     if (radius_override > 0) opt.initial_trust_region_radius = radius_override;
     LmState h;
     lm_init(h, opt);
+    // pageable source of a few hundred bytes: the call returns once the driver has staged it, no synchronisation needed before `h` dies
     LVB_CUDA(cudaMemcpyAsync(ba->st.p, &h, sizeof(h), cudaMemcpyHostToDevice, ba->ctx->stream));
-    LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream));
     return LVB_OK;
 }
 
@@ -2235,12 +2362,17 @@ int lvb_ba_reduced_system(lvb_ba* ba, double radius, double* S, double* b, doubl
 
 int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary* summary) {
     LVB_TRY(require_solvable(ba));
+    ba->host_fresh = false;
     LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
     const auto t0 = std::chrono::steady_clock::now();
+    static const bool prof_on = getenv("LVB_PROFILE") != nullptr;
+    auto prof_t = t0;
+#define PROF(name) do { if (prof_on) { const auto t_ = std::chrono::steady_clock::now(); fprintf(stderr, "[solve] %-28s %8.1f us\n", name, std::chrono::duration<double, std::micro>(t_ - prof_t).count()); prof_t = t_; } } while (0)
     lvb_solve_options opt;
     if (options) opt = *options; else lvb_default_options(&opt);
     apply_schur_mode(ba, options ? opt.schur_mode : ba->schur_mode);
     LVB_TRY(upload_state(ba, &opt, -1.0));
+    PROF("state upload");
     cudaStream_t s = ba->ctx->stream;
     LmState h;
     memset(&h, 0, sizeof(h));
@@ -2298,6 +2430,7 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
             cudaGraphDestroy(g);
             ba->pass_launches = (int)(ba->ctx->launches - before);
             ba->ctx->launches = before;                     // capture is not execution
+            PROF("capture + exec update");
         }
         for (int c = 0; c < chunk; ++c) {
             if (use_graph) { LVB_CUDA(cudaGraphLaunch(ba->pass_graph, s)); ba->ctx->launches += ba->pass_launches; }
@@ -2307,8 +2440,10 @@ int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary
         LVB_CUDA(cudaMemcpyAsync(&h, ba->st.p, sizeof(h), cudaMemcpyDeviceToHost, s));
         LVB_CUDA(cudaStreamSynchronize(s));
         LVB_TRY(comm_check(ba->ctx));
+        PROF("launch + wait");
         if (h.done) break;             // identical on every rank: the state is a function of bitwise-identical all-reduced sums
     }
+#undef PROF
     ba->solves_done++;
     if (summary) {
         int nb = 0; for (int k = 0; k < 6; ++k) nb += ba->n[k];
@@ -2386,17 +2521,31 @@ LVB_API int lvb_debug_band_solve(lvb_ctx* ctx, int n, int band, const double* S_
     return LVB_OK;
 }
 
+// The three getters share one device round trip: the first call after a solve / parameter update brings all parameter blocks back
+// (through the context's pinned staging area when it is free), the others copy from that snapshot.
+static int fetch_params(lvb_ba* ba) {
+    if (ba->host_fresh) return LVB_OK;
+    lvb_ctx* c = ba->ctx;
+    LVB_CUDA(cudaSetDevice(c->device)); lvb::g_alloc_stream = c->stream;
+    const size_t n0 = ba->h_poses.size(), n1 = ba->h_vec3.size(), n2 = ba->h_rho.size(), total = (n0 + n1 + n2) * sizeof(double);
+    ba->r_params.resize(n0 + n1 + n2);
+    const bool pinned = c->stage_h && c->stage_cap >= total && (!c->stage_busy || cudaEventQuery(c->stage_ev) == cudaSuccess);
+    double* dst = pinned ? reinterpret_cast<double*>(c->stage_h) : ba->r_params.data();
+    cudaStream_t s = c->stream;
+    LVB_TRY(ba->poses.download(dst, n0, s)); LVB_TRY(ba->vec3.download(dst + n0, n1, s)); LVB_TRY(ba->rho.download(dst + n0 + n1, n2, s));
+    LVB_CUDA(cudaStreamSynchronize(s));
+    if (pinned) { memcpy(ba->r_params.data(), dst, total); c->stage_busy = false; }
+    ba->host_fresh = true;
+    return LVB_OK;
+}
 int lvb_ba_get_poses(lvb_ba* ba, double* out) {
-    LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
-    LVB_TRY(ba->poses.download(out, ba->h_poses.size(), ba->ctx->stream)); LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream)); return LVB_OK;
+    LVB_TRY(fetch_params(ba)); memcpy(out, ba->r_params.data(), ba->h_poses.size() * sizeof(double)); return LVB_OK;
 }
 int lvb_ba_get_vec3(lvb_ba* ba, double* out) {
-    LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
-    LVB_TRY(ba->vec3.download(out, ba->h_vec3.size(), ba->ctx->stream)); LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream)); return LVB_OK;
+    LVB_TRY(fetch_params(ba)); memcpy(out, ba->r_params.data() + ba->h_poses.size(), ba->h_vec3.size() * sizeof(double)); return LVB_OK;
 }
 int lvb_ba_get_inv_depths(lvb_ba* ba, double* out) {
-    LVB_CUDA(cudaSetDevice(ba->ctx->device)); lvb::g_alloc_stream = ba->ctx->stream;
-    LVB_TRY(ba->rho.download(out, ba->h_rho.size(), ba->ctx->stream)); LVB_CUDA(cudaStreamSynchronize(ba->ctx->stream)); return LVB_OK;
+    LVB_TRY(fetch_params(ba)); memcpy(out, ba->r_params.data() + ba->h_poses.size() + ba->h_vec3.size(), ba->h_rho.size() * sizeof(double)); return LVB_OK;
 }
 
 int lvb_ba_reprojection_errors(lvb_ba* ba, int n, const double* ob_pw, const int32_t* pose_idx, double* err) {

@@ -264,6 +264,8 @@ void lvb_ctx_destroy(lvb_ctx* ctx) {
     if (ctx->xbuf) cudaFree(ctx->xbuf);
     if (ctx->scratch_i32) cudaFree(ctx->scratch_i32);
     if (ctx->graph_cache) cudaGraphExecDestroy(ctx->graph_cache);
+    if (ctx->stage_ev) { cudaEventSynchronize(ctx->stage_ev); cudaEventDestroy(ctx->stage_ev); }
+    if (ctx->stage_h) cudaFreeHost(ctx->stage_h);
     if (ctx->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(ctx->comm);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);

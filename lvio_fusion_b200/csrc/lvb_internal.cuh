@@ -47,6 +47,13 @@ struct lvb_ctx {
     cudaGraphExec_t graph_cache = nullptr;
     const void* graph_owner = nullptr;                    // the lvb_ba whose parameters the cached graph currently holds
     bool use_graph_cache = true;                          // env LVB_NO_GRAPH_CACHE=1 disables
+    // Pinned staging area for the arrays a problem uploads when it is finalised (ba.cu, Stager): they are assembled here and go to
+    // the device in ONE copy instead of ~40 pageable ones.  Grown on demand, reused by every problem of the context; `stage_ev`
+    // marks the last copy that read it.
+    unsigned char* stage_h = nullptr;
+    size_t stage_cap = 0;
+    cudaEvent_t stage_ev = nullptr;
+    bool stage_busy = false;
 };
 
 namespace lvb {
@@ -71,8 +78,10 @@ template <class T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     cudaStream_t s = nullptr;
+    bool view = false;               // p points into another allocation (a problem's upload arena): never freed from here
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFreeAsync(p, s); p = nullptr; n = 0; }
+    void release() { if (p && !view) cudaFreeAsync(p, s); p = nullptr; n = 0; view = false; }
+    void set_view(T* q, size_t count) { release(); p = q; n = count; view = true; }
     int ensure(size_t count) {
         if (count <= n && p) return LVB_OK;
         release();
