@@ -173,3 +173,57 @@ def test_banded_storage_matches_oracle(lvb_ctx, orc_ctx, n_kf, n_lm, imu):
     assert np.max(np.abs(Pg[:, 4:] - Po[:, 4:])) < 1e-5
     assert np.max(np.abs(Pg[:, :4] - Po[:, :4])) < 1e-6
     assert np.max(np.abs(pg.inv_depths() - po.inv_depths())) < 1e-5
+
+
+def test_staged_uploads_match_per_array_uploads(lvb, c1):
+    """finalize assembles its uploads in the context's pinned staging area (one copy, one allocation); LVB_NO_STAGING=1 keeps the
+    per-array uploads.  Both must build the same device problem: identical evaluation, reduced system and solve."""
+    ctx_a = backend.Context(lvb)
+    os.environ["LVB_NO_STAGING"] = "1"
+    try:
+        # the switch is read once per process at the first finalize: run the unstaged arm in a child interpreter
+        import subprocess, sys, json, tempfile
+        code = ("import json,sys,numpy as np\n"
+                "from lvio_fusion_b200 import _capi, backend, synth\n"
+                "from lvio_fusion_b200.backend import TWO_FRAME, IMU\n"
+                "sys.path.insert(0, %r)\n"
+                "import test_gpu_ba as T\n"
+                "d = synth.make_ba_problem(5, 2000, with_imu=True, seed=synth.SEED)\n"
+                "d['poses'][:, :4] *= (1.0 + 0.003 * np.arange(5))[:, None]\n"
+                "d = T._with_priors(d)\n"
+                "ctx = backend.Context(_capi.load())\n"
+                "p = backend.Problem.from_dict(ctx, d)\n"
+                "r, J = p.evaluate(TWO_FRAME); ri, Ji = p.evaluate(IMU)\n"
+                "s = p.solve(max_num_iterations=8)\n"
+                "np.savez(sys.argv[1], r=r, J=J, ri=ri, Ji=Ji, P=p.poses(), V=p.vec3(), R=p.inv_depths(), cost=np.array([s.initial_cost, s.final_cost]))\n") % os.path.dirname(os.path.abspath(__file__))
+        with tempfile.TemporaryDirectory() as td:
+            out = os.path.join(td, "u.npz")
+            subprocess.run([sys.executable, "-c", code, out], check=True, env=dict(os.environ), timeout=600)
+            u = dict(np.load(out))
+    finally:
+        del os.environ["LVB_NO_STAGING"]
+    p = backend.Problem.from_dict(ctx_a, c1)
+    r, J = p.evaluate(TWO_FRAME)
+    ri, Ji = p.evaluate(IMU)
+    s = p.solve(max_num_iterations=8)
+    assert np.array_equal(r, u["r"]) and np.array_equal(J, u["J"]) and np.array_equal(ri, u["ri"]) and np.array_equal(Ji, u["Ji"])
+    assert abs(s.initial_cost - u["cost"][0]) <= 1e-12 * abs(u["cost"][0]) and abs(s.final_cost - u["cost"][1]) <= 1e-9 * abs(u["cost"][1])
+    assert np.max(np.abs(p.poses() - u["P"])) < 1e-9 and np.max(np.abs(p.vec3() - u["V"])) < 1e-8 and np.max(np.abs(p.inv_depths() - u["R"])) < 1e-9
+
+
+def test_getters_share_one_snapshot_and_follow_updates(lvb_ctx):
+    """The three getters are served from one read-back; a solve or update_params must invalidate it."""
+    d = synth.make_ba_problem(5, 500, with_imu=True, seed=11)
+    p = backend.Problem.from_dict(lvb_ctx, d)
+    assert np.array_equal(p.poses(), d["poses"]) and np.array_equal(p.vec3(), d["vec3"]) and np.array_equal(p.inv_depths(), d["rho"])
+    p.solve(max_num_iterations=3)
+    P1, V1, R1 = p.poses(), p.vec3(), p.inv_depths()
+    assert np.max(np.abs(P1 - d["poses"])) > 0 and np.max(np.abs(R1 - d["rho"])) > 0
+    assert np.array_equal(p.poses(), P1) and np.array_equal(p.vec3(), V1)
+    p.update_params(d["poses"], d["vec3"], d["rho"])
+    assert np.array_equal(p.poses(), d["poses"]) and np.array_equal(p.inv_depths(), d["rho"])
+    # several problems on one context take turns in the staging area; the earlier one must stay intact
+    q = backend.Problem.from_dict(lvb_ctx, synth.make_ba_problem(4, 300, with_imu=False, seed=12))
+    q.solve(max_num_iterations=2)
+    p.solve(max_num_iterations=3)
+    assert np.max(np.abs(p.poses() - P1)) < 1e-9 and np.max(np.abs(p.inv_depths() - R1)) < 1e-9

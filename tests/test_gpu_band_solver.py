@@ -64,3 +64,35 @@ def test_indefinite_system_is_reported(lvb_ctx):
     rc = api.debug_band_solve(lvb_ctx.h, n, band, packed.ctypes.data_as(_capi.c_double_p), b.ctypes.data_as(_capi.c_double_p),
                               x.ctypes.data_as(_capi.c_double_p), 1, None)
     assert rc != 0 and b"pivot" in api.last_error()
+
+
+@pytest.mark.parametrize("n,true_band", [(1, 0), (20, 19), (32, 31), (33, 32), (47, 46), (64, 5), (95, 20), (129, 128), (150, 149), (160, 64), (300, 299), (300, 91), (736, 100)])
+def test_single_cta_kernel_sizes(lvb_ctx, n, true_band):
+    """The one-CTA kernel alone over the shapes its schedule distinguishes: fewer rows than a block, a partial last block, a full
+    window (150 / 300 unknowns, dense), head rows cut by the envelope (band narrower than a block), the widest dense layout."""
+    rng = np.random.default_rng(n * 7 + true_band)
+    s = _band_spd(n, true_band, rng)
+    b = rng.normal(size=n)
+    want = np.linalg.solve(s, b)
+    band = max(31, true_band + 31)
+    packed = np.ascontiguousarray(_pack(s, band)); x = np.zeros(n); lv = C.c_int(-1)
+    api = lvb_ctx.api
+    api.check(api.debug_band_solve(lvb_ctx.h, n, band, packed.ctypes.data_as(_capi.c_double_p), b.ctypes.data_as(_capi.c_double_p),
+                                   x.ctypes.data_as(_capi.c_double_p), 0, C.byref(lv)), "debug_band_solve")
+    assert lv.value == 0
+    err = np.max(np.abs(x - want)) / np.max(np.abs(want))
+    resid = np.max(np.abs(s @ x - b)) / np.max(np.abs(b))
+    assert err < 1e-9 and resid < 1e-10, (err, resid)
+
+
+def test_single_cta_kernel_reports_a_non_positive_pivot(lvb_ctx):
+    n = 150
+    rng = np.random.default_rng(3)
+    s = _band_spd(n, n - 1, rng)
+    s[101, 101] = -5.0          # inside the fourth diagonal block: found by the two-column pivot step
+    band = n - 1 + 31
+    packed = np.ascontiguousarray(_pack(s, band)); b = np.ones(n); x = np.zeros(n)
+    api = lvb_ctx.api
+    rc = api.debug_band_solve(lvb_ctx.h, n, band, packed.ctypes.data_as(_capi.c_double_p), b.ctypes.data_as(_capi.c_double_p),
+                              x.ctypes.data_as(_capi.c_double_p), 0, None)
+    assert rc != 0 and b"pivot" in api.last_error()
