@@ -1238,6 +1238,7 @@ __global__ void __launch_bounds__(CHOL_T) ba_cholesky_kernel(double* __restrict_
 }
 
 #include "ba_tree.cuh"
+#include "ba_wide.cuh"
 
 // ------------------------------------------------------------------ back-substitution + candidate point
 __global__ void __launch_bounds__(TPB) ba_update_kernel(BaDev d) {
@@ -1399,6 +1400,8 @@ struct lvb_ba {
     DevBuf<Front> fronts; DevBuf<double> front_pool;
     std::vector<int> level_first, level_count;
     int tree_levels = 0; size_t tree_factor_smem = 0, tree_back_smem = 0;
+    bool wide_solver = false;           // envelope too wide for the one-CTA panel and no tree: per-phase grids over S in global memory (ba_wide.cuh)
+    std::vector<int> h_rmax;            // host copy of the envelope (launch geometry of the wide solver)
     // device
     DevBuf<unsigned char> upload_arena;      // one allocation for everything finalize uploads (the buffers below are views into it)
     DevBuf<double> poses, vec3, rho, c_poses, c_vec3, c_rho;
@@ -1970,10 +1973,9 @@ int lvb_ba_finalize(lvb_ba* ba) {
             if (lv > 0 && fs <= 227 * 1024 - 256 && pool_doubles < ((size_t)1 << 31)) { ba->tree_levels = lv; ba->tree_factor_smem = fs; ba->tree_back_smem = bs_; }
         }
     }
-    if (ba->solvable && ba->tree_levels == 0 && (ba->chol_smem > 227 * 1024 - 256 || ba->nS > ((size_t)3 << 30))) {
-        ba->solvable = false;
-        ba->unsolvable_why = "the envelope of the reduced camera system is too wide for the direct solver of this build";
-    }
+    // loop-closure shaped envelopes: neither a tree nor a panel that fits in shared memory -- the per-phase grids of ba_wide.cuh
+    ba->wide_solver = ba->solvable && ba->tree_levels == 0 && ba->chol_smem > 227 * 1024 - 256;
+    ba->h_rmax = chol_rmax;
     if (ba->solvable && ba->nS > ((size_t)3 << 30)) { ba->solvable = false; ba->unsolvable_why = "the banded reduced camera system exceeds 24 GB"; }
     if (!ba->solvable) ba->nS = 1;
     if (sw_group.empty()) { sw_group.push_back(0); sw_lm.assign(32, -1); }
@@ -2261,6 +2263,24 @@ static int launch_linearize_and_reduce(lvb_ba* ba, bool standalone) {
 }
 
 // rhs <- S^-1 rhs (+ the LM pre-check): multifrontal tree over the banded system, or the single-CTA envelope Cholesky
+static int launch_wide_solve(lvb_ba* ba) {
+    BaDev& d = ba->dev;
+    const int n = d.dimc;
+    static bool attr_set = false;
+    if (!attr_set) { LVB_CUDA(cudaFuncSetAttribute(ba_wide_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_WARPS * 2 * 32 * 34 * 8)); attr_set = true; }
+    for (int kb = 0; kb < n; kb += 32) {
+        const int bs = std::min(32, n - kb);
+        const int m = ba->h_rmax[kb >> 5] - (kb + bs) + 2;
+        const int ntile = (m + 31) / 32, total = m > 1 ? ntile * (ntile + 1) / 2 : 0;
+        LAUNCH(ba, ba_wide_diag_kernel, 1, 32, 0, d.S, n, d.srow, d.soff, kb, ba->chol_invd.p, d.st, kb == 0 ? 1 : 0);
+        LAUNCH(ba, ba_wide_panel_kernel, nblk(m, 128), 128, 0, d.S, d.rhs, n, d.srow, d.soff, kb, ba->chol_invd.p, d.st, ba->chol_rmax.p);
+        LAUNCH(ba, ba_wide_update_kernel, nblk(total, WIDE_WARPS), WIDE_WARPS * 32, (size_t)WIDE_WARPS * 2 * 32 * 34 * 8, d.S, d.rhs, n, d.srow, d.soff, kb, d.st, ba->chol_rmax.p);
+    }
+    for (int kb = ((n - 1) / 32) * 32; kb >= 0; kb -= 32)
+        LAUNCH(ba, ba_wide_backward_kernel, 1, 256, 0, d.S, d.rhs, n, d.srow, d.soff, kb, ba->chol_invd.p, d.st, ba->chol_rmax.p);
+    return LVB_OK;
+}
+
 static int launch_reduced_solve(lvb_ba* ba) {
     BaDev& d = ba->dev;
     lvb_ctx* ctx = ba->ctx;
@@ -2275,6 +2295,8 @@ static int launch_reduced_solve(lvb_ba* ba) {
             LAUNCH(ba, ba_front_factor_kernel, ba->level_count[l], CHOL_T, ba->tree_factor_smem, fr, ba->level_first[l], d.S, d.rhs, ba->front_pool.p, d.srow, d.soff, ba->band, ba->chol_invd.p, d.st);
         for (int l = ba->tree_levels - 1; l >= 0; --l)
             LAUNCH(ba, ba_front_backward_kernel, ba->level_count[l], CHOL_T, ba->tree_back_smem, fr, ba->level_first[l], d.S, d.rhs, ba->front_pool.p, d.srow, d.soff, ba->band, ba->chol_invd.p, d.st);
+    } else if (ba->wide_solver) {
+        LVB_TRY(launch_wide_solve(ba));
     } else
     LAUNCH(ba, ba_cholesky_kernel, 1, CHOL_T, ba->chol_smem, d.S, d.rhs, d.dimc, d.srow, d.soff, ba->chol_invd.p, d.st, 1, ba->chol_rmax.p, ba->chol_cmin.p);
     return LVB_OK;
@@ -2508,7 +2530,8 @@ LVB_API int lvb_debug_band_solve(lvb_ctx* ctx, int n, int band, const double* S_
         if (lv > 0 && ba.tree_factor_smem <= 227 * 1024 - 256) { ba.tree_levels = lv; LVB_TRY(ba.fronts.upload(fr.data(), fr.size(), s)); LVB_TRY(ba.front_pool.ensure(pool)); }
     }
     if (levels_out) *levels_out = ba.tree_levels;
-    if (ba.tree_levels == 0 && ba.chol_smem > 227 * 1024 - 256) { set_error("band too wide for the single-CTA kernel"); return LVB_ERR_UNSUPPORTED; }
+    ba.wide_solver = ba.tree_levels == 0 && ba.chol_smem > 227 * 1024 - 256;      // ba_wide.cuh
+    ba.h_rmax = rmax;
     BaDev& d = ba.dev;
     memset(&d, 0, sizeof(d));
     d.dimc = n; d.srow = ba.srow; d.soff = ba.soff; d.nS = ba.nS; d.S = ba.arena.p; d.rhs = ba.arena.p + ba.nS; d.st = ba.st.p;

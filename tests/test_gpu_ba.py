@@ -227,3 +227,25 @@ def test_getters_share_one_snapshot_and_follow_updates(lvb_ctx):
     q.solve(max_num_iterations=2)
     p.solve(max_num_iterations=3)
     assert np.max(np.abs(p.poses() - P1)) < 1e-9 and np.max(np.abs(p.inv_depths() - R1)) < 1e-9
+
+
+def test_loop_closure_envelope_is_solved(lvb_ctx, orc_ctx):
+    """A relative-pose constraint between the first and the last keyframe of a map-sized problem (Relocator / PoseGraph output fed
+    back into a global BA) makes the envelope of the reduced camera system as wide as the system: no separator tree, no shared-memory
+    panel.  The solve goes through the multi-grid fallback (ba_wide.cuh) and matches the dense oracle."""
+    n_kf = 80
+    d = synth.make_ba_problem(n_kf, 3000, with_imu=True, seed=13)
+    d = dict(d); d["factors"] = dict(d["factors"])
+    P = d["poses_true"]
+    r = synth.relative_rpyxyz(P[0], P[n_kf - 1])      # PoseGraphError's measurement: rpyxyz of T_0^-1 T_last (pose_error.hpp:25-39)
+    d["factors"][POSE_GRAPH] = (np.concatenate([r, [50.0, 0.5]])[None], np.array([[0, n_kf - 1]], dtype=np.int32))
+    pg, po = backend.Problem.from_dict(lvb_ctx, d), backend.Problem.from_dict(orc_ctx, d)
+    assert pg.dims() == po.dims() and pg.dims()[0] > 736
+    Sg, bg, cg = pg.reduced_system(1e4)
+    So, bo, co = po.reduced_system(1e4)
+    assert abs(cg - co) < 1e-10 * co and _rel(Sg, So) < 1e-9 and _rel(bg, bo) < 1e-9
+    sg = pg.solve(max_num_iterations=8)
+    so = po.solve(max_num_iterations=8, num_threads=4)
+    assert sg.termination_type == so.termination_type and sg.num_iterations == so.num_iterations
+    assert abs(sg.final_cost - so.final_cost) < 1e-6 * so.final_cost and sg.final_cost < 0.5 * sg.initial_cost
+    assert np.max(np.abs(pg.poses() - po.poses())) < 1e-5

@@ -96,3 +96,23 @@ def test_single_cta_kernel_reports_a_non_positive_pivot(lvb_ctx):
     rc = api.debug_band_solve(lvb_ctx.h, n, band, packed.ctypes.data_as(_capi.c_double_p), b.ctypes.data_as(_capi.c_double_p),
                               x.ctypes.data_as(_capi.c_double_p), 0, None)
     assert rc != 0 and b"pivot" in api.last_error()
+
+
+@pytest.mark.parametrize("n,true_band", [(1500, 1200), (2100, 2099), (1000, 930)])
+def test_wide_envelope_uses_the_multi_grid_solver(lvb_ctx, n, true_band):
+    """Envelopes too wide for the one-CTA panel and with no room for a separator tree (loop closures) go through the per-phase grids
+    of ba_wide.cuh instead of LVB_ERR_UNSUPPORTED."""
+    rng = np.random.default_rng(n + true_band)
+    s = _band_spd(n, true_band, rng)
+    b = rng.normal(size=n)
+    want = np.linalg.solve(s, b)
+    band = true_band + 31
+    packed = np.ascontiguousarray(_pack(s, band)); api = lvb_ctx.api
+    for use_tree in (1, 0):
+        x = np.zeros(n); lv = C.c_int(-1)
+        api.check(api.debug_band_solve(lvb_ctx.h, n, band, packed.ctypes.data_as(_capi.c_double_p), b.ctypes.data_as(_capi.c_double_p),
+                                       x.ctypes.data_as(_capi.c_double_p), use_tree, C.byref(lv)), "debug_band_solve")
+        assert lv.value == 0
+        err = np.max(np.abs(x - want)) / np.max(np.abs(want))
+        resid = np.max(np.abs(s @ x - b)) / np.max(np.abs(b))
+        assert err < 1e-8 and resid < 1e-9, (use_tree, err, resid)
