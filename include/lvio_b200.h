@@ -142,8 +142,11 @@ LVB_API int lvb_ba_add_factors(lvb_ba* ba, int kind, int n, const double* consts
 /* ceres::HuberLoss(a) for every block of `kind` (backend.cpp:98 uses 1.0 on the visual kinds);
  * a <= 0 means NULL / TrivialLoss. */
 LVB_API int lvb_ba_set_loss(lvb_ba* ba, int kind, double huber_a);
-/* Freeze the structure, sort/transpose to the device layout, upload.  Collective when world_size > 1 (the order of
- * the unknowns and the envelope of the reduced system are agreed on across the ranks). */
+/* Freeze the structure, sort/transpose to the device layout, upload (window-sized problems: assembled in the context's pinned
+ * staging area and sent with one copy).  Collective when world_size > 1 (the order of the unknowns and the envelope of the
+ * reduced system are agreed on across the ranks).  The reduced camera system is solved by the one-CTA kernel (<= 736 unknowns or
+ * a panel that fits in shared memory), the multifrontal separator tree (banded map-scale systems) or, for loop-closure shaped
+ * envelopes, per-phase grids over global memory; LVB_ERR_UNSUPPORTED (at solve) only when its banded storage exceeds 24 GB. */
 LVB_API int lvb_ba_finalize(lvb_ba* ba);
 LVB_API int lvb_ba_dims(lvb_ba* ba, int* dim_camera, int* n_inv_depth_free, int* n_residual_rows);
 /* Re-upload parameter values only (same structure) -- used between solves / by the bench. */
@@ -170,6 +173,8 @@ LVB_API int lvb_ba_reduced_system(lvb_ba* ba, double radius, double* S, double* 
  * only when 6 x (free poses) <= 128 on a single GPU, else the handle silently stays on mode 0. */
 LVB_API int lvb_ba_set_schur_mode(lvb_ba* ba, int mode);
 LVB_API int lvb_ba_solve(lvb_ba* ba, const lvb_solve_options* options, lvb_solve_summary* summary);
+/* The three getters share one device round trip: the first call after a solve / lvb_ba_update_params reads all parameter blocks
+ * back, the others copy from that snapshot. */
 LVB_API int lvb_ba_get_poses(lvb_ba* ba, double* poses7);
 LVB_API int lvb_ba_get_vec3(lvb_ba* ba, double* v3);
 LVB_API int lvb_ba_get_inv_depths(lvb_ba* ba, double* rho);
@@ -278,9 +283,11 @@ LVB_API int lvb_debug_timing(int enable);
 LVB_API int lvb_debug_timing_report(char* out, int cap);
 /* the reduced-system solver alone (parity test of the multifrontal tree, ba_tree.cuh): S x = b for an SPD band matrix stored as
  * n rows of band + 1 entries (row i = columns i - band .. i), true half bandwidth <= band - 31; use_tree 0 forces the single-CTA
- * envelope kernel; *levels_out = tree levels used (0: single CTA) */
+ * envelope kernel (or, when its panel does not fit in shared memory, the per-phase grids of ba_wide.cuh); *levels_out = tree levels
+ * used (0: no tree) */
 LVB_API int lvb_debug_band_solve(lvb_ctx* ctx, int n, int band, const double* S_band, const double* b, double* x, int use_tree, int* levels_out);
-/* SM clock counters of ba_cholesky_kernel summed over calls: {diag, panel, trailing, backward, total, calls, -, -} */
+/* SM clock counters of ba_cholesky_kernel summed over calls, as seen by the warp that carries the pivot chain:
+ * {diagonal tile + factorisation, its panel rows, wait for the other warps, backward pass, total, calls, -, -} */
 LVB_API int lvb_debug_cholesky_clocks(long long out[8], int reset);
 
 #ifdef __cplusplus
