@@ -2547,6 +2547,7 @@ LVB_API int lvb_debug_band_solve(lvb_ctx* ctx, int n, int band, const double* S_
 // The three getters share one device round trip: the first call after a solve / parameter update brings all parameter blocks back
 // (through the context's pinned staging area when it is free), the others copy from that snapshot.
 static int fetch_params(lvb_ba* ba) {
+    if (!ba->finalized) { set_error("finalize first"); return LVB_ERR_STATE; }
     if (ba->host_fresh) return LVB_OK;
     lvb_ctx* c = ba->ctx;
     LVB_CUDA(cudaSetDevice(c->device)); lvb::g_alloc_stream = c->stream;
